@@ -1,0 +1,127 @@
+/* summarizer_b200 — C ABI of libsummarizer_b200.so (hand-written sm_100a kernels).
+ *
+ * The reference (sylvainma/Summarizer) is pure Python and has NO FFI/plugin interface
+ * (SURVEY.md §8b); this header therefore *defines* the boundary that sits directly beneath
+ * the reference's Python surface.  Each entry point names the reference function(s) it
+ * replaces (paths relative to /root/reference/summarizer/).  INTEGRATION.md shows the ctypes
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain C types only.  Every function returns int: 0 = ok,
+ *     SMZ_ERR_ARG (-1) bad argument/shape, SMZ_ERR_CUDA (-2) CUDA error,
+ *     SMZ_ERR_UNSUPPORTED (-3) configuration outside the kernels' plan,
+ *     SMZ_ERR_DEVICE (-5) not an sm_100 device.  smz_last_error() gives the message
+ *     (thread-local).  Nothing throws.
+ *   - All data pointers are DEVICE pointers owned by the caller unless the name starts with
+ *     h_.  The library never allocates or frees device memory and never synchronises the
+ *     host: work is enqueued on `stream` (a cudaStream_t passed as void*).  Work buffers are
+ *     caller-provided and sized by the matching *_workspace_bytes function.
+ *   - Ragged batches ("video batches") are described by an array of smz_video_desc in
+ *     device memory; all packed arrays are indexed through its element offsets.
+ *   - There is no CPU fallback and no other backend.
+ */
+#ifndef SUMMARIZER_B200_H
+#define SUMMARIZER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMZ_OK 0
+#define SMZ_ERR_ARG (-1)
+#define SMZ_ERR_CUDA (-2)
+#define SMZ_ERR_UNSUPPORTED (-3)
+#define SMZ_ERR_NCCL (-4)
+#define SMZ_ERR_DEVICE (-5)
+
+#define SMZ_METHOD_KNAPSACK 0 /* utils/eval.py:98-99  */
+#define SMZ_METHOD_RANK 1     /* utils/eval.py:100-107 */
+
+/* per-video status bits written by smz_select_shots */
+#define SMZ_STATUS_VALUE_RANGE 1 /* |int(score*1000)| * n_segs does not fit the int32 DP */
+#define SMZ_STATUS_INTERVALS 2   /* more upsample intervals than scores+1 (reference: IndexError) */
+
+/* frames handled by one CTA of the F-score kernel */
+#define SMZ_FSCORE_CHUNK 2048
+
+/* One video of a ragged batch.  Offsets are ELEMENT offsets into the packed arrays. 104 bytes. */
+typedef struct smz_video_desc {
+    int64_t score_off;   /* scores[]        float32, n_scores entries  (model output, one per step)      */
+    int64_t picks_off;   /* picks[]         int32,   n_picks entries   (dataset /picks, ascending)        */
+    int64_t seg_off;     /* cps[2*(seg_off+s)+{0,1}], nfps[seg_off+s]; per-segment outputs use it too    */
+    int64_t user_off;    /* user_summary[]  float32, row u at user_off + u*user_ld, n_frames per row      */
+    int64_t user_ld;     /* row stride (elements).  user_off%4==0 && user_ld%4==0 enables 128-bit loads   */
+    int64_t summ_off;    /* machine_summary[] float32 output, summ_len = sum(nfps) entries                */
+    int64_t frame_off;   /* frame_scores[]  float32 output of smz_upsample, n_frames entries              */
+    int64_t mask_off;    /* summary bit mask (uint32 words), ceil(n_frames/32) words                      */
+    int64_t ucount_off;  /* per-user outputs (overlap, gsum, f): n_users entries                          */
+    int32_t n_scores, n_picks, n_segs, n_users;
+    int32_t n_frames;    /* dataset /n_frames                                                             */
+    int32_t summ_len;    /* sum(nfps) (utils/eval.py:111-122 output length; may differ from n_frames)     */
+    int32_t capacity;    /* int(floor(n_frames * proportion)) computed in float64 (utils/eval.py:96)      */
+    int32_t reserved;    /* must be 0                                                                     */
+} smz_video_desc;
+
+/* ---- library ------------------------------------------------------------------------- */
+const char *smz_version(void);
+const char *smz_last_error(void);
+/* 0 when the current CUDA device is compute capability 10.x; SMZ_ERR_DEVICE otherwise. */
+int smz_device_check(void);
+
+/* ---- shot selection: replaces utils/eval.py:74-123 generate_summary (+ utils/eval.py:15-35
+ *      upsample inlined, utils/knapsack.py:5-23 knapsack_ortools incl. the OR-tools DP) ------
+ * For every video v < n_videos:  upsample scores -> float32 numpy-pairwise segment means ->
+ * values = trunc(double(mean)*1000) -> 0/1 knapsack (OR-tools DP semantics) or rank greedy ->
+ * summary vector (float32 0/1, summ_len entries), the same summary as a bit mask truncated/
+ * padded to n_frames, and msum = popcount(mask).
+ * Outputs (per-segment arrays indexed seg_off+s; any may be NULL except picked/mask/msum):
+ *   seg_mean float32, values int32, picked uint8, summary float32, mask uint32, msum int32[n_videos],
+ *   status int32[n_videos] (0 = ok, SMZ_STATUS_* bits otherwise).
+ * max_* are maxima over the batch (host knowledge; they size shared memory / the work buffer).
+ * ws/ws_bytes: work buffer of at least smz_select_workspace_bytes(...) bytes (may be NULL/0
+ * when that function returns 0). */
+int smz_select_workspace_bytes(int n_videos, int max_n_segs, int max_capacity, int max_n_frames,
+                               int64_t *bytes);
+int smz_select_shots(const smz_video_desc *desc, int n_videos, const float *scores, const int32_t *picks,
+                     const int32_t *cps, const int32_t *nfps, int method, int max_n_segs, int max_capacity,
+                     int max_n_frames, float *seg_mean, int32_t *values, uint8_t *picked, float *summary,
+                     uint32_t *mask, int32_t *msum, int32_t *status, void *ws, int64_t ws_bytes, void *stream);
+
+/* Stand-alone 0/1 knapsack: replaces utils/knapsack.py:5-23 knapsack_ortools when the caller
+ * already holds the quantised int values (values[seg_off+s]); weights are nfps, the capacity is
+ * desc.capacity.  Only n_segs, seg_off, capacity, n_frames (mask length, may be 0), mask_off are
+ * read from the descriptor. */
+int smz_knapsack(const smz_video_desc *desc, int n_videos, const int32_t *values, const int32_t *nfps,
+                 int max_n_segs, int max_capacity, int max_n_frames, uint8_t *picked, uint32_t *mask,
+                 int32_t *msum, int32_t *status, void *ws, int64_t ws_bytes, void *stream);
+
+/* ---- F-score: replaces utils/eval.py:125-165 evaluate_summary -------------------------------
+ * Streams user_summary once.  mask/msum come from smz_select_shots or smz_pack_summary.
+ * max_n_frames = max over the batch (grid sizing); total_users = sum of n_users (the counts are
+ * zeroed inside the call).  n_users <= 1024 per video.
+ * Outputs: overlap int32[sum n_users], gsum int32[sum n_users] (exact counts),
+ *          f float32[sum n_users] (float32 arithmetic of utils/eval.py:153-159 as numpy 2 runs it),
+ *          avg_f / max_f float64[n_videos]: np.mean / np.max of the per-user list exactly as numpy
+ *          evaluates it — a float32 pairwise mean (widened) normally, a float64 pairwise mean when
+ *          some user has zero overlap (the reference then appends the Python float 0., which
+ *          promotes the list, utils/eval.py:156-164). */
+int smz_fscore(const smz_video_desc *desc, int n_videos, int max_n_frames, int total_users,
+               const float *user_summary, const uint32_t *mask, const int32_t *msum, int32_t *overlap,
+               int32_t *gsum, float *f, double *avg_f, double *max_f, void *stream);
+
+/* Binarise (>0), truncate/zero-pad an explicit machine summary to n_frames and pack it to the
+ * bit mask smz_fscore consumes (utils/eval.py:136-145).  machine[] is indexed by summ_off /
+ * summ_len like the summary output above. */
+int smz_pack_summary(const smz_video_desc *desc, int n_videos, int max_n_frames, const float *machine,
+                     uint32_t *mask, int32_t *msum, void *stream);
+
+/* ---- upsample: replaces utils/eval.py:15-35 upsample / :37-47 generate_scores --------------- */
+int smz_upsample(const smz_video_desc *desc, int n_videos, int max_n_frames, const float *scores,
+                 const int32_t *picks, float *frame_scores, int32_t *status, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUMMARIZER_B200_H */

@@ -1,0 +1,40 @@
+// Shared host-side helpers of libsummarizer_b200.so (error convention of include/summarizer_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/summarizer_b200.h"
+
+namespace smz {
+
+char *last_error_buf();  // thread-local, 512 bytes (smz_api.cu)
+
+inline int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(last_error_buf(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define SMZ_CUDA_CHECK(expr)                                                                   \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return ::smz::fail(SMZ_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #expr,        \
+                               cudaGetErrorString(_e));                                        \
+    } while (0)
+
+#define SMZ_REQUIRE(cond, ...)                                                                 \
+    do {                                                                                       \
+        if (!(cond)) return ::smz::fail(SMZ_ERR_ARG, __VA_ARGS__);                             \
+    } while (0)
+
+// Number of SMs of the current device (cached per device id).
+int sm_count();
+// Max opt-in dynamic shared memory per block of the current device.
+int max_smem_optin();
+
+}  // namespace smz
