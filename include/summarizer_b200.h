@@ -42,6 +42,7 @@ extern "C" {
 /* per-video status bits written by smz_select_shots */
 #define SMZ_STATUS_VALUE_RANGE 1 /* |int(score*1000)| * n_segs does not fit the int32 DP */
 #define SMZ_STATUS_INTERVALS 2   /* more upsample intervals than scores+1 (reference: IndexError) */
+#define SMZ_STATUS_WEIGHT_RANGE 4 /* a segment is longer than the max_seg_frames the caller declared */
 
 /* frames handled by one CTA of the F-score kernel */
 #define SMZ_FSCORE_CHUNK 2048
@@ -79,23 +80,26 @@ int smz_device_check(void);
  * Outputs (per-segment arrays indexed seg_off+s; any may be NULL except picked/mask/msum):
  *   seg_mean float32, values int32, picked uint8, summary float32, mask uint32, msum int32[n_videos],
  *   status int32[n_videos] (0 = ok, SMZ_STATUS_* bits otherwise).
- * max_* are maxima over the batch (host knowledge; they size shared memory / the work buffer).
+ * max_* are maxima over the batch (host knowledge; they size shared memory / the work buffer);
+ * max_seg_frames = max(nfps).  values (and seg_mean for method 'rank') are required: they carry
+ * the pooled scores from the pooling kernel to the DP kernel.
  * ws/ws_bytes: work buffer of at least smz_select_workspace_bytes(...) bytes (may be NULL/0
  * when that function returns 0). */
 int smz_select_workspace_bytes(int n_videos, int max_n_segs, int max_capacity, int max_n_frames,
-                               int64_t *bytes);
+                               int max_seg_frames, int64_t *bytes);
 int smz_select_shots(const smz_video_desc *desc, int n_videos, const float *scores, const int32_t *picks,
                      const int32_t *cps, const int32_t *nfps, int method, int max_n_segs, int max_capacity,
-                     int max_n_frames, float *seg_mean, int32_t *values, uint8_t *picked, float *summary,
-                     uint32_t *mask, int32_t *msum, int32_t *status, void *ws, int64_t ws_bytes, void *stream);
+                     int max_n_frames, int max_seg_frames, float *seg_mean, int32_t *values, uint8_t *picked,
+                     float *summary, uint32_t *mask, int32_t *msum, int32_t *status, void *ws, int64_t ws_bytes,
+                     void *stream);
 
 /* Stand-alone 0/1 knapsack: replaces utils/knapsack.py:5-23 knapsack_ortools when the caller
  * already holds the quantised int values (values[seg_off+s]); weights are nfps, the capacity is
  * desc.capacity.  Only n_segs, seg_off, capacity, n_frames (mask length, may be 0), mask_off are
- * read from the descriptor. */
+ * read from the descriptor.  mask/msum may be NULL (then only picked[] is produced). */
 int smz_knapsack(const smz_video_desc *desc, int n_videos, const int32_t *values, const int32_t *nfps,
-                 int max_n_segs, int max_capacity, int max_n_frames, uint8_t *picked, uint32_t *mask,
-                 int32_t *msum, int32_t *status, void *ws, int64_t ws_bytes, void *stream);
+                 int max_n_segs, int max_capacity, int max_n_frames, int max_seg_frames, uint8_t *picked,
+                 uint32_t *mask, int32_t *msum, int32_t *status, void *ws, int64_t ws_bytes, void *stream);
 
 /* ---- F-score: replaces utils/eval.py:125-165 evaluate_summary -------------------------------
  * Streams user_summary once.  mask/msum come from smz_select_shots or smz_pack_summary.

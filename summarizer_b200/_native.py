@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libsummarizer_b200.so")
 SMZ_METHOD = {"knapsack": 0, "rank": 1}
 SMZ_STATUS_VALUE_RANGE = 1
 SMZ_STATUS_INTERVALS = 2
+SMZ_STATUS_WEIGHT_RANGE = 4
 FSCORE_MAX_USERS = 1024
 
 # struct smz_video_desc (include/summarizer_b200.h) — 104 bytes
@@ -36,9 +37,9 @@ SIGNATURES = {
     "smz_version": (C.c_char_p, []),
     "smz_last_error": (C.c_char_p, []),
     "smz_device_check": (_I, []),
-    "smz_select_workspace_bytes": (_I, [_I, _I, _I, _I, C.POINTER(C.c_int64)]),
-    "smz_select_shots": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
-    "smz_knapsack": (_I, [_P, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _L, _P]),
+    "smz_select_workspace_bytes": (_I, [_I, _I, _I, _I, _I, C.POINTER(C.c_int64)]),
+    "smz_select_shots": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
+    "smz_knapsack": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _P]),
     "smz_fscore": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "smz_pack_summary": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "smz_upsample": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),

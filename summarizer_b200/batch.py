@@ -116,6 +116,10 @@ class VideoBatch:
         self.max_n_segs = int(desc["n_segs"].max()) if B else 0
         self.max_capacity = max(int(desc["capacity"].max()), 0) if B else 0
         self.max_n_frames = int(desc["n_frames"].max()) if B else 0
+        if isinstance(nfps, torch.Tensor):
+            self.max_seg_frames = int(nfps.max().item()) if nfps.numel() else 0
+        else:
+            self.max_seg_frames = int(np.max(nfps)) if len(nfps) else 0
         self.has_users = users is not None and self.total_users > 0
         dev = self.device
         self.d_desc = torch.from_numpy(desc.view(np.uint8).reshape(-1).copy()).to(dev)
@@ -140,7 +144,7 @@ class VideoBatch:
         self.max_f = torch.empty(max(B, 1), dtype=torch.float64, device=dev)
         nbytes = ctypes.c_int64(0)
         N.check(N.lib().smz_select_workspace_bytes(B, self.max_n_segs, self.max_capacity, self.max_n_frames,
-                                                   ctypes.byref(nbytes)))
+                                                   self.max_seg_frames, ctypes.byref(nbytes)))
         self.ws_bytes = int(nbytes.value)
         self.ws = torch.empty(max(self.ws_bytes, 4), dtype=torch.uint8, device=dev)
 
@@ -156,7 +160,7 @@ class VideoBatch:
         N.check(N.lib().smz_select_shots(
             N.ptr(self.d_desc), self.n_videos, N.ptr(scores), N.ptr(self.d_picks), N.ptr(self.d_cps),
             N.ptr(self.d_nfps), N.SMZ_METHOD[method], self.max_n_segs, self.max_capacity, self.max_n_frames,
-            N.ptr(self.seg_mean), N.ptr(self.values), N.ptr(self.picked),
+            self.max_seg_frames, N.ptr(self.seg_mean), N.ptr(self.values), N.ptr(self.picked),
             N.ptr(self.summary) if write_summary else None, N.ptr(self.mask), N.ptr(self.msum),
             N.ptr(self.status), N.ptr(self.ws), self.ws_bytes, N.current_stream()))
         return self
@@ -166,7 +170,7 @@ class VideoBatch:
         values = self._to_dev(values, torch.int32)
         N.check(N.lib().smz_knapsack(
             N.ptr(self.d_desc), self.n_videos, N.ptr(values), N.ptr(self.d_nfps), self.max_n_segs,
-            self.max_capacity, self.max_n_frames, N.ptr(self.picked), N.ptr(self.mask), N.ptr(self.msum),
+            self.max_capacity, self.max_n_frames, self.max_seg_frames, N.ptr(self.picked), N.ptr(self.mask), N.ptr(self.msum),
             N.ptr(self.status), N.ptr(self.ws), self.ws_bytes, N.current_stream()))
         return self
 
@@ -203,6 +207,8 @@ class VideoBatch:
             v = int(bad[0])
             if st[v] & N.SMZ_STATUS_INTERVALS:
                 raise IndexError(f"video {v}: more upsample intervals than scores (utils/eval.py:29-34)")
+            if st[v] & N.SMZ_STATUS_WEIGHT_RANGE:
+                raise ValueError(f"video {v}: a segment is longer than the declared max_seg_frames")
             raise OverflowError(f"video {v}: segment values exceed the int32 knapsack range")
 
     # host views -----------------------------------------------------------------------------

@@ -1,0 +1,760 @@
+// Shot selection kernels (sm_100a) + their C ABI:  utils/eval.py:74-123 generate_summary and
+// utils/knapsack.py:5-23 knapsack_ortools (OR-tools 7.5 KnapsackDynamicProgrammingSolver).
+//
+// Fast path (capacity+1 <= 27*256 cells), three kernels per batch:
+//   pool_kernel     grid (segment tile, video), 8 lanes per segment: float32 segment means in
+//                   numpy's pairwise summation order, values = trunc(double(mean) * 1000).
+//   dp_kernel<K>    persistent CTAs (256 threads, K cells per thread held in registers), one
+//                   video at a time: forward DP with ONE __syncthreads per item; the shared row
+//                   only serves the shifted read dp[c-w] (front pad of -2^30 removes the c>=w
+//                   test); improvement bits are accumulated per cell in registers (32 items per
+//                   word) and flushed coalesced to an L2-resident work buffer; warp 0 then walks
+//                   the OR-tools extraction loop (one L2 round trip per picked item).
+//   summary_kernel  one CTA per video: prefix of nfps -> float summary vector, bit mask, popcount.
+// Generic path: select_generic_kernel (monolithic, rows of any size up to shared memory).
+#include "smz_common.cuh"
+#include "smz_eval_dev.cuh"
+
+#include <limits.h>
+
+namespace {
+
+using namespace smzdev;
+
+constexpr int SELECT_THREADS = 512;   // generic kernel
+constexpr int DP_THREADS = 256;       // register-DP kernel
+constexpr int POOL_THREADS = 256;     // 32 segments per CTA, 8 lanes each
+constexpr int SUMMARY_THREADS = 256;
+constexpr int kDpNeg = -(1 << 30);    // front-pad value of the DP rows: never improves a cell
+
+// ------------------------------------------------------------------------------------------
+// pool_kernel: utils/eval.py:87-94 (segment means) + utils/knapsack.py:11-15 (quantisation)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(POOL_THREADS)
+pool_kernel(const smz_video_desc *__restrict__ desc, int v0, const float *__restrict__ scores,
+            const int32_t *__restrict__ picks, const int32_t *__restrict__ cps,
+            float *__restrict__ out_mean, int32_t *__restrict__ out_values, int32_t *__restrict__ status) {
+    const int v = v0 + blockIdx.y;
+    const smz_video_desc d = desc[v];
+    const int n = d.n_segs;
+    const int s = blockIdx.x * (POOL_THREADS / 8) + (threadIdx.x >> 3);
+    if (blockIdx.x * (POOL_THREADS / 8) >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & 7, lane0 = lane & ~7;
+    const unsigned gmask = 0xffu << lane0;
+    FrameCursor cur;
+    cur.init(scores + d.score_off, picks + d.picks_off, d.n_scores, d.n_picks, d.n_frames);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && cur.n_bound - 1 > d.n_scores + 1)
+        atomicOr(status + v, SMZ_STATUS_INTERVALS);
+    if (s >= n) return;                                   // uniform within an 8-lane group
+    const int start = __ldg(cps + 2 * (d.seg_off + s));
+    int end = __ldg(cps + 2 * (d.seg_off + s) + 1) + 1;
+    end = min(end, d.n_frames);
+    const int len = end - start;
+    cur.seek(start + (len >= 8 ? gl : 0));
+    const float sum = pw_sum_group(cur, start, len, gl, gmask, lane0);
+    if (gl == 0) {
+        const float mean = __fdiv_rn(sum, (float)len);
+        long long val = __double2ll_rz(__dmul_rn((double)mean, 1000.0));
+        const int vlim = min(INT_MAX / (n > 0 ? n : 1), 1 << 29);
+        if (val > vlim || val < -vlim) { atomicOr(status + v, SMZ_STATUS_VALUE_RANGE); val = val > 0 ? vlim : -vlim; }
+        if (out_mean) out_mean[d.seg_off + s] = mean;
+        out_values[d.seg_off + s] = (int)val;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// dp_kernel<K>: knapsack DP + OR-tools extraction (or the 'rank' greedy) -> picked[]
+// ------------------------------------------------------------------------------------------
+struct DpSmem { int dp0, dp1, wp, pk, red, total, row, pad; };
+
+__host__ __device__ inline DpSmem dp_layout(int K, int max_n_segs, int max_weight) {
+    DpSmem L;
+    L.row = K * DP_THREADS;
+    L.pad = (max_weight + 31) / 32 * 32;
+    if (L.pad < 32) L.pad = 32;
+    int o = 0;
+    o += L.pad; L.dp0 = o; o += L.row;      // [pad][row0][pad][row1]
+    o += L.pad; L.dp1 = o; o += L.row;
+    L.wp = o; o += 2 * max_n_segs;          // int2 (weight, value)
+    L.pk = o; o += max_n_segs;              // picked flags; 'rank': order
+    L.red = o; o += 32;
+    L.total = o;
+    return L;
+}
+
+template <int K>
+__global__ void __launch_bounds__(DP_THREADS, K <= 18 ? 3 : 1)
+dp_kernel(const smz_video_desc *__restrict__ desc, int n_videos, const int32_t *__restrict__ nfps,
+          const int32_t *__restrict__ values, const float *__restrict__ seg_mean, int method, int max_n_segs,
+          int max_weight, uint8_t *__restrict__ out_picked, int32_t *__restrict__ status,
+          uint32_t *__restrict__ ws, int64_t ws_words_per_cta) {
+    extern __shared__ uint32_t smem[];
+    const DpSmem L = dp_layout(K, max_n_segs, max_weight);
+    int *dp0 = reinterpret_cast<int *>(smem + L.dp0);
+    int *dp1 = reinterpret_cast<int *>(smem + L.dp1);
+    int2 *swp = reinterpret_cast<int2 *>(smem + L.wp);
+    int *spk = reinterpret_cast<int *>(smem + L.pk);
+    int *sred = reinterpret_cast<int *>(smem + L.red);
+    uint32_t *bits = ws + (int64_t)blockIdx.x * ws_words_per_cta;   // [item/32][L.row]
+    constexpr int NT = DP_THREADS, NW = DP_THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int j = tid; j < L.pad; j += NT) { dp0[j - L.pad] = kDpNeg; dp1[j - L.pad] = kDpNeg; }
+
+    for (int v = blockIdx.x; v < n_videos; v += gridDim.x) {
+        const smz_video_desc d = desc[v];
+        const int n = d.n_segs, cap = d.capacity;
+        // ---- weights / values, sum of weights, weight-range check
+        int wsum = 0, bad = 0;
+        const int vlim = min(INT_MAX / (n > 0 ? n : 1), 1 << 29);
+        for (int i = tid; i < n; i += NT) {
+            const int w = __ldg(nfps + d.seg_off + i);
+            int p = __ldg(values + d.seg_off + i);
+            if (p > vlim || p < -vlim) { bad |= SMZ_STATUS_VALUE_RANGE; p = p > 0 ? vlim : -vlim; }
+            if (w <= cap && w > L.pad) bad |= SMZ_STATUS_WEIGHT_RANGE;   // host passed a wrong max_weight
+            swp[i] = make_int2(w, p);
+            spk[i] = 0;
+            wsum += w;
+        }
+        wsum = __reduce_add_sync(0xffffffffu, wsum);
+        bad = __reduce_or_sync(0xffffffffu, bad);
+        if (lane == 0) { sred[warp] = wsum; sred[NW + warp] = bad; }
+        __syncthreads();
+        wsum = 0; bad = 0;
+#pragma unroll
+        for (int k = 0; k < NW; k++) { wsum += sred[k]; bad |= sred[NW + k]; }
+        if (bad && tid == 0) atomicOr(status + v, bad);
+        __syncthreads();   // sred is reused below
+
+        if (method == SMZ_METHOD_KNAPSACK) {
+            if (wsum <= cap) {
+                // KnapsackSolver::ReduceCapacities: the capacity constraint is inactive, all items in
+                for (int i = tid; i < n; i += NT) spk[i] = 1;
+            } else if (cap > 0 && n > 0 && !(bad & SMZ_STATUS_WEIGHT_RANGE)) {
+                // forward DP == KnapsackDynamicProgrammingSolver::SolveSubProblem over ALL items.
+                // Thread t owns cells t, t+NT, ...: values in registers; cells above the capacity
+                // (row padding) are ordinary cells of a larger knapsack: harmless.
+                int val[K];
+                uint32_t acc[K];
+                int *cur = dp0, *nxt = dp1;
+#pragma unroll
+                for (int k = 0; k < K; k++) { val[k] = 0; acc[k] = 0u; cur[tid + k * NT] = 0; }
+                __syncthreads();
+                for (int i = 0; i < n; i++) {
+                    const int2 wp = swp[i];
+                    if (wp.x <= cap) {                         // uniform: upstream's loop body is empty otherwise
+                        const int *src = cur + (tid - wp.x);   // c < w lands in the kDpNeg pad
+                        const uint32_t bit = 1u << (i & 31);
+#pragma unroll
+                        for (int k0 = 0; k0 < K; k0 += 9) {
+                            int cand[9];
+#pragma unroll
+                            for (int k = k0; k < K && k < k0 + 9; k++) cand[k - k0] = src[k * NT];
+#pragma unroll
+                            for (int k = k0; k < K && k < k0 + 9; k++) {
+                                const int c = cand[k - k0] + wp.y;
+                                if (c > val[k]) acc[k] |= bit;    // strict '>' of upstream
+                                val[k] = max(val[k], c);
+                                nxt[tid + k * NT] = val[k];
+                            }
+                        }
+                        __syncthreads();
+                        int *t = cur; cur = nxt; nxt = t;
+                    }
+                    if ((i & 31) == 31 || i == n - 1) {        // flush 32 items' take bits, coalesced
+                        uint32_t *dst = bits + (int64_t)(i >> 5) * L.row + tid;
+#pragma unroll
+                        for (int k = 0; k < K; k++) { dst[k * NT] = acc[k]; acc[k] = 0u; }
+                    }
+                }
+                __syncthreads();   // take bits visible to warp 0
+                // KnapsackDynamicProgrammingSolver::Solve extraction loop.  SolveSubProblem(c, k)
+                // == highest item < k whose take bit at cell c is set, else 0 (ids[] default).
+                if (warp == 0) {
+                    int remaining = cap, num = n;
+                    while (remaining > 0 && num > 0) {
+                        const int last = (num - 1) >> 5;
+                        int sel = -1;
+                        for (int j0 = 0; j0 <= last; j0 += 32) {
+                            const int j = j0 + lane;
+                            uint32_t wv = 0u;
+                            if (j <= last) {
+                                wv = __ldcg(bits + (int64_t)j * L.row + remaining);
+                                const int nb = num - (j << 5);
+                                if (nb < 32) wv &= (1u << nb) - 1u;
+                            }
+                            const int c = wv ? (j << 5) + 31 - __clz(wv) : -1;
+                            sel = max(sel, warp_max(c));
+                        }
+                        sel = max(sel, 0);
+                        remaining -= swp[sel].x;
+                        num = sel;
+                        if (remaining >= 0 && lane == 0) spk[sel] = 1;
+                    }
+                }
+            }
+        } else {
+            // utils/eval.py:100-107: descending score, ties -> higher index first (see oracle);
+            // strict '<' against the budget, no early break.
+            int *order = dp0, *rank = dp1;        // n <= max_n_segs <= row is enforced by the host plan
+            for (int i = tid; i < n; i += NT) {
+                const float mi = __ldg(seg_mean + d.seg_off + i);
+                int r = 0;
+                for (int j = 0; j < n; j++) {
+                    const float mj = __ldg(seg_mean + d.seg_off + j);
+                    r += (mj > mi) || (mj == mi && j > i);
+                }
+                rank[i] = r;
+            }
+            __syncthreads();
+            for (int i = tid; i < n; i += NT) order[rank[i]] = i;
+            __syncthreads();
+            if (tid == 0) {
+                long long total = 0;
+                for (int r = 0; r < n; r++) {
+                    const int i = order[r];
+                    if (total + swp[i].x < (long long)cap) { spk[i] = 1; total += swp[i].x; }
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += NT) out_picked[d.seg_off + i] = (uint8_t)spk[i];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// summary_kernel: utils/eval.py:111-122 summary vector (+ bit mask truncated to n_frames, msum)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SUMMARY_THREADS)
+summary_kernel(const smz_video_desc *__restrict__ desc, int v0, const int32_t *__restrict__ nfps,
+               const uint8_t *__restrict__ picked, int max_n_segs, int max_n_frames,
+               float *__restrict__ out_summary, uint32_t *__restrict__ out_mask, int32_t *__restrict__ out_msum) {
+    extern __shared__ uint32_t smem[];
+    int *spre = reinterpret_cast<int *>(smem);                  // max_n_segs + 1
+    uint32_t *smask = smem + max_n_segs + 1;                    // ceil(max_n_frames / 32)
+    __shared__ int swarp[SUMMARY_THREADS / 32];
+    constexpr int NT = SUMMARY_THREADS, NW = SUMMARY_THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int v = v0 + blockIdx.x;
+    const smz_video_desc d = desc[v];
+    const int n = d.n_segs, n_frames = d.n_frames;
+    const int mwords = (n_frames + 31) >> 5;
+    for (int j = tid; j < mwords; j += NT) smask[j] = 0u;
+    // exclusive prefix of nfps = positions in the summary vector
+    int carry = 0;
+    for (int base = 0; base < n; base += NT) {
+        const int i = base + tid;
+        const int x = i < n ? __ldg(nfps + d.seg_off + i) : 0;
+        int incl = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) swarp[warp] = incl;
+        __syncthreads();
+        int woff = 0, tile_total = 0;
+#pragma unroll
+        for (int k = 0; k < NW; k++) { const int t = swarp[k]; if (k < warp) woff += t; tile_total += t; }
+        if (i < n) spre[i] = carry + woff + incl - x;
+        carry += tile_total;
+        __syncthreads();
+    }
+    if (tid == 0) spre[n] = carry;
+    __syncthreads();
+    for (int s = tid; s < n; s += NT) {
+        if (picked[d.seg_off + s]) {
+            const int a = spre[s];
+            const int b = min(spre[s + 1], n_frames);
+            if (a < b) {
+                const int wa = a >> 5, wb = (b - 1) >> 5;
+                for (int wd = wa; wd <= wb; wd++) {
+                    const int lo = max(a, wd << 5) & 31;
+                    const int hi = min(b, (wd + 1) << 5) - (wd << 5);  // 1..32
+                    const uint32_t m = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+                    atomicOr(&smask[wd], m);
+                }
+            }
+        }
+    }
+    if (out_summary) {
+        float *dst = out_summary + d.summ_off;
+        for (int s = warp; s < n; s += NW) {
+            const int a = spre[s], nf = spre[s + 1] - a;
+            const float val = picked[d.seg_off + s] ? 1.f : 0.f;
+            for (int j = lane; j < nf; j += 32) dst[a + j] = val;
+        }
+    }
+    __syncthreads();
+    int cnt = 0;
+    for (int j = tid; j < mwords; j += NT) {
+        const uint32_t m = smask[j];
+        out_mask[d.mask_off + j] = m;
+        cnt += __popc(m);
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) swarp[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int k = 0; k < NW; k++) tot += swarp[k];
+        out_msum[v] = tot;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// select_generic_kernel — one persistent CTA does everything for a video.  Fallback for
+// capacities whose DP row does not fit the register-DP plan (very long videos).
+// ------------------------------------------------------------------------------------------
+struct SelectSmem {  // word offsets into dynamic shared memory (generic kernel)
+    int dp0, dp1, w, p, wp, pk, mean, pre, mask, sel, bits, total, row;
+};
+
+__host__ __device__ inline SelectSmem select_layout(int max_n_segs, int max_capacity, int max_n_frames,
+                                                    bool bits_in_smem) {
+    SelectSmem L;
+    const int ncell = max_capacity + 1;
+    // the dp rows double as scratch (warp totals, 'rank' order): at least 32 and max_n_segs words
+    int row = ncell > max_n_segs ? ncell : max_n_segs;
+    row = row > 32 ? row : 32;
+    L.row = row;
+    int o = 0;
+    L.dp0 = o; o += row;
+    L.dp1 = o; o += row;
+    L.w = o; o += max_n_segs;
+    L.p = o; o += max_n_segs;
+    L.wp = o; o += 2 * max_n_segs;
+    L.pk = o; o += max_n_segs;
+    L.mean = o; o += max_n_segs;
+    L.pre = o; o += max_n_segs + 1;
+    L.mask = o; o += (max_n_frames + 31) / 32;
+    L.sel = o; o += 4;
+    L.bits = o;
+    if (bits_in_smem) o += max_n_segs * ((ncell + 31) / 32);
+    L.total = o;
+    return L;
+}
+
+template <bool BITS_IN_SMEM>
+__global__ void __launch_bounds__(SELECT_THREADS)
+select_generic_kernel(const smz_video_desc *__restrict__ desc, int n_videos, const float *__restrict__ scores,
+              const int32_t *__restrict__ picks, const int32_t *__restrict__ cps,
+              const int32_t *__restrict__ nfps, const int32_t *__restrict__ values_in, int method,
+              int max_n_segs, int max_capacity, int max_n_frames, float *__restrict__ out_mean, int32_t *__restrict__ out_values,
+              uint8_t *__restrict__ out_picked, float *__restrict__ out_summary,
+              uint32_t *__restrict__ out_mask, int32_t *__restrict__ out_msum,
+              int32_t *__restrict__ out_status, uint32_t *__restrict__ ws, int64_t ws_words_per_cta) {
+    extern __shared__ uint32_t smem[];
+    const SelectSmem L = select_layout(max_n_segs, max_capacity, max_n_frames, BITS_IN_SMEM);
+    int *dp0 = reinterpret_cast<int *>(smem + L.dp0);
+    int *dp1 = reinterpret_cast<int *>(smem + L.dp1);
+    int *sw = reinterpret_cast<int *>(smem + L.w);
+    int *sp = reinterpret_cast<int *>(smem + L.p);
+    int *spk = reinterpret_cast<int *>(smem + L.pk);
+    float *smean = reinterpret_cast<float *>(smem + L.mean);
+    int *spre = reinterpret_cast<int *>(smem + L.pre);
+    uint32_t *smask = smem + L.mask;
+    int *ssel = reinterpret_cast<int *>(smem + L.sel);
+    int2 *swp = reinterpret_cast<int2 *>(smem + L.wp);
+    uint32_t *bits = BITS_IN_SMEM ? (smem + L.bits) : (ws + (int64_t)blockIdx.x * ws_words_per_cta);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NT = SELECT_THREADS, NW = SELECT_THREADS / 32;
+
+    for (int v = blockIdx.x; v < n_videos; v += gridDim.x) {
+        const smz_video_desc d = desc[v];
+        const int n = d.n_segs;
+        const int cap = d.capacity;
+        const int n_frames = d.n_frames;
+        int status = 0;
+
+        // ---- A. segment pooling (utils/eval.py:87-94) + value quantisation (knapsack.py:11-15)
+        if (values_in != nullptr) {
+            // stand-alone knapsack (utils/knapsack.py:5-23): values already quantised by the caller
+            const int vlim = min(INT_MAX / (n > 0 ? n : 1), 1 << 29);
+            for (int s = tid; s < n; s += NT) {
+                int val = __ldg(values_in + d.seg_off + s);
+                if (val > vlim || val < -vlim) { status |= SMZ_STATUS_VALUE_RANGE; val = val > 0 ? vlim : -vlim; }
+                smean[s] = (float)val;
+                sp[s] = val;
+                sw[s] = __ldg(nfps + d.seg_off + s);
+                spk[s] = 0;
+            }
+            if (tid == 0) { ssel[0] = -1; ssel[1] = -1; ssel[2] = -1; }
+        } else {
+            FrameCursor cur;
+            cur.init(scores + d.score_off, picks + d.picks_off, d.n_scores, d.n_picks, n_frames);
+            if (cur.n_bound - 1 > d.n_scores + 1) status |= SMZ_STATUS_INTERVALS;
+            const int vlim = min(INT_MAX / (n > 0 ? n : 1), 1 << 29);
+            const int gl = lane & 7, lane0 = lane & ~7;
+            const unsigned gmask = 0xffu << lane0;
+            for (int s0 = 0; s0 < n; s0 += NT / 8) {        // 8 lanes per segment
+                const int s = s0 + (tid >> 3);
+                if (s < n) {                                 // uniform within a group
+                    const int start = __ldg(cps + 2 * (d.seg_off + s));
+                    int end = __ldg(cps + 2 * (d.seg_off + s) + 1) + 1;
+                    end = min(end, n_frames);
+                    const int len = end - start;
+                    cur.seek(start + (len >= 8 ? gl : 0));
+                    const float sum = pw_sum_group(cur, start, len, gl, gmask, lane0);
+                    if (gl == 0) {
+                        const float mean = __fdiv_rn(sum, (float)len);
+                        long long val = __double2ll_rz(__dmul_rn((double)mean, 1000.0));
+                        if (val > vlim || val < -vlim) { status |= SMZ_STATUS_VALUE_RANGE; val = val > 0 ? vlim : -vlim; }
+                        smean[s] = mean;
+                        sp[s] = (int)val;
+                        sw[s] = __ldg(nfps + d.seg_off + s);
+                        spk[s] = 0;
+                        if (out_mean) out_mean[d.seg_off + s] = mean;
+                        if (out_values) out_values[d.seg_off + s] = (int)val;
+                    }
+                }
+            }
+            if (tid == 0) { ssel[0] = -1; ssel[1] = -1; ssel[2] = -1; }
+        }
+        {
+            const int s1 = __syncthreads_or(status & SMZ_STATUS_VALUE_RANGE);
+            const int s2 = __syncthreads_or(status & SMZ_STATUS_INTERVALS);
+            status = (s1 ? SMZ_STATUS_VALUE_RANGE : 0) | (s2 ? SMZ_STATUS_INTERVALS : 0);
+        }
+
+        // ---- B. exclusive prefix of nfps (positions in the summary vector, utils/eval.py:111-122)
+        {
+            int carry = 0;
+            for (int base = 0; base < n; base += NT) {
+                const int i = base + tid;
+                const int x = i < n ? sw[i] : 0;
+                int incl = x;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                if (lane == 31) dp0[warp] = incl;  // dp rows are not live yet (rows hold >= 32 words)
+                __syncthreads();
+                int woff = 0;
+                for (int k = 0; k < warp; k++) woff += dp0[k];
+                int tile_total = 0;
+                for (int k = 0; k < NW; k++) tile_total += dp0[k];
+                if (i < n) spre[i] = carry + woff + incl - x;
+                carry += tile_total;
+                __syncthreads();
+            }
+            if (tid == 0) spre[n] = carry;
+            for (int i = tid; i < n; i += NT) swp[i] = make_int2(sw[i], sp[i]);
+            const int mwords = (n_frames + 31) >> 5;
+            for (int j = tid; j < mwords; j += NT) smask[j] = 0u;
+        }
+        __syncthreads();
+
+        // ---- C. selection
+        if (method == SMZ_METHOD_KNAPSACK) {
+            if (spre[n] <= cap) {
+                // KnapsackSolver::ReduceCapacities: the capacity constraint is inactive, all items in
+                for (int s = tid; s < n; s += NT) spk[s] = 1;
+            } else if (cap > 0 && n > 0) {
+                const int ncell = cap + 1;
+                // take-bit row stride: the register DP writes one word per (warp, k) pass
+                const int words = (ncell + 31) >> 5;
+                int *cur = dp0, *nxt = dp1;
+                // forward DP, KnapsackDynamicProgrammingSolver::SolveSubProblem for ALL items; the
+                // strict '>' of upstream is kept per cell in the take-bit row of the item
+                {
+                    for (int c = tid; c < ncell; c += NT) cur[c] = 0;
+                    __syncthreads();
+                    for (int i = 0; i < n; i++) {
+                        const int w = sw[i], p = sp[i];
+                        uint32_t *row = bits + (int64_t)i * words;
+                        if (w > cap) {
+                            for (int j = tid; j < words; j += NT) row[j] = 0u;
+                            continue;
+                        }
+                        for (int base = warp * 32; base < ncell; base += NT) {
+                            const int c = base + lane;
+                            bool imp = false;
+                            if (c < ncell) {
+                                const int old = cur[c];
+                                int v2 = old;
+                                if (c >= w) {
+                                    const int cand = cur[c - w] + p;
+                                    if (cand > old) { v2 = cand; imp = true; }
+                                }
+                                nxt[c] = v2;
+                            }
+                            const uint32_t b = __ballot_sync(0xffffffffu, imp);
+                            if (lane == 0) row[base >> 5] = b;
+                        }
+                        __syncthreads();
+                        int *t = cur; cur = nxt; nxt = t;
+                    }
+                }
+                __syncthreads();
+                // KnapsackDynamicProgrammingSolver::Solve extraction loop.  SolveSubProblem(c, k)
+                // == highest item < k whose take bit at cell c is set, else 0 (ids[] default).
+                int remaining = cap, num = n, round = 0;
+                while (remaining > 0 && num > 0) {
+                    const int slot = round % 3;
+                    if (tid == 0) ssel[(round + 1) % 3] = -1;
+                    const int widx = remaining >> 5, bit = remaining & 31;
+                    int local = -1;
+                    for (int i = tid; i < num; i += NT)
+                        if ((bits[(int64_t)i * words + widx] >> bit) & 1u) local = i;
+                    local = warp_max(local);
+                    if (lane == 0 && local >= 0) atomicMax(&ssel[slot], local);
+                    __syncthreads();
+                    const int sel = max(ssel[slot], 0);
+                    remaining -= sw[sel];
+                    num = sel;
+                    if (remaining >= 0 && tid == 0) spk[sel] = 1;
+                    ++round;
+                }
+            }
+        } else {
+            // utils/eval.py:100-107: descending score, ties -> higher index first (see oracle);
+            // strict '<' against the budget, no early break.
+            int *order = sp;  // values are not needed by 'rank'
+            int *rank = dp1;  // n <= max_n_segs; dp1 is sized below to hold it
+            for (int i = tid; i < n; i += NT) {
+                const float mi = smean[i];
+                int r = 0;
+                for (int j = 0; j < n; j++) {
+                    const float mj = smean[j];
+                    r += (mj > mi) || (mj == mi && j > i);
+                }
+                rank[i] = r;
+            }
+            __syncthreads();
+            for (int i = tid; i < n; i += NT) order[rank[i]] = i;
+            __syncthreads();
+            if (tid == 0) {
+                long long total = 0;
+                for (int r = 0; r < n; r++) {
+                    const int i = order[r];
+                    if (total + sw[i] < (long long)cap) { spk[i] = 1; total += sw[i]; }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- D. outputs: picked flags, float summary vector, bit mask (truncated to n_frames)
+        for (int s = tid; s < n; s += NT) {
+            const int pk = spk[s];
+            out_picked[d.seg_off + s] = (uint8_t)pk;
+            if (pk) {
+                const int a = spre[s];
+                const int b = min(a + sw[s], n_frames);
+                if (a < b) {
+                    const int wa = a >> 5, wb = (b - 1) >> 5;
+                    for (int wd = wa; wd <= wb; wd++) {
+                        const int lo = max(a, wd << 5) & 31;
+                        const int hi = min(b, (wd + 1) << 5) - (wd << 5);  // 1..32
+                        const uint32_t m = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+                        atomicOr(&smask[wd], m);
+                    }
+                }
+            }
+        }
+        if (out_summary) {
+            float *dst = out_summary + d.summ_off;
+            for (int s = warp; s < n; s += NW) {
+                const int a = spre[s], nf = sw[s];
+                const float val = spk[s] ? 1.f : 0.f;
+                for (int j = lane; j < nf; j += 32) dst[a + j] = val;
+            }
+        }
+        __syncthreads();
+        {
+            const int mwords = (n_frames + 31) >> 5;
+            int cnt = 0;
+            for (int j = tid; j < mwords; j += NT) {
+                const uint32_t m = smask[j];
+                out_mask[d.mask_off + j] = m;
+                cnt += __popc(m);
+            }
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0) dp1[warp] = cnt;
+            __syncthreads();
+            if (tid == 0) {
+                int tot = 0;
+                for (int k = 0; k < NW; k++) tot += dp1[k];
+                out_msum[v] = tot;
+                if (out_status) out_status[v] = status;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: plan + launch
+// ------------------------------------------------------------------------------------------
+struct SelectPlan {
+    int k;               // cells per thread of dp_kernel; 0 = generic monolithic kernel
+    bool bits_in_smem;   // generic kernel only
+    int smem_bytes;
+    int grid;
+    int64_t ws_words_per_cta;
+    int pad_weight;      // max weight the dp rows' front pad is sized for
+};
+
+constexpr int kDpK[] = {2, 5, 9, 18, 27, 36, 54};
+
+typedef void (*dp_fn)(const smz_video_desc *, int, const int32_t *, const int32_t *, const float *, int, int, int,
+                      uint8_t *, int32_t *, uint32_t *, int64_t);
+typedef void (*generic_fn)(const smz_video_desc *, int, const float *, const int32_t *, const int32_t *,
+                           const int32_t *, const int32_t *, int, int, int, int, float *, int32_t *, uint8_t *,
+                           float *, uint32_t *, int32_t *, int32_t *, uint32_t *, int64_t);
+
+dp_fn dp_fn_for(int k) {
+    switch (k) {
+        case 2: return dp_kernel<2>;
+        case 5: return dp_kernel<5>;
+        case 9: return dp_kernel<9>;
+        case 18: return dp_kernel<18>;
+        case 27: return dp_kernel<27>;
+        case 36: return dp_kernel<36>;
+        case 54: return dp_kernel<54>;
+        default: return nullptr;
+    }
+}
+
+generic_fn generic_fn_for(bool bits_in_smem) {
+    return bits_in_smem ? (generic_fn)select_generic_kernel<true> : (generic_fn)select_generic_kernel<false>;
+}
+
+}  // namespace
+
+static int select_plan(int n_videos, int max_n_segs, int max_capacity, int max_n_frames, int max_weight,
+                       SelectPlan *plan) {
+    if (max_n_segs < 0 || max_capacity < 0 || max_n_frames < 0 || max_weight < 0)
+        return smz::fail(SMZ_ERR_ARG, "negative batch maxima");
+    const int optin = smz::max_smem_optin();
+    const int ncell = max_capacity + 1;
+    const int need = ncell > max_n_segs ? ncell : max_n_segs;
+    plan->pad_weight = max_weight < max_capacity ? max_weight : max_capacity;   // heavier items are never read
+    plan->k = 0;
+    for (int k : kDpK)
+        if (k * DP_THREADS >= need) { plan->k = k; break; }
+    int per_sm = 0;
+    if (plan->k > 0) {
+        plan->smem_bytes = dp_layout(plan->k, max_n_segs, plan->pad_weight).total * 4;
+        if (plan->smem_bytes > optin) plan->k = 0;
+    }
+    if (plan->k > 0) {
+        dp_fn fn = dp_fn_for(plan->k);
+        plan->bits_in_smem = false;
+        SMZ_CUDA_CHECK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes));
+        SMZ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, DP_THREADS, plan->smem_bytes));
+        plan->ws_words_per_cta = (int64_t)((max_n_segs + 31) / 32) * plan->k * DP_THREADS;
+    } else {
+        const int with_bits = select_layout(max_n_segs, max_capacity, max_n_frames, true).total * 4;
+        const int without = select_layout(max_n_segs, max_capacity, max_n_frames, false).total * 4;
+        if (with_bits <= optin) { plan->bits_in_smem = true; plan->smem_bytes = with_bits; }
+        else if (without <= optin) { plan->bits_in_smem = false; plan->smem_bytes = without; }
+        else
+            return smz::fail(SMZ_ERR_UNSUPPORTED,
+                             "select_shots: DP rows for capacity %d, %d segments and %d frames need %d B of shared "
+                             "memory (> %d B per CTA)", max_capacity, max_n_segs, max_n_frames, without, optin);
+        generic_fn fn = generic_fn_for(plan->bits_in_smem);
+        SMZ_CUDA_CHECK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes));
+        SMZ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, SELECT_THREADS, plan->smem_bytes));
+        plan->ws_words_per_cta = plan->bits_in_smem ? 0 : (int64_t)max_n_segs * ((ncell + 31) / 32);
+    }
+    if (per_sm < 1) per_sm = 1;
+    const int g = smz::sm_count() * per_sm;
+    plan->grid = n_videos < g ? n_videos : g;
+    return SMZ_OK;
+}
+
+extern "C" int smz_select_workspace_bytes(int n_videos, int max_n_segs, int max_capacity, int max_n_frames,
+                                          int max_seg_frames, int64_t *bytes) {
+    SMZ_REQUIRE(bytes != nullptr, "bytes is NULL");
+    *bytes = 0;
+    if (n_videos <= 0) return SMZ_OK;
+    SelectPlan plan;
+    int rc = select_plan(n_videos, max_n_segs, max_capacity, max_n_frames, max_seg_frames, &plan);
+    if (rc != SMZ_OK) return rc;
+    *bytes = (int64_t)plan.grid * plan.ws_words_per_cta * 4;
+    return SMZ_OK;
+}
+
+static int select_launch(const smz_video_desc *desc, int n_videos, const float *scores, const int32_t *picks,
+                         const int32_t *cps, const int32_t *nfps, const int32_t *values_in, int method,
+                         int max_n_segs, int max_capacity, int max_n_frames, int max_weight, float *seg_mean,
+                         int32_t *values, uint8_t *picked, float *summary, uint32_t *mask, int32_t *msum,
+                         int32_t *status, void *ws, int64_t ws_bytes, void *stream) {
+    if (n_videos == 0) return SMZ_OK;
+    SMZ_REQUIRE(n_videos > 0, "n_videos < 0");
+    SMZ_REQUIRE(desc && nfps && picked && status, "NULL pointer (desc, nfps, picked and status are required)");
+    SMZ_REQUIRE(method == SMZ_METHOD_KNAPSACK || method == SMZ_METHOD_RANK, "unknown method %d", method);
+    int rc = smz_device_check();
+    if (rc != SMZ_OK) return rc;
+    SelectPlan plan;
+    rc = select_plan(n_videos, max_n_segs, max_capacity, max_n_frames, max_weight, &plan);
+    if (rc != SMZ_OK) return rc;
+    const int64_t need = (int64_t)plan.grid * plan.ws_words_per_cta * 4;
+    SMZ_REQUIRE(need == 0 || (ws != nullptr && ws_bytes >= need), "work buffer too small: need %lld bytes", (long long)need);
+    cudaStream_t st = (cudaStream_t)stream;
+    SMZ_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)n_videos, st));
+    if (plan.k == 0) {
+        SMZ_REQUIRE(mask && msum, "mask and msum outputs are required on the generic path");
+        generic_fn fn = generic_fn_for(plan.bits_in_smem);
+        fn<<<plan.grid, SELECT_THREADS, plan.smem_bytes, st>>>(
+            desc, n_videos, scores, picks, cps, nfps, values_in, method, max_n_segs, max_capacity, max_n_frames,
+            seg_mean, values, picked, summary, mask, msum, status, (uint32_t *)ws, plan.ws_words_per_cta);
+        SMZ_CUDA_CHECK(cudaGetLastError());
+        return SMZ_OK;
+    }
+    const int32_t *vals = values_in;
+    if (values_in == nullptr) {
+        SMZ_REQUIRE(values != nullptr, "values output is required (it feeds the DP kernel)");
+        SMZ_REQUIRE(method == SMZ_METHOD_KNAPSACK || seg_mean != nullptr, "seg_mean output is required by method 'rank'");
+        const int tiles = (max_n_segs + POOL_THREADS / 8 - 1) / (POOL_THREADS / 8);
+        for (int v0 = 0; v0 < n_videos && tiles > 0; v0 += 65535) {
+            const int nv = n_videos - v0 < 65535 ? n_videos - v0 : 65535;
+            pool_kernel<<<dim3(tiles, nv), POOL_THREADS, 0, st>>>(desc, v0, scores, picks, cps, seg_mean, values, status);
+        }
+        SMZ_CUDA_CHECK(cudaGetLastError());
+        vals = values;
+    }
+    dp_fn fn = dp_fn_for(plan.k);
+    fn<<<plan.grid, DP_THREADS, plan.smem_bytes, st>>>(desc, n_videos, nfps, vals, seg_mean, method, max_n_segs,
+                                                      plan.pad_weight, picked, status, (uint32_t *)ws,
+                                                      plan.ws_words_per_cta);
+    SMZ_CUDA_CHECK(cudaGetLastError());
+    if (mask != nullptr) {
+        SMZ_REQUIRE(msum != nullptr, "msum is required with mask");
+        const int sm_bytes = (max_n_segs + 1 + (max_n_frames + 31) / 32) * 4;
+        SMZ_REQUIRE(sm_bytes <= smz::max_smem_optin(), "summary: %d B of shared memory needed", sm_bytes);
+        SMZ_CUDA_CHECK(cudaFuncSetAttribute((const void *)summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes));
+        summary_kernel<<<n_videos, SUMMARY_THREADS, sm_bytes, st>>>(desc, 0, nfps, picked, max_n_segs, max_n_frames,
+                                                                   summary, mask, msum);
+        SMZ_CUDA_CHECK(cudaGetLastError());
+    }
+    return SMZ_OK;
+}
+
+extern "C" int smz_select_shots(const smz_video_desc *desc, int n_videos, const float *scores,
+                                const int32_t *picks, const int32_t *cps, const int32_t *nfps, int method,
+                                int max_n_segs, int max_capacity, int max_n_frames, int max_seg_frames,
+                                float *seg_mean, int32_t *values, uint8_t *picked, float *summary, uint32_t *mask,
+                                int32_t *msum, int32_t *status, void *ws, int64_t ws_bytes, void *stream) {
+    SMZ_REQUIRE(n_videos == 0 || (scores && picks && cps), "NULL input pointer");
+    SMZ_REQUIRE(n_videos == 0 || (mask && msum), "mask and msum outputs are required");
+    return select_launch(desc, n_videos, scores, picks, cps, nfps, nullptr, method, max_n_segs, max_capacity,
+                         max_n_frames, max_seg_frames, seg_mean, values, picked, summary, mask, msum, status, ws,
+                         ws_bytes, stream);
+}
+
+extern "C" int smz_knapsack(const smz_video_desc *desc, int n_videos, const int32_t *values, const int32_t *nfps,
+                            int max_n_segs, int max_capacity, int max_n_frames, int max_seg_frames,
+                            uint8_t *picked, uint32_t *mask, int32_t *msum, int32_t *status, void *ws,
+                            int64_t ws_bytes, void *stream) {
+    SMZ_REQUIRE(n_videos == 0 || values, "NULL values pointer");
+    return select_launch(desc, n_videos, nullptr, nullptr, nullptr, nfps, values, SMZ_METHOD_KNAPSACK, max_n_segs,
+                         max_capacity, max_n_frames, max_seg_frames, nullptr, nullptr, picked, nullptr, mask, msum,
+                         status, ws, ws_bytes, stream);
+}
