@@ -136,7 +136,7 @@ class VideoBatch:
         self.summary = torch.empty(max(self.total_summary, 1), **f32)
         self.mask = torch.empty(max(self.total_mask_words, 1), **i32)
         self.msum = torch.empty(max(B, 1), **i32)
-        self.status = torch.empty(max(B, 1), **i32)
+        self.status = torch.zeros(max(B, 1), **i32)
         self.overlap = torch.empty(max(self.total_users, 1), **i32)
         self.gsum = torch.empty(max(self.total_users, 1), **i32)
         self.f = torch.empty(max(self.total_users, 1), **f32)
