@@ -125,6 +125,21 @@ int smz_pack_summary(const smz_video_desc *desc, int n_videos, int max_n_frames,
 int smz_upsample(const smz_video_desc *desc, int n_videos, int max_n_frames, const float *scores,
                  const int32_t *picks, float *frame_scores, int32_t *status, void *stream);
 
+/* ---- dense building block ------------------------------------------------------------------------
+ * C[M,N] = epilogue(alpha * A[M,K] * B[N,K]^T) on the tcgen05 tensor cores: A and B bfloat16, K
+ * contiguous (lda/ldb in elements, multiples of 8, 16-byte aligned bases), fp32 accumulation.
+ * Epilogue, in this order: * alpha, + bias (float32, per column n; per row m with SMZ_GEMM_BIAS_M),
+ * + residual[m,n] (bfloat16, or float32 with SMZ_GEMM_RES_F32; leading dimension ldr), ReLU with
+ * SMZ_GEMM_RELU; C is bfloat16 or float32 (SMZ_GEMM_OUT_F32).  This is what replaces the cuBLAS
+ * calls behind nn.Linear / torch.bmm in models/vasnet.py:114-140 and models/dsn.py:45,215-228. */
+#define SMZ_GEMM_OUT_F32 1
+#define SMZ_GEMM_RELU 2
+#define SMZ_GEMM_RES_F32 4
+#define SMZ_GEMM_BIAS_M 8
+int smz_gemm_bf16_tn(const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc, int M, int N,
+                     int K, float alpha, const float *bias, const void *residual, int64_t ldr, int flags,
+                     void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,336 @@
+// tcgen05 GEMM building block (sm_100a):  C = epilogue(alpha * A * B^T), bf16 operands, fp32
+// accumulation in tensor memory.  Every dense contraction of the scorers goes through this kernel:
+// VASNet's packed Q|K projection, V^T projection, Q.K^T logits, alpha.V, output projection and k1
+// (vasnet.py:114-140), DSN's LSTM input projection (dsn.py:45) and the reward Gram matrix
+// (dsn.py:215-216,226-228).
+//
+// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
+//   warp 0      TMA producer: 128x64 (A) and 256x64 (B) bf16 boxes, 128-byte swizzle, 4-stage
+//               mbarrier ring (48 KB per stage).
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256, K=16) into one of two
+//               256-column TMEM accumulators; tcgen05.commit releases smem stages / publishes tiles.
+//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per warp), alpha / bias / residual /
+//               ReLU in fp32, 16-byte stores; overlaps the next tile's main loop (double-buffered TMEM).
+// Tiles are enumerated problem-major over a ragged batch (one problem per video for the attention
+// contractions), N fastest so that CTAs running concurrently share the A tile and the weights in L2.
+#include "smz_gemm.cuh"
+#include "smz_tc.cuh"
+
+#include <cudaTypedefs.h>
+
+namespace {
+
+using namespace smztc;
+using smz::GemmEpilogue;
+using smz::GemmProblem;
+
+constexpr int BM = smz::GEMM_BM, BN = smz::GEMM_BN, BK = smz::GEMM_BK;
+constexpr int STAGES = 4;
+constexpr int A_STAGE = BM * BK * 2;   // 16 KB
+constexpr int B_STAGE = BN * BK * 2;   // 32 KB
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 2 * BN;      // two accumulators
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + BAR_BYTES + 1024;   // + alignment slack
+static_assert(TMEM_COLS == 512, "TMEM allocation must be a power of two <= 512 columns");
+
+struct Params {
+    const GemmProblem *probs;
+    GemmProblem single;
+    int n_probs, total_tiles;
+    GemmEpilogue epi;
+};
+
+struct Cursor {
+    int p = -1;
+    GemmProblem cur;
+    __device__ __forceinline__ void seek(const Params &P, int tile) {
+        if (P.probs == nullptr) { cur = P.single; return; }
+        int q = p < 0 ? 0 : p;
+        while (q + 1 < P.n_probs && tile >= __ldg(&P.probs[q + 1].tile0)) ++q;
+        if (q != p) { p = q; cur = P.probs[q]; }
+    }
+};
+
+__device__ __forceinline__ float4 ld_f4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + STAGES * A_STAGE;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * (A_STAGE + B_STAGE));
+    uint64_t *empty = full + STAGES;
+    uint64_t *tfull = empty + STAGES;
+    uint64_t *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            Cursor c;
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+                c.seek(P, tile);
+                const int lt = tile - c.cur.tile0;
+                const int mt = lt / c.cur.tiles_n, nt = lt - mt * c.cur.tiles_n;
+                const int nkb = (c.cur.K + BK - 1) / BK;
+                const int arow = c.cur.a_row0 + mt * BM, brow = c.cur.b_row0 + nt * BN;
+                for (int kb = 0; kb < nkb; kb++) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    mbar_arrive_expect_tx(&full[stage], A_STAGE + B_STAGE);
+                    tma_load_2d(sA + stage * A_STAGE, &tmA, &full[stage], c.cur.a_col0 + kb * BK, arow);
+                    tma_load_2d(sB + stage * B_STAGE, &tmB, &full[stage], c.cur.b_col0 + kb * BK, brow);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            Cursor c;
+            const uint32_t idesc = make_idesc_bf16(BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+                c.seek(P, tile);
+                const int nkb = (c.cur.K + BK - 1) / BK;
+                const int as = it & 1;
+                mbar_wait(&tempty[as], (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < nkb; kb++) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(sA + stage * A_STAGE));
+                    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sB + stage * B_STAGE));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++)   // +32 bytes per K=16 slice inside the swizzle atom
+                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+                    umma_commit(&empty[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tfull[as]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        Cursor c;
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+        const int row = q * 32 + lane;
+        const float alpha = P.epi.alpha;
+        const int flags = P.epi.flags;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+            c.seek(P, tile);
+            const GemmProblem &g = c.cur;
+            const int lt = tile - g.tile0;
+            const int mt = lt / g.tiles_n, nt = lt - mt * g.tiles_n;
+            const int as = it & 1;
+            mbar_wait(&tfull[as], ((uint32_t)it >> 1) & 1u);
+            tc_fence_after();
+            const int m = mt * BM + row;
+            const bool row_ok = m < g.M;
+            const float bias_m = (P.epi.bias != nullptr && (flags & smz::GEMM_BIAS_M) && row_ok) ? __ldg(P.epi.bias + m) : 0.f;
+            const bool out_f32 = flags & smz::GEMM_OUT_F32;
+            const bool c_vec = ((g.c_off | (int64_t)g.ldc) & 7) == 0 && (reinterpret_cast<uintptr_t>(P.epi.C) & 15) == 0;
+            const bool r_vec = ((g.r_off | (int64_t)g.ldr) & 7) == 0 && (reinterpret_cast<uintptr_t>(P.epi.residual) & 15) == 0;
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int n0 = nt * BN + c0;
+                if (n0 >= g.N) break;   // warp-uniform
+                uint32_t v[32];
+                __syncwarp();           // tcgen05.ld is .sync.aligned: reconverge after the row mask
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
+                tmem_ld_wait();
+                if (!row_ok) continue;
+                float x[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) x[j] = alpha * __uint_as_float(v[j]);
+                const bool full32 = n0 + 32 <= g.N;
+                if (P.epi.bias != nullptr) {
+                    if (flags & smz::GEMM_BIAS_M) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) x[j] += bias_m;
+                    } else if (full32) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = ld_f4(P.epi.bias + n0 + j);
+                            x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) if (n0 + j < g.N) x[j] += __ldg(P.epi.bias + n0 + j);
+                    }
+                }
+                if (P.epi.residual != nullptr) {
+                    const int64_t ro = g.r_off + (int64_t)m * g.ldr + n0;
+                    if (flags & smz::GEMM_RES_F32) {
+                        const float *r = reinterpret_cast<const float *>(P.epi.residual) + ro;
+                        if (full32 && r_vec) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b = ld_f4(r + j);
+                                x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) if (n0 + j < g.N) x[j] += r[j];
+                        }
+                    } else {
+                        const __nv_bfloat16 *r = reinterpret_cast<const __nv_bfloat16 *>(P.epi.residual) + ro;
+                        if (full32 && r_vec) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                const uint4 b = *reinterpret_cast<const uint4 *>(r + j);
+                                const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                                for (int t = 0; t < 4; t++) {
+                                    x[j + 2 * t] += __uint_as_float(w[t] << 16);
+                                    x[j + 2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) if (n0 + j < g.N) x[j] += __bfloat162float(r[j]);
+                        }
+                    }
+                }
+                if (flags & smz::GEMM_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) x[j] = fmaxf(x[j], 0.f);
+                }
+                const int64_t co = g.c_off + (int64_t)m * g.ldc + n0;
+                if (out_f32) {
+                    float *dst = reinterpret_cast<float *>(P.epi.C) + co;
+                    if (full32 && c_vec) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4 *>(dst + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) if (n0 + j < g.N) dst[j] = x[j];
+                    }
+                } else {
+                    __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(P.epi.C) + co;
+                    if (full32 && c_vec) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8)
+                            *reinterpret_cast<uint4 *>(dst + j) =
+                                make_uint4(pack_bf16x2(x[j], x[j + 1]), pack_bf16x2(x[j + 2], x[j + 3]),
+                                           pack_bf16x2(x[j + 4], x[j + 5]), pack_bf16x2(x[j + 6], x[j + 7]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) if (n0 + j < g.N) dst[j] = __float2bfloat16_rn(x[j]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (fn == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+int make_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    PFN_cuTensorMapEncodeTiled_v12000 enc = encode_fn();
+    if (enc == nullptr) return smz::fail(SMZ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 7) != 0 || rows <= 0 || cols <= 0)
+        return smz::fail(SMZ_ERR_ARG, "gemm operand must be 16-byte aligned with a leading dimension multiple of 8 "
+                         "(base %p, ld %lld, %lld x %lld)", base, (long long)ld, (long long)rows, (long long)cols);
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return smz::fail(SMZ_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return SMZ_OK;
+}
+
+}  // namespace
+
+namespace smz {
+
+int gemm_bf16_tn(const void *A, int64_t a_rows, int64_t a_cols, int64_t lda, const void *B, int64_t b_rows,
+                 int64_t b_cols, int64_t ldb, const GemmProblem *d_probs, int n_probs, int total_tiles,
+                 const GemmProblem &single, const GemmEpilogue &epi, cudaStream_t st) {
+    if (total_tiles <= 0) return SMZ_OK;
+    SMZ_REQUIRE(A && B && epi.C, "gemm: NULL operand");
+    SMZ_REQUIRE(d_probs != nullptr || n_probs == 1, "gemm: a batch needs a device problem array");
+    alignas(64) CUtensorMap ma, mb;
+    int rc = make_map(&ma, A, a_rows, a_cols, lda, BM);
+    if (rc != SMZ_OK) return rc;
+    rc = make_map(&mb, B, b_rows, b_cols, ldb, BN);
+    if (rc != SMZ_OK) return rc;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    SMZ_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        SMZ_CUDA_CHECK(cudaFuncSetAttribute((const void *)gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set[dev] = true;
+    }
+    Params P;
+    P.probs = d_probs;
+    P.single = single;
+    P.n_probs = n_probs;
+    P.total_tiles = total_tiles;
+    P.epi = epi;
+    const int sms = sm_count();
+    const int grid = total_tiles < sms ? total_tiles : sms;
+    gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
+    SMZ_CUDA_CHECK(cudaGetLastError());
+    return SMZ_OK;
+}
+
+}  // namespace smz
+
+// C[M,N] = epilogue(alpha * A[M,K] * B[N,K]^T): the stand-alone entry point (tests, host-side reuse).
+extern "C" int smz_gemm_bf16_tn(const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc, int M,
+                                int N, int K, float alpha, const float *bias, const void *residual, int64_t ldr,
+                                int flags, void *stream) {
+    if (M == 0 || N == 0) return SMZ_OK;
+    SMZ_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape %d x %d x %d", M, N, K);
+    SMZ_REQUIRE(ldc >= N && lda >= K && ldb >= K, "gemm: leading dimension smaller than the row length");
+    int rc = smz_device_check();
+    if (rc != SMZ_OK) return rc;
+    smz::GemmProblem g = {};
+    g.M = M; g.N = N; g.K = K;
+    g.ldc = (int32_t)ldc; g.ldr = (int32_t)ldr;
+    g.tiles_n = (N + smz::GEMM_BN - 1) / smz::GEMM_BN;
+    smz::GemmEpilogue e = {C, bias, residual, alpha, flags};
+    return smz::gemm_bf16_tn(A, M, K, lda, B, N, K, ldb, nullptr, 1, smz::gemm_tiles(M, N), g, e, (cudaStream_t)stream);
+}

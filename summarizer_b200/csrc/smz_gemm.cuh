@@ -1,0 +1,49 @@
+// Host-side interface of the tcgen05 GEMM building block (smz_gemm.cu), shared by the scorer kernels.
+#pragma once
+#include "smz_common.cuh"
+
+namespace smz {
+
+// One GEMM of a (possibly ragged) batch:  C[M,N] = epilogue(alpha * A[M,K] * B[N,K]^T).
+// A and B are K-major (row = m resp. n, K contiguous) bf16 sub-matrices of two big 2-D arrays that
+// one TMA tensor map each describes; *_row0 / *_col0 locate the sub-matrix inside them.
+struct GemmProblem {
+    int32_t a_row0, a_col0, b_row0, b_col0;
+    int32_t M, N, K;
+    int32_t tile0;       // first flat tile index of this problem (prefix sum over the batch)
+    int64_t c_off;       // element offset of C[0,0] in the output array
+    int64_t r_off;       // element offset of residual[0,0]
+    int32_t ldc, ldr;    // leading dimensions (elements) of C and the residual
+    int32_t tiles_n;     // ceil(N / BN)
+    int32_t pad;
+};
+static_assert(sizeof(GemmProblem) == 64, "GemmProblem layout");
+
+enum : int {
+    GEMM_OUT_F32 = 1,    // C is float32 (default bf16)
+    GEMM_RELU = 2,       // max(x, 0) last
+    GEMM_RES_F32 = 4,    // residual is float32 (default bf16)
+    GEMM_BIAS_M = 8,     // bias indexed by row m (default: by column n)
+};
+
+struct GemmEpilogue {
+    void *C;                 // bf16 or float32
+    const float *bias;       // optional
+    const void *residual;    // optional, added after bias
+    float alpha;
+    int flags;
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BN = 256;
+constexpr int GEMM_BK = 64;
+
+inline int gemm_tiles(int M, int N) { return ((M + GEMM_BM - 1) / GEMM_BM) * ((N + GEMM_BN - 1) / GEMM_BN); }
+
+// A: [a_rows, a_cols] bf16 with leading dimension lda (elements, multiple of 8), likewise B.
+// probs: device array of n_probs problems (or nullptr with n_probs == 1 -> `single` is used).
+int gemm_bf16_tn(const void *A, int64_t a_rows, int64_t a_cols, int64_t lda, const void *B, int64_t b_rows,
+                 int64_t b_cols, int64_t ldb, const GemmProblem *d_probs, int n_probs, int total_tiles,
+                 const GemmProblem &single, const GemmEpilogue &epi, cudaStream_t st);
+
+}  // namespace smz

@@ -1,0 +1,94 @@
+"""tcgen05 GEMM building block (smz_gemm_bf16_tn) against a plain PyTorch fp32 reference of the same op
+(bf16-rounded operands, fp32 accumulation).  Runs on the B200 box only."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from summarizer_b200 import _native as N
+
+pytestmark = pytest.mark.gpu
+
+OUT_F32, RELU, RES_F32, BIAS_M = 1, 2, 4, 8
+
+
+def gemm(a, b, alpha=1.0, bias=None, residual=None, flags=0, ldc=None):
+    M, K = a.shape
+    Nn = b.shape[0]
+    ldc = Nn if ldc is None else ldc
+    out = torch.full((M, ldc), float("nan"), device=a.device,
+                     dtype=torch.float32 if flags & OUT_F32 else torch.bfloat16)
+    N.check(N.lib().smz_gemm_bf16_tn(N.ptr(a), a.stride(0), N.ptr(b), b.stride(0), N.ptr(out), ldc, M, Nn, K,
+                                     C.c_float(alpha), N.ptr(bias), N.ptr(residual),
+                                     0 if residual is None else residual.stride(0), flags, N.current_stream()))
+    return out[:, :Nn]
+
+
+def ref(a, b, alpha=1.0, bias=None, residual=None, flags=0):
+    r = alpha * (a.float() @ b.float().t())
+    if bias is not None:
+        r = r + (bias[:, None] if flags & BIAS_M else bias[None, :])
+    if residual is not None:
+        r = r + residual.float()
+    if flags & RELU:
+        r = torch.relu(r)
+    return r
+
+
+def describe_mismatch(got, want, tol):
+    """Blind-debugging aid: where do the errors sit (rows / column blocks)?"""
+    err = (got.float() - want).abs()
+    bad = err > tol
+    rows = torch.nonzero(bad.any(1)).flatten()[:8].tolist()
+    cols = torch.nonzero(bad.any(0)).flatten()[:16].tolist()
+    return (f"max err {err.max().item():.4g} (tol {tol:.3g}), bad {int(bad.sum())}/{bad.numel()}, "
+            f"first bad rows {rows}, cols {cols}, nan {int(torch.isnan(got.float()).sum())}")
+
+
+@pytest.mark.parametrize("M,Nn,K", [(128, 256, 64), (128, 256, 128), (128, 256, 1024), (256, 512, 1024),
+                                    (300, 2048, 1024), (1024, 300, 1024), (77, 40, 64), (2000, 2000, 1024),
+                                    (707, 1024, 768), (5000, 1024, 1024)])
+def test_gemm_matches_torch(M, Nn, K):
+    N.require_device()
+    g = torch.Generator(device="cuda"); g.manual_seed(M * 7 + Nn * 3 + K)
+    a = torch.randn(M, K, generator=g, device="cuda").bfloat16()
+    b = torch.randn(Nn, K, generator=g, device="cuda").bfloat16()
+    ldc = (Nn + 7) // 8 * 8
+    got = gemm(a, b, flags=OUT_F32, ldc=ldc)
+    want = ref(a, b)
+    tol = 1e-3 * (K ** 0.5) + 1e-3
+    assert torch.allclose(got, want, atol=tol, rtol=1e-3), describe_mismatch(got, want, tol)
+    got16 = gemm(a, b, alpha=0.125, ldc=ldc)
+    want16 = ref(a, b, alpha=0.125)
+    assert torch.allclose(got16.float(), want16, atol=tol, rtol=1e-2), describe_mismatch(got16, want16, tol)
+
+
+def test_gemm_epilogue_variants():
+    N.require_device()
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    M, Nn, K = 333, 1024, 1024
+    a = torch.randn(M, K, generator=g, device="cuda").bfloat16()
+    b = (torch.randn(Nn, K, generator=g, device="cuda") / 32).bfloat16()
+    bias_n = torch.randn(Nn, generator=g, device="cuda")
+    bias_m = torch.randn(M, generator=g, device="cuda")
+    res32 = torch.randn(M, Nn, generator=g, device="cuda")
+    res16 = res32.bfloat16()
+    for kw in (dict(bias=bias_n, flags=OUT_F32), dict(bias=bias_m, flags=OUT_F32 | BIAS_M),
+               dict(bias=bias_n, residual=res32, flags=OUT_F32 | RES_F32), dict(residual=res16, flags=OUT_F32),
+               dict(bias=bias_n, flags=OUT_F32 | RELU), dict(bias=bias_n, residual=res16, flags=RELU)):
+        got = gemm(a, b, **kw)
+        want = ref(a, b, **kw)
+        tol = 2e-2 if not kw["flags"] & OUT_F32 else 2e-3
+        assert torch.allclose(got.float(), want, atol=tol, rtol=1e-2), (kw["flags"], describe_mismatch(got, want, tol))
+
+
+def test_gemm_submatrix_operands():
+    """Operands that are column slices of wider arrays (the Q and K halves of the packed projection)."""
+    N.require_device()
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    T = 450
+    qk = torch.randn(T, 2048, generator=g, device="cuda").bfloat16()
+    got = gemm(qk[:, :1024], qk[:, 1024:], alpha=1 / 32, flags=OUT_F32, ldc=456)
+    want = ref(qk[:, :1024], qk[:, 1024:], alpha=1 / 32)
+    assert torch.allclose(got, want, atol=2e-2, rtol=1e-3), describe_mismatch(got, want, 2e-2)
