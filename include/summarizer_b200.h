@@ -140,6 +140,35 @@ int smz_gemm_bf16_tn(const void *A, int64_t lda, const void *B, int64_t ldb, voi
                      int K, float alpha, const float *bias, const void *residual, int64_t ldr, int flags,
                      void *stream);
 
+/* ---- VASNet scorer: replaces models/vasnet.py:92-148 VASNet.forward (and, with
+ *      smz_vasnet_backward, the autograd graph behind vasnet.py:209-211) -------------------------
+ * Parameters are DEVICE pointers.  The four square matrices are bfloat16 copies of the module's
+ * float32 nn.Linear weights ([out, in] row-major, as stored by torch):
+ *   wqk [2048,1024]  rows 0..1023 = Q.weight, rows 1024..2047 = K.weight   (vasnet.py:57-58)
+ *   wv, wo, w1 [1024,1024]  V.weight, attention_head_projection.weight, k1.weight (vasnet.py:59-60,64)
+ *   b1 [1024], w2 [1024], b2 [1], ln_g / ln_b [1024] float32  (k1.bias, k2.weight, k2.bias and the ONE
+ *   LayerNorm the reference applies twice, vasnet.py:54,137,143)
+ * scale multiplies the logits (vasnet.py:34,119); aperture < 0 = global attention, else the band
+ * |i-j| <= aperture of vasnet.py:124-127; ignore_self masks the diagonal (vasnet.py:121-122). */
+typedef struct smz_vasnet_params {
+    const void *wqk, *wv, *wo, *w1;
+    const float *b1, *w2, *b2, *ln_g, *ln_b;
+    float scale, eps;
+    int32_t aperture, ignore_self;
+} smz_vasnet_params;
+
+/* x: packed features [sum T, 1024] (float32, or bfloat16 when x_is_bf16), video v owns rows
+ * h_cu_seqlens[v] .. h_cu_seqlens[v+1]-1 (HOST array of n_videos+1 prefix offsets, [0] == 0; the
+ * reference's (T, B, 1024) batch is B videos of equal length).  scores: float32 [sum T] in (0,1).
+ * training != 0 keeps every intermediate in the work buffer for smz_vasnet_backward and enables the
+ * three p=0.5 dropouts (vasnet.py:130,136,142) through caller-supplied KEEP masks (uint8, 1 = keep;
+ * NULL = no dropout at that site): drop_att packed per video [T*T], drop_y / drop_h [sum T, 1024]. */
+int smz_vasnet_workspace_bytes(const int32_t *h_cu_seqlens, int n_videos, int training, int x_is_bf16,
+                               int64_t *bytes);
+int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h_cu_seqlens, int n_videos,
+                       const smz_vasnet_params *p, int training, const uint8_t *drop_att, const uint8_t *drop_y,
+                       const uint8_t *drop_h, float *scores, void *ws, int64_t ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

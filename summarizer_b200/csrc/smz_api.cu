@@ -1,11 +1,19 @@
 // Library-level entry points: version, error string, device check.
 #include "smz_common.cuh"
 
+#include <stdlib.h>
+
 namespace smz {
 
 char *last_error_buf() {
     static thread_local char buf[512] = {0};
     return buf;
+}
+
+bool debug_sync_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("SMZ_DEBUG_SYNC"); v = (e != nullptr && e[0] == '1') ? 1 : 0; }
+    return v == 1;
 }
 
 int sm_count() {

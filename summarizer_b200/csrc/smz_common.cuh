@@ -32,6 +32,18 @@ inline int fail(int code, const char *fmt, ...) {
         if (!(cond)) return ::smz::fail(SMZ_ERR_ARG, __VA_ARGS__);                             \
     } while (0)
 
+// SMZ_DEBUG_SYNC=1: synchronise after every launch and report the step that failed (debugging aid;
+// never set in production — the library is otherwise fully asynchronous).
+bool debug_sync_enabled();
+#define SMZ_DEBUG_STEP(st, name)                                                               \
+    do {                                                                                       \
+        if (::smz::debug_sync_enabled()) {                                                     \
+            cudaError_t _e = cudaStreamSynchronize(st);                                        \
+            if (_e != cudaSuccess)                                                             \
+                return ::smz::fail(SMZ_ERR_CUDA, "step '%s' failed: %s", name, cudaGetErrorString(_e)); \
+        }                                                                                      \
+    } while (0)
+
 // Number of SMs of the current device (cached per device id).
 int sm_count();
 // Max opt-in dynamic shared memory per block of the current device.

@@ -15,7 +15,7 @@ struct GemmProblem {
     int64_t r_off;       // element offset of residual[0,0]
     int32_t ldc, ldr;    // leading dimensions (elements) of C and the residual
     int32_t tiles_n;     // ceil(N / BN)
-    int32_t pad;
+    int32_t pad;         // free for the caller (VASNet: leading zero columns of the video's P block)
 };
 static_assert(sizeof(GemmProblem) == 64, "GemmProblem layout");
 

@@ -1,0 +1,32 @@
+// Row-wise kernels of the scorers (softmax with VASNet's masks, LayerNorm, regressor head, dtype
+// conversion).  One warp per row, 128-bit loads; launched by smz_vasnet.cu / smz_dsn.cu.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "smz_gemm.cuh"
+
+namespace smz {
+
+constexpr int kFeat = 1024;   // feature / hidden width of VASNet (vasnet.py:18)
+
+int launch_cvt_bf16(const float *x, __nv_bfloat16 *y, int64_t n, cudaStream_t st);
+
+// alpha = softmax(mask(S)) over the keys of each row (vasnet.py:121-130).  `probs` are the problems of
+// the logits GEMM (M = N = T, c_off / ldc locate the video's block in S); alpha/P use the same offsets.
+// drop (optional): keep-mask bytes of the attention dropout, video v at drop + drop_off[v]; then
+// P = 2 * keep * alpha, else P == alpha (one buffer).  A row of P holds probs[v].pad zero columns, the
+// T probabilities, then zeros up to the next multiple of 64 (the K extent alpha.V reads).
+int launch_softmax(const GemmProblem *d_probs, int n_probs, int total_rows, const float *S, __nv_bfloat16 *alpha,
+                   __nv_bfloat16 *P, const uint8_t *drop, const int64_t *d_drop_off, int aperture, int ignore_self,
+                   cudaStream_t st);
+
+// yn = LayerNorm(2*keep*y or y) * g + b  (vasnet.py:136-137), rows of 1024; optional mean / rstd.
+int launch_layernorm(const float *y, const uint8_t *keep, const float *g, const float *b, float eps, int rows,
+                     __nv_bfloat16 *yn, float *mean, float *rstd, cudaStream_t st);
+
+// score = sigmoid(LayerNorm(2*keep*h or h) . w2 + b2)  (vasnet.py:142-145); h is post-ReLU float32.
+int launch_head(const float *h, const uint8_t *keep, const float *g, const float *b, float eps,
+                const float *w2, const float *b2, int rows, float *scores, float *mean, float *rstd,
+                cudaStream_t st);
+
+}  // namespace smz

@@ -1,0 +1,263 @@
+// VASNet scorer (models/vasnet.py:92-148) on the tcgen05 GEMM building block.
+//
+// forward, per row chunk of the packed batch (rows of all videos, [sum T, 1024]):
+//   xb  = bf16(x)                                              (skipped when the features are bf16)
+//   QK  = xb . [Wq;Wk]^T                      [R, 2048] bf16    vasnet.py:114-115, one packed GEMM
+//   Vt  = Wv . xb^T                           [1024, R] bf16    vasnet.py:116, produced transposed so that
+//                                                               alpha.V is a K-major GEMM too
+//   per attention sub-chunk (logits stay L2-resident):
+//     S   = scale * Q_v . K_v^T               [T, T]   fp32     vasnet.py:118-119, one GEMM problem per video
+//     P   = dropout(softmax(mask(S)))         [T, ld]  bf16     vasnet.py:121-130 (zero padded columns)
+//     O   = P . V_v                           [R, 1024] bf16    vasnet.py:131
+//   Y   = O . Wo^T + x                        [R, 1024] fp32    vasnet.py:132-135
+//   Yn  = LayerNorm(dropout(Y))               bf16              vasnet.py:136-137
+//   H   = relu(Yn . W1^T + b1)                fp32              vasnet.py:140-141
+//   s   = sigmoid(LayerNorm(dropout(H)) . w2 + b2)              vasnet.py:142-145
+// In training mode the whole batch is one chunk and every intermediate stays in the work buffer for
+// smz_vasnet_backward.
+#include <vector>
+
+#include "smz_gemm.cuh"
+#include "smz_rows.cuh"
+
+namespace {
+
+using smz::GemmEpilogue;
+using smz::GemmProblem;
+using smz::kFeat;
+typedef __nv_bfloat16 bf16;
+
+constexpr int kRowChunk = 8192;                 // rows per chunk of the row-wise GEMMs
+constexpr int64_t kLogitBudget = 12ll << 20;    // fp32 logits kept in flight per sub-chunk (48 MB)
+
+inline int64_t up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+struct Sub { int v0, v1, rows, ld; };
+struct Chunk { int v0, v1, row0, rows; std::vector<Sub> subs; };
+
+struct Plan {
+    std::vector<Chunk> chunks;
+    int n_videos = 0, total_rows = 0, max_rows = 0;
+    int64_t max_logits = 0;
+    bool training = false, x_bf16 = false;
+    int64_t off_xb, off_qk, off_vt, off_o, off_y, off_yn, off_h, off_s, off_p, off_alpha, off_probs, off_dropoff,
+        off_stats, total;
+};
+
+int make_plan(const int32_t *cu, int n_videos, bool training, bool x_bf16, Plan *pl) {
+    SMZ_REQUIRE(cu != nullptr && n_videos > 0, "vasnet: empty batch");
+    SMZ_REQUIRE(cu[0] == 0, "vasnet: cu_seqlens[0] must be 0");
+    for (int v = 0; v < n_videos; v++) SMZ_REQUIRE(cu[v + 1] > cu[v], "vasnet: video %d has no frames", v);
+    pl->n_videos = n_videos;
+    pl->total_rows = cu[n_videos];
+    pl->training = training;
+    pl->x_bf16 = x_bf16;
+    int v = 0;
+    while (v < n_videos) {
+        Chunk c;
+        c.v0 = v; c.row0 = cu[v];
+        int rows = 0;
+        while (v < n_videos && (training || rows == 0 || rows + (cu[v + 1] - cu[v]) <= kRowChunk)) { rows += cu[v + 1] - cu[v]; ++v; }
+        c.v1 = v; c.rows = rows;
+        int u = c.v0;
+        while (u < c.v1) {
+            Sub s;
+            s.v0 = u; s.rows = 0;
+            int maxT = 0;
+            while (u < c.v1) {
+                const int T = cu[u + 1] - cu[u];
+                const int nm = T > maxT ? T : maxT;
+                const int64_t elems = (int64_t)(s.rows + T) * up(nm + 7, 64);
+                if (!training && s.rows > 0 && elems > kLogitBudget) break;
+                maxT = nm; s.rows += T; ++u;
+            }
+            s.v1 = u; s.ld = (int)up(maxT + 7, 64);   // + up to 7 leading pad columns, see build_problems
+            const int64_t elems = (int64_t)s.rows * s.ld;
+            if (elems > pl->max_logits) pl->max_logits = elems;
+            c.subs.push_back(s);
+        }
+        if (c.rows > pl->max_rows) pl->max_rows = c.rows;
+        pl->chunks.push_back(c);
+    }
+    const int64_t R = up(pl->max_rows, 8);
+    int64_t o = 0;
+    auto take = [&](int64_t bytes) { const int64_t at = o; o += up(bytes, 1024); return at; };
+    pl->off_xb = take(x_bf16 ? 0 : R * kFeat * 2);
+    pl->off_qk = take(R * 2 * kFeat * 2);
+    pl->off_vt = take((int64_t)kFeat * R * 2);
+    pl->off_o = take(R * kFeat * 2);
+    pl->off_y = take(R * kFeat * 4);
+    pl->off_yn = take(R * kFeat * 2);
+    pl->off_h = take(R * kFeat * 4);
+    pl->off_s = take(pl->max_logits * 4);
+    pl->off_p = take(pl->max_logits * 2);
+    pl->off_alpha = take(training ? pl->max_logits * 2 : 0);
+    pl->off_probs = take((int64_t)n_videos * 2 * sizeof(GemmProblem));
+    pl->off_dropoff = take(training ? (int64_t)n_videos * 8 : 0);
+    pl->off_stats = take(training ? R * 4 * 4 : 0);
+    pl->total = o;
+    return SMZ_OK;
+}
+
+// host-side GEMM problem tables: [0, n) logits problems, [n, 2n) alpha.V problems
+void build_problems(const Plan &pl, const int32_t *cu, std::vector<GemmProblem> *out) {
+    const int n = pl.n_videos;
+    out->assign((size_t)2 * n, GemmProblem{});
+    for (const Chunk &c : pl.chunks)
+        for (const Sub &s : c.subs) {
+            int tile_s = 0, tile_pv = 0, sub_row = 0;
+            for (int v = s.v0; v < s.v1; v++) {
+                const int T = cu[v + 1] - cu[v];
+                const int crow = cu[v] - c.row0;          // chunk-local row of the video
+                // TMA needs 16-byte aligned coordinates along the contiguous dimension: the video's columns
+                // of V^T start at crow, so alpha.V reads V^T from crow - lead and P carries `lead` zero
+                // columns in front (written by the softmax kernel).
+                const int lead = crow & 7;
+                GemmProblem &a = (*out)[v];
+                a.a_row0 = crow; a.a_col0 = 0; a.b_row0 = crow; a.b_col0 = kFeat;
+                a.M = T; a.N = T; a.K = kFeat; a.tile0 = tile_s;
+                a.c_off = (int64_t)sub_row * s.ld; a.ldc = s.ld;
+                a.tiles_n = (T + smz::GEMM_BN - 1) / smz::GEMM_BN;
+                a.pad = lead;
+                tile_s += smz::gemm_tiles(T, T);
+                GemmProblem &b = (*out)[n + v];
+                b.a_row0 = sub_row; b.a_col0 = 0; b.b_row0 = 0; b.b_col0 = crow - lead;
+                b.M = T; b.N = kFeat; b.K = T + lead; b.tile0 = tile_pv;
+                b.c_off = (int64_t)crow * kFeat; b.ldc = kFeat;
+                b.tiles_n = kFeat / smz::GEMM_BN;
+                tile_pv += smz::gemm_tiles(T, kFeat);
+                sub_row += T;
+            }
+        }
+}
+
+GemmProblem dense_problem(int M, int N, int K, int ldc, int ldr) {
+    GemmProblem g = {};
+    g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.ldr = ldr;
+    g.tiles_n = (N + smz::GEMM_BN - 1) / smz::GEMM_BN;
+    return g;
+}
+
+}  // namespace
+
+extern "C" int smz_vasnet_workspace_bytes(const int32_t *h_cu_seqlens, int n_videos, int training, int x_is_bf16,
+                                          int64_t *bytes) {
+    SMZ_REQUIRE(bytes != nullptr, "bytes is NULL");
+    Plan pl;
+    int rc = make_plan(h_cu_seqlens, n_videos, training != 0, x_is_bf16 != 0, &pl);
+    if (rc != SMZ_OK) return rc;
+    *bytes = pl.total;
+    return SMZ_OK;
+}
+
+extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h_cu_seqlens, int n_videos,
+                                  const smz_vasnet_params *p, int training, const uint8_t *drop_att,
+                                  const uint8_t *drop_y, const uint8_t *drop_h, float *scores, void *ws,
+                                  int64_t ws_bytes, void *stream) {
+    SMZ_REQUIRE(x && p && scores && ws, "vasnet_forward: NULL pointer");
+    SMZ_REQUIRE(p->wqk && p->wv && p->wo && p->w1 && p->b1 && p->w2 && p->b2 && p->ln_g && p->ln_b,
+                "vasnet_forward: NULL parameter pointer");
+    int rc = smz_device_check();
+    if (rc != SMZ_OK) return rc;
+    Plan pl;
+    rc = make_plan(h_cu_seqlens, n_videos, training != 0, x_is_bf16 != 0, &pl);
+    if (rc != SMZ_OK) return rc;
+    SMZ_REQUIRE(ws_bytes >= pl.total, "vasnet_forward: work buffer too small (%lld < %lld bytes)", (long long)ws_bytes,
+                (long long)pl.total);
+    SMZ_REQUIRE(training || (!drop_att && !drop_y && !drop_h), "dropout masks are only meaningful in training mode");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *w = reinterpret_cast<uint8_t *>(ws);
+    const int n = n_videos;
+
+    std::vector<GemmProblem> probs;
+    build_problems(pl, h_cu_seqlens, &probs);
+    GemmProblem *d_probs = reinterpret_cast<GemmProblem *>(w + pl.off_probs);
+    SMZ_CUDA_CHECK(cudaMemcpyAsync(d_probs, probs.data(), probs.size() * sizeof(GemmProblem), cudaMemcpyHostToDevice, st));
+    int64_t *d_dropoff = nullptr;
+    if (drop_att != nullptr) {
+        std::vector<int64_t> off((size_t)n);
+        int64_t acc = 0;
+        for (int v = 0; v < n; v++) { off[v] = acc; const int64_t T = h_cu_seqlens[v + 1] - h_cu_seqlens[v]; acc += T * T; }
+        d_dropoff = reinterpret_cast<int64_t *>(w + pl.off_dropoff);
+        SMZ_CUDA_CHECK(cudaMemcpyAsync(d_dropoff, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
+    }
+
+    bf16 *qk = reinterpret_cast<bf16 *>(w + pl.off_qk);
+    bf16 *vt = reinterpret_cast<bf16 *>(w + pl.off_vt);
+    bf16 *o = reinterpret_cast<bf16 *>(w + pl.off_o);
+    float *y = reinterpret_cast<float *>(w + pl.off_y);
+    bf16 *yn = reinterpret_cast<bf16 *>(w + pl.off_yn);
+    float *h = reinterpret_cast<float *>(w + pl.off_h);
+    float *S = reinterpret_cast<float *>(w + pl.off_s);
+    bf16 *P = reinterpret_cast<bf16 *>(w + pl.off_p);
+    bf16 *alpha = (training && drop_att) ? reinterpret_cast<bf16 *>(w + pl.off_alpha) : P;
+    float *stats = training ? reinterpret_cast<float *>(w + pl.off_stats) : nullptr;
+    const int64_t Rs = up(pl.max_rows, 8);   // stride of the stats arrays
+
+    for (const Chunk &c : pl.chunks) {
+        const int R = c.rows;
+        const int64_t Rpad = up(R, 8);
+        const bf16 *xb;
+        if (x_is_bf16) {
+            xb = reinterpret_cast<const bf16 *>(x) + (int64_t)c.row0 * kFeat;
+        } else {
+            bf16 *dst = reinterpret_cast<bf16 *>(w + pl.off_xb);
+            rc = smz::launch_cvt_bf16(reinterpret_cast<const float *>(x) + (int64_t)c.row0 * kFeat, dst, (int64_t)R * kFeat, st);
+            if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "cvt");
+            xb = dst;
+        }
+        // Q|K projection and V^T projection
+        rc = smz::gemm_bf16_tn(xb, R, kFeat, kFeat, p->wqk, 2 * kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, 2 * kFeat),
+                               dense_problem(R, 2 * kFeat, kFeat, 2 * kFeat, 0), GemmEpilogue{qk, nullptr, nullptr, 1.f, 0}, st);
+        if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "gemm_qk");
+        rc = smz::gemm_bf16_tn(p->wv, kFeat, kFeat, kFeat, xb, R, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(kFeat, R),
+                               dense_problem(kFeat, R, kFeat, (int)Rpad, 0), GemmEpilogue{vt, nullptr, nullptr, 1.f, 0}, st);
+        if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "gemm_vt");
+        // attention, one GEMM problem per video
+        for (const Sub &s : c.subs) {
+            const int nv = s.v1 - s.v0;
+            int tiles_s = 0, tiles_pv = 0;
+            for (int v = s.v0; v < s.v1; v++) {
+                const int T = h_cu_seqlens[v + 1] - h_cu_seqlens[v];
+                tiles_s += smz::gemm_tiles(T, T);
+                tiles_pv += smz::gemm_tiles(T, kFeat);
+            }
+            rc = smz::gemm_bf16_tn(qk, R, 2 * kFeat, 2 * kFeat, qk, R, 2 * kFeat, 2 * kFeat, d_probs + s.v0, nv, tiles_s,
+                                   GemmProblem{}, GemmEpilogue{S, nullptr, nullptr, p->scale, smz::GEMM_OUT_F32}, st);
+            if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "gemm_logits");
+            rc = smz::launch_softmax(d_probs + s.v0, nv, s.rows, S, alpha, P, drop_att, d_dropoff ? d_dropoff + s.v0 : nullptr,
+                                     p->aperture, p->ignore_self, st);
+            if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "softmax");
+            rc = smz::gemm_bf16_tn(P, s.rows, s.ld, s.ld, vt, kFeat, R, Rpad, d_probs + n + s.v0, nv, tiles_pv, GemmProblem{},
+                                   GemmEpilogue{o, nullptr, nullptr, 1.f, 0}, st);
+            if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "gemm_pv");
+        }
+        // output projection + residual, LayerNorm, k1 + ReLU, head
+        const void *res = x_is_bf16 ? (const void *)(reinterpret_cast<const bf16 *>(x) + (int64_t)c.row0 * kFeat)
+                                    : (const void *)(reinterpret_cast<const float *>(x) + (int64_t)c.row0 * kFeat);
+        rc = smz::gemm_bf16_tn(o, R, kFeat, kFeat, p->wo, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
+                               dense_problem(R, kFeat, kFeat, kFeat, kFeat),
+                               GemmEpilogue{y, nullptr, res, 1.f, smz::GEMM_OUT_F32 | (x_is_bf16 ? 0 : smz::GEMM_RES_F32)}, st);
+        if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "gemm_out");
+        rc = smz::launch_layernorm(y, drop_y ? drop_y + (int64_t)c.row0 * kFeat : nullptr, p->ln_g, p->ln_b, p->eps, R, yn,
+                                   stats, stats ? stats + Rs : nullptr, st);
+        if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "layernorm");
+        rc = smz::gemm_bf16_tn(yn, R, kFeat, kFeat, p->w1, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
+                               dense_problem(R, kFeat, kFeat, kFeat, 0), GemmEpilogue{h, p->b1, nullptr, 1.f, smz::GEMM_RELU | smz::GEMM_OUT_F32}, st);
+        if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "gemm_k1");
+        rc = smz::launch_head(h, drop_h ? drop_h + (int64_t)c.row0 * kFeat : nullptr, p->ln_g, p->ln_b, p->eps, p->w2, p->b2,
+                              R, scores + c.row0, stats ? stats + 2 * Rs : nullptr, stats ? stats + 3 * Rs : nullptr, st);
+        if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "head");
+    }
+    return SMZ_OK;
+}

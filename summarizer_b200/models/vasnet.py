@@ -1,0 +1,170 @@
+"""VASNet — "Summarizing Videos with Attention" scorer with the reference's class, constructor,
+parameter names and ``forward((T, B, 1024)) -> (T, B, 1)`` contract (models/vasnet.py:17-148), computed
+by the sm_100a kernels of libsummarizer_b200.so (smz_vasnet_forward / smz_vasnet_backward).
+
+The module keeps ordinary float32 ``nn.Parameter``s under the reference's names, so reference ``.pth``
+files load unchanged (``layer_norm.{weight,bias}``, ``{K,Q,V,attention_head_projection}.weight``,
+``k1.{weight,bias}``, ``k2.{weight,bias}``, optional ``pos_embed.weight``); bfloat16 copies for the
+tensor cores are derived on the fly and never saved.  There is no CPU / eager fallback.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.init as init
+
+from .. import _native as N
+
+
+class VasnetParams(C.Structure):
+    """struct smz_vasnet_params (include/summarizer_b200.h)."""
+    _fields_ = [("wqk", C.c_void_p), ("wv", C.c_void_p), ("wo", C.c_void_p), ("w1", C.c_void_p),
+                ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("ln_g", C.c_void_p),
+                ("ln_b", C.c_void_p), ("scale", C.c_float), ("eps", C.c_float), ("aperture", C.c_int32),
+                ("ignore_self", C.c_int32)]
+
+
+def _cu_seqlens(lengths):
+    cu = np.zeros(len(lengths) + 1, dtype=np.int32)
+    np.cumsum(np.asarray(lengths, dtype=np.int64), out=cu[1:])
+    return cu
+
+
+class _Workspace:
+    """Grow-only device work buffer, one per (device, purpose)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(max(int(nbytes), 1024), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+class VASNet(nn.Module):
+    def __init__(self, input_size=1024, max_length=None, pos_embed="simple", ignore_self=False,
+                 attention_aperture=None, scale=None, epsilon=1e-6, weight_init="xavier"):
+        super().__init__()
+        if input_size != 1024:
+            raise ValueError("the sm_100a VASNet kernels are built for 1024-d features (GoogLeNet pool5)")
+        self.input_size = input_size
+        self.aperture = attention_aperture          # None = global attention, w = frames [t-w, t+w]
+        self.ignore_self = ignore_self
+        self.scale = scale if scale is not None else 1 / np.sqrt(self.input_size)
+        self.epsilon = epsilon
+
+        # optional positional information (vasnet.py:37-51): a learned table or the fixed sin/cos one,
+        # which the reference keeps as a plain tensor outside the state dict
+        self.max_length = max_length
+        if self.max_length:
+            self.pos_embed_type = pos_embed
+            if pos_embed == "simple":
+                self.pos_embed = nn.Embedding(self.max_length, self.input_size)
+            elif pos_embed == "attention":
+                pos = np.arange(self.max_length, dtype=np.float64)[:, None]
+                i = np.arange(self.input_size, dtype=np.float64)[None, :]
+                table = np.where(i % 2 == 0, np.sin(pos / 10000 ** (2 * i / self.input_size)),
+                                 np.cos(pos / 10000 ** (2 * i / self.input_size)))
+                self.pos_embed = torch.from_numpy(table).float()
+            else:
+                self.max_length = None
+
+        self.dropout = nn.Dropout(0.5)
+        self.layer_norm = nn.LayerNorm(self.input_size, epsilon)
+        d = self.input_size
+        self.K = nn.Linear(d, d, bias=False)
+        self.Q = nn.Linear(d, d, bias=False)
+        self.V = nn.Linear(d, d, bias=False)
+        self.attention_head_projection = nn.Linear(d, d, bias=False)
+        self.softmax = nn.Softmax(dim=2)
+        self.k1 = nn.Linear(d, d)
+        self.k2 = nn.Linear(d, 1)
+        self.sigmoid = nn.Sigmoid()
+        self.relu = nn.ReLU()
+
+        mats = (self.K, self.Q, self.V, self.attention_head_projection, self.k1, self.k2)
+        for m in mats:                               # vasnet.py:71-86
+            if weight_init.lower() in ("he", "kaiming"):
+                init.kaiming_uniform_(m.weight)
+            else:
+                init.xavier_uniform_(m.weight, gain=np.sqrt(2.0))
+        init.constant_(self.k1.bias, 0.1)
+        init.constant_(self.k2.bias, 0.1)
+
+        self._shadow = None
+        self._shadow_key = None
+        self._ws = _Workspace()
+
+    # ---------------------------------------------------------------------------------------------
+    def _weights(self):
+        """bfloat16 shadow copies + the parameter struct; rebuilt when a parameter changed."""
+        ps = (self.Q.weight, self.K.weight, self.V.weight, self.attention_head_projection.weight,
+              self.k1.weight, self.k1.bias, self.k2.weight, self.k2.bias, self.layer_norm.weight,
+              self.layer_norm.bias)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if key != self._shadow_key:
+            with torch.no_grad():
+                sh = dict(
+                    wqk=torch.cat([self.Q.weight, self.K.weight], 0).to(torch.bfloat16).contiguous(),
+                    wv=self.V.weight.to(torch.bfloat16).contiguous(),
+                    wo=self.attention_head_projection.weight.to(torch.bfloat16).contiguous(),
+                    w1=self.k1.weight.to(torch.bfloat16).contiguous(),
+                    b1=self.k1.bias.float().contiguous(), w2=self.k2.weight.float().reshape(-1).contiguous(),
+                    b2=self.k2.bias.float().contiguous(), ln_g=self.layer_norm.weight.float().contiguous(),
+                    ln_b=self.layer_norm.bias.float().contiguous())
+            self._shadow, self._shadow_key = sh, key
+        sh = self._shadow
+        st = VasnetParams(*(sh[k].data_ptr() for k in ("wqk", "wv", "wo", "w1", "b1", "w2", "b2", "ln_g", "ln_b")),
+                          float(self.scale), float(self.epsilon),
+                          -1 if self.aperture is None else int(self.aperture), int(bool(self.ignore_self)))
+        return sh, st
+
+    def score_packed(self, x, lengths):
+        """Inference over a ragged batch: ``x`` packed [sum T, 1024] (float32 or bfloat16, device),
+        ``lengths`` the per-video frame counts.  Returns float32 scores [sum T]."""
+        N.require_device()
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        x = x.contiguous()
+        cu = _cu_seqlens(lengths)
+        assert x.shape == (int(cu[-1]), self.input_size)
+        _, st = self._weights()
+        nbytes = C.c_int64(0)
+        cu_p = cu.ctypes.data_as(C.c_void_p)
+        is_bf16 = int(x.dtype == torch.bfloat16)
+        N.check(N.lib().smz_vasnet_workspace_bytes(cu_p, len(lengths), 0, is_bf16, C.byref(nbytes)))
+        ws = self._ws.get(nbytes.value, x.device)
+        scores = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        N.check(N.lib().smz_vasnet_forward(N.ptr(x), is_bf16, cu_p, len(lengths), C.byref(st), 0, None, None, None,
+                                           N.ptr(scores), N.ptr(ws), ws.numel(), N.current_stream()))
+        return scores
+
+    def forward(self, x):
+        """
+        Input
+          x: (seq_len, batch_size, input_size)
+        Output
+          y: (seq_len, batch_size, 1)
+        """
+        seq_len, batch_size, input_size = x.shape
+        assert self.input_size == input_size
+        if not x.is_cuda:
+            raise N.NativeError("summarizer_b200.VASNet runs on a CUDA (sm_100a) device only; move the input with .cuda()")
+        if self.max_length is not None:
+            assert self.max_length >= seq_len, "input sequence has higher length than max_length"
+            xb = x.permute(1, 0, 2)                 # a view: the in-place add reaches the caller's tensor
+            if self.pos_embed_type == "simple":     # (vasnet.py:110,112 quirk kept)
+                pos = torch.arange(seq_len, device=x.device).repeat(1, batch_size).view(batch_size, seq_len)
+                xb += self.pos_embed(pos)
+            else:
+                xb += self.pos_embed[:seq_len, :].repeat(1, batch_size).view(batch_size, seq_len, input_size).to(x.device)
+        packed = x.permute(1, 0, 2).reshape(batch_size * seq_len, input_size)
+        if torch.is_grad_enabled() and (self.training or any(p.requires_grad for p in self.parameters())):
+            from .vasnet_autograd import vasnet_apply
+            s = vasnet_apply(self, packed, [seq_len] * batch_size)
+        else:
+            s = self.score_packed(packed, [seq_len] * batch_size)
+        return s.view(batch_size, seq_len, 1).permute(1, 0, 2)
