@@ -5,17 +5,18 @@
   python bench.py --impl reference --gpus N --steps K --warmup W
 
 Workload (BASELINE.json configs[4], the largest single-GPU configuration): the synthetic sweep —
-10 000 videos x 2 000 steps (30 000 frames at the dataset's 15x subsampling), 20 annotators — per
-GPU (weak scaling: every rank owns its own 10 000 videos, no data-path collective).
+10 000 videos x 2 000 steps of 1024-d bf16 features (30 000 frames at the dataset's 15x subsampling),
+20 annotators — per GPU (weak scaling: every rank owns its own videos, no data-path collective).
 A *step* is one pass of the hot path over the whole resident batch:
-    [VASNet scoring of every video — when --score is on]  ->  shot selection (segment pooling +
-    0/1 knapsack)  ->  per-user F-score.
-Metric: videos/s (whole job, all ranks).  Inputs are resident in HBM when the timed region starts;
-`e2e` is the same metric through the public API with HOST (pinned) buffers, H2D/D2H inside the
-timed region, on a bounded sample.  The 24 GB of annotator summaries per rank are far larger than
-the 126 MB L2, so no explicit L2 flush is needed between steps.
+    VASNet scoring of every video (tcgen05 GEMMs)  ->  shot selection (segment pooling + 0/1 knapsack)
+    ->  per-user F-score.
+Metric: videos/s (whole job, all ranks); frames/s is reported beside it.  Inputs are resident in HBM when
+the timed region starts; `e2e` is the same metric through the public API with HOST (pinned) buffers, H2D/D2H
+inside the timed region, on a bounded sample.  Features (41 GB) and annotator summaries (24 GB) per rank are
+far larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -29,19 +30,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-N_FRAMES, N_STEPS, N_USERS = 30000, 2000, 20
-METRIC = "knapsack-eval videos/sec (sweep: shot selection + F-score)"
+N_FRAMES, N_STEPS, N_USERS, FEAT = 30000, 2000, 20, 1024
+METRIC = "VASNet scoring + knapsack/F-score eval videos/sec (sweep)"
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--videos", type=int, default=int(os.environ.get("SMZ_BENCH_VIDEOS", 10000)),
                     help="videos per GPU (10000 = BASELINE config 5)")
-    ap.add_argument("--e2e-videos", type=int, default=256)
+    ap.add_argument("--e2e-videos", type=int, default=128)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
 
@@ -50,9 +51,14 @@ def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
             p = json.load(fh)
-        return float(p["hbm_gbs"]), float(p["bf16_tflops_sustained"]), "measured"
+        return float(p["hbm_gbs"]), float(p["bf16_tflops_sustained"]), float(p["bf16_tflops"]), "measured"
     except Exception:
-        return 6650.0, 1400.0, "fallback"
+        return 6650.0, 1400.0, 1590.0, "fallback"
+
+
+def flops_vasnet_fwd(T, D=FEAT):
+    """F_fwd = 10 T D^2 + 4 T^2 D + 2 T D (no credit for recompute or padding)."""
+    return 10 * T * D * D + 4 * T * T * D + 2 * T * D
 
 
 class ClockSampler:
@@ -86,17 +92,17 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
             except (ValueError, IndexError):
                 continue
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -112,67 +118,120 @@ def algorithmic_bytes(batch):
 
 
 def host_sample(n, seed0=900000):
-    """Host-side sweep-shaped videos (numpy) for the CPU arms."""
+    """Host-side sweep-shaped videos (numpy) for the CPU arms: (features fp32, eval tuple)."""
     from summarizer_b200 import synthetic
     out = []
     for i in range(n):
-        v = synthetic.make_video("sweep", seed0 + i, n_frames=N_FRAMES, n_users=N_USERS, with_features=False,
+        v = synthetic.make_video("sweep", seed0 + i, n_frames=N_FRAMES, n_users=N_USERS, with_features=True,
                                  uniform_segments=60 if i % 16 == 15 else None)
-        rng = np.random.default_rng(seed0 + i)
-        scores = rng.random(N_STEPS).astype(np.float32)
-        out.append((scores, v["change_points"], N_FRAMES, v["n_frame_per_seg"].tolist(), v["picks"], v["user_summary"]))
+        out.append((v["features"], (v["change_points"], N_FRAMES, v["n_frame_per_seg"].tolist(), v["picks"],
+                                    v["user_summary"])))
     return out
 
 
-def cpu_baseline(seconds):
-    """Reference-shaped port (oracle/ref_port.py) on ONE host core over a bounded sample."""
+def cpu_model():
+    """The scorer of the CPU arms: oracle/models_torch.py (the reference's VASNet.forward restated op by op
+    in float32 torch — the same ATen/MKL kernels the reference reaches) on reference-initialised weights."""
+    import torch
+    from summarizer_b200.models.vasnet import VASNet
+    torch.manual_seed(0)
+    m = VASNet().eval()
+    return m.state_dict(), float(m.scale), float(m.epsilon)
+
+
+def cpu_score(sd, scale, eps, feats):
+    import torch
+    from oracle import models_torch
+    with torch.no_grad():
+        return models_torch.vasnet_forward(sd, torch.from_numpy(feats), scale=scale, eps=eps).numpy()
+
+
+def _eval_one(args):
     from oracle import ref_port
-    vids = host_sample(8)
-    ref_port.eval_video(vids[0])
+    scores, (cps, n_frames, nfps, picks, user_summary) = args
+    return ref_port.eval_video((scores, cps, n_frames, nfps, picks, user_summary))
+
+
+def cpu_baseline(seconds):
+    """Scoring (torch CPU, all threads) + reference-shaped eval port, bounded sample, rank 0 only."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd, scale, eps = cpu_model()
+    vids = host_sample(4)
+    _eval_one((cpu_score(sd, scale, eps, vids[0][0]), vids[0][1]))
     t0 = time.perf_counter(); n = 0
     while time.perf_counter() - t0 < seconds:
-        ref_port.eval_video(vids[n % len(vids)]); n += 1
+        f, ev = vids[n % len(vids)]
+        _eval_one((cpu_score(sd, scale, eps, f), ev)); n += 1
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "videos/s", "cores": 1, "kind": "port",
-            "sample": f"{n} sweep-shaped videos (30000 frames, 20 users) in {dt:.1f}s, oracle/ref_port.py "
-                      "(numpy+Python loops as the reference, C restatement of the OR-tools DP)"}
+    return {"value": n / dt, "unit": "videos/s", "cores": cores, "kind": "port",
+            "sample": f"{n} sweep-shaped videos (2000 x 1024 fp32 features, 30000 frames, 20 users) in {dt:.1f}s: "
+                      "VASNet forward in float32 torch on all host threads (oracle/models_torch.py) + "
+                      "oracle/ref_port.py eval (numpy+Python loops as the reference, C restatement of the OR-tools DP)"}
 
 
 def run_reference(args):
-    """--impl reference: the reference-shaped CPU port with all host threads; rank 0 only."""
+    """--impl reference: the reference's CPU path (torch fp32 scorer + reference-shaped eval port) with all
+    host threads; rank 0 only."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     import multiprocessing as mp
-    from oracle import ref_port
+    import torch
     cores = os.cpu_count() or 1
-    per_step = max(cores, min(64, 4 * cores))
+    torch.set_num_threads(cores)
+    sd, scale, eps = cpu_model()
+    per_step = max(8, min(32, cores))
     vids = host_sample(per_step)
-    with mp.Pool(cores) as pool:
+
+    def step(pool, sub):
+        scored = [(cpu_score(sd, scale, eps, f), ev) for f, ev in sub]
+        pool.map(_eval_one, scored, chunksize=max(1, len(sub) // (2 * cores)))
+
+    with mp.get_context("fork").Pool(cores) as pool:
         for _ in range(max(args.warmup, 1)):
-            pool.map(ref_port.eval_video, vids[:cores])
+            step(pool, vids[:4])
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            pool.map(ref_port.eval_video, vids, chunksize=max(1, per_step // (4 * cores)))
+            step(pool, vids)
         dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "videos/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/int64", "data": "synthetic",
-            "config": {"workload": "sweep eval (config 5 shapes): 30000 frames, 2000 steps, 20 users per video",
+            "frames_per_s": value * N_STEPS,
+            "config": {"workload": "sweep (config 5 shapes): 2000 steps x 1024-d features, 30000 frames, 20 users per video",
                        "videos_per_step": per_step},
             "cpu_baseline": {"value": value, "unit": "videos/s", "cores": cores, "kind": "port",
-                             "sample": f"{per_step} videos/step x {args.steps} steps, multiprocessing over {cores} cores, "
-                                       "oracle/ref_port.py (reference is pure Python + un-installable OR-tools)"},
+                             "sample": f"{per_step} videos/step x {args.steps} steps: float32 torch VASNet forward on {cores} "
+                                       "threads (oracle/models_torch.py) + oracle/ref_port.py eval over a process pool "
+                                       "(the reference is pure Python + un-installable OR-tools, so the port is timed)"},
             "e2e": {"value": value, "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+def make_features(n_videos, dev, seed):
+    """[n_videos*2000, 1024] bf16, non-negative L2-normalised rows (post-ReLU pool5-like), built on the device."""
+    import torch
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    x = torch.empty(n_videos * N_STEPS, FEAT, dtype=torch.bfloat16, device=dev)
+    step = 64 * N_STEPS
+    for r0 in range(0, x.shape[0], step):
+        r1 = min(r0 + step, x.shape[0])
+        t = torch.randn(r1 - r0, FEAT, generator=g, device=dev).abs_()
+        t /= t.norm(dim=1, keepdim=True)
+        x[r0:r1] = t.to(torch.bfloat16)
+    return x
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
+    from summarizer_b200 import _native as N
     from summarizer_b200 import synthetic
+    from summarizer_b200.models.vasnet import VASNet
 
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -186,19 +245,27 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    batch = synthetic.make_sweep_batch(args.videos, dev, seed=5000 + 100000 * rank)
-    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
-    scores = torch.rand(batch.total_scores, generator=g, device=dev)
+    V = args.videos
+    torch.manual_seed(0)
+    model = VASNet().to(dev).eval()
+    batch = synthetic.make_sweep_batch(V, dev, seed=5000 + 100000 * rank)
+    feats = make_features(V, dev, seed=77 + rank)
+    lengths = [N_STEPS] * V
     stream = torch.cuda.current_stream()
     b_eval, b_fscore = algorithmic_bytes(batch)
+    f_score_stage = V * flops_vasnet_fwd(N_STEPS)
 
     def step(ev=None):
-        batch.select(scores)
+        scores = model.score_packed(feats, lengths)
         if ev is not None:
             ev[0].record(stream)
-        batch.fscore()
+        batch.select(scores)
         if ev is not None:
             ev[1].record(stream)
+        batch.fscore()
+        if ev is not None:
+            ev[2].record(stream)
+        return scores
 
     for _ in range(args.warmup):
         step()
@@ -207,41 +274,47 @@ def run_native(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mk = lambda: torch.cuda.Event(enable_timing=True)
+    evs = [(mk(), mk(), mk(), mk()) for _ in range(args.steps)]
+    t_start, t_end = mk(), mk()
     barrier()
     t_start.record(stream)
     for i in range(args.steps):
+        evs[i][3].record(stream)
         step(evs[i])
     t_end.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = t_start.elapsed_time(t_end)
-    fscore_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    t = torch.tensor([ms, fscore_ms], dtype=torch.float64, device=dev)
+    score_ms = float(np.mean([e[3].elapsed_time(e[0]) for e in evs]))
+    select_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    fscore_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    t = torch.tensor([ms, score_ms, select_ms, fscore_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, fscore_ms = t.tolist()
-    value = args.videos * world * args.steps / (ms / 1e3)
+    ms, score_ms, select_ms, fscore_ms = t.tolist()
+    value = V * world * args.steps / (ms / 1e3)
 
     # ---- e2e: public batched API with host (pinned) inputs, H2D + D2H inside the timed region
-    ne = min(args.e2e_videos, args.videos)
+    ne = min(args.e2e_videos, V)
     eb = synthetic.make_sweep_batch(ne, dev, seed=777 + rank)
     h_users = torch.empty(eb.d_users.shape, dtype=torch.float32, pin_memory=True); h_users.copy_(eb.d_users)
-    h_scores = torch.empty(eb.total_scores, dtype=torch.float32, pin_memory=True); h_scores.copy_(scores[: eb.total_scores])
+    h_feats = torch.empty((ne * N_STEPS, FEAT), dtype=torch.bfloat16, pin_memory=True); h_feats.copy_(feats[: ne * N_STEPS])
     h_out = torch.empty((2, ne), dtype=torch.float64, pin_memory=True)
-    d_scores = torch.empty_like(h_scores, device=dev)
+    d_feats = torch.empty_like(h_feats, device=dev)
+    le = [N_STEPS] * ne
 
     def e2e_step():
+        d_feats.copy_(h_feats, non_blocking=True)
         eb.d_users.copy_(h_users, non_blocking=True)
-        d_scores.copy_(h_scores, non_blocking=True)
-        eb.select(d_scores); eb.fscore()
+        s = model.score_packed(d_feats, le)
+        eb.select(s); eb.fscore()
         h_out[0].copy_(eb.avg_f[:ne], non_blocking=True); h_out[1].copy_(eb.max_f[:ne], non_blocking=True)
 
     for _ in range(2):
         e2e_step()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = mk(), mk()
     e0.record(stream)
     for _ in range(args.steps):
         e2e_step()
@@ -253,25 +326,34 @@ def run_native(args):
     e2e_value = ne * world * args.steps / (te.item() / 1e3)
 
     if rank == 0:
-        hbm, _, which = peaks()
-        achieved = b_fscore / (fscore_ms / 1e3) / 1e9
+        hbm, tf_sus, tf_burst, which = peaks()
+        cu = np.arange(V + 1, dtype=np.int32) * N_STEPS
+        nl = ctypes.c_int64(0)
+        N.check(N.lib().smz_vasnet_launch_count(cu.ctypes.data_as(ctypes.c_void_p), V, 0, 1, ctypes.byref(nl)))
+        achieved_tf = f_score_stage / (score_ms / 1e3) / 1e12
+        achieved_gb = b_fscore / (fscore_ms / 1e3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "videos/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8/i32 (bit masks, int32 DP; float32 segment means and F)",
-            "data": "synthetic",
-            "config": {"workload": "sweep eval (BASELINE config 5 shapes): per GPU %d videos x 2000 steps "
-                                   "(30000 frames), 20 annotators, 15%% knapsack" % args.videos,
-                       "videos_per_gpu": args.videos, "l2": "inputs (24 GB/GPU at 10k videos) exceed the 126 MB L2; no flush",
-                       "scoring": "not in the timed step yet (VASNet kernels measured separately)"},
-            "roofline": {"bound": "hbm", "kernel": "fscore_kernel", "achieved": achieved, "peak": hbm,
-                         "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": which,
-                         "ms_per_launch": fscore_ms, "algorithmic_bytes_per_launch": b_fscore,
-                         "eval_path_frac": (b_eval / (ms / args.steps / 1e3) / 1e9) / hbm},
+            "vs_baseline": None, "dtype": "bf16 (tcgen05 operands, fp32 accumulate/softmax/LayerNorm); i32/u8 eval",
+            "data": "synthetic", "frames_per_s": value * N_STEPS,
+            "config": {"workload": "sweep (BASELINE config 5 shapes): per GPU %d videos x 2000 steps x 1024-d bf16 features "
+                                   "(30000 frames), 20 annotators, VASNet scoring -> 15%% knapsack -> F-score" % V,
+                       "videos_per_gpu": V,
+                       "l2": "inputs (41 GB features + 24 GB annotations per GPU at 10k videos) exceed the 126 MB L2; no flush"},
+            "stages_ms": {"vasnet_scoring": score_ms, "shot_selection": select_ms, "fscore": fscore_ms},
+            "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05; all launches of the VASNet scoring stage, "
+                                                      "softmax/LayerNorm/head row kernels included in the time)",
+                         "achieved": achieved_tf, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved_tf / tf_sus,
+                         "frac_of_burst_peak": achieved_tf / tf_burst, "traffic": None, "peak_source": which + " (sustained)",
+                         "ms_per_launch": score_ms, "algorithmic_flops_per_launch": f_score_stage},
+            "roofline_eval": {"bound": "hbm", "kernel": "fscore_kernel", "achieved": achieved_gb, "peak": hbm, "unit": "GB/s",
+                              "frac": achieved_gb / hbm, "ms_per_launch": fscore_ms, "algorithmic_bytes_per_launch": b_fscore,
+                              "eval_path_frac": (b_eval / ((select_ms + fscore_ms) / 1e3) / 1e9) / hbm},
             "e2e": {"value": e2e_value, "unit": "videos/s",
-                    "h2d_bytes_per_step": int(h_users.numel() * 4 + h_scores.numel() * 4),
+                    "h2d_bytes_per_step": int(h_feats.numel() * 2 + h_users.numel() * 4),
                     "d2h_bytes_per_step": int(h_out.numel() * 8), "videos_per_step": ne},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": int((nl.value + 6) * args.steps),
             "clocks": clocks,
         }
         if world == 1:

@@ -165,6 +165,8 @@ typedef struct smz_vasnet_params {
  * NULL = no dropout at that site): drop_att packed per video [T*T], drop_y / drop_h [sum T, 1024]. */
 int smz_vasnet_workspace_bytes(const int32_t *h_cu_seqlens, int n_videos, int training, int x_is_bf16,
                                int64_t *bytes);
+int smz_vasnet_launch_count(const int32_t *h_cu_seqlens, int n_videos, int training, int x_is_bf16,
+                            int64_t *launches);   /* kernels one forward call launches (reporting) */
 int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h_cu_seqlens, int n_videos,
                        const smz_vasnet_params *p, int training, const uint8_t *drop_att, const uint8_t *drop_y,
                        const uint8_t *drop_h, float *scores, void *ws, int64_t ws_bytes, void *stream);

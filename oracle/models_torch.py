@@ -1,0 +1,73 @@
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Plain float32 PyTorch restatement of the reference scorers' forward passes, written against a state
+dict with the reference's key names so it can be fed with the product modules' parameters:
+
+  vasnet_forward   models/vasnet.py:92-148 (eval mode, or training mode with explicit keep-masks)
+  dsn_forward      models/dsn.py:38-47     (nn.LSTM semantics restated step by step: gates i,f,g,o)
+
+Pinned by tests/test_oracle_models.py against tests/golden/models_golden.npz, i.e. against outputs of the
+UNMODIFIED reference modules.  Used by the GPU parity tests (gradients through autograd), by
+__graft_entry__.smoke() and as bench.py's timed CPU baseline for the scoring stage.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def vasnet_forward(sd, x, scale=None, eps=1e-6, aperture=None, ignore_self=False, keep_att=None, keep_y=None,
+                   keep_h=None):
+    """x: (T, 1024) float32 of ONE video -> scores (T,).  keep_*: optional 0/1 masks of the three
+    p=0.5 dropouts (vasnet.py:130,136,142): kept entries are scaled by 2."""
+    T, D = x.shape
+    scale = 1.0 / math.sqrt(D) if scale is None else scale
+    K = x @ sd["K.weight"].t()                                   # vasnet.py:114
+    Q = x @ sd["Q.weight"].t()                                   # :115
+    V = x @ sd["V.weight"].t()                                   # :116
+    e = (Q @ K.t()) * scale                                      # :118-119
+    if ignore_self:                                              # :121-122
+        e = e.masked_fill(torch.eye(T, dtype=torch.bool, device=x.device), float("-inf"))
+    if aperture is not None:                                     # :124-127 (incl. the e*e == 0 quirk)
+        scope = torch.tril(e, diagonal=aperture) * torch.triu(e, diagonal=-aperture)
+        e = e.masked_fill(scope == 0, float("-inf"))
+    alpha = torch.softmax(e, dim=1)                              # :129
+    if keep_att is not None:
+        alpha = alpha * keep_att * 2.0                           # :130
+    c = (alpha @ V) @ sd["attention_head_projection.weight"].t()  # :131-132
+    y = c + x                                                    # :135
+    if keep_y is not None:
+        y = y * keep_y * 2.0                                     # :136
+    y = F.layer_norm(y, (D,), sd["layer_norm.weight"], sd["layer_norm.bias"], eps)       # :137
+    y = torch.relu(y @ sd["k1.weight"].t() + sd["k1.bias"])      # :140-141
+    if keep_h is not None:
+        y = y * keep_h * 2.0                                     # :142
+    y = F.layer_norm(y, (D,), sd["layer_norm.weight"], sd["layer_norm.bias"], eps)       # :143
+    return torch.sigmoid(y @ sd["k2.weight"].t() + sd["k2.bias"]).reshape(T)             # :144-145
+
+
+def lstm_direction(x, w_ih, w_hh, b_ih, b_hh, reverse=False):
+    """One direction of torch.nn.LSTM (zero initial state): x (T, I) -> h (T, H).
+    Gate order i, f, g, o; c_t = f*c + i*g; h_t = o*tanh(c_t)."""
+    T = x.shape[0]
+    H = w_hh.shape[1]
+    pre = x @ w_ih.t() + b_ih + b_hh
+    h = x.new_zeros(H)
+    c = x.new_zeros(H)
+    out = [None] * T
+    for t in (range(T - 1, -1, -1) if reverse else range(T)):
+        g = pre[t] + w_hh @ h
+        i, f, gg, o = g[:H], g[H:2 * H], g[2 * H:3 * H], g[3 * H:]
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        out[t] = h
+    return torch.stack(out, 0)
+
+
+def dsn_forward(sd, x):
+    """x: (T, 1024) of ONE video -> probs (T,)   (dsn.py:38-47: BiLSTM(1024->256) + Linear(512,1) + sigmoid)."""
+    hf = lstm_direction(x, sd["rnn.weight_ih_l0"], sd["rnn.weight_hh_l0"], sd["rnn.bias_ih_l0"], sd["rnn.bias_hh_l0"])
+    hb = lstm_direction(x, sd["rnn.weight_ih_l0_reverse"], sd["rnn.weight_hh_l0_reverse"],
+                        sd["rnn.bias_ih_l0_reverse"], sd["rnn.bias_hh_l0_reverse"], reverse=True)
+    h = torch.cat([hf, hb], 1)
+    return torch.sigmoid(h @ sd["out.0.weight"].t() + sd["out.0.bias"]).reshape(-1)

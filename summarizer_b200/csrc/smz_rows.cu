@@ -52,6 +52,9 @@ __device__ __forceinline__ float mask_logit(float e, int i, int j, int aperture,
     return e;
 }
 
+// One warp per query row.  Fast path (row fits 16 float4 per lane, no leading pad, no dropout): the
+// logits are read ONCE into registers (16 independent 128-bit loads in flight per lane), max / exp /
+// sum / normalise happen there, P is written once.  Other rows take the three-pass path.
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 softmax_kernel(const GemmProblem *__restrict__ probs, int n_probs, int total_rows, const float *__restrict__ S,
                __nv_bfloat16 *__restrict__ alpha, __nv_bfloat16 *__restrict__ P, const uint8_t *__restrict__ drop,
@@ -70,6 +73,53 @@ softmax_kernel(const GemmProblem *__restrict__ probs, int n_probs, int total_row
     const int64_t off = g.c_off + (int64_t)i * ld;
     const float *s = S + off;
     const bool plain = aperture < 0 && !ignore_self;
+    const int lead = g.pad;
+    const int W64 = (lead + T + 63) & ~63;
+
+    if (T <= 2048 && lead == 0 && drop == nullptr) {
+        constexpr int NV = 16;
+        float v[NV][4];
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            const int j = lane * 4 + 128 * k;
+            if (j < T) {
+                const float4 e = *reinterpret_cast<const float4 *>(s + j);
+                v[k][0] = e.x; v[k][1] = e.y; v[k][2] = e.z; v[k][3] = e.w;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    if (j + t >= T) v[k][t] = -INFINITY;
+                    else if (!plain) v[k][t] = mask_logit(v[k][t], i, j + t, aperture, ignore_self);
+                    m = fmaxf(m, v[k][t]);
+                }
+            }
+        }
+        m = warp_max(m);
+        float l = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            const int j = lane * 4 + 128 * k;
+            if (j < T) {
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    v[k][t] = (j + t < T) ? __expf(v[k][t] - m) : 0.f;   // a fully masked row gives NaN, as torch does
+                    l += v[k][t];
+                }
+            }
+        }
+        l = warp_sum(l);
+        const float inv = 1.f / l;
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            const int j = lane * 4 + 128 * k;
+            if (j < W64) {
+                uint2 o = make_uint2(0u, 0u);
+                if (j < T) o = make_uint2(pack2(v[k][0] * inv, v[k][1] * inv), pack2(v[k][2] * inv, v[k][3] * inv));
+                *reinterpret_cast<uint2 *>(P + off + j) = o;
+            }
+        }
+        return;
+    }
 
     float m = -INFINITY;
     for (int j = lane * 4; j < T; j += 128) {
@@ -92,8 +142,6 @@ softmax_kernel(const GemmProblem *__restrict__ probs, int n_probs, int total_row
     const float inv = 1.f / l;
     const uint8_t *keep = drop != nullptr ? drop + drop_off[lo] + (int64_t)i * T : nullptr;
     // P / alpha rows: `lead` zero columns, the T probabilities, zeros up to the next multiple of 64
-    const int lead = g.pad;
-    const int W64 = (lead + T + 63) & ~63;
     for (int jo = lane * 4; jo < W64; jo += 128) {
         float a[4], p[4];
 #pragma unroll

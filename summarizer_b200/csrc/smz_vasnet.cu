@@ -27,8 +27,11 @@ using smz::GemmProblem;
 using smz::kFeat;
 typedef __nv_bfloat16 bf16;
 
-constexpr int kRowChunk = 8192;                 // rows per chunk of the row-wise GEMMs
-constexpr int64_t kLogitBudget = 12ll << 20;    // fp32 logits kept in flight per sub-chunk (48 MB)
+// Chunk sizes trade L2 residency of the intermediates against wave quantisation of the per-video
+// attention problems (one T=2000 video is only 128 logits tiles / 64 alpha.V tiles for 148 SMs): 16k rows
+// (8 sweep videos) give >= 512 tiles per launch; the spilled intermediates cost < 25 % of HBM bandwidth.
+constexpr int kRowChunk = 16384;                // rows per chunk of the row-wise GEMMs
+constexpr int64_t kLogitBudget = 34ll << 20;    // fp32 logits in flight per sub-chunk (8 x 2000 x 2048)
 
 inline int64_t up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
@@ -147,6 +150,19 @@ extern "C" int smz_vasnet_workspace_bytes(const int32_t *h_cu_seqlens, int n_vid
     int rc = make_plan(h_cu_seqlens, n_videos, training != 0, x_is_bf16 != 0, &pl);
     if (rc != SMZ_OK) return rc;
     *bytes = pl.total;
+    return SMZ_OK;
+}
+
+// number of kernel launches smz_vasnet_forward issues for this batch (bench.py reports it)
+extern "C" int smz_vasnet_launch_count(const int32_t *h_cu_seqlens, int n_videos, int training, int x_is_bf16,
+                                       int64_t *launches) {
+    SMZ_REQUIRE(launches != nullptr, "launches is NULL");
+    Plan pl;
+    int rc = make_plan(h_cu_seqlens, n_videos, training != 0, x_is_bf16 != 0, &pl);
+    if (rc != SMZ_OK) return rc;
+    int64_t n = 0;
+    for (const Chunk &c : pl.chunks) n += (x_is_bf16 ? 0 : 1) + 6 + 3 * (int64_t)c.subs.size();
+    *launches = n;
     return SMZ_OK;
 }
 
