@@ -139,6 +139,12 @@ int smz_upsample(const smz_video_desc *desc, int n_videos, int max_n_frames, con
 int smz_gemm_bf16_tn(const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc, int M, int N,
                      int K, float alpha, const float *bias, const void *residual, int64_t ldr, int flags,
                      void *stream);
+/* General operand storage: a_mn != 0 means A is given as [K, M] (m contiguous, lda >= M) instead of
+ * [M, K]; b_mn != 0 means B is given as [K, N].  With these the autograd GEMMs of vasnet.py:209-211
+ * (dX = dY.W, dW = dY^T.X) read the row-major activations directly, no transposed copies. */
+int smz_gemm_bf16(int a_mn, int b_mn, const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc,
+                  int M, int N, int K, float alpha, const float *bias, const void *residual, int64_t ldr, int flags,
+                  void *stream);
 
 /* ---- VASNet scorer: replaces models/vasnet.py:92-148 VASNet.forward (and, with
  *      smz_vasnet_backward, the autograd graph behind vasnet.py:209-211) -------------------------

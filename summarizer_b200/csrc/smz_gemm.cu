@@ -54,6 +54,12 @@ struct Cursor {
 
 __device__ __forceinline__ float4 ld_f4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 
+// A_MN / B_MN: the operand is stored "MN-major" (k rows, m resp. n contiguous) instead of K-major; it is
+// then loaded as 64x64 boxes (64 k-rows of 128 bytes, one box per 64 m/n) and described to the tensor
+// core with the MN-major canonical layout (LBO = one box = 8 KB between 64-element m/n groups, SBO =
+// 1 KB between 8-row k groups, +2 KB per K=16 slice).  This is what lets the backward pass run
+// dX = dY.W and dW = dY^T.X on the row-major activations without materialising any transpose.
+template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params P) {
     extern __shared__ uint8_t smem_raw[];
@@ -90,12 +96,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int lt = tile - c.cur.tile0;
                 const int mt = lt / c.cur.tiles_n, nt = lt - mt * c.cur.tiles_n;
                 const int nkb = (c.cur.K + BK - 1) / BK;
-                const int arow = c.cur.a_row0 + mt * BM, brow = c.cur.b_row0 + nt * BN;
+                // K-major: (row0, col0) = (first m/n row, first k column); MN-major: (first k row, first m/n column)
+                const int a_mn = (A_MN ? c.cur.a_col0 : c.cur.a_row0) + mt * BM;
+                const int b_mn = (B_MN ? c.cur.b_col0 : c.cur.b_row0) + nt * BN;
+                const int a_k = A_MN ? c.cur.a_row0 : c.cur.a_col0, b_k = B_MN ? c.cur.b_row0 : c.cur.b_col0;
                 for (int kb = 0; kb < nkb; kb++) {
                     mbar_wait(&empty[stage], phase ^ 1u);
                     mbar_arrive_expect_tx(&full[stage], A_STAGE + B_STAGE);
-                    tma_load_2d(sA + stage * A_STAGE, &tmA, &full[stage], c.cur.a_col0 + kb * BK, arow);
-                    tma_load_2d(sB + stage * B_STAGE, &tmB, &full[stage], c.cur.b_col0 + kb * BK, brow);
+                    if (A_MN) {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; j++)
+                            tma_load_2d(sA + stage * A_STAGE + j * 8192, &tmA, &full[stage], a_mn + 64 * j, a_k + kb * BK);
+                    } else {
+                        tma_load_2d(sA + stage * A_STAGE, &tmA, &full[stage], a_k + kb * BK, a_mn);
+                    }
+                    if (B_MN) {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; j++)
+                            tma_load_2d(sB + stage * B_STAGE + j * 8192, &tmB, &full[stage], b_mn + 64 * j, b_k + kb * BK);
+                    } else {
+                        tma_load_2d(sB + stage * B_STAGE, &tmB, &full[stage], b_k + kb * BK, b_mn);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -104,7 +125,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             Cursor c;
-            const uint32_t idesc = make_idesc_bf16(BM, BN);
+            const uint32_t idesc = make_idesc_bf16(BM, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
@@ -117,11 +138,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 for (int kb = 0; kb < nkb; kb++) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(sA + stage * A_STAGE));
-                    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sB + stage * B_STAGE));
+                    const uint32_t a_addr = smem_u32(sA + stage * A_STAGE), b_addr = smem_u32(sB + stage * B_STAGE);
+                    const uint64_t adesc = A_MN ? make_mnmajor_sw128_desc(a_addr) : make_kmajor_sw128_desc(a_addr);
+                    const uint64_t bdesc = B_MN ? make_mnmajor_sw128_desc(b_addr) : make_kmajor_sw128_desc(b_addr);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; k++)   // +32 bytes per K=16 slice inside the swizzle atom
-                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+                    for (int k = 0; k < BK / 16; k++)   // per K=16 slice: +32 B inside the swizzle atom (K-major), +2 KB (MN-major)
+                        umma_bf16(d_tmem, adesc + (A_MN ? 128 : 2) * k, bdesc + (B_MN ? 128 : 2) * k, idesc,
+                                  (uint32_t)((kb | k) != 0));
                     umma_commit(&empty[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -264,6 +287,7 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
     return fn;
 }
 
+// K-major operand: box = 64 k-columns x box_rows rows.  MN-major operand: box = 64 m/n-columns x 64 k-rows.
 int make_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
     PFN_cuTensorMapEncodeTiled_v12000 enc = encode_fn();
     if (enc == nullptr) return smz::fail(SMZ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
@@ -288,20 +312,31 @@ namespace smz {
 int gemm_bf16_tn(const void *A, int64_t a_rows, int64_t a_cols, int64_t lda, const void *B, int64_t b_rows,
                  int64_t b_cols, int64_t ldb, const GemmProblem *d_probs, int n_probs, int total_tiles,
                  const GemmProblem &single, const GemmEpilogue &epi, cudaStream_t st) {
+    return gemm_bf16(false, false, A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, d_probs, n_probs, total_tiles, single,
+                     epi, st);
+}
+
+int gemm_bf16(bool a_mn, bool b_mn, const void *A, int64_t a_rows, int64_t a_cols, int64_t lda, const void *B,
+              int64_t b_rows, int64_t b_cols, int64_t ldb, const GemmProblem *d_probs, int n_probs, int total_tiles,
+              const GemmProblem &single, const GemmEpilogue &epi, cudaStream_t st) {
     if (total_tiles <= 0) return SMZ_OK;
     SMZ_REQUIRE(A && B && epi.C, "gemm: NULL operand");
     SMZ_REQUIRE(d_probs != nullptr || n_probs == 1, "gemm: a batch needs a device problem array");
     alignas(64) CUtensorMap ma, mb;
-    int rc = make_map(&ma, A, a_rows, a_cols, lda, BM);
+    int rc = make_map(&ma, A, a_rows, a_cols, lda, a_mn ? 64 : BM);
     if (rc != SMZ_OK) return rc;
-    rc = make_map(&mb, B, b_rows, b_cols, ldb, BN);
+    rc = make_map(&mb, B, b_rows, b_cols, ldb, b_mn ? 64 : BN);
     if (rc != SMZ_OK) return rc;
-    static bool attr_set[64] = {false};
+    typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const Params);
+    const kern_t kern = a_mn ? (b_mn ? (kern_t)gemm_kernel<true, true> : (kern_t)gemm_kernel<true, false>)
+                             : (b_mn ? (kern_t)gemm_kernel<false, true> : (kern_t)gemm_kernel<false, false>);
+    const int variant = (a_mn ? 2 : 0) + (b_mn ? 1 : 0);
+    static bool attr_set[64][4] = {{false}};
     int dev = 0;
     SMZ_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        SMZ_CUDA_CHECK(cudaFuncSetAttribute((const void *)gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set[dev] = true;
+    if (dev >= 0 && dev < 64 && !attr_set[dev][variant]) {
+        SMZ_CUDA_CHECK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set[dev][variant] = true;
     }
     Params P;
     P.probs = d_probs;
@@ -311,7 +346,7 @@ int gemm_bf16_tn(const void *A, int64_t a_rows, int64_t a_cols, int64_t lda, con
     P.epi = epi;
     const int sms = sm_count();
     const int grid = total_tiles < sms ? total_tiles : sms;
-    gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
+    kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
     SMZ_CUDA_CHECK(cudaGetLastError());
     return SMZ_OK;
 }
@@ -333,4 +368,23 @@ extern "C" int smz_gemm_bf16_tn(const void *A, int64_t lda, const void *B, int64
     g.tiles_n = (N + smz::GEMM_BN - 1) / smz::GEMM_BN;
     smz::GemmEpilogue e = {C, bias, residual, alpha, flags};
     return smz::gemm_bf16_tn(A, M, K, lda, B, N, K, ldb, nullptr, 1, smz::gemm_tiles(M, N), g, e, (cudaStream_t)stream);
+}
+
+// General form: op(A) / op(B) may be stored MN-major (k rows, m resp. n contiguous):
+//   a_mn == 0: A is [M, K] (lda >= K);  a_mn != 0: A is [K, M] (lda >= M).  Likewise B with N.
+extern "C" int smz_gemm_bf16(int a_mn, int b_mn, const void *A, int64_t lda, const void *B, int64_t ldb, void *C,
+                             int64_t ldc, int M, int N, int K, float alpha, const float *bias, const void *residual,
+                             int64_t ldr, int flags, void *stream) {
+    if (M == 0 || N == 0) return SMZ_OK;
+    SMZ_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape %d x %d x %d", M, N, K);
+    SMZ_REQUIRE(ldc >= N && lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K), "gemm: leading dimension smaller than the row length");
+    int rc = smz_device_check();
+    if (rc != SMZ_OK) return rc;
+    smz::GemmProblem g = {};
+    g.M = M; g.N = N; g.K = K;
+    g.ldc = (int32_t)ldc; g.ldr = (int32_t)ldr;
+    g.tiles_n = (N + smz::GEMM_BN - 1) / smz::GEMM_BN;
+    smz::GemmEpilogue e = {C, bias, residual, alpha, flags};
+    return smz::gemm_bf16(a_mn != 0, b_mn != 0, A, a_mn ? K : M, a_mn ? M : K, lda, B, b_mn ? K : N, b_mn ? N : K, ldb,
+                          nullptr, 1, smz::gemm_tiles(M, N), g, e, (cudaStream_t)stream);
 }

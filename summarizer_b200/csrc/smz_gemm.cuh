@@ -46,4 +46,11 @@ int gemm_bf16_tn(const void *A, int64_t a_rows, int64_t a_cols, int64_t lda, con
                  int64_t b_cols, int64_t ldb, const GemmProblem *d_probs, int n_probs, int total_tiles,
                  const GemmProblem &single, const GemmEpilogue &epi, cudaStream_t st);
 
+// General form: a_mn / b_mn select MN-major storage of the operand ([K, M] resp. [K, N] arrays, m / n
+// contiguous); then (*_row0, *_col0) of a problem are (first k row, first m/n column), which must be a
+// multiple of 8 columns (TMA alignment).
+int gemm_bf16(bool a_mn, bool b_mn, const void *A, int64_t a_rows, int64_t a_cols, int64_t lda, const void *B,
+              int64_t b_rows, int64_t b_cols, int64_t ldb, const GemmProblem *d_probs, int n_probs, int total_tiles,
+              const GemmProblem &single, const GemmEpilogue &epi, cudaStream_t st);
+
 }  // namespace smz

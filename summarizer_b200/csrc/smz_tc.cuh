@@ -77,6 +77,14 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     return lo | (hi << 32);
 }
 
+// MN-major operand tile: 64x64 boxes ([64 k-rows][64 m/n] = 128-byte rows, 128-byte swizzle), one box
+// per 64 m/n.  LBO = 8192 B (next 64-element m/n group = next box), SBO = 1024 B (next 8 k-rows).
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+    const uint64_t lo = (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(8192u >> 4) << 16);
+    const uint64_t hi = (uint64_t)(1024u >> 4) | (1ull << 14) | (2ull << 29);
+    return lo | (hi << 32);
+}
+
 // Instruction descriptor, kind::f16, bf16 x bf16 -> fp32, both operands K-major.
 //   [4,6) D format 1 = f32   [7,10) A format 1 = bf16   [10,13) B format 1 = bf16
 //   [15] A major 0 = K   [16] B major 0 = K   [17,23) N >> 3   [24,29) M >> 4

@@ -92,3 +92,41 @@ def test_gemm_submatrix_operands():
     got = gemm(qk[:, :1024], qk[:, 1024:], alpha=1 / 32, flags=OUT_F32, ldc=456)
     want = ref(qk[:, :1024], qk[:, 1024:], alpha=1 / 32)
     assert torch.allclose(got, want, atol=2e-2, rtol=1e-3), describe_mismatch(got, want, 2e-2)
+
+
+def gemm_general(a_mn, b_mn, a, b, M, Nn, K, flags=OUT_F32, residual=None):
+    out = torch.full((M, Nn), float("nan"), device=a.device, dtype=torch.float32 if flags & OUT_F32 else torch.bfloat16)
+    N.check(N.lib().smz_gemm_bf16(int(a_mn), int(b_mn), N.ptr(a), a.stride(0), N.ptr(b), b.stride(0), N.ptr(out), Nn,
+                                  M, Nn, K, C.c_float(1.0), None, N.ptr(residual), Nn if residual is not None else 0,
+                                  flags, N.current_stream()))
+    return out
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,Nn,K", [(128, 256, 64), (128, 256, 256), (1024, 1024, 300), (300, 1024, 1024),
+                                    (2048, 1024, 707), (707, 707, 1024), (1024, 600, 777)])
+def test_gemm_mn_major_operands(a_mn, b_mn, M, Nn, K):
+    """op(A) stored [K, M] and/or op(B) stored [K, N] (the backward-pass forms), K tails zero-filled by TMA."""
+    N.require_device()
+    g = torch.Generator(device="cuda"); g.manual_seed(M + 3 * Nn + 5 * K + a_mn + 2 * b_mn)
+    pad8 = lambda n: (n + 7) // 8 * 8
+    am = torch.randn(M, K, generator=g, device="cuda").bfloat16()
+    bm = torch.randn(Nn, K, generator=g, device="cuda").bfloat16()
+    if a_mn:
+        a = torch.zeros(K, pad8(M), device="cuda", dtype=torch.bfloat16); a[:, :M] = am.t()
+    else:
+        a = torch.zeros(M, pad8(K), device="cuda", dtype=torch.bfloat16); a[:, :K] = am
+    if b_mn:
+        b = torch.zeros(K, pad8(Nn), device="cuda", dtype=torch.bfloat16); b[:, :Nn] = bm.t()
+    else:
+        b = torch.zeros(Nn, pad8(K), device="cuda", dtype=torch.bfloat16); b[:, :K] = bm
+    want = am.float() @ bm.float().t()
+    got = gemm_general(a_mn, b_mn, a, b, M, Nn, K)
+    tol = 1e-3 * (K ** 0.5) + 1e-3
+    assert torch.allclose(got, want, atol=tol, rtol=1e-3), describe_mismatch(got, want, tol)
+    # accumulate into an existing float32 buffer (weight-gradient accumulation): C = A.B^T + C
+    acc = torch.randn(M, Nn, generator=g, device="cuda")
+    out = acc.clone()
+    N.check(N.lib().smz_gemm_bf16(int(a_mn), int(b_mn), N.ptr(a), a.stride(0), N.ptr(b), b.stride(0), N.ptr(out), Nn,
+                                  M, Nn, K, C.c_float(1.0), None, N.ptr(out), Nn, OUT_F32 | RES_F32, N.current_stream()))
+    assert torch.allclose(out, want + acc, atol=tol, rtol=1e-3), describe_mismatch(out, want + acc, tol)
