@@ -177,6 +177,20 @@ int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h_cu_seqlens
                        const smz_vasnet_params *p, int training, const uint8_t *drop_att, const uint8_t *drop_y,
                        const uint8_t *drop_h, float *scores, void *ws, int64_t ws_bytes, void *stream);
 
+/* Backward of the scorer (what loss.backward() computes for vasnet.py:209-211): consumes the work buffer
+ * a smz_vasnet_forward(training=1) call on the SAME batch left behind, the scores it produced and
+ * d(loss)/d(scores); ACCUMULATES (+=) float32 gradients with the parameters' shapes.  wqk is
+ * [2048,1024] (rows 0..1023 = d Q.weight, 1024..2047 = d K.weight).  dx (optional, [sum T, 1024])
+ * receives d(loss)/d(x) — only needed when a learned positional embedding feeds x (vasnet.py:110). */
+typedef struct smz_vasnet_grads {
+    float *wqk, *wv, *wo, *w1, *b1, *w2, *b2, *ln_g, *ln_b;
+    float *dx;
+} smz_vasnet_grads;
+int smz_vasnet_backward(const void *x, int x_is_bf16, const int32_t *h_cu_seqlens, int n_videos,
+                        const smz_vasnet_params *p, const uint8_t *drop_att, const uint8_t *drop_y,
+                        const uint8_t *drop_h, const float *scores, const float *dscores,
+                        const smz_vasnet_grads *grads, void *ws, int64_t ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -247,9 +247,216 @@ head_kernel(const float *__restrict__ h, const uint8_t *__restrict__ keep, const
     }
 }
 
+
+// ---- backward row kernels -------------------------------------------------------------------------
+// Column sums over rows (bias / LayerNorm-affine / k2 gradients) are accumulated per CTA in shared
+// memory and flushed with one float atomic per column and CTA.
+template <int NACC>
+struct ColAcc {
+    float *acc;   // [NACC][kFeat] in shared memory
+    __device__ __forceinline__ void zero() {
+        for (int i = threadIdx.x; i < NACC * kFeat; i += blockDim.x) acc[i] = 0.f;
+        __syncthreads();
+    }
+    __device__ __forceinline__ void add(int a, int c, float v) { atomicAdd(acc + a * kFeat + c, v); }
+    __device__ __forceinline__ void flush(int a, float *dst) {
+        if (dst == nullptr) return;
+        for (int c = threadIdx.x; c < kFeat; c += blockDim.x) atomicAdd(dst + c, acc[a * kFeat + c]);
+    }
+};
+
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+head_bwd_kernel(const float *__restrict__ h, const uint8_t *__restrict__ keep, const float *__restrict__ g,
+                const float *__restrict__ b, const float *__restrict__ w2, const float *__restrict__ mean,
+                const float *__restrict__ rstd, const float *__restrict__ scores, const float *__restrict__ dscores,
+                int rows, __nv_bfloat16 *__restrict__ dh, float *__restrict__ d_w2, float *__restrict__ d_b2,
+                float *__restrict__ d_g, float *__restrict__ d_b, float *__restrict__ d_b1) {
+    extern __shared__ float s_acc[];
+    ColAcc<4> A{s_acc};
+    A.zero();
+    const int lane = threadIdx.x & 31;
+    float db2 = 0.f;
+    for (int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < rows; r += gridDim.x * ROW_WARPS) {
+        const float *row = h + (int64_t)r * kFeat;
+        float xh[32], dx[32];
+        uint32_t live = 0u;      // bit k: the unit passes gradient (ReLU active and kept by dropout)
+        const float mu = mean[r], rs = rstd[r];
+        const float sc = scores[r];
+        const float dz = dscores[r] * sc * (1.f - sc);            // sigmoid'
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = lane * 4 + 128 * k;
+            const float4 v = *reinterpret_cast<const float4 *>(row + c);
+            float x[4] = {v.x, v.y, v.z, v.w};
+            uint32_t kb = 0xfu;
+            if (keep != nullptr) {
+                const uchar4 kp = *reinterpret_cast<const uchar4 *>(keep + (int64_t)r * kFeat + c);
+                kb = (kp.x ? 1u : 0u) | (kp.y ? 2u : 0u) | (kp.z ? 4u : 0u) | (kp.w ? 8u : 0u);
+            }
+            const float4 gg = *reinterpret_cast<const float4 *>(g + c);
+            const float4 bb = *reinterpret_cast<const float4 *>(b + c);
+            const float4 ww = *reinterpret_cast<const float4 *>(w2 + c);
+            const float gv[4] = {gg.x, gg.y, gg.z, gg.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w}, wv[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const bool kept = (kb >> t) & 1u;
+                if (x[t] > 0.f && kept) live |= 1u << (4 * k + t);
+                const float hd = keep != nullptr ? (kept ? 2.f * x[t] : 0.f) : x[t];
+                const float xhat = (hd - mu) * rs;
+                const float ln = xhat * gv[t] + bv[t];
+                const float dln = dz * wv[t];
+                A.add(0, c + t, dz * ln);        // d k2.weight
+                A.add(1, c + t, dln * xhat);     // d layer_norm.weight
+                A.add(2, c + t, dln);            // d layer_norm.bias
+                const float dxh = dln * gv[t];
+                xh[4 * k + t] = xhat; dx[4 * k + t] = dxh;
+                s1 += dxh; s2 += dxh * xhat;
+            }
+        }
+        const float c1 = warp_sum(s1) * (1.f / kFeat), c2 = warp_sum(s2) * (1.f / kFeat);
+        const float dscale = keep != nullptr ? 2.f : 1.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = lane * 4 + 128 * k;
+            float o[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const float d = rs * (dx[4 * k + t] - c1 - xh[4 * k + t] * c2) * dscale;
+                o[t] = ((live >> (4 * k + t)) & 1u) ? d : 0.f;
+                A.add(3, c + t, o[t]);           // d k1.bias
+            }
+            *reinterpret_cast<uint2 *>(dh + (int64_t)r * kFeat + c) = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
+        }
+        if (lane == 0) db2 += dz;
+    }
+    __syncthreads();
+    A.flush(0, d_w2); A.flush(1, d_g); A.flush(2, d_b); A.flush(3, d_b1);
+    if (lane == 0 && db2 != 0.f && d_b2 != nullptr) atomicAdd(d_b2, db2);
+}
+
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+layernorm_bwd_kernel(const float *__restrict__ dyn, const float *__restrict__ y, const uint8_t *__restrict__ keep,
+                     const float *__restrict__ g, const float *__restrict__ mean, const float *__restrict__ rstd,
+                     int rows, __nv_bfloat16 *__restrict__ dy, float *__restrict__ dy_f32, float *__restrict__ d_g,
+                     float *__restrict__ d_b) {
+    extern __shared__ float s_acc[];
+    ColAcc<2> A{s_acc};
+    A.zero();
+    const int lane = threadIdx.x & 31;
+    for (int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < rows; r += gridDim.x * ROW_WARPS) {
+        float xh[32], dx[32];
+        uint32_t kept_bits = 0xffffffffu;
+        const float mu = mean[r], rs = rstd[r];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = lane * 4 + 128 * k;
+            const float4 v = *reinterpret_cast<const float4 *>(y + (int64_t)r * kFeat + c);
+            const float4 d = *reinterpret_cast<const float4 *>(dyn + (int64_t)r * kFeat + c);
+            const float4 gg = *reinterpret_cast<const float4 *>(g + c);
+            float x[4] = {v.x, v.y, v.z, v.w};
+            const float dv[4] = {d.x, d.y, d.z, d.w}, gv[4] = {gg.x, gg.y, gg.z, gg.w};
+            if (keep != nullptr) {
+                const uchar4 kp = *reinterpret_cast<const uchar4 *>(keep + (int64_t)r * kFeat + c);
+                const uint32_t kb = (kp.x ? 1u : 0u) | (kp.y ? 2u : 0u) | (kp.z ? 4u : 0u) | (kp.w ? 8u : 0u);
+                kept_bits = (kept_bits & ~(0xfu << (4 * k))) | (kb << (4 * k));
+#pragma unroll
+                for (int t = 0; t < 4; t++) x[t] = ((kb >> t) & 1u) ? 2.f * x[t] : 0.f;
+            }
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const float xhat = (x[t] - mu) * rs;
+                A.add(0, c + t, dv[t] * xhat);
+                A.add(1, c + t, dv[t]);
+                const float dxh = dv[t] * gv[t];
+                xh[4 * k + t] = xhat; dx[4 * k + t] = dxh;
+                s1 += dxh; s2 += dxh * xhat;
+            }
+        }
+        const float c1 = warp_sum(s1) * (1.f / kFeat), c2 = warp_sum(s2) * (1.f / kFeat);
+        const float dscale = keep != nullptr ? 2.f : 1.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = lane * 4 + 128 * k;
+            float o[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const float d = rs * (dx[4 * k + t] - c1 - xh[4 * k + t] * c2) * dscale;
+                o[t] = ((kept_bits >> (4 * k + t)) & 1u) ? d : 0.f;
+            }
+            *reinterpret_cast<uint2 *>(dy + (int64_t)r * kFeat + c) = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
+            if (dy_f32 != nullptr)
+                *reinterpret_cast<float4 *>(dy_f32 + (int64_t)r * kFeat + c) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    __syncthreads();
+    A.flush(0, d_g); A.flush(1, d_b);
+}
+
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+softmax_bwd_kernel(const float *__restrict__ dP, const __nv_bfloat16 *__restrict__ alpha,
+                   const uint8_t *__restrict__ keep, int T, int ld, __nv_bfloat16 *__restrict__ dS) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+    if (i >= T) return;
+    const float *dp = dP + (int64_t)i * ld;
+    const __nv_bfloat16 *al = alpha + (int64_t)i * ld;
+    const uint8_t *kp = keep != nullptr ? keep + (int64_t)i * T : nullptr;
+    float dot = 0.f;
+    for (int j = lane; j < T; j += 32) {
+        float da = dp[j];
+        if (kp != nullptr) da = kp[j] ? 2.f * da : 0.f;
+        dot += da * __bfloat162float(al[j]);
+    }
+    dot = warp_sum(dot);
+    const int W64 = (T + 63) & ~63;
+    for (int j = lane; j < W64; j += 32) {
+        float o = 0.f;
+        if (j < T) {
+            float da = dp[j];
+            if (kp != nullptr) da = kp[j] ? 2.f * da : 0.f;
+            o = __bfloat162float(al[j]) * (da - dot);
+        }
+        dS[(int64_t)i * ld + j] = __float2bfloat16_rn(o);
+    }
+}
+
 }  // namespace
 
 namespace smz {
+
+int launch_head_bwd(const float *h, const uint8_t *keep, const float *g, const float *b, const float *w2,
+                    const float *mean, const float *rstd, const float *scores, const float *dscores, int rows,
+                    __nv_bfloat16 *dh, float *d_w2, float *d_b2, float *d_g, float *d_b, float *d_b1, cudaStream_t st) {
+    if (rows <= 0) return SMZ_OK;
+    int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
+    if (grid > 2 * sm_count()) grid = 2 * sm_count();
+    head_bwd_kernel<<<grid, ROW_WARPS * 32, 4 * kFeat * sizeof(float), st>>>(h, keep, g, b, w2, mean, rstd, scores, dscores,
+                                                                           rows, dh, d_w2, d_b2, d_g, d_b, d_b1);
+    SMZ_CUDA_CHECK(cudaGetLastError());
+    return SMZ_OK;
+}
+
+int launch_layernorm_bwd(const float *dyn, const float *y, const uint8_t *keep, const float *g, const float *mean,
+                         const float *rstd, int rows, __nv_bfloat16 *dy, float *dy_f32, float *d_g, float *d_b,
+                         cudaStream_t st) {
+    if (rows <= 0) return SMZ_OK;
+    int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
+    if (grid > 2 * sm_count()) grid = 2 * sm_count();
+    layernorm_bwd_kernel<<<grid, ROW_WARPS * 32, 2 * kFeat * sizeof(float), st>>>(dyn, y, keep, g, mean, rstd, rows, dy,
+                                                                                dy_f32, d_g, d_b);
+    SMZ_CUDA_CHECK(cudaGetLastError());
+    return SMZ_OK;
+}
+
+int launch_softmax_bwd(const float *dP, const __nv_bfloat16 *alpha, const uint8_t *keep, int T, int ld,
+                       __nv_bfloat16 *dS, cudaStream_t st) {
+    if (T <= 0) return SMZ_OK;
+    softmax_bwd_kernel<<<(T + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, st>>>(dP, alpha, keep, T, ld, dS);
+    SMZ_CUDA_CHECK(cudaGetLastError());
+    return SMZ_OK;
+}
 
 int launch_cvt_bf16(const float *x, __nv_bfloat16 *y, int64_t n, cudaStream_t st) {
     if (n <= 0) return SMZ_OK;

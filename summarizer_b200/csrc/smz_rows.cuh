@@ -29,4 +29,18 @@ int launch_head(const float *h, const uint8_t *keep, const float *g, const float
                 const float *w2, const float *b2, int rows, float *scores, float *mean, float *rstd,
                 cudaStream_t st);
 
+// ---- backward (autograd of vasnet.py:136-145 and :129-130) -----------------------------------------
+// Regressor head + second LayerNorm + ReLU: dh = d(loss)/d(k1 pre-activation) as bf16; accumulates
+// (+=, float32 atomics) d_w2, d_b2, d_g, d_b (LayerNorm affine) and d_b1 (column sums of dh).
+int launch_head_bwd(const float *h, const uint8_t *keep, const float *g, const float *b, const float *w2,
+                    const float *mean, const float *rstd, const float *scores, const float *dscores, int rows,
+                    __nv_bfloat16 *dh, float *d_w2, float *d_b2, float *d_g, float *d_b, float *d_b1, cudaStream_t st);
+// First LayerNorm (+ dropout): dy = d(loss)/d(y before dropout) as bf16 (and float32 when dy_f32 != NULL).
+int launch_layernorm_bwd(const float *dyn, const float *y, const uint8_t *keep, const float *g, const float *mean,
+                         const float *rstd, int rows, __nv_bfloat16 *dy, float *dy_f32, float *d_g, float *d_b,
+                         cudaStream_t st);
+// Softmax (+ attention dropout) of ONE video: dS = alpha * (dalpha - rowsum(dalpha * alpha)), dalpha = 2*keep*dP.
+int launch_softmax_bwd(const float *dP, const __nv_bfloat16 *alpha, const uint8_t *keep, int T, int ld,
+                       __nv_bfloat16 *dS, cudaStream_t st);
+
 }  // namespace smz

@@ -36,15 +36,20 @@ constexpr int64_t kLogitBudget = 34ll << 20;    // fp32 logits in flight per sub
 inline int64_t up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 struct Sub { int v0, v1, rows, ld; };
-struct Chunk { int v0, v1, row0, rows; std::vector<Sub> subs; };
+// In inference mode the buffers are recycled chunk after chunk (all offsets 0); in training mode every
+// video is its own chunk and owns a region of each buffer (rows at row0, V^T / logits at vt_off / lg_off).
+struct Chunk { int v0, v1, row0, rows; int64_t vt_off, lg_off; std::vector<Sub> subs; };
 
 struct Plan {
     std::vector<Chunk> chunks;
     int n_videos = 0, total_rows = 0, max_rows = 0;
     int64_t max_logits = 0;
     bool training = false, x_bf16 = false;
+    int64_t rows_cap = 0;   // row capacity of the row-wise buffers (and stride of the stats arrays)
     int64_t off_xb, off_qk, off_vt, off_o, off_y, off_yn, off_h, off_s, off_p, off_alpha, off_probs, off_dropoff,
         off_stats, total;
+    // backward-only buffers (training)
+    int64_t off_dh, off_dyn, off_dy, off_dyf, off_do, off_dqk, off_dvt, off_dp, off_ds;
 };
 
 int make_plan(const int32_t *cu, int n_videos, bool training, bool x_bf16, Plan *pl) {
@@ -56,12 +61,16 @@ int make_plan(const int32_t *cu, int n_videos, bool training, bool x_bf16, Plan 
     pl->training = training;
     pl->x_bf16 = x_bf16;
     int v = 0;
+    int64_t vt_elems = 0, lg_elems = 0;
     while (v < n_videos) {
         Chunk c;
         c.v0 = v; c.row0 = cu[v];
         int rows = 0;
-        while (v < n_videos && (training || rows == 0 || rows + (cu[v + 1] - cu[v]) <= kRowChunk)) { rows += cu[v + 1] - cu[v]; ++v; }
+        while (v < n_videos && (rows == 0 || (!training && rows + (cu[v + 1] - cu[v]) <= kRowChunk))) { rows += cu[v + 1] - cu[v]; ++v; }
         c.v1 = v; c.rows = rows;
+        c.vt_off = training ? vt_elems : 0;
+        c.lg_off = training ? lg_elems : 0;
+        int64_t chunk_logits = 0;
         int u = c.v0;
         while (u < c.v1) {
             Sub s;
@@ -71,33 +80,48 @@ int make_plan(const int32_t *cu, int n_videos, bool training, bool x_bf16, Plan 
                 const int T = cu[u + 1] - cu[u];
                 const int nm = T > maxT ? T : maxT;
                 const int64_t elems = (int64_t)(s.rows + T) * up(nm + 7, 64);
-                if (!training && s.rows > 0 && elems > kLogitBudget) break;
+                if (s.rows > 0 && elems > kLogitBudget) break;
                 maxT = nm; s.rows += T; ++u;
             }
             s.v1 = u; s.ld = (int)up(maxT + 7, 64);   // + up to 7 leading pad columns, see build_problems
             const int64_t elems = (int64_t)s.rows * s.ld;
             if (elems > pl->max_logits) pl->max_logits = elems;
+            chunk_logits += elems;
             c.subs.push_back(s);
         }
+        if (training) { vt_elems += (int64_t)kFeat * up(rows, 8); lg_elems += chunk_logits; }
         if (c.rows > pl->max_rows) pl->max_rows = c.rows;
         pl->chunks.push_back(c);
     }
-    const int64_t R = up(pl->max_rows, 8);
+    const int64_t R = training ? up(pl->total_rows, 8) : up(pl->max_rows, 8);
+    const int64_t VT = training ? vt_elems : (int64_t)kFeat * R;
+    const int64_t LG = training ? lg_elems : pl->max_logits;
+    pl->rows_cap = R;
     int64_t o = 0;
     auto take = [&](int64_t bytes) { const int64_t at = o; o += up(bytes, 1024); return at; };
     pl->off_xb = take(x_bf16 ? 0 : R * kFeat * 2);
     pl->off_qk = take(R * 2 * kFeat * 2);
-    pl->off_vt = take((int64_t)kFeat * R * 2);
+    pl->off_vt = take(VT * 2);
     pl->off_o = take(R * kFeat * 2);
     pl->off_y = take(R * kFeat * 4);
     pl->off_yn = take(R * kFeat * 2);
     pl->off_h = take(R * kFeat * 4);
-    pl->off_s = take(pl->max_logits * 4);
-    pl->off_p = take(pl->max_logits * 2);
-    pl->off_alpha = take(training ? pl->max_logits * 2 : 0);
+    pl->off_s = take(LG * 4);
+    pl->off_p = take(LG * 2);
+    pl->off_alpha = take(training ? LG * 2 : 0);
     pl->off_probs = take((int64_t)n_videos * 2 * sizeof(GemmProblem));
     pl->off_dropoff = take(training ? (int64_t)n_videos * 8 : 0);
     pl->off_stats = take(training ? R * 4 * 4 : 0);
+    const int64_t t = training ? 1 : 0;
+    pl->off_dh = take(t * R * kFeat * 2);
+    pl->off_dyn = take(t * R * kFeat * 4);
+    pl->off_dy = take(t * R * kFeat * 2);
+    pl->off_dyf = take(t * R * kFeat * 4);
+    pl->off_do = take(t * R * kFeat * 2);
+    pl->off_dqk = take(t * R * 2 * kFeat * 2);
+    pl->off_dvt = take(t * VT * 2);
+    pl->off_dp = pl->off_s;              // dP (float32) reuses the logits buffer, dS (bf16) gets its own
+    pl->off_ds = take(t * LG * 2);
     pl->total = o;
     return SMZ_OK;
 }
@@ -208,16 +232,22 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
     bf16 *P = reinterpret_cast<bf16 *>(w + pl.off_p);
     bf16 *alpha = (training && drop_att) ? reinterpret_cast<bf16 *>(w + pl.off_alpha) : P;
     float *stats = training ? reinterpret_cast<float *>(w + pl.off_stats) : nullptr;
-    const int64_t Rs = up(pl.max_rows, 8);   // stride of the stats arrays
+    const int64_t Rs = pl.rows_cap;          // stride of the stats arrays
+    bf16 *const qk0 = qk, *const vt0 = vt, *const o0 = o, *const yn0 = yn, *const P0 = P, *const alpha0 = alpha;
+    float *const y0 = y, *const h0 = h, *const S0 = S, *const stats0 = stats;
 
     for (const Chunk &c : pl.chunks) {
         const int R = c.rows;
         const int64_t Rpad = up(R, 8);
+        const int64_t rb = training ? c.row0 : 0;       // row base inside the row-wise buffers
+        qk = qk0 + rb * 2 * kFeat; vt = vt0 + c.vt_off; o = o0 + rb * kFeat; y = y0 + rb * kFeat;
+        yn = yn0 + rb * kFeat; h = h0 + rb * kFeat; S = S0 + c.lg_off; P = P0 + c.lg_off; alpha = alpha0 + c.lg_off;
+        stats = training ? stats0 + rb : nullptr;
         const bf16 *xb;
         if (x_is_bf16) {
             xb = reinterpret_cast<const bf16 *>(x) + (int64_t)c.row0 * kFeat;
         } else {
-            bf16 *dst = reinterpret_cast<bf16 *>(w + pl.off_xb);
+            bf16 *dst = reinterpret_cast<bf16 *>(w + pl.off_xb) + rb * kFeat;
             rc = smz::launch_cvt_bf16(reinterpret_cast<const float *>(x) + (int64_t)c.row0 * kFeat, dst, (int64_t)R * kFeat, st);
             if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "cvt");
@@ -274,6 +304,150 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
                               R, scores + c.row0, stats ? stats + 2 * Rs : nullptr, stats ? stats + 3 * Rs : nullptr, st);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "head");
+    }
+    return SMZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward: the autograd graph behind vasnet.py:209-211 (loss.backward()) for the scorer, video by video,
+// on the activations smz_vasnet_forward(training=1) left in the work buffer.  Every contraction runs on
+// the same tcgen05 GEMM; MN-major operand forms read the row-major activations / weights directly:
+//   dYn = dh . W1            dW1  += dh^T . Yn
+//   dO  = dY . Wo            dWo  += dY^T . O
+//   dP  = dO . V^T           dV^T  = dO^T . P
+//   dQ  = s dS . K           dK    = s dS^T . Q          (s = scale)
+//   dWqk += [dQ|dK]^T . xb   dWv  += dV^T . xb           dx = dY + [dQ|dK] . Wqk + dV . Wv   (optional)
+// Gradients are ACCUMULATED (+=) into the caller's float32 buffers.
+namespace {
+
+int gemm1(bool a_mn, bool b_mn, const void *A, int64_t a_rows, int64_t a_cols, int64_t lda, const void *B,
+          int64_t b_rows, int64_t b_cols, int64_t ldb, GemmProblem g, const GemmEpilogue &e, cudaStream_t st) {
+    g.tiles_n = (g.N + smz::GEMM_BN - 1) / smz::GEMM_BN;
+    return smz::gemm_bf16(a_mn, b_mn, A, a_rows, a_cols, lda, B, b_rows, b_cols, ldb, nullptr, 1, smz::gemm_tiles(g.M, g.N), g, e, st);
+}
+
+GemmProblem prob(int M, int N, int K, int ldc, int64_t c_off = 0, int ldr = 0, int64_t r_off = 0) {
+    GemmProblem g = {};
+    g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.c_off = c_off; g.ldr = ldr; g.r_off = r_off;
+    return g;
+}
+
+}  // namespace
+
+extern "C" int smz_vasnet_backward(const void *x, int x_is_bf16, const int32_t *h_cu_seqlens, int n_videos,
+                                   const smz_vasnet_params *p, const uint8_t *drop_att, const uint8_t *drop_y,
+                                   const uint8_t *drop_h, const float *scores, const float *dscores,
+                                   const smz_vasnet_grads *gr, void *ws, int64_t ws_bytes, void *stream) {
+    SMZ_REQUIRE(x && p && scores && dscores && gr && ws, "vasnet_backward: NULL pointer");
+    SMZ_REQUIRE(gr->wqk && gr->wv && gr->wo && gr->w1 && gr->b1 && gr->w2 && gr->b2 && gr->ln_g && gr->ln_b,
+                "vasnet_backward: NULL gradient pointer");
+    int rc = smz_device_check();
+    if (rc != SMZ_OK) return rc;
+    Plan pl;
+    rc = make_plan(h_cu_seqlens, n_videos, true, x_is_bf16 != 0, &pl);
+    if (rc != SMZ_OK) return rc;
+    SMZ_REQUIRE(ws_bytes >= pl.total, "vasnet_backward: work buffer too small (%lld < %lld bytes)", (long long)ws_bytes,
+                (long long)pl.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *w = reinterpret_cast<uint8_t *>(ws);
+    const int64_t Rs = pl.rows_cap;
+    const int F32ACC = smz::GEMM_OUT_F32 | smz::GEMM_RES_F32;   // C = A.B^T + C (float32)
+    int64_t att_off = 0;                                         // offset of the video's attention keep-mask
+
+    for (const Chunk &c : pl.chunks) {
+        const int T = c.rows;
+        const int64_t rb = c.row0, Tpad = up(T, 8);
+        const int ld = c.subs[0].ld;
+        const bf16 *xb = x_is_bf16 ? reinterpret_cast<const bf16 *>(x) + rb * kFeat
+                                   : reinterpret_cast<const bf16 *>(w + pl.off_xb) + rb * kFeat;
+        const bf16 *qk = reinterpret_cast<const bf16 *>(w + pl.off_qk) + rb * 2 * kFeat;
+        const bf16 *vt = reinterpret_cast<const bf16 *>(w + pl.off_vt) + c.vt_off;
+        const bf16 *o = reinterpret_cast<const bf16 *>(w + pl.off_o) + rb * kFeat;
+        const float *y = reinterpret_cast<const float *>(w + pl.off_y) + rb * kFeat;
+        const bf16 *yn = reinterpret_cast<const bf16 *>(w + pl.off_yn) + rb * kFeat;
+        const float *h = reinterpret_cast<const float *>(w + pl.off_h) + rb * kFeat;
+        const bf16 *P = reinterpret_cast<const bf16 *>(w + pl.off_p) + c.lg_off;
+        const bf16 *alpha = drop_att ? reinterpret_cast<const bf16 *>(w + pl.off_alpha) + c.lg_off : P;
+        const float *stats = reinterpret_cast<const float *>(w + pl.off_stats) + rb;
+        bf16 *dh = reinterpret_cast<bf16 *>(w + pl.off_dh) + rb * kFeat;
+        float *dyn = reinterpret_cast<float *>(w + pl.off_dyn) + rb * kFeat;
+        bf16 *dy = reinterpret_cast<bf16 *>(w + pl.off_dy) + rb * kFeat;
+        float *dyf = gr->dx ? reinterpret_cast<float *>(w + pl.off_dyf) + rb * kFeat : nullptr;
+        bf16 *dO = reinterpret_cast<bf16 *>(w + pl.off_do) + rb * kFeat;
+        bf16 *dqk = reinterpret_cast<bf16 *>(w + pl.off_dqk) + rb * 2 * kFeat;
+        bf16 *dvt = reinterpret_cast<bf16 *>(w + pl.off_dvt) + c.vt_off;
+        float *dP = reinterpret_cast<float *>(w + pl.off_dp) + c.lg_off;
+        bf16 *dS = reinterpret_cast<bf16 *>(w + pl.off_ds) + c.lg_off;
+
+        // regressor head, second LayerNorm, dropout, ReLU  ->  dh (k1 pre-activation gradient)
+        rc = smz::launch_head_bwd(h, drop_h ? drop_h + rb * kFeat : nullptr, p->ln_g, p->ln_b, p->w2, stats + 2 * Rs,
+                                  stats + 3 * Rs, scores + rb, dscores + rb, T, dh, gr->w2, gr->b2, gr->ln_g, gr->ln_b,
+                                  gr->b1, st);
+        if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "head_bwd");
+        // k1: dYn = dh . W1 ; dW1 += dh^T . Yn
+        rc = gemm1(false, true, dh, T, kFeat, kFeat, p->w1, kFeat, kFeat, kFeat, prob(T, kFeat, kFeat, kFeat),
+                   GemmEpilogue{dyn, nullptr, nullptr, 1.f, smz::GEMM_OUT_F32}, st);
+        if (rc != SMZ_OK) return rc;
+        rc = gemm1(true, true, dh, T, kFeat, kFeat, yn, T, kFeat, kFeat, prob(kFeat, kFeat, T, kFeat, 0, kFeat),
+                   GemmEpilogue{gr->w1, nullptr, gr->w1, 1.f, F32ACC}, st);
+        if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "k1_bwd");
+        // first LayerNorm + dropout -> dY (also the gradient of the residual branch)
+        rc = smz::launch_layernorm_bwd(dyn, y, drop_y ? drop_y + rb * kFeat : nullptr, p->ln_g, stats, stats + Rs, T, dy, dyf,
+                                       gr->ln_g, gr->ln_b, st);
+        if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "ln_bwd");
+        // output projection: dO = dY . Wo ; dWo += dY^T . O
+        rc = gemm1(false, true, dy, T, kFeat, kFeat, p->wo, kFeat, kFeat, kFeat, prob(T, kFeat, kFeat, kFeat),
+                   GemmEpilogue{dO, nullptr, nullptr, 1.f, 0}, st);
+        if (rc != SMZ_OK) return rc;
+        rc = gemm1(true, true, dy, T, kFeat, kFeat, o, T, kFeat, kFeat, prob(kFeat, kFeat, T, kFeat, 0, kFeat),
+                   GemmEpilogue{gr->wo, nullptr, gr->wo, 1.f, F32ACC}, st);
+        if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "out_bwd");
+        // attention: dP = dO . V^T (B = V^T stored [d][j]: MN-major) ; dV^T = dO^T . P
+        rc = gemm1(false, true, dO, T, kFeat, kFeat, vt, kFeat, T, Tpad, prob(T, T, kFeat, ld),
+                   GemmEpilogue{dP, nullptr, nullptr, 1.f, smz::GEMM_OUT_F32}, st);
+        if (rc != SMZ_OK) return rc;
+        rc = gemm1(true, true, dO, T, kFeat, kFeat, P, T, T, ld, prob(kFeat, T, T, (int)Tpad),
+                   GemmEpilogue{dvt, nullptr, nullptr, 1.f, 0}, st);
+        if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "att_bwd1");
+        rc = smz::launch_softmax_bwd(dP, alpha, drop_att ? drop_att + att_off : nullptr, T, ld, dS, st);
+        if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "softmax_bwd");
+        // dQ = scale dS . K (B = K half of QK, stored [j][d]: MN-major at column 1024) ; dK = scale dS^T . Q
+        {
+            GemmProblem g = prob(T, kFeat, T, 2 * kFeat, 0);
+            g.b_col0 = kFeat;
+            rc = gemm1(false, true, dS, T, T, ld, qk, T, 2 * kFeat, 2 * kFeat, g, GemmEpilogue{dqk, nullptr, nullptr, p->scale, 0}, st);
+            if (rc != SMZ_OK) return rc;
+            g = prob(T, kFeat, T, 2 * kFeat, kFeat);
+            rc = gemm1(true, true, dS, T, T, ld, qk, T, 2 * kFeat, 2 * kFeat, g, GemmEpilogue{dqk, nullptr, nullptr, p->scale, 0}, st);
+            if (rc != SMZ_OK) return rc;
+        }
+        SMZ_DEBUG_STEP(st, "att_bwd2");
+        // projections: dWqk += [dQ|dK]^T . xb ; dWv += dV^T . xb
+        rc = gemm1(true, true, dqk, T, 2 * kFeat, 2 * kFeat, xb, T, kFeat, kFeat, prob(2 * kFeat, kFeat, T, kFeat, 0, kFeat),
+                   GemmEpilogue{gr->wqk, nullptr, gr->wqk, 1.f, F32ACC}, st);
+        if (rc != SMZ_OK) return rc;
+        rc = gemm1(false, true, dvt, kFeat, T, Tpad, xb, T, kFeat, kFeat, prob(kFeat, kFeat, T, kFeat, 0, kFeat),
+                   GemmEpilogue{gr->wv, nullptr, gr->wv, 1.f, F32ACC}, st);
+        if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "proj_bwd");
+        if (gr->dx != nullptr) {
+            float *dx = gr->dx + rb * kFeat;
+            // dx = dY + [dQ|dK] . Wqk   (B = Wqk stored [c][i]: MN-major), then += dV . Wv (A = dV^T: MN-major)
+            rc = gemm1(false, true, dqk, T, 2 * kFeat, 2 * kFeat, p->wqk, 2 * kFeat, kFeat, kFeat,
+                       prob(T, kFeat, 2 * kFeat, kFeat, 0, kFeat), GemmEpilogue{dx, nullptr, dyf, 1.f, F32ACC}, st);
+            if (rc != SMZ_OK) return rc;
+            rc = gemm1(true, true, dvt, kFeat, T, Tpad, p->wv, kFeat, kFeat, kFeat, prob(T, kFeat, kFeat, kFeat, 0, kFeat),
+                       GemmEpilogue{dx, nullptr, dx, 1.f, F32ACC}, st);
+            if (rc != SMZ_OK) return rc;
+            SMZ_DEBUG_STEP(st, "dx");
+        }
+        att_off += (int64_t)T * T;
     }
     return SMZ_OK;
 }

@@ -1,0 +1,84 @@
+"""Autograd shell around smz_vasnet_forward(training=1) / smz_vasnet_backward.
+
+PyTorch only records the node and owns the buffers; forward and backward are the sm_100a kernels.  The three
+p=0.5 dropouts of the reference (models/vasnet.py:130,136,142) are driven by torch's CUDA generator
+(``torch.manual_seed`` reproduces them): the KEEP masks are drawn here and handed to the kernels, which is
+also what lets the tests replay the very same masks through the float32 oracle.
+"""
+import ctypes as C
+
+import torch
+
+from .. import _native as N
+from .vasnet import VasnetParams, _cu_seqlens
+
+
+class VasnetGrads(C.Structure):
+    """struct smz_vasnet_grads (include/summarizer_b200.h)."""
+    _fields_ = [(k, C.c_void_p) for k in ("wqk", "wv", "wo", "w1", "b1", "w2", "b2", "ln_g", "ln_b", "dx")]
+
+
+def draw_keep_masks(lengths, device, generator=None):
+    """KEEP masks (uint8, 1 = keep) of nn.Dropout(0.5) at the three sites, for a packed batch."""
+    rows = int(sum(lengths))
+    n_att = int(sum(t * t for t in lengths))
+    rnd = lambda n: (torch.rand(n, device=device, generator=generator) >= 0.5).to(torch.uint8)
+    return rnd(n_att), rnd(rows * 1024).view(rows, 1024), rnd(rows * 1024).view(rows, 1024)
+
+
+class _VasnetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, module, lengths, masks, wq, wk, wv, wo, w1, b1, w2, b2, ln_g, ln_b):
+        N.require_device()
+        x = x.contiguous()
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        cu = _cu_seqlens(lengths)
+        cu_p = cu.ctypes.data_as(C.c_void_p)
+        is_bf16 = int(x.dtype == torch.bfloat16)
+        sh, st = module._weights()
+        nbytes = C.c_int64(0)
+        N.check(N.lib().smz_vasnet_workspace_bytes(cu_p, len(lengths), 1, is_bf16, C.byref(nbytes)))
+        ws = torch.empty(max(nbytes.value, 1024), dtype=torch.uint8, device=x.device)   # lives until backward
+        scores = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        m_att, m_y, m_h = masks if masks is not None else (None, None, None)
+        N.check(N.lib().smz_vasnet_forward(N.ptr(x), is_bf16, cu_p, len(lengths), C.byref(st), 1, N.ptr(m_att), N.ptr(m_y),
+                                           N.ptr(m_h), N.ptr(scores), N.ptr(ws), ws.numel(), N.current_stream()))
+        ctx.module, ctx.cu, ctx.masks, ctx.ws, ctx.shadow = module, cu, masks, ws, sh
+        ctx.save_for_backward(x, scores)
+        return scores
+
+    @staticmethod
+    def backward(ctx, dscores):
+        x, scores = ctx.saved_tensors
+        m = ctx.module
+        dev = x.device
+        z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
+        g = dict(wqk=z(2048, 1024), wv=z(1024, 1024), wo=z(1024, 1024), w1=z(1024, 1024), b1=z(1024), w2=z(1024), b2=z(1),
+                 ln_g=z(1024), ln_b=z(1024))
+        dx = z(x.shape[0], 1024) if ctx.needs_input_grad[0] else None
+        gs = VasnetGrads(*(g[k].data_ptr() for k in ("wqk", "wv", "wo", "w1", "b1", "w2", "b2", "ln_g", "ln_b")),
+                         dx.data_ptr() if dx is not None else None)
+        sh = ctx.shadow   # the bf16 weights the forward used
+        st = VasnetParams(*(sh[k].data_ptr() for k in ("wqk", "wv", "wo", "w1", "b1", "w2", "b2", "ln_g", "ln_b")),
+                          float(m.scale), float(m.epsilon), -1 if m.aperture is None else int(m.aperture),
+                          int(bool(m.ignore_self)))
+        m_att, m_y, m_h = ctx.masks if ctx.masks is not None else (None, None, None)
+        cu = ctx.cu
+        N.check(N.lib().smz_vasnet_backward(N.ptr(x), int(x.dtype == torch.bfloat16), cu.ctypes.data_as(C.c_void_p),
+                                            len(cu) - 1, C.byref(st), N.ptr(m_att), N.ptr(m_y), N.ptr(m_h), N.ptr(scores),
+                                            N.ptr(dscores.contiguous().float()), C.byref(gs), N.ptr(ctx.ws), ctx.ws.numel(),
+                                            N.current_stream()))
+        ctx.ws = None
+        return (dx, None, None, None, g["wqk"][:1024], g["wqk"][1024:], g["wv"], g["wo"], g["w1"], g["b1"],
+                g["w2"].view(1, 1024), g["b2"], g["ln_g"], g["ln_b"])
+
+
+def vasnet_apply(module, packed, lengths, masks="auto"):
+    """scores [sum T] with autograd.  masks: "auto" draws dropout keep-masks when module.training,
+    None disables dropout, or an explicit (att, y, h) tuple (tests)."""
+    if masks == "auto":
+        masks = draw_keep_masks(lengths, packed.device) if module.training else None
+    return _VasnetFunction.apply(packed, module, list(lengths), masks, module.Q.weight, module.K.weight, module.V.weight,
+                                 module.attention_head_projection.weight, module.k1.weight, module.k1.bias,
+                                 module.k2.weight, module.k2.bias, module.layer_norm.weight, module.layer_norm.bias)
