@@ -125,6 +125,23 @@ int smz_pack_summary(const smz_video_desc *desc, int n_videos, int max_n_frames,
 int smz_upsample(const smz_video_desc *desc, int n_videos, int max_n_frames, const float *scores,
                  const int32_t *picks, float *frame_scores, int32_t *status, void *stream);
 
+/* ---- rank correlation: replaces utils/eval.py:49-72 evaluate_scores -------------------------------
+ * For every video: ranks = scipy.stats.rankdata(-x) (average ties) of the machine frame scores and of each
+ * annotator row, then Spearman rho (Pearson of the ranks, float64) or Kendall tau-b per annotator, and the
+ * np.mean over annotators.  machine[] holds n_frames float32 per video at m_off (e.g. the output of
+ * smz_upsample), user[] the annotator rows at u_off + u*u_ld.  rank_ws: float32 work buffer, video v uses
+ * (1 + n_users) * n_frames entries at rank_off.  corr: float64 per annotator at row0 + u; corr_avg: per video
+ * (NaN for a constant row, as scipy).  n_frames <= 32768 (one shared-memory sort per row). */
+#define SMZ_METRIC_SPEARMAN 0
+#define SMZ_METRIC_KENDALL 1
+typedef struct smz_corr_desc {
+    int64_t m_off, u_off, u_ld, rank_off;
+    int32_t n_frames, n_users, row0, reserved;
+} smz_corr_desc;
+int smz_rank_correlation(const smz_corr_desc *desc, int n_videos, int max_n_frames, int max_n_users,
+                         const float *machine, const float *user, int metric, float *rank_ws, double *corr,
+                         double *corr_avg, void *stream);
+
 /* ---- dense building block ------------------------------------------------------------------------
  * C[M,N] = epilogue(alpha * A[M,K] * B[N,K]^T) on the tcgen05 tensor cores: A and B bfloat16, K
  * contiguous (lda/ldb in elements, multiples of 8, 16-byte aligned bases), fp32 accumulation.

@@ -28,6 +28,12 @@ VIDEO_DESC = np.dtype([
 ], align=True)
 assert VIDEO_DESC.itemsize == 104
 
+# struct smz_corr_desc — 48 bytes
+CORR_DESC = np.dtype([("m_off", "<i8"), ("u_off", "<i8"), ("u_ld", "<i8"), ("rank_off", "<i8"),
+                      ("n_frames", "<i4"), ("n_users", "<i4"), ("row0", "<i4"), ("reserved", "<i4")], align=True)
+assert CORR_DESC.itemsize == 48
+SMZ_METRIC = {"spearmanr": 0, "kendalltau": 1}
+
 _P = C.c_void_p
 _I = C.c_int
 _L = C.c_int64
@@ -43,6 +49,7 @@ SIGNATURES = {
     "smz_fscore": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "smz_pack_summary": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "smz_upsample": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
+    "smz_rank_correlation": (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P]),
     "smz_vasnet_workspace_bytes": (_I, [_P, _I, _I, _I, C.POINTER(C.c_int64)]),
     "smz_vasnet_launch_count": (_I, [_P, _I, _I, _I, C.POINTER(C.c_int64)]),
     "smz_vasnet_forward": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _L, _P]),
