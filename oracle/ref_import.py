@@ -106,6 +106,9 @@ def load():
     saved = {k: v for k, v in sys.modules.items() if k == "summarizer" or k.startswith("summarizer.")}
     for k in saved:
         del sys.modules[k]
+    alias = [f for f in sys.meta_path if type(f).__name__ == "_AliasFinder"]   # the product's `summarizer` alias
+    for f in alias:
+        sys.meta_path.remove(f)
     sys.path.insert(0, REFERENCE_ROOT)
     try:
         import importlib
@@ -120,6 +123,8 @@ def load():
         ns.utils = importlib.import_module("summarizer.utils")
     finally:
         sys.path.remove(REFERENCE_ROOT)
+        for f in alias:
+            sys.meta_path.insert(0, f)
         ref_mods = {k: v for k, v in sys.modules.items() if k == "summarizer" or k.startswith("summarizer.")}
         for k in ref_mods:
             del sys.modules[k]

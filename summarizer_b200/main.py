@@ -1,0 +1,154 @@
+"""Split-driven training / cross-validation driver with the reference's ``train(hps)`` contract and CLI
+(main.py:10-104): for every split file, for every fold: reset -> train -> keep the best fold's weights; then
+cross-validation means, TensorBoard hparams, predictions over the whole dataset.
+
+Multi-GPU (one process per GPU, ``torchrun --nproc-per-node N main.py ...``): the (split file, fold) jobs are
+independent (main.py:14,26), so they are dealt to the ranks longest-first and run with NO data-path
+collective; rank 0 gathers the per-fold results (and the best fold's weights) through torch.distributed and
+returns the same ``results`` list as a single-process run."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from summarizer_b200.utils import Proportion  # noqa: E402
+from summarizer_b200.utils.config import HParameters  # noqa: E402
+
+
+def plan_folds(costs, world):
+    """Longest-processing-time assignment of jobs to ranks.  ``costs``: list of (job, cost).
+    Returns one job list per rank; deterministic (ties by job order)."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i][1], i))
+    load = [0.0] * world
+    out = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        out[r].append(costs[i][0])
+        load[r] += costs[i][1]
+    return [sorted(jobs) for jobs in out]
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def fold_cost(hps, model, splits_file, fold):
+    """epochs x number of training steps (frames) of the fold — the scheduling weight."""
+    keys = hps.splits_of_file[splits_file][fold]["train_keys"]
+    return float(hps.epochs) * sum(int(np.shape(model.dataset[k]["features"])[0]) for k in keys)
+
+
+def train(hps):
+    """Training.  Returns [(splits_file, mean corr, mean avg F, mean max F), ...] (main.py:10-72)."""
+    dist, rank, world = _dist()
+    results = []
+    for splits_file in hps.splits_files:
+        hps.logger.info(f"Start training on {splits_file}")
+        n_folds = len(hps.splits_of_file[splits_file])
+        weights_path = hps.weights_path[splits_file]
+        pred_path = hps.pred_path[splits_file]
+        model = hps.model_class(hps, splits_file)
+        mine = plan_folds([(f, fold_cost(hps, model, splits_file, f)) for f in range(n_folds)], world)[rank]
+
+        fold_results, corr_max = {}, -1.0
+        for fold in mine:
+            best_corr, best_avg_f, best_max_f = model.reset().train(fold)
+            fold_results[fold] = (float(best_corr), float(best_avg_f), float(best_max_f))
+            if best_corr > corr_max:
+                corr_max = best_corr
+                model.save_best_weights(weights_path if world == 1 else f"{weights_path}.rank{rank}")
+            hps.logger.info(f"File: {splits_file}   Fold: {fold+1}/{n_folds}   Corr: {best_corr: 0.5f}  "
+                            f"Avg F-score: {best_avg_f:0.5f}  Max F-score: {best_max_f:0.5f}")
+
+        if world > 1:   # gather the fold results on every rank; rank 0 adopts the best fold's weights
+            gathered = [None] * world
+            dist.all_gather_object(gathered, (fold_results, corr_max))
+            fold_results = {f: r for g, _ in gathered for f, r in g.items()}
+            best_rank = int(np.argmax([c for _, c in gathered]))
+            dist.barrier()
+            if rank == 0 and os.path.exists(f"{weights_path}.rank{best_rank}"):
+                os.replace(f"{weights_path}.rank{best_rank}", weights_path)
+        corrs_cv = [fold_results[f][0] for f in range(n_folds)]
+        avg_fscores_cv = [fold_results[f][1] for f in range(n_folds)]
+        max_fscores_cv = [fold_results[f][2] for f in range(n_folds)]
+
+        hps.logger.info(f"File: {splits_file}   Cross-validation Corr: {np.mean(corrs_cv): 0.5f}  "
+                        f"Avg F-score: {np.mean(avg_fscores_cv):0.5f}  Max F-score: {np.mean(max_fscores_cv):0.5f}")
+        hps.logger.info(f"File: {splits_file}   Best weights: {weights_path}")
+        if rank == 0:
+            hparam_dict = hps.get_full_hps_dict()
+            hparam_dict["dataset"] = hps.dataset_name_of_file[splits_file]
+            metric_dict = {f"F-score_max/Fold_{f+1}": s for f, s in enumerate(max_fscores_cv)}   # main.py:56-58 keeps the last
+            metric_dict["Correlation/CV_Average"] = np.mean(corrs_cv)
+            metric_dict["F-score_avg/CV_Average"] = np.mean(avg_fscores_cv)
+            metric_dict["F-score_max/CV_Average"] = np.mean(max_fscores_cv)
+            hps.writer.add_hparams(hparam_dict, metric_dict)
+            if os.path.exists(weights_path):
+                model.reset().load_weights(weights_path)
+                model.best_weights = model.model.state_dict()
+                model.predict_dataset(pred_path)
+                hps.logger.info(f"File: {splits_file}   Machine predictions: {pred_path}")
+        results.append((splits_file, np.mean(corrs_cv), np.mean(avg_fscores_cv), np.mean(max_fscores_cv)))
+    return results
+
+
+def parse_extra(unknown_args):
+    """main.py:91 — unknown ``--key value`` pairs / ``--flag`` become extra_params strings / True."""
+    if not unknown_args:
+        return {}
+    nxt = unknown_args[1:] + ["-"]
+    return {unknown_args[i].lstrip("-"): (u.lstrip("-") if u[0] != "-" else True)
+            for i, u in enumerate(nxt) if unknown_args[i][0] == "-"}
+
+
+def build_parser():
+    parser = argparse.ArgumentParser("Summarizer : Model Training")
+    parser.add_argument("-c", "--use-cuda", choices=["yes", "no", "default"], default="default", help="Use cuda for pytorch models")
+    parser.add_argument("-i", "--cuda-device", type=int, help="If cuda-enabled, ID of GPU to use")
+    parser.add_argument("-s", "--splits-files", type=str, help="Comma separated list of split files (shorthands: minimal, overfit, all)")
+    parser.add_argument("-m", "--model", type=str, help="Model class name")
+    parser.add_argument("-e", "--epochs", type=int, help="Number of epochs for train mode")
+    parser.add_argument("-r", "--lr", type=float, help="Learning rate for train mode")
+    parser.add_argument("-d", "--weight-decay", type=float, help="Weight decay (L2 penalty-based regularization)")
+    parser.add_argument("-t", "--test-every-epochs", type=int, help="Evaluate the model every nth epoch on the current fold's validation set")
+    parser.add_argument("-p", "--summary-proportion", type=float, choices=Proportion(), help="Length of video summary (as a proportion of original video length)")
+    parser.add_argument("-a", "--selection-algorithm", choices=["knapsack", "rank"], help="Keyshot selection algorithm to build the summary video")
+    parser.add_argument("-l", "--log-level", choices=["critical", "error", "warning", "info", "debug"], default="info", help="Set logger to custom level")
+    return parser
+
+
+def main(argv=None):
+    args, unknown_args = build_parser().parse_known_args(argv)
+    hps_init = dict(args.__dict__)
+    hps_init["extra_params"] = parse_extra(unknown_args)
+    if "WORLD_SIZE" in os.environ and int(os.environ["WORLD_SIZE"]) > 1:
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", 0))
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+            hps_init["cuda_device"] = local
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
+    hps = HParameters()
+    hps.load_from_args(hps_init)
+    print("Hyperparameters:")
+    print("----------------------------------------------------------------------")
+    print(hps)
+    print("----------------------------------------------------------------------")
+    results = train(hps)
+    hps.writer.close()
+    return results
+
+
+if __name__ == "__main__":
+    main()

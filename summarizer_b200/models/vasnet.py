@@ -168,3 +168,40 @@ class VASNet(nn.Module):
         else:
             s = self.score_packed(packed, [seq_len] * batch_size)
         return s.view(batch_size, seq_len, 1).permute(1, 0, 2)
+
+
+from . import Trainer  # noqa: E402
+
+
+class VASNetTrainer(Trainer):
+    """models/vasnet.py:151-238 — MSE regression of the (min-max normalised) ground-truth scores, one
+    Adam step per video; extra parameters as the reference parses them (vasnet.py:153-161)."""
+
+    def _init_model(self):
+        ep = self.hps.extra_params or {}
+        model = VASNet(
+            max_length=int(ep["max_pos"]) if "max_pos" in ep else None,
+            pos_embed=ep.get("pos_embed", "simple"),
+            ignore_self=bool(ep.get("ignore_self", False)),
+            attention_aperture=int(ep["local"]) if "local" in ep else None,
+            scale=float(ep["scale"]) if "scale" in ep else None,
+            epsilon=float(ep.get("epsilon", 1e-6)),
+            weight_init=ep.get("weight_init", "xavier"))
+        if self.hps.use_cuda:
+            self.log.info(f"Setting CUDA device: {self.hps.cuda_device}")
+            torch.cuda.set_device(self.hps.cuda_device)
+            model.cuda()
+        return model
+
+    def _score_keys(self, keys):
+        """All test videos in ONE packed forward call (ragged batch) instead of one launch chain per video."""
+        if getattr(self.model, "max_length", None) is not None:
+            return super()._score_keys(keys)
+        feats = [self._video_tensors(k)[0][:, 0] for k in keys]
+        lengths = [f.shape[0] for f in feats]
+        with torch.no_grad():
+            packed = self.model.score_packed(torch.cat(feats), lengths)
+        return list(torch.split(packed, lengths))
+
+    def train(self, fold):
+        return self._train_supervised(fold)

@@ -1,0 +1,103 @@
+"""CPU: host-side logic of the drop-in surface — configuration, CLI parsing, fold scheduling, the `summarizer`
+alias package, split fixtures, state-dict compatibility with the reference modules."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from summarizer_b200.main import parse_extra, plan_folds
+from summarizer_b200.utils import Proportion, parse_splits_filename
+from summarizer_b200.utils.config import HParameters
+
+PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "summarizer_b200")
+
+
+def make_hps(tmp_path, **kw):
+    hps = HParameters()
+    hps.log_root = str(tmp_path)
+    hps.tensorboard = False
+    args = dict(model="vasnet", use_cuda="no", splits_files="summe", log_level="error", extra_params={})
+    args.update(kw)
+    hps.load_from_args(args)
+    return hps
+
+
+def test_hparameters_defaults_and_shorthands(tmp_path):
+    hps = make_hps(tmp_path)
+    assert (hps.lr, hps.weight_decay, hps.epochs, hps.test_every_epochs) == (5e-5, 1e-5, 10, 2)
+    assert hps.summary_proportion == 0.15 and hps.selection_algorithm == "knapsack"
+    (sf,) = hps.splits_files
+    assert sf.endswith("splits/summe_splits.json") and hps.dataset_name_of_file[sf] == "summe"
+    assert "summe" in hps.dataset_of_file[sf] and len(hps.splits_of_file[sf]) == 5
+    assert hps.weights_path[sf].endswith("summe_splits.json.pth") and hps.pred_path[sf].endswith("summe_splits.json_preds.h5")
+    assert os.path.exists(os.path.join(hps.log_path, "train.log")) and os.path.exists(os.path.join(hps.log_path, "vasnet.py"))
+    assert hps.model_class.__name__ == "VASNetTrainer"
+    all_ = make_hps(tmp_path, splits_files="overfit")
+    assert [os.path.basename(s) for s in all_.splits_files] == ["tvsum_splits_overfit.json", "summe_splits_overfit.json"]
+    lst = make_hps(tmp_path, splits_files="splits/tvsum_splits.json,splits/summe_splits.json")   # documented superset
+    assert len(lst.splits_files) == 2
+    with pytest.raises(KeyError):
+        make_hps(tmp_path, model="no_such_model")
+
+
+def test_cli_extra_params_parsing():
+    assert parse_extra(["--local", "12", "--ignore_self", "--scale", "0.06"]) == {"local": "12", "ignore_self": True, "scale": "0.06"}
+    assert parse_extra([]) == {}
+    assert 0.15 in Proportion() and 0 not in Proportion() and 1.5 not in Proportion()
+
+
+def test_fold_scheduler_is_balanced_and_complete():
+    costs = [(f, c) for f, c in enumerate([40, 10, 35, 12, 30, 11, 9, 41, 8, 10])]   # SumMe+TVSum-like: 10 jobs
+    for world in (1, 2, 4, 8):
+        plan = plan_folds(costs, world)
+        assert sorted(j for r in plan for j in r) == list(range(10))
+        loads = [sum(dict(costs)[j] for j in r) for r in plan]
+        assert max(loads) <= sum(dict(costs).values()) / world + max(c for _, c in costs)
+    assert plan_folds(costs, 3) == plan_folds(costs, 3)
+
+
+def test_split_fixtures_shape():
+    for name, n_train, n_test in (("summe", 20, 5), ("tvsum", 40, 10)):
+        ds, splits = parse_splits_filename(os.path.join(PKG, "splits", f"{name}_splits.json"))
+        assert ds == name and len(splits) == 5
+        for s in splits:
+            assert len(s["train_keys"]) == n_train and len(s["test_keys"]) == n_test
+            assert not set(s["train_keys"]) & set(s["test_keys"])
+        _, over = parse_splits_filename(os.path.join(PKG, "splits", f"{name}_splits_overfit.json"))
+        assert len(over) == 1 and over[0]["train_keys"] == over[0]["test_keys"] and len(over[0]["train_keys"]) == 10
+
+
+def test_summarizer_alias_package_serves_the_same_objects():
+    import summarizer  # noqa: F401
+    from summarizer.models.vasnet import VASNet as A
+    from summarizer.utils.eval import generate_summary as g
+    from summarizer_b200.models.vasnet import VASNet as B
+    from summarizer_b200.utils.eval import generate_summary as h
+    assert A is B and g is h
+    from summarizer.main import train  # noqa: F401
+
+
+def test_trainer_opens_synthetic_dataset_and_stages_keys(tmp_path):
+    hps = make_hps(tmp_path, splits_files="summe")
+    t = hps.model_class(hps, hps.splits_files[0])
+    train_keys, test_keys = t._get_train_test_keys(0)
+    assert len(train_keys) == 20 and len(test_keys) == 5
+    d = t.dataset["video_1"]
+    assert int(d["n_frames"][()]) == 4494 and d["features"][...].shape == (300, 1024)
+    seq, target = t._video_tensors("video_1")
+    assert seq.shape == (300, 1, 1024) and float(target.min()) == 0.0 and float(target.max()) == 1.0
+
+
+@pytest.mark.reference
+def test_state_dict_matches_reference_modules():
+    from oracle import ref_import
+    from summarizer_b200.models.vasnet import VASNet
+    ref = ref_import.load()
+    for kw in ({}, {"max_length": 32, "pos_embed": "simple"}):
+        a, b = ref.vasnet.VASNet(**kw).state_dict(), VASNet(**kw).state_dict()
+        assert list(a.keys()) == list(b.keys())
+        assert all(a[k].shape == b[k].shape for k in a)
+    m = VASNet()
+    m.load_state_dict(ref.vasnet.VASNet().state_dict())   # a reference .pth loads unchanged

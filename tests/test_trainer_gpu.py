@@ -1,0 +1,64 @@
+"""Trainer.test / main.train on the device against the CPU oracle evaluated on the same model scores."""
+import numpy as np
+import pytest
+import torch
+from scipy import stats
+
+from oracle import eval_np as E
+from summarizer_b200.main import train
+from summarizer_b200.utils.config import HParameters
+
+pytestmark = pytest.mark.gpu
+
+
+def make_hps(tmp_path, **kw):
+    hps = HParameters()
+    hps.log_root = str(tmp_path)
+    hps.tensorboard = False
+    args = dict(model="vasnet", use_cuda="yes", splits_files="summe", log_level="error", extra_params={})
+    args.update(kw)
+    hps.load_from_args(args)
+    return hps
+
+
+def oracle_test_metrics(trainer, keys, scores, proportion, method):
+    corrs, avg_f, max_f = [], [], []
+    for key, s in zip(keys, scores):
+        d = trainer.dataset[key]
+        n_frames = int(d["n_frames"][()])
+        s = s.cpu().numpy()
+        frame = E.upsample(s, n_frames, d["picks"][...])
+        us = d["user_scores"][...]
+        corrs.append(np.mean([stats.spearmanr(stats.rankdata(-frame), stats.rankdata(-us[i]))[0] for i in range(us.shape[0])]))
+        summary = E.generate_summary(s, d["change_points"][...], n_frames, d["n_frame_per_seg"][...].tolist(),
+                                     d["picks"][...], proportion, method)
+        a, m = E.evaluate_summary(summary, d["user_summary"][...])
+        avg_f.append(a); max_f.append(m)
+    return np.mean(corrs), np.mean(avg_f), np.mean(max_f)
+
+
+@pytest.mark.parametrize("splits,method", [("summe", "knapsack"), ("tvsum", "rank")])
+def test_trainer_test_matches_oracle(tmp_path, splits, method):
+    hps = make_hps(tmp_path, splits_files=splits, selection_algorithm=method)
+    t = hps.model_class(hps, hps.splits_files[0]).reset()
+    _, test_keys = t._get_train_test_keys(1)
+    avg_corr, (avg_f, max_f) = t.test(1)
+    t.model.eval()
+    scores = t._score_keys(test_keys)
+    c, a, m = oracle_test_metrics(t, test_keys, scores, hps.summary_proportion, method)
+    assert avg_corr == pytest.approx(c, abs=1e-10)
+    assert float(avg_f) == pytest.approx(float(a), rel=1e-6) and float(max_f) == pytest.approx(float(m), rel=1e-6)
+
+
+def test_cross_validation_run_end_to_end(tmp_path):
+    hps = make_hps(tmp_path, splits_files="overfit", epochs=3, test_every_epochs=1, lr=1e-4)
+    results = train(hps)
+    assert [r[0].split("/")[-1] for r in results] == ["tvsum_splits_overfit.json", "summe_splits_overfit.json"]
+    for _, corr, avg_f, max_f in results:
+        assert np.isfinite([corr, avg_f, max_f]).all() and 0 <= avg_f <= max_f <= 1
+    import os
+    for sf in hps.splits_files:
+        assert os.path.exists(hps.weights_path[sf])
+        assert os.path.exists(hps.pred_path[sf]) or os.path.exists(hps.pred_path[sf] + ".npz")
+    sd = torch.load(hps.weights_path[hps.splits_files[0]])
+    assert "attention_head_projection.weight" in sd and sd["k2.weight"].shape == (1, 1024)
