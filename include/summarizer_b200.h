@@ -208,6 +208,27 @@ int smz_vasnet_backward(const void *x, int x_is_bf16, const int32_t *h_cu_seqlen
                         const uint8_t *drop_h, const float *scores, const float *dscores,
                         const smz_vasnet_grads *grads, void *ws, int64_t ws_bytes, void *stream);
 
+/* ---- DSN scorer: replaces models/dsn.py:38-47 DSN.forward (nn.LSTM(1024, 256, bidirectional) through
+ *      cuDNN + Linear(512,1) + sigmoid) and, with smz_dsn_backward, its autograd graph ---------------------
+ * Device pointers:
+ *   w_ih   bfloat16 [2048,1024]: rows 0..1023 = rnn.weight_ih_l0, 1024..2047 = rnn.weight_ih_l0_reverse
+ *   bias   float32 [2048]: bias_ih + bias_hh of the two directions (torch gate order i,f,g,o)
+ *   whh_packed / whh_t_packed: uint32 [2*8*64*256] each, W_hh / W_hh^T of both directions in the register
+ *          order of the recurrence kernels — produced (on the device) by smz_dsn_pack_whh from the float32
+ *          rnn.weight_hh_l0 / _reverse ([1024,256])
+ *   w_out  float32 [512] (out.0.weight), b_out float32 [1] (out.0.bias)
+ * x / h_cu_seqlens as for smz_vasnet_forward; probs: float32 [sum T]. */
+typedef struct smz_dsn_params {
+    const void *w_ih;
+    const float *bias;
+    const void *whh_packed, *whh_t_packed;
+    const float *w_out, *b_out;
+} smz_dsn_params;
+int smz_dsn_pack_whh(const float *whh_fwd, const float *whh_bwd, uint32_t *out_fwd, uint32_t *out_bwd, void *stream);
+int smz_dsn_workspace_bytes(int total_rows, int n_videos, int training, int x_is_bf16, int64_t *bytes);
+int smz_dsn_forward(const void *x, int x_is_bf16, const int32_t *h_cu_seqlens, int n_videos, const smz_dsn_params *p,
+                    int training, float *probs, void *ws, int64_t ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,97 @@
+"""DSN — Deep Summarization Network scorer with the reference's class, constructor, parameter names and
+``forward((T, B, 1024)) -> (T, B, 1)`` contract (models/dsn.py:17-47), computed by smz_dsn_forward /
+smz_dsn_backward: one tcgen05 GEMM for the input projections of both directions and a persistent
+8-CTA-cluster recurrence kernel with W_hh resident in registers.
+
+Parameters live in an ``nn.LSTM`` / ``nn.Sequential`` pair exactly like the reference, so the state-dict keys
+(``rnn.weight_ih_l0``, ``rnn.weight_hh_l0``, ``rnn.bias_ih_l0``, ``rnn.bias_hh_l0``, ``*_reverse``,
+``out.0.weight``, ``out.0.bias``) and the initialisation stream are the reference's; the torch modules are
+never executed.  Only the default configuration the reference trainer builds (LSTM cell, 1 layer, hidden 256,
+dsn.py:58) is implemented; there is no CPU fallback."""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _native as N
+from .vasnet import _cu_seqlens, _Workspace
+
+
+class DsnParams(C.Structure):
+    """struct smz_dsn_params (include/summarizer_b200.h)."""
+    _fields_ = [(k, C.c_void_p) for k in ("w_ih", "bias", "whh_packed", "whh_t_packed", "w_out", "b_out")]
+
+
+class DSN(nn.Module):
+    """Deep Summarization Network"""
+
+    def __init__(self, input_size=1024, hidden_size=256, num_layers=1, cell="lstm"):
+        super().__init__()
+        assert cell in ["lstm", "gru"], "cell must be either 'lstm' or 'gru'"
+        if cell != "lstm" or input_size != 1024 or hidden_size != 256 or num_layers != 1:
+            raise NotImplementedError("the sm_100a DSN kernels implement the configuration the reference trainer uses: "
+                                      "LSTM cell, 1024-d input, hidden size 256, one layer (dsn.py:58)")
+        self.rnn = nn.LSTM(input_size, hidden_size, num_layers=num_layers, bidirectional=True)
+        self.out = nn.Sequential(nn.Linear(hidden_size * 2, 1), nn.Sigmoid())
+        self._shadow, self._shadow_key, self._ws = None, None, _Workspace()
+
+    def _params(self):
+        r, o = self.rnn, self.out[0]
+        return (r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0, r.weight_ih_l0_reverse, r.weight_hh_l0_reverse,
+                r.bias_ih_l0_reverse, r.bias_hh_l0_reverse, o.weight, o.bias)
+
+    def _weights(self):
+        """bf16 / packed shadow copies for the kernels; rebuilt when a parameter changed."""
+        ps = self._params()
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if key != self._shadow_key:
+            wih_f, whh_f, bih_f, bhh_f, wih_b, whh_b, bih_b, bhh_b, w_out, b_out = ps
+            with torch.no_grad():
+                dev = wih_f.device
+                sh = dict(w_ih=torch.cat([wih_f, wih_b], 0).to(torch.bfloat16).contiguous(),
+                          bias=torch.cat([bih_f + bhh_f, bih_b + bhh_b]).float().contiguous(),
+                          whh=torch.empty(2 * 8 * 64 * 256, dtype=torch.int32, device=dev),
+                          whh_t=torch.empty(2 * 8 * 64 * 256, dtype=torch.int32, device=dev),
+                          w_out=w_out.float().reshape(-1).contiguous(), b_out=b_out.float().contiguous())
+                N.check(N.lib().smz_dsn_pack_whh(N.ptr(whh_f.float().contiguous()), N.ptr(whh_b.float().contiguous()),
+                                                 N.ptr(sh["whh"]), N.ptr(sh["whh_t"]), N.current_stream()))
+            self._shadow, self._shadow_key = sh, key
+        sh = self._shadow
+        st = DsnParams(*(sh[k].data_ptr() for k in ("w_ih", "bias", "whh", "whh_t", "w_out", "b_out")))
+        return sh, st
+
+    def score_packed(self, x, lengths):
+        """Inference over a ragged batch: x packed [sum T, 1024] (float32 / bfloat16) -> probs [sum T]."""
+        N.require_device()
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        x = x.contiguous()
+        cu = _cu_seqlens(lengths)
+        _, st = self._weights()
+        is_bf16 = int(x.dtype == torch.bfloat16)
+        nbytes = C.c_int64(0)
+        N.check(N.lib().smz_dsn_workspace_bytes(int(cu[-1]), len(lengths), 0, is_bf16, C.byref(nbytes)))
+        ws = self._ws.get(nbytes.value, x.device)
+        probs = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        N.check(N.lib().smz_dsn_forward(N.ptr(x), is_bf16, cu.ctypes.data_as(C.c_void_p), len(lengths), C.byref(st), 0,
+                                        N.ptr(probs), N.ptr(ws), ws.numel(), N.current_stream()))
+        return probs
+
+    def forward(self, x):
+        """Pass the input video through the LSTM.
+        Input
+          x: (seq_len, batch_size, input_size)
+        Output
+          probs: (seq_len, batch_size, 1)
+        """
+        seq_len, batch_size, _ = x.shape
+        if not x.is_cuda:
+            raise N.NativeError("summarizer_b200.DSN runs on a CUDA (sm_100a) device only; move the input with .cuda()")
+        packed = x.permute(1, 0, 2).reshape(batch_size * seq_len, -1)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .dsn_autograd import dsn_apply
+            p = dsn_apply(self, packed, [seq_len] * batch_size)
+        else:
+            p = self.score_packed(packed, [seq_len] * batch_size)
+        return p.view(batch_size, seq_len, 1).permute(1, 0, 2)
