@@ -228,6 +228,16 @@ int smz_dsn_pack_whh(const float *whh_fwd, const float *whh_bwd, uint32_t *out_f
 int smz_dsn_workspace_bytes(int total_rows, int n_videos, int training, int x_is_bf16, int64_t *bytes);
 int smz_dsn_forward(const void *x, int x_is_bf16, const int32_t *h_cu_seqlens, int n_videos, const smz_dsn_params *p,
                     int training, float *probs, void *ws, int64_t ws_bytes, void *stream);
+/* Backward (BPTT) of a smz_dsn_forward(training=1) call on the same batch and work buffer: what
+ * loss.backward() computes for dsn.py:143-144.  ACCUMULATES (+=) float32 gradients: w_ih [2048,1024] and
+ * w_hh [2048,256] (rows 0..1023 = forward direction, 1024..2047 = reverse), bias [2048] (the gradient of both
+ * bias_ih and bias_hh), w_out [512], b_out [1]. */
+typedef struct smz_dsn_grads {
+    float *w_ih, *w_hh, *bias, *w_out, *b_out;
+} smz_dsn_grads;
+int smz_dsn_backward(const void *x, int x_is_bf16, const int32_t *h_cu_seqlens, int n_videos, const smz_dsn_params *p,
+                     const float *probs, const float *dprobs, const smz_dsn_grads *grads, void *ws, int64_t ws_bytes,
+                     void *stream);
 
 #ifdef __cplusplus
 }

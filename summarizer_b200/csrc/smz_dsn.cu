@@ -76,7 +76,7 @@ __device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
 // ---------------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
 lstm_fwd_kernel(const float *__restrict__ pre, const uint32_t *__restrict__ whh, const int32_t *__restrict__ cu,
-                int n_videos, float *__restrict__ y, float *__restrict__ save) {
+                int n_videos, float *__restrict__ y, float *__restrict__ save, __nv_bfloat16 *__restrict__ hprev) {
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ __align__(16) float hbuf[2][H];
     const int cta = (int)cluster.block_rank();
@@ -141,6 +141,10 @@ lstm_fwd_kernel(const float *__restrict__ pre, const uint32_t *__restrict__ whh,
             const int d = lane & 7;
             const size_t row = (size_t)(row0 + t);
             if (d == 0) y[row * (2 * H) + dir * H + unit] = hn;
+            if (hprev != nullptr && d == 5) {           // h_{t-1} rows for the dW_hh GEMM (zero at the sequence start)
+                if (s == 0) hprev[row * (2 * H) + dir * H + unit] = __float2bfloat16_rn(0.f);
+                if (s + 1 < T) hprev[(size_t)(row0 + tn) * (2 * H) + dir * H + unit] = __float2bfloat16_rn(hn);
+            }
             if (save != nullptr && d < SAVE) {
                 const float val = d == 0 ? gi : d == 1 ? gf : d == 2 ? gg : d == 3 ? go : c_state;
                 save[((row * 2 + dir) * SAVE + d) * H + unit] = val;
@@ -172,10 +176,128 @@ dsn_head_kernel(const float *__restrict__ y, const float *__restrict__ w, const 
     if (lane == 0) probs[r] = sigmoidf_(dot + __ldg(b));
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// backward recurrence (BPTT).  wt: W_hh^T packed by smz_dsn_pack_whh: thread (warp w, lane l) owns units
+// 4w+u (u<4) and gate columns 32l + 2q, +1 (q<16); register u*16+q.  dz[t] = dL/d(pre-sigmoid head logit).
+// Writes the gate gradients of every step as bf16 (dgb [R, 2048]) for the weight-gradient GEMMs and
+// accumulates the bias gradients (d_bias [2048], float atomics at the end of a sequence).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
+lstm_bwd_kernel(const uint32_t *__restrict__ wt, const int32_t *__restrict__ cu, int n_videos,
+                const float *__restrict__ save, const float *__restrict__ dz, const float *__restrict__ w_out,
+                __nv_bfloat16 *__restrict__ dgb, float *__restrict__ d_bias) {
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ __align__(16) float dgbuf[2][G4];
+    const int cta = (int)cluster.block_rank();
+    const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int unit = cta * UNITS + warp * 4 + (lane >> 3);
+    const int d = lane & 7;
+    float *remote = cluster.map_shared_rank(&dgbuf[0][0], d);
+
+    int loaded_dir = -1;
+    uint32_t W[WREGS];
+    for (int job = cluster_id; job < 2 * n_videos; job += n_clusters) {
+        const int v = job >> 1, dir = job & 1;
+        const int row0 = cu[v], T = cu[v + 1] - row0;
+        if (dir != loaded_dir) {
+            const uint32_t *src = wt + ((size_t)(dir * CL + cta) * WREGS) * LSTM_THREADS + tid;
+#pragma unroll
+            for (int k = 0; k < WREGS; k++) W[k] = __ldg(src + (size_t)k * LSTM_THREADS);
+            loaded_dir = dir;
+        }
+        for (int j = tid; j < G4; j += LSTM_THREADS) dgbuf[0][j] = 0.f;     // no gradient flows in from beyond the last step
+        const float wo = __ldg(w_out + dir * H + unit);
+        float dc_carry = 0.f, bsum[4] = {0.f, 0.f, 0.f, 0.f};
+        cluster.sync();
+        // steps are visited in the reverse of the forward order of this direction
+        int t = dir ? 0 : T - 1;
+        const float *sv = save + ((size_t)(row0 + t) * 2 + dir) * SAVE * H + unit;
+        float gi = sv[0], gf = sv[H], gg = sv[2 * H], go = sv[3 * H], cc = sv[4 * H];
+        for (int s = 0; s < T; s++) {
+            const int cur = s & 1;
+            const int tp = dir ? t + 1 : t - 1;            // the step BEFORE t in forward order (next to visit)
+            // prefetch the next visited step's saved activations; its cell state is this step's c_{prev}
+            float n_i = 0.f, n_f = 0.f, n_g = 0.f, n_o = 0.f, n_c = 0.f;
+            if (s + 1 < T) {
+                const float *q = save + ((size_t)(row0 + tp) * 2 + dir) * SAVE * H + unit;
+                n_i = q[0]; n_f = q[H]; n_g = q[2 * H]; n_o = q[3 * H]; n_c = q[4 * H];
+            }
+            const float dzt = dz[row0 + t];
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q4 = 0; q4 < 8; q4++) {
+                const float4 g4 = *reinterpret_cast<const float4 *>(&dgbuf[cur][32 * lane + 4 * q4]);
+                const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t w0 = W[u * 16 + 2 * q4], w1 = W[u * 16 + 2 * q4 + 1];
+                    acc[u] = fmaf(bf_lo(w0), gv[0], acc[u]); acc[u] = fmaf(bf_hi(w0), gv[1], acc[u]);
+                    acc[u] = fmaf(bf_lo(w1), gv[2], acc[u]); acc[u] = fmaf(bf_hi(w1), gv[3], acc[u]);
+                }
+            }
+            // 4 values x 32 lanes -> lanes 8u..8u+7 hold the total of unit u
+            {
+                const bool hi = lane & 16;
+                const float s0 = hi ? acc[0] : acc[2], k0 = hi ? acc[2] : acc[0];
+                const float s1 = hi ? acc[1] : acc[3], k1 = hi ? acc[3] : acc[1];
+                acc[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+                acc[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+            }
+            {
+                const bool hi = lane & 8;
+                const float s0 = hi ? acc[0] : acc[1], k0 = hi ? acc[1] : acc[0];
+                acc[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 8);
+            }
+            float rec = acc[0];
+            rec += __shfl_xor_sync(0xffffffffu, rec, 4);
+            rec += __shfl_xor_sync(0xffffffffu, rec, 2);
+            rec += __shfl_xor_sync(0xffffffffu, rec, 1);
+            const float dh = dzt * wo + rec;
+            const float tc = tanhf_(cc);
+            const float dO = dh * tc * go * (1.f - go);
+            const float dc = dh * go * (1.f - tc * tc) + dc_carry;
+            const float dI = dc * gg * gi * (1.f - gi);
+            const float dG = dc * gi * (1.f - gg * gg);
+            const float dF = dc * n_c * gf * (1.f - gf);      // n_c = c_{t-1} (0 at the sequence start)
+            dc_carry = dc * gf;
+            float *dst = remote + (cur ^ 1) * G4 + unit;      // lane d -> CTA d
+            dst[0] = dI; dst[H] = dF; dst[2 * H] = dG; dst[3 * H] = dO;
+            if (d < 4) {
+                const float val = d == 0 ? dI : d == 1 ? dF : d == 2 ? dG : dO;
+                dgb[(size_t)(row0 + t) * (2 * G4) + dir * G4 + d * H + unit] = __float2bfloat16_rn(val);
+            }
+            bsum[0] += dI; bsum[1] += dF; bsum[2] += dG; bsum[3] += dO;
+            gi = n_i; gf = n_f; gg = n_g; go = n_o; cc = n_c;
+            t = tp;
+            cluster.sync();
+        }
+        if (d < 4) atomicAdd(d_bias + dir * G4 + d * H + unit, d == 0 ? bsum[0] : d == 1 ? bsum[1] : d == 2 ? bsum[2] : bsum[3]);
+    }
+}
+
+// dz = dprobs * p * (1 - p);  d w_out += sum_t dz_t * y_t;  d b_out += sum_t dz_t
+__global__ void __launch_bounds__(256)
+dsn_head_bwd_kernel(const float *__restrict__ y, const float *__restrict__ probs, const float *__restrict__ dprobs, int rows,
+                    float *__restrict__ dz, float *__restrict__ d_w_out, float *__restrict__ d_b_out) {
+    float a0 = 0.f, a1 = 0.f, ab = 0.f;
+    const int c = threadIdx.x * 2;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const float pr = probs[r];
+        const float z = dprobs[r] * pr * (1.f - pr);
+        if (threadIdx.x == 0) { dz[r] = z; ab += z; }
+        const float2 yy = *reinterpret_cast<const float2 *>(y + (size_t)r * (2 * H) + c);
+        a0 = fmaf(z, yy.x, a0); a1 = fmaf(z, yy.y, a1);
+    }
+    atomicAdd(d_w_out + c, a0); atomicAdd(d_w_out + c + 1, a1);
+    if (threadIdx.x == 0) atomicAdd(d_b_out, ab);
+}
+
 int64_t up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 struct DsnPlan {
-    int64_t rows, off_xb, off_pre, off_y, off_save, off_cu, off_dy, off_dg, off_dgb, total;
+    int64_t rows, off_xb, off_pre, off_y, off_save, off_cu, off_hprev, off_dz, off_dgb, total;
 };
 
 DsnPlan dsn_plan(int64_t rows, int n_videos, bool training, bool x_bf16) {
@@ -188,8 +310,8 @@ DsnPlan dsn_plan(int64_t rows, int n_videos, bool training, bool x_bf16) {
     p.off_y = take(rows * 2 * H * 4);
     p.off_save = take(training ? rows * 2 * SAVE * H * 4 : 0);
     p.off_cu = take((int64_t)(n_videos + 1) * 4);
-    p.off_dy = take(training ? rows * 2 * H * 4 : 0);
-    p.off_dg = take(training ? rows * 2 * G4 * 4 : 0);
+    p.off_hprev = take(training ? rows * 2 * H * 2 : 0);
+    p.off_dz = take(training ? rows * 4 : 0);
     p.off_dgb = take(training ? rows * 2 * G4 * 2 : 0);
     p.total = o;
     return p;
@@ -282,12 +404,68 @@ extern "C" int smz_dsn_forward(const void *x, int x_is_bf16, const int32_t *h_cu
                            smz::gemm_tiles(R, 2 * G4), g, GemmEpilogue{pre, p->bias, nullptr, 1.f, smz::GEMM_OUT_F32}, st);
     if (rc != SMZ_OK) return rc;
     SMZ_DEBUG_STEP(st, "dsn_input_projection");
+    bf16 *hprev = training ? reinterpret_cast<bf16 *>(w + pl.off_hprev) : nullptr;
     lstm_fwd_kernel<<<lstm_grid(n_videos), LSTM_THREADS, 0, st>>>(pre, reinterpret_cast<const uint32_t *>(p->whh_packed), d_cu,
-                                                                  n_videos, y, save);
+                                                                  n_videos, y, save, hprev);
     SMZ_CUDA_CHECK(cudaGetLastError());
     SMZ_DEBUG_STEP(st, "dsn_lstm_fwd");
     dsn_head_kernel<<<(R + 7) / 8, 256, 0, st>>>(y, p->w_out, p->b_out, R, probs);
     SMZ_CUDA_CHECK(cudaGetLastError());
     SMZ_DEBUG_STEP(st, "dsn_head");
+    return SMZ_OK;
+}
+
+// Backward of smz_dsn_forward(training=1) on the same batch / work buffer.  ACCUMULATES (+=) float32 gradients:
+//   d_w_ih [2048,1024] (rows 0..1023 forward direction), d_w_hh [2048,256] (rows 0..1023 = weight_hh_l0,
+//   1024..2047 = weight_hh_l0_reverse), d_bias [2048] (the gradient of BOTH bias_ih and bias_hh), d_w_out [512],
+//   d_b_out [1].
+extern "C" int smz_dsn_backward(const void *x, int x_is_bf16, const int32_t *h_cu_seqlens, int n_videos,
+                                const smz_dsn_params *p, const float *probs, const float *dprobs,
+                                const smz_dsn_grads *gr, void *ws, int64_t ws_bytes, void *stream) {
+    SMZ_REQUIRE(x && h_cu_seqlens && p && probs && dprobs && gr && ws && n_videos > 0, "dsn_backward: NULL pointer");
+    SMZ_REQUIRE(gr->w_ih && gr->w_hh && gr->bias && gr->w_out && gr->b_out, "dsn_backward: NULL gradient pointer");
+    int rc = smz_device_check();
+    if (rc != SMZ_OK) return rc;
+    const int R = h_cu_seqlens[n_videos];
+    const DsnPlan pl = dsn_plan(R, n_videos, true, x_is_bf16 != 0);
+    SMZ_REQUIRE(ws_bytes >= pl.total, "dsn_backward: work buffer too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *w = reinterpret_cast<uint8_t *>(ws);
+    const int32_t *d_cu = reinterpret_cast<const int32_t *>(w + pl.off_cu);      // uploaded by the forward call
+    const bf16 *xb = x_is_bf16 ? reinterpret_cast<const bf16 *>(x) : reinterpret_cast<const bf16 *>(w + pl.off_xb);
+    const float *y = reinterpret_cast<const float *>(w + pl.off_y);
+    const float *save = reinterpret_cast<const float *>(w + pl.off_save);
+    const bf16 *hprev = reinterpret_cast<const bf16 *>(w + pl.off_hprev);
+    float *dz = reinterpret_cast<float *>(w + pl.off_dz);
+    bf16 *dgb = reinterpret_cast<bf16 *>(w + pl.off_dgb);
+
+    int hb_grid = R < 296 ? R : 296;
+    dsn_head_bwd_kernel<<<hb_grid, 256, 0, st>>>(y, probs, dprobs, R, dz, gr->w_out, gr->b_out);
+    SMZ_CUDA_CHECK(cudaGetLastError());
+    SMZ_DEBUG_STEP(st, "dsn_head_bwd");
+    lstm_bwd_kernel<<<lstm_grid(n_videos), LSTM_THREADS, 0, st>>>(reinterpret_cast<const uint32_t *>(p->whh_t_packed), d_cu, n_videos,
+                                                                  save, dz, p->w_out, dgb, gr->bias);
+    SMZ_CUDA_CHECK(cudaGetLastError());
+    SMZ_DEBUG_STEP(st, "dsn_lstm_bwd");
+    const int ACC = smz::GEMM_OUT_F32 | smz::GEMM_RES_F32;
+    // dW_ih += dG^T . xb  (both directions at once: M = 2048 gate rows)
+    {
+        GemmProblem g = {};
+        g.M = 2 * G4; g.N = smz::kFeat; g.K = R; g.ldc = smz::kFeat; g.ldr = smz::kFeat; g.tiles_n = smz::kFeat / smz::GEMM_BN;
+        rc = smz::gemm_bf16(true, true, dgb, R, 2 * G4, 2 * G4, xb, R, smz::kFeat, smz::kFeat, nullptr, 1,
+                            smz::gemm_tiles(g.M, g.N), g, GemmEpilogue{gr->w_ih, nullptr, gr->w_ih, 1.f, ACC}, st);
+        if (rc != SMZ_OK) return rc;
+    }
+    // dW_hh[dir] += dG_dir^T . h_{t-1, dir}
+    for (int dir = 0; dir < 2; dir++) {
+        GemmProblem g = {};
+        g.M = G4; g.N = H; g.K = R; g.ldc = H; g.ldr = H; g.tiles_n = 1;
+        g.a_col0 = dir * G4; g.b_col0 = dir * H;
+        g.c_off = (int64_t)dir * G4 * H; g.r_off = g.c_off;
+        rc = smz::gemm_bf16(true, true, dgb, R, 2 * G4, 2 * G4, hprev, R, 2 * H, 2 * H, nullptr, 1, smz::gemm_tiles(g.M, g.N), g,
+                            GemmEpilogue{gr->w_hh, nullptr, gr->w_hh, 1.f, ACC}, st);
+        if (rc != SMZ_OK) return rc;
+    }
+    SMZ_DEBUG_STEP(st, "dsn_wgrad");
     return SMZ_OK;
 }

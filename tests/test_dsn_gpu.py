@@ -53,3 +53,46 @@ def test_ragged_batch_and_long_sequence():
             want = MT.dsn_forward(sd, x.cpu())
             assert torch.allclose(alone.cpu(), want, rtol=2e-2, atol=2e-3), (T, (alone.cpu() - want).abs().max())
         o += T
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lengths", [[64], [300], [50, 77, 8]])
+def test_backward_matches_oracle_autograd(lengths):
+    """BPTT on the device (smz_dsn_backward) against torch autograd over the float32 restatement."""
+    from summarizer_b200.models.dsn_autograd import dsn_apply
+    torch.manual_seed(7)
+    m = DSN().cuda().train()
+    with torch.no_grad():
+        m.rnn.weight_hh_l0.mul_(2.0); m.rnn.weight_hh_l0_reverse.mul_(2.0)
+    xs = [make_input(300 + i, T, 1)[:, 0].cuda() * 8 for i, T in enumerate(lengths)]
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    target = torch.rand(sum(lengths), generator=g, device="cuda")
+    probs = dsn_apply(m, torch.cat(xs), lengths)
+    loss = ((probs - target) ** 2).mean()
+    loss.backward()
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    ref = torch.cat([MT.dsn_forward(sd, x) for x in xs])
+    ref_loss = ((ref - target) ** 2).mean()
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) / ref_loss.item() < 1e-2
+    errs = {}
+    for name, p in m.named_parameters():
+        errs[name] = (p.grad - sd[name].grad).norm().item() / max(sd[name].grad.norm().item(), 1e-12)
+    report = ", ".join(f"{k} {v:.2e}" for k, v in errs.items())
+    print("relative gradient errors:", report)
+    assert max(errs.values()) < 3e-2, report
+
+
+@pytest.mark.gpu
+def test_module_forward_backward_through_nn_module():
+    torch.manual_seed(0)
+    m = DSN().cuda().train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    x = make_input(9, 120, 1).cuda()
+    target = torch.linspace(0.1, 0.9, 120, device="cuda").view(120, 1, 1)
+    losses = []
+    for _ in range(25):
+        loss = torch.nn.functional.mse_loss(m(x), target)
+        opt.zero_grad(); loss.backward(); torch.nn.utils.clip_grad_norm_(m.parameters(), 5.0); opt.step()
+        losses.append(float(loss))
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
