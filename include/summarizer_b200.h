@@ -239,6 +239,15 @@ int smz_dsn_backward(const void *x, int x_is_bf16, const int32_t *h_cu_seqlens, 
                      const float *probs, const float *dprobs, const smz_dsn_grads *grads, void *ws, int64_t ws_bytes,
                      void *stream);
 
+/* ---- DSN reward: replaces models/dsn.py:185-236 DSNTrainer.compute_reward for ALL episodes of one video ----
+ * x: float32 features [T,1024]; actions: uint8 [n_episodes, T] (1 = frame picked, the Bernoulli samples of
+ * dsn.py:125); rewards: float32 [n_episodes] = 0.5 * (R_div + R_rep); 0 when no frame is picked; with a single
+ * picked frame R_div = 0 and R_rep is evaluated normally (the reference raises there, dsn.py:229-230).
+ * n_episodes <= 8. */
+int smz_dsn_reward_workspace_bytes(int T, int n_episodes, int64_t *bytes);
+int smz_dsn_reward(const float *x, int T, const uint8_t *actions, int n_episodes, int temp_dist_thre, int far_sim,
+                   float *rewards, void *ws, int64_t ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

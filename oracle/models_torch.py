@@ -71,3 +71,28 @@ def dsn_forward(sd, x):
                         sd["rnn.bias_ih_l0_reverse"], sd["rnn.bias_hh_l0_reverse"], reverse=True)
     h = torch.cat([hf, hb], 1)
     return torch.sigmoid(h @ sd["out.0.weight"].t() + sd["out.0.bias"]).reshape(-1)
+
+
+def dsn_reward(seq, actions, far_sim=False, temp_dist_thre=20):
+    """models/dsn.py:185-236 compute_reward for ONE episode: seq (T, 1024) float32, actions (T,) 0/1 ->
+    0.5 * (R_div + R_rep) as a python float.  No frame picked -> 0 (dsn.py:199-203); a single picked frame:
+    R_div = 0 (dsn.py:207-210) and R_rep over that one column (the reference raises on the 0-d index there)."""
+    pick = torch.nonzero(actions.reshape(-1) > 0).reshape(-1)
+    P = int(pick.numel())
+    if P == 0:
+        return 0.0
+    T = seq.shape[0]
+    if P == 1:
+        reward_div = torch.tensor(0.)
+    else:
+        normed = seq / seq.norm(p=2, dim=1, keepdim=True)                      # :214
+        dissim = 1. - normed @ normed.t()                                      # :215
+        sub = dissim[pick][:, pick]                                            # :216
+        if not far_sim:
+            td = (pick[None, :] - pick[:, None]).abs()                         # :219-221
+            sub = torch.where(td > temp_dist_thre, torch.ones_like(sub), sub)  # :222
+        reward_div = sub.sum() / (P * (P - 1.))                                # :223
+    sq = seq.pow(2).sum(dim=1, keepdim=True).expand(T, T)                      # :226
+    dist = sq + sq.t() - 2 * (seq @ seq.t())                                   # :227-228
+    reward_rep = torch.exp(-dist[:, pick].min(1)[0].mean())                    # :229-231
+    return float((reward_div + reward_rep) * 0.5)

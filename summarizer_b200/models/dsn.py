@@ -95,3 +95,107 @@ class DSN(nn.Module):
         else:
             p = self.score_packed(packed, [seq_len] * batch_size)
         return p.view(batch_size, seq_len, 1).permute(1, 0, 2)
+
+
+from torch.distributions import Bernoulli  # noqa: E402
+
+from . import Trainer  # noqa: E402
+
+
+def compute_rewards(seq, actions, far_sim=False, temp_dist_thre=20, workspace=None):
+    """Rewards of all episodes of one video on the device (dsn.py:185-236 for each row of ``actions``).
+    seq: (T, 1024) float32 cuda; actions: (E, T) 0/1.  Returns float32 (E,) cuda tensor."""
+    N.require_device()
+    seq = seq.detach().reshape(-1, 1024).float().contiguous()
+    act = actions.detach().reshape(actions.shape[0], -1).to(torch.uint8).contiguous()
+    E, T = act.shape
+    nbytes = C.c_int64(0)
+    N.check(N.lib().smz_dsn_reward_workspace_bytes(T, E, C.byref(nbytes)))
+    ws = (workspace or _Workspace()).get(nbytes.value, seq.device)
+    rewards = torch.empty(E, dtype=torch.float32, device=seq.device)
+    N.check(N.lib().smz_dsn_reward(N.ptr(seq), T, N.ptr(act), E, int(temp_dist_thre), int(bool(far_sim)), N.ptr(rewards),
+                                   N.ptr(ws), ws.numel(), N.current_stream()))
+    return rewards
+
+
+class DSNTrainer(Trainer):
+    """models/dsn.py:50-236 — REINFORCE with the diversity-representativeness reward; extra parameters parsed as
+    the reference does (dsn.py:52-57; note ``beta = int(0.01) = 0`` unless ``--beta`` >= 1)."""
+
+    def _init_model(self):
+        ep = self.hps.extra_params or {}
+        self.beta = int(ep.get("beta", 0.01))
+        self.num_episodes = int(ep.get("num_episodes", 5))
+        self.eps = float(ep.get("eps", 0.5))
+        self.far_sim = bool(ep.get("far_sim", False))
+        self.temp_dist_thre = int(ep.get("temp_dist_thre", 20))
+        self.sup = bool(ep.get("sup", False))
+        self._reward_ws = _Workspace()
+        return DSN()
+
+    def compute_reward(self, seq, actions, far_sim=False, temp_dist_thre=20):
+        """One episode (reference signature, dsn.py:185): seq (T,1,1024), actions (T,1,1) -> scalar tensor."""
+        return compute_rewards(seq.reshape(-1, 1024), actions.reshape(1, -1), far_sim, temp_dist_thre, self._reward_ws)[0]
+
+    def _score_keys(self, keys):
+        feats = [self._video_tensors(k)[0][:, 0] for k in keys]
+        lengths = [f.shape[0] for f in feats]
+        with torch.no_grad():
+            packed = self.model.score_packed(torch.cat(feats), lengths)
+        return list(torch.split(packed, lengths))
+
+    def train(self, fold):
+        import random
+        self.model.train()
+        train_keys, _ = self._get_train_test_keys(fold)
+        self.draw_gtscores(fold, train_keys)
+        self.log.debug("Parameters: {}".format(sum(p.numel() for p in self.model.parameters())))
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.hps.lr, weight_decay=self.hps.weight_decay)
+        loss_BCE = torch.nn.BCELoss()
+        dev = self._device()
+        baselines = {key: torch.zeros((), device=dev) for key in train_keys}      # device-resident: no sync per step
+        reward_writers = {key: [] for key in train_keys}
+        best_corr, best_avg_f_score, best_max_f_score = -1.0, 0.0, 0.0
+        for epoch in range(self.hps.epochs):
+            epoch_losses, dist_scores = [], {}
+            random.shuffle(train_keys)
+            for key in train_keys:
+                seq, target = self._video_tensors(key)
+                probs = self.model(seq)                                           # (T,1,1), autograd through the device BPTT
+                dist = Bernoulli(probs)
+                loss = self.beta * (probs.mean() - self.eps) ** 2                 # summary-length penalty [Eq.11]
+                if self.sup:
+                    loss = loss + loss_BCE(probs, target)
+                actions = torch.stack([dist.sample() for _ in range(self.num_episodes)])      # (E,T,1,1)
+                rewards = compute_rewards(seq, actions.reshape(self.num_episodes, -1), self.far_sim, self.temp_dist_thre,
+                                          self._reward_ws)
+                for e in range(self.num_episodes):                                # policy gradient [Eq.10]
+                    loss = loss - dist.log_prob(actions[e]).mean() * (rewards[e] - baselines[key])
+                loss = loss / float(self.num_episodes)
+                self.optimizer.zero_grad()
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(self.model.parameters(), 5.0)
+                self.optimizer.step()
+                mean_reward = rewards.mean()
+                baselines[key] = 0.9 * baselines[key] + 0.1 * mean_reward
+                reward_writers[key].append(mean_reward)
+                epoch_losses.append(loss.detach())
+                dist_scores[key] = probs.detach()
+            epoch_avg_reward = float(torch.stack([reward_writers[key][epoch] for key in train_keys]).mean())
+            epoch_avg_loss = float(torch.stack(epoch_losses).mean())
+            self.log.info(f"Epoch: {f'{epoch+1}/{self.hps.epochs}':6}   Reward: {epoch_avg_reward:.05f}  Loss: {epoch_avg_loss:.05f}")
+            self.hps.writer.add_scalar(f"{self.dataset_name}/Fold_{fold+1}/Train/Reward", epoch_avg_reward, epoch)
+            self.hps.writer.add_scalar(f"{self.dataset_name}/Fold_{fold+1}/Train/Loss", epoch_avg_loss, epoch)
+            if epoch % self.hps.test_every_epochs == 0:
+                avg_corr, (avg_f_score, max_f_score) = self.test(fold)
+                self.model.train()
+                self.hps.writer.add_scalar(f"{self.dataset_name}/Fold_{fold+1}/Test/Correlation", avg_corr, epoch)
+                self.hps.writer.add_scalar(f"{self.dataset_name}/Fold_{fold+1}/Test/F-score_avg", avg_f_score, epoch)
+                self.hps.writer.add_scalar(f"{self.dataset_name}/Fold_{fold+1}/Test/F-score_max", max_f_score, epoch)
+                best_avg_f_score = max(best_avg_f_score, avg_f_score)
+                best_max_f_score = max(best_max_f_score, max_f_score)
+                if avg_corr > best_corr:
+                    best_corr = avg_corr
+                    self.best_weights = self.model.state_dict()
+        self.draw_scores(fold, {k: v.cpu().numpy() for k, v in dist_scores.items()})
+        return best_corr, best_avg_f_score, best_max_f_score

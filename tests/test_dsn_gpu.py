@@ -96,3 +96,31 @@ def test_module_forward_backward_through_nn_module():
         opt.zero_grad(); loss.backward(); torch.nn.utils.clip_grad_norm_(m.parameters(), 5.0); opt.step()
         losses.append(float(loss))
     assert np.isfinite(losses).all() and losses[-1] < losses[0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,far", [(64, False), (300, False), (707, False), (200, True)])
+def test_reward_matches_oracle(T, far):
+    """smz_dsn_reward (Gram once per video, all episodes in one pass) vs the float32 restatement of
+    compute_reward, episode by episode."""
+    from summarizer_b200.models.dsn import compute_rewards
+    seq = make_input(500 + T, T, 1)[:, 0]
+    g = torch.Generator().manual_seed(T)
+    probs = [0.5, 0.3, 0.7, 0.02, 0.0]
+    actions = torch.stack([(torch.rand(T, generator=g) < p).float() for p in probs])
+    actions[3] = 0; actions[3, T // 2] = 1                      # exactly one picked frame; row 4: none
+    got = compute_rewards(seq.cuda(), actions.cuda(), far_sim=far, temp_dist_thre=20).cpu()
+    want = torch.tensor([MT.dsn_reward(seq, actions[e], far_sim=far, temp_dist_thre=20) for e in range(len(probs))])
+    assert torch.allclose(got, want, rtol=2e-4, atol=1e-6), (got, want)
+
+
+@pytest.mark.gpu
+def test_dsn_trainer_reinforce_runs(tmp_path):
+    from summarizer_b200.main import train
+    from summarizer_b200.utils.config import HParameters
+    hps = HParameters()
+    hps.log_root, hps.tensorboard = str(tmp_path), False
+    hps.load_from_args(dict(model="dsn", use_cuda="yes", splits_files="splits/summe_splits_overfit.json", log_level="error",
+                            epochs=2, test_every_epochs=1, extra_params={}))
+    (res,) = train(hps)
+    assert np.isfinite(res[1:]).all() and 0 <= res[2] <= res[3] <= 1

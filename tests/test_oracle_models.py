@@ -38,3 +38,19 @@ def test_dsn_restatement_matches_golden(case):
     with torch.no_grad():
         y = torch.stack([MT.dsn_forward(sd, x[:, b]) for b in range(B)], 1)
     np.testing.assert_allclose(y.numpy(), GOLDEN[f"{name}/y"][:, :, 0], rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.reference
+def test_dsn_reward_restatement_matches_live_reference():
+    """oracle.models_torch.dsn_reward == the reference's DSNTrainer.compute_reward (dsn.py:185-236)."""
+    import types
+    from oracle import ref_import
+    ref = ref_import.load().dsn.DSNTrainer
+    me = types.SimpleNamespace(hps=types.SimpleNamespace(use_cuda=False))
+    g = torch.Generator().manual_seed(4)
+    for T, p, far in [(60, 0.5, False), (200, 0.3, False), (150, 0.6, True), (80, 0.0, False)]:
+        seq = make_input(70 + T, T, 1)
+        actions = (torch.rand(T, 1, 1, generator=g) < p).float()
+        want = float(ref.compute_reward(me, seq, actions, far_sim=far, temp_dist_thre=20))
+        got = MT.dsn_reward(seq[:, 0], actions.reshape(-1), far_sim=far, temp_dist_thre=20)
+        assert got == pytest.approx(want, rel=1e-5, abs=1e-7)
