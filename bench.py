@@ -226,6 +226,66 @@ def make_features(n_videos, dev, seed):
     return x
 
 
+def train_stage(dev, seconds=4.0):
+    """Secondary metric of BASELINE.json ("VASNet/DSN frames/sec fwd+bwd"): the reference's per-video training
+    steps (vasnet.py:193-212: forward + MSE + backward + Adam; dsn.py:96-149: forward + 5 REINFORCE episodes with
+    rewards + backward + clip + Adam) on TVSum-shaped synthetic videos, one video per optimizer step."""
+    import torch
+    from torch.distributions import Bernoulli
+    from summarizer_b200.models.dsn import DSN, compute_rewards
+    from summarizer_b200.models.vasnet import VASNet
+    rng = np.random.default_rng(2)
+    lens = [int(t) for t in rng.integers(167, 1295, size=16)]
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    vids = []
+    for T in lens:
+        x = torch.randn(T, 1, FEAT, generator=g, device=dev).abs_()
+        vids.append((x / x.norm(dim=2, keepdim=True), torch.rand(T, 1, 1, generator=g, device=dev)))
+    out = {"videos": len(lens), "frames": int(sum(lens)), "shape": "TVSum-like T in [167,1294], batch 1 per optimizer step"}
+
+    def timed(step):
+        for v in vids[:3]:
+            step(*v)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n, t0 = 0, time.perf_counter()
+        e0.record()
+        while time.perf_counter() - t0 < seconds:
+            for v in vids:
+                step(*v)
+            n += 1
+        e1.record(); torch.cuda.synchronize()
+        return n * sum(lens) / (e0.elapsed_time(e1) / 1e3)
+
+    torch.manual_seed(0)
+    vas = VASNet().to(dev).train()
+    opt = torch.optim.Adam(vas.parameters(), lr=5e-5, weight_decay=1e-5)
+
+    def vas_step(x, tgt):
+        loss = torch.nn.functional.mse_loss(vas(x), tgt)
+        opt.zero_grad(); loss.backward(); opt.step()
+    out["vasnet_train_frames_per_s"] = timed(vas_step)
+    f_train = sum(24 * T * FEAT * FEAT + 12 * T * T * FEAT + 6 * T * FEAT for T in lens)
+    out["vasnet_train_tflops"] = out["vasnet_train_frames_per_s"] / sum(lens) * f_train / 1e12
+
+    dsn = DSN().to(dev).train()
+    opt2 = torch.optim.Adam(dsn.parameters(), lr=5e-5, weight_decay=1e-5)
+    base = torch.zeros((), device=dev)
+
+    def dsn_step(x, tgt):
+        probs = dsn(x)
+        dist = Bernoulli(probs)
+        actions = torch.stack([dist.sample() for _ in range(5)])
+        rewards = compute_rewards(x, actions.reshape(5, -1))
+        loss = 0.
+        for e in range(5):
+            loss = loss - dist.log_prob(actions[e]).mean() * (rewards[e] - base)
+        loss = loss / 5.
+        opt2.zero_grad(); loss.backward(); torch.nn.utils.clip_grad_norm_(dsn.parameters(), 5.0); opt2.step()
+    out["dsn_reinforce_frames_per_s"] = timed(dsn_step)
+    return out
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -357,6 +417,7 @@ def run_native(args):
             "clocks": clocks,
         }
         if world == 1:
+            line["train"] = train_stage(dev)
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
         print(json.dumps(line), flush=True)
     if world > 1:

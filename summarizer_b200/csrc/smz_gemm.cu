@@ -165,22 +165,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int lt = tile - g.tile0;
             const int mt = lt / g.tiles_n, nt = lt - mt * g.tiles_n;
             const int as = it & 1;
-            mbar_wait(&tfull[as], ((uint32_t)it >> 1) & 1u);
-            tc_fence_after();
             const int m = mt * BM + row;
             const bool row_ok = m < g.M;
             const float bias_m = (P.epi.bias != nullptr && (flags & smz::GEMM_BIAS_M) && row_ok) ? __ldg(P.epi.bias + m) : 0.f;
             const bool out_f32 = flags & smz::GEMM_OUT_F32;
+            const bool res_f32 = flags & smz::GEMM_RES_F32;
             const bool c_vec = ((g.c_off | (int64_t)g.ldc) & 7) == 0 && (reinterpret_cast<uintptr_t>(P.epi.C) & 15) == 0;
             const bool r_vec = ((g.r_off | (int64_t)g.ldr) & 7) == 0 && (reinterpret_cast<uintptr_t>(P.epi.residual) & 15) == 0;
+            // The residual of the NEXT 32-column chunk is fetched while the current one is processed (and the
+            // first one while the MMAs of this tile are still running): its ~1 us L2/HBM latency would otherwise
+            // serialise 8 times per tile and make the epilogue, not the tensor pipe, the pace of the kernel.
+            const char *res_row = P.epi.residual == nullptr ? nullptr
+                : reinterpret_cast<const char *>(P.epi.residual) + (g.r_off + (int64_t)m * g.ldr) * (res_f32 ? 4 : 2);
+            auto res_vec_ok = [&](int n0) { return res_row != nullptr && row_ok && r_vec && n0 + 32 <= g.N; };
+            auto res_fetch = [&](int n0, uint4 (&buf)[8]) {
+                if (!res_vec_ok(n0)) return;
+                const uint4 *src = reinterpret_cast<const uint4 *>(res_row + (int64_t)n0 * (res_f32 ? 4 : 2));
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (res_f32 || j < 4) buf[j] = src[j];
+            };
+            uint4 rcur[8], rnext[8];
+            res_fetch(nt * BN, rcur);
+            mbar_wait(&tfull[as], ((uint32_t)it >> 1) & 1u);
+            tc_fence_after();
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 const int n0 = nt * BN + c0;
                 if (n0 >= g.N) break;   // warp-uniform
                 uint32_t v[32];
                 __syncwarp();           // tcgen05.ld is .sync.aligned: reconverge after the row mask
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
+                if (c0 + 32 < BN) res_fetch(n0 + 32, rnext);
                 tmem_ld_wait();
-                if (!row_ok) continue;
+                if (row_ok) {
                 float x[32];
 #pragma unroll
                 for (int j = 0; j < 32; j++) x[j] = alpha * __uint_as_float(v[j]);
@@ -200,37 +217,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         for (int j = 0; j < 32; j++) if (n0 + j < g.N) x[j] += __ldg(P.epi.bias + n0 + j);
                     }
                 }
-                if (P.epi.residual != nullptr) {
-                    const int64_t ro = g.r_off + (int64_t)m * g.ldr + n0;
-                    if (flags & smz::GEMM_RES_F32) {
-                        const float *r = reinterpret_cast<const float *>(P.epi.residual) + ro;
-                        if (full32 && r_vec) {
+                if (res_row != nullptr) {
+                    if (res_vec_ok(n0)) {
+                        if (res_f32) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 b = ld_f4(r + j);
-                                x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+                            for (int j = 0; j < 8; j++) {
+                                x[4 * j] += __uint_as_float(rcur[j].x); x[4 * j + 1] += __uint_as_float(rcur[j].y);
+                                x[4 * j + 2] += __uint_as_float(rcur[j].z); x[4 * j + 3] += __uint_as_float(rcur[j].w);
                             }
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 32; j++) if (n0 + j < g.N) x[j] += r[j];
-                        }
-                    } else {
-                        const __nv_bfloat16 *r = reinterpret_cast<const __nv_bfloat16 *>(P.epi.residual) + ro;
-                        if (full32 && r_vec) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                const uint4 b = *reinterpret_cast<const uint4 *>(r + j);
-                                const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+                            for (int j = 0; j < 4; j++) {
+                                const uint32_t w4[4] = {rcur[j].x, rcur[j].y, rcur[j].z, rcur[j].w};
 #pragma unroll
                                 for (int t = 0; t < 4; t++) {
-                                    x[j + 2 * t] += __uint_as_float(w[t] << 16);
-                                    x[j + 2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
+                                    x[8 * j + 2 * t] += __uint_as_float(w4[t] << 16);
+                                    x[8 * j + 2 * t + 1] += __uint_as_float(w4[t] & 0xffff0000u);
                                 }
                             }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; j++) if (n0 + j < g.N) x[j] += __bfloat162float(r[j]);
                         }
+                    } else if (res_f32) {
+                        const float *r = reinterpret_cast<const float *>(res_row) + n0;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) if (n0 + j < g.N) x[j] += r[j];
+                    } else {
+                        const __nv_bfloat16 *r = reinterpret_cast<const __nv_bfloat16 *>(res_row) + n0;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) if (n0 + j < g.N) x[j] += __bfloat162float(r[j]);
                     }
                 }
                 if (flags & smz::GEMM_RELU) {
@@ -261,6 +274,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         for (int j = 0; j < 32; j++) if (n0 + j < g.N) dst[j] = __float2bfloat16_rn(x[j]);
                     }
                 }
+                }   // row_ok
+#pragma unroll
+                for (int j = 0; j < 8; j++) rcur[j] = rnext[j];
             }
             tc_fence_before();
             mbar_arrive(&tempty[as]);

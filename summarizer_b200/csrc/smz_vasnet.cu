@@ -46,6 +46,8 @@ struct Plan {
     int64_t max_logits = 0;
     bool training = false, x_bf16 = false;
     int64_t rows_cap = 0;   // row capacity of the row-wise buffers (and stride of the stats arrays)
+    int lanes = 1;          // inference with several chunks: two copies of the recycled buffers, one per stream
+    int64_t lane_bytes = 0;
     int64_t off_xb, off_qk, off_vt, off_o, off_y, off_yn, off_h, off_s, off_p, off_alpha, off_probs, off_dropoff,
         off_stats, total;
     // backward-only buffers (training)
@@ -109,6 +111,9 @@ int make_plan(const int32_t *cu, int n_videos, bool training, bool x_bf16, Plan 
     pl->off_s = take(LG * 4);
     pl->off_p = take(LG * 2);
     pl->off_alpha = take(training ? LG * 2 : 0);
+    pl->lane_bytes = o;
+    pl->lanes = (!training && pl->chunks.size() > 1) ? 2 : 1;
+    if (pl->lanes == 2) o += pl->lane_bytes;     // second copy of everything above
     pl->off_probs = take((int64_t)n_videos * 2 * sizeof(GemmProblem));
     pl->off_dropoff = take(training ? (int64_t)n_videos * 8 : 0);
     pl->off_stats = take(training ? R * 4 * 4 : 0);
@@ -156,6 +161,26 @@ void build_problems(const Plan &pl, const int32_t *cu, std::vector<GemmProblem> 
                 sub_row += T;
             }
         }
+}
+
+// Two internal streams per device: consecutive chunks run on alternating streams (each with its own copy of
+// the chunk buffers) so that the tail wave of one chunk's GEMM overlaps the next chunk's kernels.  They are
+// forked from / joined back into the caller's stream with events, so the call stays asynchronous and ordered.
+struct SideStreams { cudaStream_t s[2]; cudaEvent_t fork, join[2]; bool ok; };
+SideStreams *side_streams() {
+    static SideStreams table[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideStreams &t = table[dev];
+    if (!t.ok) {
+        for (int i = 0; i < 2; i++) {
+            if (cudaStreamCreateWithFlags(&t.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&t.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        if (cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        t.ok = true;
+    }
+    return &t;
 }
 
 GemmProblem dense_problem(int M, int N, int K, int ldc, int ldr) {
@@ -236,18 +261,31 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
     bf16 *const qk0 = qk, *const vt0 = vt, *const o0 = o, *const yn0 = yn, *const P0 = P, *const alpha0 = alpha;
     float *const y0 = y, *const h0 = h, *const S0 = S, *const stats0 = stats;
 
+    SideStreams *ss = pl.lanes == 2 ? side_streams() : nullptr;
+    const cudaStream_t caller = st;
+    if (ss != nullptr) {
+        SMZ_CUDA_CHECK(cudaEventRecord(ss->fork, caller));
+        for (int i = 0; i < 2; i++) SMZ_CUDA_CHECK(cudaStreamWaitEvent(ss->s[i], ss->fork, 0));
+    }
+    int chunk_index = 0;
     for (const Chunk &c : pl.chunks) {
         const int R = c.rows;
         const int64_t Rpad = up(R, 8);
         const int64_t rb = training ? c.row0 : 0;       // row base inside the row-wise buffers
-        qk = qk0 + rb * 2 * kFeat; vt = vt0 + c.vt_off; o = o0 + rb * kFeat; y = y0 + rb * kFeat;
-        yn = yn0 + rb * kFeat; h = h0 + rb * kFeat; S = S0 + c.lg_off; P = P0 + c.lg_off; alpha = alpha0 + c.lg_off;
+        const int lane_id = ss != nullptr ? (chunk_index & 1) : 0;
+        ++chunk_index;
+        if (ss != nullptr) st = ss->s[lane_id];
+        const int64_t lb = (int64_t)lane_id * pl.lane_bytes;   // byte offset of this lane's buffer copy
+        auto lane = [&](auto *ptr) { return reinterpret_cast<decltype(ptr)>(reinterpret_cast<uint8_t *>(ptr) + lb); };
+        qk = lane(qk0) + rb * 2 * kFeat; vt = lane(vt0) + c.vt_off; o = lane(o0) + rb * kFeat; y = lane(y0) + rb * kFeat;
+        yn = lane(yn0) + rb * kFeat; h = lane(h0) + rb * kFeat; S = lane(S0) + c.lg_off; P = lane(P0) + c.lg_off;
+        alpha = lane(alpha0) + c.lg_off;
         stats = training ? stats0 + rb : nullptr;
         const bf16 *xb;
         if (x_is_bf16) {
             xb = reinterpret_cast<const bf16 *>(x) + (int64_t)c.row0 * kFeat;
         } else {
-            bf16 *dst = reinterpret_cast<bf16 *>(w + pl.off_xb) + rb * kFeat;
+            bf16 *dst = reinterpret_cast<bf16 *>(w + pl.off_xb + lb) + rb * kFeat;
             rc = smz::launch_cvt_bf16(reinterpret_cast<const float *>(x) + (int64_t)c.row0 * kFeat, dst, (int64_t)R * kFeat, st);
             if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "cvt");
@@ -304,6 +342,12 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
                               R, scores + c.row0, stats ? stats + 2 * Rs : nullptr, stats ? stats + 3 * Rs : nullptr, st);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "head");
+    }
+    if (ss != nullptr) {
+        for (int i = 0; i < 2; i++) {
+            SMZ_CUDA_CHECK(cudaEventRecord(ss->join[i], ss->s[i]));
+            SMZ_CUDA_CHECK(cudaStreamWaitEvent(caller, ss->join[i], 0));
+        }
     }
     return SMZ_OK;
 }
