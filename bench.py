@@ -355,29 +355,43 @@ def run_native(args):
     ms, score_ms, select_ms, fscore_ms = t.tolist()
     value = V * world * args.steps / (ms / 1e3)
 
-    # ---- e2e: public batched API with host (pinned) inputs, H2D + D2H inside the timed region
+    # ---- e2e: public batched API with host (pinned) inputs; every step copies ITS features and annotator
+    # summaries host->device and its F-scores device->host inside the timed region.  Two buffer sets and a copy
+    # stream let step i+1's H2D overlap step i's kernels (steady-state streaming, as a data loader would do).
     ne = min(args.e2e_videos, V)
-    eb = synthetic.make_sweep_batch(ne, dev, seed=777 + rank)
-    h_users = torch.empty(eb.d_users.shape, dtype=torch.float32, pin_memory=True); h_users.copy_(eb.d_users)
-    h_feats = torch.empty((ne * N_STEPS, FEAT), dtype=torch.bfloat16, pin_memory=True); h_feats.copy_(feats[: ne * N_STEPS])
-    h_out = torch.empty((2, ne), dtype=torch.float64, pin_memory=True)
-    d_feats = torch.empty_like(h_feats, device=dev)
     le = [N_STEPS] * ne
+    sets = []
+    for k in range(2):
+        eb = synthetic.make_sweep_batch(ne, dev, seed=777 + rank)
+        sets.append(dict(eb=eb, d_feats=torch.empty((ne * N_STEPS, FEAT), dtype=torch.bfloat16, device=dev),
+                         ready=mk(), done=mk()))
+    h_users = torch.empty(sets[0]["eb"].d_users.shape, dtype=torch.float32, pin_memory=True); h_users.copy_(sets[0]["eb"].d_users)
+    h_feats = torch.empty((ne * N_STEPS, FEAT), dtype=torch.bfloat16, pin_memory=True); h_feats.copy_(feats[: ne * N_STEPS])
+    h_out = torch.empty((2, 2, ne), dtype=torch.float64, pin_memory=True)
+    copy_stream = torch.cuda.Stream(device=dev)
+    for st_ in sets:
+        st_["done"].record(stream)
 
-    def e2e_step():
-        d_feats.copy_(h_feats, non_blocking=True)
-        eb.d_users.copy_(h_users, non_blocking=True)
-        s = model.score_packed(d_feats, le)
-        eb.select(s); eb.fscore()
-        h_out[0].copy_(eb.avg_f[:ne], non_blocking=True); h_out[1].copy_(eb.max_f[:ne], non_blocking=True)
+    def e2e_step(i):
+        st_ = sets[i & 1]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(st_["done"])                    # the kernels that last used this set are finished
+            st_["d_feats"].copy_(h_feats, non_blocking=True)
+            st_["eb"].d_users.copy_(h_users, non_blocking=True)
+            st_["ready"].record(copy_stream)
+        stream.wait_event(st_["ready"])
+        sc = model.score_packed(st_["d_feats"], le)
+        st_["eb"].select(sc); st_["eb"].fscore()
+        h_out[i & 1, 0].copy_(st_["eb"].avg_f[:ne], non_blocking=True); h_out[i & 1, 1].copy_(st_["eb"].max_f[:ne], non_blocking=True)
+        st_["done"].record(stream)
 
-    for _ in range(2):
-        e2e_step()
+    for i in range(2):
+        e2e_step(i)
     barrier()
     e0, e1 = mk(), mk()
     e0.record(stream)
-    for _ in range(args.steps):
-        e2e_step()
+    for i in range(args.steps):
+        e2e_step(i)
     e1.record(stream)
     barrier()
     te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -412,7 +426,8 @@ def run_native(args):
                               "eval_path_frac": (b_eval / ((select_ms + fscore_ms) / 1e3) / 1e9) / hbm},
             "e2e": {"value": e2e_value, "unit": "videos/s",
                     "h2d_bytes_per_step": int(h_feats.numel() * 2 + h_users.numel() * 4),
-                    "d2h_bytes_per_step": int(h_out.numel() * 8), "videos_per_step": ne},
+                    "d2h_bytes_per_step": int(2 * ne * 8), "videos_per_step": ne,
+                    "pipelining": "two buffer sets: step i+1 H2D on a copy stream overlaps step i kernels"},
             "gpu_launches": int((nl.value + 6) * args.steps),
             "clocks": clocks,
         }

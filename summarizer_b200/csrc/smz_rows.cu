@@ -79,13 +79,20 @@ softmax_kernel(const GemmProblem *__restrict__ probs, int n_probs, int total_row
     if (T <= 2048 && lead == 0 && drop == nullptr) {
         constexpr int NV = 16;
         float v[NV][4];
+        // all loads first, nothing consumes them inside this loop: 16 independent 128-bit requests in flight per
+        // lane (a load-use pair per iteration serialises 16 DRAM round trips per row)
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            const int j = lane * 4 + 128 * k;
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < ld) e = *reinterpret_cast<const float4 *>(s + j);     // [T, ld) is allocated padding
+            v[k][0] = e.x; v[k][1] = e.y; v[k][2] = e.z; v[k][3] = e.w;
+        }
         float m = -INFINITY;
 #pragma unroll
         for (int k = 0; k < NV; k++) {
             const int j = lane * 4 + 128 * k;
             if (j < T) {
-                const float4 e = *reinterpret_cast<const float4 *>(s + j);
-                v[k][0] = e.x; v[k][1] = e.y; v[k][2] = e.z; v[k][3] = e.w;
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
                     if (j + t >= T) v[k][t] = -INFINITY;
