@@ -30,7 +30,7 @@ typedef __nv_bfloat16 bf16;
 // Chunk sizes trade L2 residency of the intermediates against wave quantisation of the per-video
 // attention problems (one T=2000 video is only 128 logits tiles / 64 alpha.V tiles for 148 SMs): 16k rows
 // (8 sweep videos) give >= 512 tiles per launch; the spilled intermediates cost < 25 % of HBM bandwidth.
-constexpr int kRowChunk = 16384;                // rows per chunk of the row-wise GEMMs
+constexpr int kRowChunk = 32768;                // rows per chunk of the row-wise GEMMs (1000+ tiles: < 4 % wave tail)
 constexpr int64_t kLogitBudget = 34ll << 20;    // fp32 logits in flight per sub-chunk (8 x 2000 x 2048)
 
 inline int64_t up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
