@@ -17,6 +17,7 @@
 #include "smz_tc.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -24,15 +25,26 @@ using namespace smztc;
 using smz::GemmEpilogue;
 using smz::GemmProblem;
 
-constexpr int BM = smz::GEMM_BM, BN = smz::GEMM_BN, BK = smz::GEMM_BK;
-constexpr int STAGES = 4;
+constexpr int BM = 128;                // accumulator rows per CTA (TMEM lanes)
+constexpr int BN = smz::GEMM_BN, BK = smz::GEMM_BK;
 constexpr int A_STAGE = BM * BK * 2;   // 16 KB
-constexpr int B_STAGE = BN * BK * 2;   // 32 KB
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 2 * BN;      // two accumulators
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + BAR_BYTES + 1024;   // + alignment slack
 static_assert(TMEM_COLS == 512, "TMEM allocation must be a power of two <= 512 columns");
+// PAIR = false: one CTA per 128 x 256 tile, 4 stages of 16 KB (A) + 32 KB (B).
+// PAIR = true : a cluster of two CTAs (one TPC) per 256 x 256 tile with tcgen05 cta_group::2: each CTA loads ITS
+//               128 rows of A and ITS 128 of the 256 B rows (16 + 16 KB per stage, 6 stages), the leader CTA issues
+//               M=256 MMAs that read both CTAs' shared memory and write both CTAs' tensor memory.  Per MMA the
+//               pair moves 2/3 of the L2->SM bytes of two independent CTAs — the operand traffic, not the tensor
+//               pipe, is what caps the one-CTA kernel at ~1.1 PFLOP/s.
+template <bool PAIR> struct Cfg {
+    static constexpr int STAGES = PAIR ? 6 : 4;
+    static constexpr int B_ROWS = PAIR ? BN / 2 : BN;          // B rows (n) loaded by one CTA
+    static constexpr int B_STAGE = B_ROWS * BK * 2;
+    static constexpr int TILE_M = PAIR ? 2 * BM : BM;
+    static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + BAR_BYTES + 1024;   // + alignment slack
+};
 
 struct Params {
     const GemmProblem *probs;
@@ -59,9 +71,11 @@ __device__ __forceinline__ float4 ld_f4(const float *p) { return *reinterpret_ca
 // core with the MN-major canonical layout (LBO = one box = 8 KB between 64-element m/n groups, SBO =
 // 1 KB between 8-row k groups, +2 KB per K=16 slice).  This is what lets the backward pass run
 // dX = dY.W and dW = dY^T.X on the row-major activations without materialising any transpose.
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params P) {
+    constexpr int STAGES = Cfg<PAIR>::STAGES, B_STAGE = Cfg<PAIR>::B_STAGE, B_ROWS = Cfg<PAIR>::B_ROWS;
+    constexpr int TILE_M = Cfg<PAIR>::TILE_M;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms
     uint8_t *sA = smem;
@@ -73,66 +87,73 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;           // 0 = leader CTA of the pair
+    const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    if (PAIR) cluster_sync_all();                                 // both CTAs alive before the pair allocates TMEM
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], PAIR ? 2 : 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], PAIR ? 256 : 128); }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    if (warp == 1) { if (PAIR) tmem_alloc_pair<TMEM_COLS>(tmem_slot); else tmem_alloc<TMEM_COLS>(tmem_slot); }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
+        // ------------------------------------------------------------------ TMA producer (every CTA)
         if (lane == 0) {
             Cursor c;
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+            for (int tile = first_tile; tile < P.total_tiles; tile += tile_step) {
                 c.seek(P, tile);
                 const int lt = tile - c.cur.tile0;
                 const int mt = lt / c.cur.tiles_n, nt = lt - mt * c.cur.tiles_n;
                 const int nkb = (c.cur.K + BK - 1) / BK;
                 // K-major: (row0, col0) = (first m/n row, first k column); MN-major: (first k row, first m/n column)
-                const int a_mn = (A_MN ? c.cur.a_col0 : c.cur.a_row0) + mt * BM;
-                const int b_mn = (B_MN ? c.cur.b_col0 : c.cur.b_row0) + nt * BN;
+                const int a_mn = (A_MN ? c.cur.a_col0 : c.cur.a_row0) + mt * TILE_M + rank * BM;
+                const int b_mn = (B_MN ? c.cur.b_col0 : c.cur.b_row0) + nt * BN + rank * B_ROWS;
                 const int a_k = A_MN ? c.cur.a_row0 : c.cur.a_col0, b_k = B_MN ? c.cur.b_row0 : c.cur.b_col0;
                 for (int kb = 0; kb < nkb; kb++) {
                     mbar_wait(&empty[stage], phase ^ 1u);
-                    mbar_arrive_expect_tx(&full[stage], A_STAGE + B_STAGE);
+                    // the bytes of BOTH CTAs are accounted on the leader's barrier, which the MMA thread waits on
+                    if (!PAIR) mbar_arrive_expect_tx(&full[stage], A_STAGE + B_STAGE);
+                    else if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (A_STAGE + B_STAGE));
+                    else mbar_arrive_remote(&full[stage], 0);
                     if (A_MN) {
 #pragma unroll
                         for (int j = 0; j < BM / 64; j++)
-                            tma_load_2d(sA + stage * A_STAGE + j * 8192, &tmA, &full[stage], a_mn + 64 * j, a_k + kb * BK);
+                            tma_load<PAIR>(sA + stage * A_STAGE + j * 8192, &tmA, &full[stage], a_mn + 64 * j, a_k + kb * BK);
                     } else {
-                        tma_load_2d(sA + stage * A_STAGE, &tmA, &full[stage], a_k + kb * BK, a_mn);
+                        tma_load<PAIR>(sA + stage * A_STAGE, &tmA, &full[stage], a_k + kb * BK, a_mn);
                     }
                     if (B_MN) {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; j++)
-                            tma_load_2d(sB + stage * B_STAGE + j * 8192, &tmB, &full[stage], b_mn + 64 * j, b_k + kb * BK);
+                        for (int j = 0; j < B_ROWS / 64; j++)
+                            tma_load<PAIR>(sB + stage * B_STAGE + j * 8192, &tmB, &full[stage], b_mn + 64 * j, b_k + kb * BK);
                     } else {
-                        tma_load_2d(sB + stage * B_STAGE, &tmB, &full[stage], b_k + kb * BK, b_mn);
+                        tma_load<PAIR>(sB + stage * B_STAGE, &tmB, &full[stage], b_k + kb * BK, b_mn);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (lane == 0 && rank == 0) {
             Cursor c;
-            const uint32_t idesc = make_idesc_bf16(BM, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+            const uint32_t idesc = make_idesc_bf16(TILE_M, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = first_tile; tile < P.total_tiles; tile += tile_step, ++it) {
                 c.seek(P, tile);
                 const int nkb = (c.cur.K + BK - 1) / BK;
                 const int as = it & 1;
-                mbar_wait(&tempty[as], (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
+                mbar_wait(&tempty[as], (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue(s) drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
                 for (int kb = 0; kb < nkb; kb++) {
@@ -143,12 +164,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     const uint64_t bdesc = B_MN ? make_mnmajor_sw128_desc(b_addr) : make_kmajor_sw128_desc(b_addr);
 #pragma unroll
                     for (int k = 0; k < BK / 16; k++)   // per K=16 slice: +32 B inside the swizzle atom (K-major), +2 KB (MN-major)
-                        umma_bf16(d_tmem, adesc + (A_MN ? 128 : 2) * k, bdesc + (B_MN ? 128 : 2) * k, idesc,
-                                  (uint32_t)((kb | k) != 0));
-                    umma_commit(&empty[stage]);
+                        umma_bf16<PAIR>(d_tmem, adesc + (A_MN ? 128 : 2) * k, bdesc + (B_MN ? 128 : 2) * k, idesc,
+                                        (uint32_t)((kb | k) != 0));
+                    umma_commit<PAIR>(&empty[stage]);       // PAIR: multicast to the same barrier of both CTAs
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(&tfull[as]);
+                umma_commit<PAIR>(&tfull[as]);
             }
         }
     } else {
@@ -159,13 +180,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const float alpha = P.epi.alpha;
         const int flags = P.epi.flags;
         int it = 0;
-        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = first_tile; tile < P.total_tiles; tile += tile_step, ++it) {
             c.seek(P, tile);
             const GemmProblem &g = c.cur;
             const int lt = tile - g.tile0;
             const int mt = lt / g.tiles_n, nt = lt - mt * g.tiles_n;
             const int as = it & 1;
-            const int m = mt * BM + row;
+            const int m = mt * TILE_M + rank * BM + row;
             const bool row_ok = m < g.M;
             const float bias_m = (P.epi.bias != nullptr && (flags & smz::GEMM_BIAS_M) && row_ok) ? __ldg(P.epi.bias + m) : 0.f;
             const bool out_f32 = flags & smz::GEMM_OUT_F32;
@@ -279,14 +300,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 for (int j = 0; j < 8; j++) rcur[j] = rnext[j];
             }
             tc_fence_before();
-            mbar_arrive(&tempty[as]);
+            if (PAIR) mbar_arrive_remote(&tempty[as], 0); else mbar_arrive(&tempty[as]);
         }
     }
+    __syncwarp();          // the single-lane roles rejoin their warps before the block / cluster barrier
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<TMEM_COLS>(tmem_base);
+        if (PAIR) tmem_dealloc_pair<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base);
     }
 }
 
@@ -332,6 +354,49 @@ int gemm_bf16_tn(const void *A, int64_t a_rows, int64_t a_cols, int64_t lda, con
                      epi, st);
 }
 
+bool gemm_pair_mode() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("SMZ_GEMM_PAIR"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
+int gemm_tile_m() { return gemm_pair_mode() ? 2 * BM : BM; }
+
+int gemm_tiles(int M, int N) { return ((M + gemm_tile_m() - 1) / gemm_tile_m()) * ((N + GEMM_BN - 1) / GEMM_BN); }
+
+template <bool PAIR>
+static int launch_variant(bool a_mn, bool b_mn, const CUtensorMap &ma, const CUtensorMap &mb, const Params &P, int total_tiles,
+                          cudaStream_t st) {
+    typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const Params);
+    const kern_t kern = a_mn ? (b_mn ? (kern_t)gemm_kernel<true, true, PAIR> : (kern_t)gemm_kernel<true, false, PAIR>)
+                             : (b_mn ? (kern_t)gemm_kernel<false, true, PAIR> : (kern_t)gemm_kernel<false, false, PAIR>);
+    const int variant = (a_mn ? 2 : 0) + (b_mn ? 1 : 0);
+    static bool attr_set[64][4] = {{false}};
+    int dev = 0;
+    SMZ_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_set[dev][variant]) {
+        SMZ_CUDA_CHECK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<PAIR>::SMEM_BYTES));
+        attr_set[dev][variant] = true;
+    }
+    const int sms = sm_count();
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg<PAIR>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (PAIR) {
+        const int pairs = total_tiles < sms / 2 ? total_tiles : sms / 2;
+        cfg.gridDim = dim3(2 * pairs);
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    } else {
+        cfg.gridDim = dim3(total_tiles < sms ? total_tiles : sms);
+    }
+    SMZ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ma, mb, P));
+    return SMZ_OK;
+}
+
 int gemm_bf16(bool a_mn, bool b_mn, const void *A, int64_t a_rows, int64_t a_cols, int64_t lda, const void *B,
               int64_t b_rows, int64_t b_cols, int64_t ldb, const GemmProblem *d_probs, int n_probs, int total_tiles,
               const GemmProblem &single, const GemmEpilogue &epi, cudaStream_t st) {
@@ -339,32 +404,19 @@ int gemm_bf16(bool a_mn, bool b_mn, const void *A, int64_t a_rows, int64_t a_col
     SMZ_REQUIRE(A && B && epi.C, "gemm: NULL operand");
     SMZ_REQUIRE(d_probs != nullptr || n_probs == 1, "gemm: a batch needs a device problem array");
     alignas(64) CUtensorMap ma, mb;
+    const bool pair = gemm_pair_mode();
     int rc = make_map(&ma, A, a_rows, a_cols, lda, a_mn ? 64 : BM);
     if (rc != SMZ_OK) return rc;
-    rc = make_map(&mb, B, b_rows, b_cols, ldb, b_mn ? 64 : BN);
+    rc = make_map(&mb, B, b_rows, b_cols, ldb, b_mn ? 64 : (pair ? BN / 2 : BN));
     if (rc != SMZ_OK) return rc;
-    typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const Params);
-    const kern_t kern = a_mn ? (b_mn ? (kern_t)gemm_kernel<true, true> : (kern_t)gemm_kernel<true, false>)
-                             : (b_mn ? (kern_t)gemm_kernel<false, true> : (kern_t)gemm_kernel<false, false>);
-    const int variant = (a_mn ? 2 : 0) + (b_mn ? 1 : 0);
-    static bool attr_set[64][4] = {{false}};
-    int dev = 0;
-    SMZ_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !attr_set[dev][variant]) {
-        SMZ_CUDA_CHECK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set[dev][variant] = true;
-    }
     Params P;
     P.probs = d_probs;
     P.single = single;
     P.n_probs = n_probs;
     P.total_tiles = total_tiles;
     P.epi = epi;
-    const int sms = sm_count();
-    const int grid = total_tiles < sms ? total_tiles : sms;
-    kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
-    SMZ_CUDA_CHECK(cudaGetLastError());
-    return SMZ_OK;
+    return pair ? launch_variant<true>(a_mn, b_mn, ma, mb, P, total_tiles, st)
+                : launch_variant<false>(a_mn, b_mn, ma, mb, P, total_tiles, st);
 }
 
 }  // namespace smz

@@ -34,11 +34,13 @@ struct GemmEpilogue {
     int flags;
 };
 
-constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 256;
 constexpr int GEMM_BK = 64;
 
-inline int gemm_tiles(int M, int N) { return ((M + GEMM_BM - 1) / GEMM_BM) * ((N + GEMM_BN - 1) / GEMM_BN); }
+// Tile rows: 256 with the default CTA-pair kernel (tcgen05 cta_group::2), 128 with SMZ_GEMM_PAIR=0.  Every
+// caller sizes its tile prefix sums through gemm_tiles().
+int gemm_tile_m();
+int gemm_tiles(int M, int N);
 
 // A: [a_rows, a_cols] bf16 with leading dimension lda (elements, multiple of 8), likewise B.
 // probs: device array of n_probs problems (or nullptr with n_probs == 1 -> `single` is used).
