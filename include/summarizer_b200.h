@@ -70,6 +70,8 @@ const char *smz_version(void);
 const char *smz_last_error(void);
 /* 0 when the current CUDA device is compute capability 10.x; SMZ_ERR_DEVICE otherwise. */
 int smz_device_check(void);
+/* SMZ_PROFILE=1 (development aid): prints the per-step device times collected so far to stderr. */
+void smz_profile_report(void);
 
 /* ---- shot selection: replaces utils/eval.py:74-123 generate_summary (+ utils/eval.py:15-35
  *      upsample inlined, utils/knapsack.py:5-23 knapsack_ortools incl. the OR-tools DP) ------

@@ -43,6 +43,7 @@ SIGNATURES = {
     "smz_version": (C.c_char_p, []),
     "smz_last_error": (C.c_char_p, []),
     "smz_device_check": (_I, []),
+    "smz_profile_report": (None, []),
     "smz_select_workspace_bytes": (_I, [_I, _I, _I, _I, _I, C.POINTER(C.c_int64)]),
     "smz_select_shots": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
     "smz_knapsack": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _P]),

@@ -3,6 +3,10 @@
 
 #include <stdlib.h>
 
+#include <map>
+#include <string>
+#include <vector>
+
 namespace smz {
 
 char *last_error_buf() {
@@ -14,6 +18,54 @@ bool debug_sync_enabled() {
     static int v = -1;
     if (v < 0) { const char *e = getenv("SMZ_DEBUG_SYNC"); v = (e != nullptr && e[0] == '1') ? 1 : 0; }
     return v == 1;
+}
+
+bool profile_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("SMZ_PROFILE"); v = (e != nullptr && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+namespace {
+struct Mark { cudaEvent_t ev; const char *step; cudaStream_t st; };
+std::vector<Mark> &marks() { static std::vector<Mark> m; return m; }
+}  // namespace
+
+void profile_mark(cudaStream_t st, const char *step) {
+    if (!profile_enabled()) return;
+    Mark m;
+    m.step = step; m.st = st;
+    if (cudaEventCreate(&m.ev) != cudaSuccess) return;
+    cudaEventRecord(m.ev, st);
+    marks().push_back(m);
+}
+
+void profile_report() {
+    if (!profile_enabled()) return;
+    cudaDeviceSynchronize();
+    std::map<std::string, std::pair<double, int>> acc;
+    std::vector<Mark> &m = marks();
+    // consecutive marks on the same stream delimit a step
+    std::map<cudaStream_t, size_t> last;
+    for (size_t i = 0; i < m.size(); i++) {
+        auto it = last.find(m[i].st);
+        if (it != last.end() && m[it->second].step[0] != 0) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, m[it->second].ev, m[i].ev) == cudaSuccess) {
+                auto &a = acc[m[it->second].step];
+                a.first += ms; a.second += 1;
+            }
+        }
+        last[m[i].st] = i;
+    }
+    double tot = 0.;
+    for (auto &kv : acc) tot += kv.second.first;
+    fprintf(stderr, "[smz profile] %zu marks, %.3f ms of stream time\n", m.size(), tot);
+    for (auto &kv : acc)
+        fprintf(stderr, "[smz profile] %-14s %9.3f ms %6.1f%%  %5d launches  %8.1f us/launch\n", kv.first.c_str(), kv.second.first,
+                100. * kv.second.first / tot, kv.second.second, 1e3 * kv.second.first / kv.second.second);
+    for (auto &x : m) cudaEventDestroy(x.ev);
+    m.clear();
 }
 
 int sm_count() {
@@ -52,3 +104,5 @@ extern "C" int smz_device_check(void) {
                          "(no other backend, no CPU fallback)", dev, major, minor);
     return SMZ_OK;
 }
+
+extern "C" void smz_profile_report(void) { smz::profile_report(); }

@@ -44,6 +44,12 @@ bool debug_sync_enabled();
         }                                                                                      \
     } while (0)
 
+// SMZ_PROFILE=1: per-step device timing of the scorer pipelines (CUDA events around every launch, summary
+// printed to stderr by smz_profile_report()).  Development aid; off by default.
+bool profile_enabled();
+void profile_mark(cudaStream_t st, const char *step);   // call before a step; "" closes the last one
+void profile_report();
+
 // Number of SMs of the current device (cached per device id).
 int sm_count();
 // Max opt-in dynamic shared memory per block of the current device.

@@ -31,6 +31,7 @@ constexpr int A_STAGE = BM * BK * 2;   // 16 KB
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 2 * BN;      // two accumulators
 constexpr int BAR_BYTES = 256;
+constexpr int STG_BYTES = 4 * 32 * 33 * 4;   // per epilogue warp: a 32 x 32 fp32 transposition pad (row stride 33 words)
 static_assert(TMEM_COLS == 512, "TMEM allocation must be a power of two <= 512 columns");
 // PAIR = false: one CTA per 128 x 256 tile, 4 stages of 16 KB (A) + 32 KB (B).
 // PAIR = true : a cluster of two CTAs (one TPC) per 256 x 256 tile with tcgen05 cta_group::2: each CTA loads ITS
@@ -43,7 +44,7 @@ template <bool PAIR> struct Cfg {
     static constexpr int B_ROWS = PAIR ? BN / 2 : BN;          // B rows (n) loaded by one CTA
     static constexpr int B_STAGE = B_ROWS * BK * 2;
     static constexpr int TILE_M = PAIR ? 2 * BM : BM;
-    static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + BAR_BYTES + 1024;   // + alignment slack
+    static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + BAR_BYTES + STG_BYTES + 1024;   // + alignment slack
 };
 
 struct Params {
@@ -85,6 +86,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint64_t *tfull = empty + STAGES;
     uint64_t *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    float *stg_all = reinterpret_cast<float *>(smem + STAGES * (A_STAGE + B_STAGE) + BAR_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = PAIR ? (int)cluster_ctarank() : 0;           // 0 = leader CTA of the pair
@@ -176,6 +178,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ------------------------------------------------------------------ epilogue (warps 2..5)
         Cursor c;
         const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+        float *stg = stg_all + q * (32 * 33);
         const int row = q * 32 + lane;
         const float alpha = P.epi.alpha;
         const int flags = P.epi.flags;
@@ -274,10 +277,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int64_t co = g.c_off + (int64_t)m * g.ldc + n0;
                 if (out_f32) {
                     float *dst = reinterpret_cast<float *>(P.epi.C) + co;
-                    if (full32 && c_vec) {
+                    if (full32) {
+                        // float32 tiles leave through the transposition pad (below): a thread owns a ROW of the
+                        // accumulator, so direct 16-byte stores would touch 32 different 128-byte lines per
+                        // instruction and make the store unit, not the tensor pipe, the pace of the kernel
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4 *>(dst + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+                        for (int j = 0; j < 32; j++) stg[lane * 33 + j] = x[j];
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; j++) if (n0 + j < g.N) dst[j] = x[j];
@@ -296,6 +301,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 }
                 }   // row_ok
+                if (out_f32 && n0 + 32 <= g.N) {       // warp-uniform: coalesced 128-byte row stores
+                    __syncwarp();
+                    const int m_base = m - lane;       // first row of this warp's 32 accumulator rows
+                    float *base = reinterpret_cast<float *>(P.epi.C) + g.c_off + n0 + lane;
+#pragma unroll 8
+                    for (int r = 0; r < 32; r++)
+                        if (m_base + r < g.M) base[(int64_t)(m_base + r) * g.ldc] = stg[r * 33 + lane];
+                    __syncwarp();
+                }
 #pragma unroll
                 for (int j = 0; j < 8; j++) rcur[j] = rnext[j];
             }

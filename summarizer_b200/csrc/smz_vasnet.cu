@@ -261,7 +261,7 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
     bf16 *const qk0 = qk, *const vt0 = vt, *const o0 = o, *const yn0 = yn, *const P0 = P, *const alpha0 = alpha;
     float *const y0 = y, *const h0 = h, *const S0 = S, *const stats0 = stats;
 
-    SideStreams *ss = pl.lanes == 2 ? side_streams() : nullptr;
+    SideStreams *ss = (pl.lanes == 2 && !smz::profile_enabled()) ? side_streams() : nullptr;   // profiling: one stream
     const cudaStream_t caller = st;
     if (ss != nullptr) {
         SMZ_CUDA_CHECK(cudaEventRecord(ss->fork, caller));
@@ -292,10 +292,12 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
             xb = dst;
         }
         // Q|K projection and V^T projection
+        smz::profile_mark(st, "gemm_qk");
         rc = smz::gemm_bf16_tn(xb, R, kFeat, kFeat, p->wqk, 2 * kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, 2 * kFeat),
                                dense_problem(R, 2 * kFeat, kFeat, 2 * kFeat, 0), GemmEpilogue{qk, nullptr, nullptr, 1.f, 0}, st);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "gemm_qk");
+        smz::profile_mark(st, "gemm_vt");
         rc = smz::gemm_bf16_tn(p->wv, kFeat, kFeat, kFeat, xb, R, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(kFeat, R),
                                dense_problem(kFeat, R, kFeat, (int)Rpad, 0), GemmEpilogue{vt, nullptr, nullptr, 1.f, 0}, st);
         if (rc != SMZ_OK) return rc;
@@ -309,14 +311,17 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
                 tiles_s += smz::gemm_tiles(T, T);
                 tiles_pv += smz::gemm_tiles(T, kFeat);
             }
+            smz::profile_mark(st, "gemm_logits");
             rc = smz::gemm_bf16_tn(qk, R, 2 * kFeat, 2 * kFeat, qk, R, 2 * kFeat, 2 * kFeat, d_probs + s.v0, nv, tiles_s,
                                    GemmProblem{}, GemmEpilogue{S, nullptr, nullptr, p->scale, smz::GEMM_OUT_F32}, st);
             if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "gemm_logits");
+            smz::profile_mark(st, "softmax");
             rc = smz::launch_softmax(d_probs + s.v0, nv, s.rows, S, alpha, P, drop_att, d_dropoff ? d_dropoff + s.v0 : nullptr,
                                      p->aperture, p->ignore_self, st);
             if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "softmax");
+            smz::profile_mark(st, "gemm_pv");
             rc = smz::gemm_bf16_tn(P, s.rows, s.ld, s.ld, vt, kFeat, R, Rpad, d_probs + n + s.v0, nv, tiles_pv, GemmProblem{},
                                    GemmEpilogue{o, nullptr, nullptr, 1.f, 0}, st);
             if (rc != SMZ_OK) return rc;
@@ -325,23 +330,28 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
         // output projection + residual, LayerNorm, k1 + ReLU, head
         const void *res = x_is_bf16 ? (const void *)(reinterpret_cast<const bf16 *>(x) + (int64_t)c.row0 * kFeat)
                                     : (const void *)(reinterpret_cast<const float *>(x) + (int64_t)c.row0 * kFeat);
+        smz::profile_mark(st, "gemm_out");
         rc = smz::gemm_bf16_tn(o, R, kFeat, kFeat, p->wo, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
                                dense_problem(R, kFeat, kFeat, kFeat, kFeat),
                                GemmEpilogue{y, nullptr, res, 1.f, smz::GEMM_OUT_F32 | (x_is_bf16 ? 0 : smz::GEMM_RES_F32)}, st);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "gemm_out");
+        smz::profile_mark(st, "layernorm");
         rc = smz::launch_layernorm(y, drop_y ? drop_y + (int64_t)c.row0 * kFeat : nullptr, p->ln_g, p->ln_b, p->eps, R, yn,
                                    stats, stats ? stats + Rs : nullptr, st);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "layernorm");
+        smz::profile_mark(st, "gemm_k1");
         rc = smz::gemm_bf16_tn(yn, R, kFeat, kFeat, p->w1, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
                                dense_problem(R, kFeat, kFeat, kFeat, 0), GemmEpilogue{h, p->b1, nullptr, 1.f, smz::GEMM_RELU | smz::GEMM_OUT_F32}, st);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "gemm_k1");
+        smz::profile_mark(st, "head");
         rc = smz::launch_head(h, drop_h ? drop_h + (int64_t)c.row0 * kFeat : nullptr, p->ln_g, p->ln_b, p->eps, p->w2, p->b2,
                               R, scores + c.row0, stats ? stats + 2 * Rs : nullptr, stats ? stats + 3 * Rs : nullptr, st);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "head");
+        smz::profile_mark(st, "");
     }
     if (ss != nullptr) {
         for (int i = 0; i < 2; i++) {
