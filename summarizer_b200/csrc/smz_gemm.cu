@@ -4,12 +4,12 @@
 // (vasnet.py:114-140), DSN's LSTM input projection (dsn.py:45) and the reward Gram matrix
 // (dsn.py:215-216,226-228).
 //
-// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
+// Structure (one persistent CTA per SM, 320 threads, warp-specialised):
 //   warp 0      TMA producer: 128x64 (A) and 256x64 (B) bf16 boxes, 128-byte swizzle, 4-stage
 //               mbarrier ring (48 KB per stage).
 //   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256, K=16) into one of two
 //               256-column TMEM accumulators; tcgen05.commit releases smem stages / publishes tiles.
-//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per warp), alpha / bias / residual /
+//   warps 2-9   epilogue (two per TMEM lane quadrant, 128 columns each): tcgen05.ld (32 lanes x 32 columns per warp), alpha / bias / residual /
 //               ReLU in fp32, 16-byte stores; overlaps the next tile's main loop (double-buffered TMEM).
 // Tiles are enumerated problem-major over a ragged batch (one problem per video for the attention
 // contractions), N fastest so that CTAs running concurrently share the A tile and the weights in L2.
@@ -28,10 +28,11 @@ using smz::GemmProblem;
 constexpr int BM = 128;                // accumulator rows per CTA (TMEM lanes)
 constexpr int BN = smz::GEMM_BN, BK = smz::GEMM_BK;
 constexpr int A_STAGE = BM * BK * 2;   // 16 KB
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;           // two warps per TMEM lane quadrant, each drains half of the 256 columns
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 2 * BN;      // two accumulators
 constexpr int BAR_BYTES = 256;
-constexpr int STG_BYTES = 4 * 32 * 33 * 4;   // per epilogue warp: a 32 x 32 fp32 transposition pad (row stride 33 words)
+constexpr int STG_BYTES = EPI_WARPS * 32 * 33 * 4;   // per epilogue warp: a 32 x 32 fp32 transposition pad (row stride 33 words)
 static_assert(TMEM_COLS == 512, "TMEM allocation must be a power of two <= 512 columns");
 // PAIR = false: one CTA per 128 x 256 tile, 4 stages of 16 KB (A) + 32 KB (B).
 // PAIR = true : a cluster of two CTAs (one TPC) per 256 x 256 tile with tcgen05 cta_group::2: each CTA loads ITS
@@ -40,7 +41,7 @@ static_assert(TMEM_COLS == 512, "TMEM allocation must be a power of two <= 512 c
 //               pair moves 2/3 of the L2->SM bytes of two independent CTAs — the operand traffic, not the tensor
 //               pipe, is what caps the one-CTA kernel at ~1.1 PFLOP/s.
 template <bool PAIR> struct Cfg {
-    static constexpr int STAGES = PAIR ? 6 : 4;
+    static constexpr int STAGES = PAIR ? 5 : 3;               // 32 KB / 48 KB per stage
     static constexpr int B_ROWS = PAIR ? BN / 2 : BN;          // B rows (n) loaded by one CTA
     static constexpr int B_STAGE = B_ROWS * BK * 2;
     static constexpr int TILE_M = PAIR ? 2 * BM : BM;
@@ -97,7 +98,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], PAIR ? 2 : 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], PAIR ? 256 : 128); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], (PAIR ? 2 : 1) * 32 * EPI_WARPS); }
         fence_mbar_init();
     }
     if (warp == 1) { if (PAIR) tmem_alloc_pair<TMEM_COLS>(tmem_slot); else tmem_alloc<TMEM_COLS>(tmem_slot); }
@@ -175,10 +176,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------------ epilogue (warps 2..9)
         Cursor c;
         const int q = warp & 3;                 // TMEM lane quadrant this warp may read
-        float *stg = stg_all + q * (32 * 33);
+        const int half = (warp - 2) >> 2;       // which 128 of the 256 accumulator columns this warp drains
+        float *stg = stg_all + (warp - 2) * (32 * 33);
         const int row = q * 32 + lane;
         const float alpha = P.epi.alpha;
         const int flags = P.epi.flags;
@@ -210,16 +212,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if (res_f32 || j < 4) buf[j] = src[j];
             };
             uint4 rcur[8], rnext[8];
-            res_fetch(nt * BN, rcur);
+            if (res_row != nullptr && row_ok) {     // pull this thread's residual segment towards L2 while the MMAs run
+                const char *pf = res_row + (int64_t)(nt * BN + half * (BN / 2)) * (res_f32 ? 4 : 2);
+                const int bytes = (BN / 2) * (res_f32 ? 4 : 2);
+                for (int b = 0; b < bytes; b += 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + b));
+            }
+            res_fetch(nt * BN + half * (BN / 2), rcur);
             mbar_wait(&tfull[as], ((uint32_t)it >> 1) & 1u);
             tc_fence_after();
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
                 const int n0 = nt * BN + c0;
                 if (n0 >= g.N) break;   // warp-uniform
                 uint32_t v[32];
                 __syncwarp();           // tcgen05.ld is .sync.aligned: reconverge after the row mask
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
-                if (c0 + 32 < BN) res_fetch(n0 + 32, rnext);
+                if (c0 + 32 < (half + 1) * (BN / 2)) res_fetch(n0 + 32, rnext);
                 tmem_ld_wait();
                 if (row_ok) {
                 float x[32];
