@@ -180,6 +180,10 @@ typedef struct smz_vasnet_params {
     const float *b1, *w2, *b2, *ln_g, *ln_b;
     float scale, eps;
     int32_t aperture, ignore_self;
+    /* optional (inference): head_gw [1024] = ln_g * w2 and head_c [2] = {sum(ln_g * w2), sum(ln_b * w2) + b2}
+     * (float32, device).  When both are given the regressor head (vasnet.py:143-145) is folded into the k1
+     * GEMM epilogue and the hidden activations never reach memory; NULL keeps the separate head kernel. */
+    const float *head_gw, *head_c;
 } smz_vasnet_params;
 
 /* x: packed features [sum T, 1024] (float32, or bfloat16 when x_is_bf16), video v owns rows

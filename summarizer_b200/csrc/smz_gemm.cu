@@ -212,6 +212,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if (res_f32 || j < 4) buf[j] = src[j];
             };
             uint4 rcur[8], rnext[8];
+            float st1 = 0.f, st2 = 0.f, st3 = 0.f;      // GEMM_ROWSTATS accumulators of this thread's row
             if (res_row != nullptr && row_ok) {     // pull this thread's residual segment towards L2 while the MMAs run
                 const char *pf = res_row + (int64_t)(nt * BN + half * (BN / 2)) * (res_f32 ? 4 : 2);
                 const int bytes = (BN / 2) * (res_f32 ? 4 : 2);
@@ -282,6 +283,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                     for (int j = 0; j < 32; j++) x[j] = fmaxf(x[j], 0.f);
                 }
+                if (flags & smz::GEMM_ROWSTATS) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (full32 || n0 + j < g.N) {
+                            st1 += x[j];
+                            st2 = fmaf(x[j], x[j], st2);
+                            st3 = fmaf(x[j], __ldg(P.epi.stat_w + n0 + j), st3);
+                        }
+                }
+                if (!(flags & smz::GEMM_NO_STORE)) {
                 const int64_t co = g.c_off + (int64_t)m * g.ldc + n0;
                 if (out_f32) {
                     float *dst = reinterpret_cast<float *>(P.epi.C) + co;
@@ -308,8 +319,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         for (int j = 0; j < 32; j++) if (n0 + j < g.N) dst[j] = __float2bfloat16_rn(x[j]);
                     }
                 }
+                }   // !GEMM_NO_STORE
                 }   // row_ok
-                if (out_f32 && n0 + 32 <= g.N) {       // warp-uniform: coalesced 128-byte row stores
+                if (out_f32 && n0 + 32 <= g.N && !(flags & smz::GEMM_NO_STORE)) {   // warp-uniform: coalesced 128-byte row stores
                     __syncwarp();
                     const int m_base = m - lane;       // first row of this warp's 32 accumulator rows
                     float *base = reinterpret_cast<float *>(P.epi.C) + g.c_off + n0 + lane;
@@ -320,6 +332,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
 #pragma unroll
                 for (int j = 0; j < 8; j++) rcur[j] = rnext[j];
+            }
+            if ((flags & smz::GEMM_ROWSTATS) && row_ok) {
+                float *so = P.epi.stat_out + ((int64_t)m * (2 * g.tiles_n) + (nt * 2 + half)) * 3;
+                so[0] = st1; so[1] = st2; so[2] = st3;
             }
             tc_fence_before();
             if (PAIR) mbar_arrive_remote(&tempty[as], 0); else mbar_arrive(&tempty[as]);

@@ -24,6 +24,10 @@ enum : int {
     GEMM_RELU = 2,       // max(x, 0) last
     GEMM_RES_F32 = 4,    // residual is float32 (default bf16)
     GEMM_BIAS_M = 8,     // bias indexed by row m (default: by column n)
+    GEMM_ROWSTATS = 16,  // per row and (n-tile, column half) slot: sum x, sum x^2, sum x * stat_w[n] of the epilogue
+                         // OUTPUT x -> stat_out[(m * 2 * tiles_n + slot) * 3 + {0,1,2}] (LayerNorm + dot folded into
+                         // the producer: the consumer needs three numbers per row, not the row)
+    GEMM_NO_STORE = 32,  // do not write C (only meaningful with GEMM_ROWSTATS)
 };
 
 struct GemmEpilogue {
@@ -32,6 +36,8 @@ struct GemmEpilogue {
     const void *residual;    // optional, added after bias
     float alpha;
     int flags;
+    const float *stat_w = nullptr;   // GEMM_ROWSTATS: weight vector [N]
+    float *stat_out = nullptr;       // GEMM_ROWSTATS: [M][2 * tiles_n][3]
 };
 
 constexpr int GEMM_BN = 256;

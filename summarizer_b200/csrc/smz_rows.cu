@@ -255,6 +255,22 @@ head_kernel(const float *__restrict__ h, const uint8_t *__restrict__ keep, const
 }
 
 
+__global__ void head_from_stats_kernel(const float *__restrict__ stats, int slots, const float *__restrict__ c, float eps,
+                                       int rows, float *__restrict__ scores) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (int k = 0; k < slots; k++) {                         // fixed order: bitwise reproducible
+        const float *p = stats + ((int64_t)r * slots + k) * 3;
+        s1 += p[0]; s2 += p[1]; s3 += p[2];
+    }
+    const float mu = s1 * (1.f / kFeat);
+    const float var = fmaxf(s2 * (1.f / kFeat) - mu * mu, 0.f);
+    const float rs = rsqrtf(var + eps);
+    const float z = rs * (s3 - mu * __ldg(c)) + __ldg(c + 1);
+    scores[r] = 1.f / (1.f + __expf(-z));
+}
+
 // ---- backward row kernels -------------------------------------------------------------------------
 // Column sums over rows (bias / LayerNorm-affine / k2 gradients) are accumulated per CTA in shared
 // memory and flushed with one float atomic per column and CTA.
@@ -432,6 +448,14 @@ softmax_bwd_kernel(const float *__restrict__ dP, const __nv_bfloat16 *__restrict
 }  // namespace
 
 namespace smz {
+
+int launch_head_from_stats(const float *stats, int slots, const float *c, float eps, int rows, float *scores,
+                           cudaStream_t st) {
+    if (rows <= 0) return SMZ_OK;
+    head_from_stats_kernel<<<(rows + 255) / 256, 256, 0, st>>>(stats, slots, c, eps, rows, scores);
+    SMZ_CUDA_CHECK(cudaGetLastError());
+    return SMZ_OK;
+}
 
 int launch_head_bwd(const float *h, const uint8_t *keep, const float *g, const float *b, const float *w2,
                     const float *mean, const float *rstd, const float *scores, const float *dscores, int rows,

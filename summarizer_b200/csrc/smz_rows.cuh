@@ -29,6 +29,12 @@ int launch_head(const float *h, const uint8_t *keep, const float *g, const float
                 const float *w2, const float *b2, int rows, float *scores, float *mean, float *rstd,
                 cudaStream_t st);
 
+// score = sigmoid(LayerNorm(h) . w2 + b2) from the three row sums the k1 GEMM epilogue left behind
+// (GEMM_ROWSTATS: sum h, sum h^2, sum h * (g * w2) per slot):  z = rstd * (S3 - mean * c[0]) + c[1] with
+// c[0] = sum g*w2, c[1] = sum b*w2 + b2.  stats: [rows][slots][3].
+int launch_head_from_stats(const float *stats, int slots, const float *c, float eps, int rows, float *scores,
+                           cudaStream_t st);
+
 // ---- backward (autograd of vasnet.py:136-145 and :129-130) -----------------------------------------
 // Regressor head + second LayerNorm + ReLU: dh = d(loss)/d(k1 pre-activation) as bf16; accumulates
 // (+=, float32 atomics) d_w2, d_b2, d_g, d_b (LayerNorm affine) and d_b1 (column sums of dh).

@@ -48,7 +48,7 @@ struct Plan {
     int64_t rows_cap = 0;   // row capacity of the row-wise buffers (and stride of the stats arrays)
     int lanes = 1;          // inference with several chunks: two copies of the recycled buffers, one per stream
     int64_t lane_bytes = 0;
-    int64_t off_xb, off_qk, off_vt, off_o, off_y, off_yn, off_h, off_s, off_p, off_alpha, off_probs, off_dropoff,
+    int64_t off_xb, off_qk, off_vt, off_o, off_y, off_yn, off_h, off_s, off_p, off_alpha, off_hstat, off_probs, off_dropoff,
         off_stats, total;
     // backward-only buffers (training)
     int64_t off_dh, off_dyn, off_dy, off_dyf, off_do, off_dqk, off_dvt, off_dp, off_ds;
@@ -111,6 +111,7 @@ int make_plan(const int32_t *cu, int n_videos, bool training, bool x_bf16, Plan 
     pl->off_s = take(LG * 4);
     pl->off_p = take(LG * 2);
     pl->off_alpha = take(training ? LG * 2 : 0);
+    pl->off_hstat = take(training ? 0 : R * (2 * kFeat / smz::GEMM_BN) * 3 * 4);   // fused head: [R][8 slots][3]
     pl->lane_bytes = o;
     pl->lanes = (!training && pl->chunks.size() > 1) ? 2 : 1;
     if (pl->lanes == 2) o += pl->lane_bytes;     // second copy of everything above
@@ -341,7 +342,22 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
                                    stats, stats ? stats + Rs : nullptr, st);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "layernorm");
+        const bool fused_head = !training && p->head_gw != nullptr && p->head_c != nullptr;
         smz::profile_mark(st, "gemm_k1");
+        if (fused_head) {
+            // inference: H never reaches memory — the k1 epilogue reduces relu(h) to the three row sums the second
+            // LayerNorm + k2 dot need (GEMM_ROWSTATS), a one-thread-per-frame kernel finishes the score
+            float *hstat = reinterpret_cast<float *>(w + pl.off_hstat + lb);
+            GemmEpilogue e{h, p->b1, nullptr, 1.f, smz::GEMM_RELU | smz::GEMM_OUT_F32 | smz::GEMM_ROWSTATS | smz::GEMM_NO_STORE};
+            e.stat_w = p->head_gw; e.stat_out = hstat;
+            rc = smz::gemm_bf16_tn(yn, R, kFeat, kFeat, p->w1, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
+                                   dense_problem(R, kFeat, kFeat, kFeat, 0), e, st);
+            if (rc != SMZ_OK) return rc;
+            SMZ_DEBUG_STEP(st, "gemm_k1");
+            smz::profile_mark(st, "head");
+            rc = smz::launch_head_from_stats(hstat, 2 * kFeat / smz::GEMM_BN, p->head_c, p->eps, R, scores + c.row0, st);
+            if (rc != SMZ_OK) return rc;
+        } else {
         rc = smz::gemm_bf16_tn(yn, R, kFeat, kFeat, p->w1, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
                                dense_problem(R, kFeat, kFeat, kFeat, 0), GemmEpilogue{h, p->b1, nullptr, 1.f, smz::GEMM_RELU | smz::GEMM_OUT_F32}, st);
         if (rc != SMZ_OK) return rc;
@@ -350,6 +366,7 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
         rc = smz::launch_head(h, drop_h ? drop_h + (int64_t)c.row0 * kFeat : nullptr, p->ln_g, p->ln_b, p->eps, p->w2, p->b2,
                               R, scores + c.row0, stats ? stats + 2 * Rs : nullptr, stats ? stats + 3 * Rs : nullptr, st);
         if (rc != SMZ_OK) return rc;
+        }
         SMZ_DEBUG_STEP(st, "head");
         smz::profile_mark(st, "");
     }

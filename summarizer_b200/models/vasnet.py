@@ -23,7 +23,7 @@ class VasnetParams(C.Structure):
     _fields_ = [("wqk", C.c_void_p), ("wv", C.c_void_p), ("wo", C.c_void_p), ("w1", C.c_void_p),
                 ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("ln_g", C.c_void_p),
                 ("ln_b", C.c_void_p), ("scale", C.c_float), ("eps", C.c_float), ("aperture", C.c_int32),
-                ("ignore_self", C.c_int32)]
+                ("ignore_self", C.c_int32), ("head_gw", C.c_void_p), ("head_c", C.c_void_p)]
 
 
 def _cu_seqlens(lengths):
@@ -115,11 +115,15 @@ class VASNet(nn.Module):
                     b1=self.k1.bias.float().contiguous(), w2=self.k2.weight.float().reshape(-1).contiguous(),
                     b2=self.k2.bias.float().contiguous(), ln_g=self.layer_norm.weight.float().contiguous(),
                     ln_b=self.layer_norm.bias.float().contiguous())
+                # regressor head folded into the k1 epilogue (inference): z = rstd * (sum h*gw - mean * c0) + c1
+                sh["head_gw"] = (sh["ln_g"] * sh["w2"]).contiguous()
+                sh["head_c"] = torch.stack([sh["head_gw"].sum(), (sh["ln_b"] * sh["w2"]).sum() + sh["b2"][0]]).contiguous()
             self._shadow, self._shadow_key = sh, key
         sh = self._shadow
         st = VasnetParams(*(sh[k].data_ptr() for k in ("wqk", "wv", "wo", "w1", "b1", "w2", "b2", "ln_g", "ln_b")),
                           float(self.scale), float(self.epsilon),
-                          -1 if self.aperture is None else int(self.aperture), int(bool(self.ignore_self)))
+                          -1 if self.aperture is None else int(self.aperture), int(bool(self.ignore_self)),
+                          sh["head_gw"].data_ptr(), sh["head_c"].data_ptr())
         return sh, st
 
     def score_packed(self, x, lengths):
