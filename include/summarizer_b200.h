@@ -194,6 +194,10 @@ typedef struct smz_vasnet_params {
  * NULL = no dropout at that site): drop_att packed per video [T*T], drop_y / drop_h [sum T, 1024]. */
 int smz_vasnet_workspace_bytes(const int32_t *h_cu_seqlens, int n_videos, int training, int x_is_bf16,
                                int64_t *bytes);
+/* Inference computes attention as exp(logit) / row sum straight out of the logits GEMM epilogue and falls back,
+ * on the device, to the max-subtracted softmax when a |logit| exceeds 80.  on != 0 forces the fallback path for
+ * every call of this process (testing / A-B aid). */
+void smz_vasnet_set_exact_softmax(int on);
 int smz_vasnet_launch_count(const int32_t *h_cu_seqlens, int n_videos, int training, int x_is_bf16,
                             int64_t *launches);   /* kernels one forward call launches (reporting) */
 int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h_cu_seqlens, int n_videos,

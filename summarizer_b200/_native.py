@@ -52,6 +52,7 @@ SIGNATURES = {
     "smz_upsample": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
     "smz_rank_correlation": (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P]),
     "smz_vasnet_workspace_bytes": (_I, [_P, _I, _I, _I, C.POINTER(C.c_int64)]),
+    "smz_vasnet_set_exact_softmax": (None, [_I]),
     "smz_vasnet_launch_count": (_I, [_P, _I, _I, _I, C.POINTER(C.c_int64)]),
     "smz_vasnet_forward": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _L, _P]),
     "smz_vasnet_backward": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),

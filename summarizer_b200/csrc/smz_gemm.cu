@@ -73,7 +73,13 @@ __device__ __forceinline__ float4 ld_f4(const float *p) { return *reinterpret_ca
 // core with the MN-major canonical layout (LBO = one box = 8 KB between 64-element m/n groups, SBO =
 // 1 KB between 8-row k groups, +2 KB per K=16 slice).  This is what lets the backward pass run
 // dX = dY.W and dW = dY^T.X on the row-major activations without materialising any transpose.
-template <bool A_MN, bool B_MN, bool PAIR>
+// EPI selects the epilogue at COMPILE time (the epilogue must stay shorter than the MMA time of a tile, so the
+// special modes cannot be paid for by the plain one): EPI_PLAIN = alpha / bias or row scale / residual / ReLU /
+// store; EPI_HEAD = bias + ReLU + three row sums, no store (GEMM_ROWSTATS | GEMM_NO_STORE); EPI_EXP = masked exp +
+// row sum + bf16 store (GEMM_EXP | GEMM_ROWSTATS).
+enum { EPI_PLAIN = 0, EPI_HEAD = 1, EPI_EXP = 2 };
+
+template <bool A_MN, bool B_MN, bool PAIR, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params P) {
     constexpr int STAGES = Cfg<PAIR>::STAGES, B_STAGE = Cfg<PAIR>::B_STAGE, B_ROWS = Cfg<PAIR>::B_ROWS;
@@ -89,6 +95,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
     float *stg_all = reinterpret_cast<float *>(smem + STAGES * (A_STAGE + B_STAGE) + BAR_BYTES);
 
+    if (P.epi.gate != nullptr && __ldg(P.epi.gate) == 0) return;  // gated launch (fallback path not needed): every CTA leaves
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = PAIR ? (int)cluster_ctarank() : 0;           // 0 = leader CTA of the pair
     const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -193,7 +200,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int as = it & 1;
             const int m = mt * TILE_M + rank * BM + row;
             const bool row_ok = m < g.M;
-            const float bias_m = (P.epi.bias != nullptr && (flags & smz::GEMM_BIAS_M) && row_ok) ? __ldg(P.epi.bias + m) : 0.f;
+            const float bias_m = (P.epi.bias != nullptr && (flags & smz::GEMM_BIAS_M) && !(flags & smz::GEMM_SCALE_M) && row_ok) ? __ldg(P.epi.bias + m) : 0.f;
             const bool out_f32 = flags & smz::GEMM_OUT_F32;
             const bool res_f32 = flags & smz::GEMM_RES_F32;
             const bool c_vec = ((g.c_off | (int64_t)g.ldc) & 7) == 0 && (reinterpret_cast<uintptr_t>(P.epi.C) & 15) == 0;
@@ -213,7 +220,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             };
             uint4 rcur[8], rnext[8];
             float st1 = 0.f, st2 = 0.f, st3 = 0.f;      // GEMM_ROWSTATS accumulators of this thread's row
-            if (res_row != nullptr && row_ok) {     // pull this thread's residual segment towards L2 while the MMAs run
+            constexpr bool do_exp = EPI == EPI_EXP;
+            const int n_store = do_exp ? ((g.N + 63) & ~63) : g.N;   // GEMM_EXP also writes the zero padding columns
+            float amax = 0.f;
+            if (EPI == EPI_PLAIN && res_row != nullptr && row_ok) {     // pull this thread's residual segment towards L2 while the MMAs run
                 const char *pf = res_row + (int64_t)(nt * BN + half * (BN / 2)) * (res_f32 ? 4 : 2);
                 const int bytes = (BN / 2) * (res_f32 ? 4 : 2);
                 for (int b = 0; b < bytes; b += 128)
@@ -224,7 +234,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tc_fence_after();
             for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
                 const int n0 = nt * BN + c0;
-                if (n0 >= g.N) break;   // warp-uniform
+                if (n0 >= n_store) break;   // warp-uniform
                 uint32_t v[32];
                 __syncwarp();           // tcgen05.ld is .sync.aligned: reconverge after the row mask
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
@@ -234,8 +244,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 float x[32];
 #pragma unroll
                 for (int j = 0; j < 32; j++) x[j] = alpha * __uint_as_float(v[j]);
-                const bool full32 = n0 + 32 <= g.N;
-                if (P.epi.bias != nullptr) {
+                const bool full32 = n0 + 32 <= n_store;
+                if constexpr (do_exp) {
+                    const int ap = P.epi.aperture, ig = P.epi.ignore_self;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const int col = n0 + j;
+                        float e = x[j];
+                        bool live = col < g.N;
+                        if (ig && col == m) live = false;                                   // vasnet.py:121-122
+                        if (ap >= 0) {                                                      // vasnet.py:124-127
+                            int d = m - col; d = d < 0 ? -d : d;
+                            if (d > ap || e * e == 0.f) live = false;
+                        }
+                        if (live) amax = fmaxf(amax, fabsf(e));
+                        x[j] = live ? __expf(e) : 0.f;
+                    }
+                }
+                if (EPI == EPI_PLAIN && (flags & smz::GEMM_SCALE_M)) {
+                    const float sc = __ldg(P.epi.bias + g.r_off + m);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) x[j] *= sc;
+                }
+                if (EPI != EPI_EXP && P.epi.bias != nullptr && !(flags & smz::GEMM_SCALE_M)) {
                     if (flags & smz::GEMM_BIAS_M) {
 #pragma unroll
                         for (int j = 0; j < 32; j++) x[j] += bias_m;
@@ -250,7 +281,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         for (int j = 0; j < 32; j++) if (n0 + j < g.N) x[j] += __ldg(P.epi.bias + n0 + j);
                     }
                 }
-                if (res_row != nullptr) {
+                if (EPI == EPI_PLAIN && res_row != nullptr) {
                     if (res_vec_ok(n0)) {
                         if (res_f32) {
 #pragma unroll
@@ -279,20 +310,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         for (int j = 0; j < 32; j++) if (n0 + j < g.N) x[j] += __bfloat162float(r[j]);
                     }
                 }
-                if (flags & smz::GEMM_RELU) {
+                if (EPI != EPI_EXP && (flags & smz::GEMM_RELU)) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) x[j] = fmaxf(x[j], 0.f);
                 }
-                if (flags & smz::GEMM_ROWSTATS) {
+                if constexpr (EPI == EPI_HEAD) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        if (full32 || n0 + j < g.N) {
-                            st1 += x[j];
-                            st2 = fmaf(x[j], x[j], st2);
-                            st3 = fmaf(x[j], __ldg(P.epi.stat_w + n0 + j), st3);
-                        }
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 sw = ld_f4(P.epi.stat_w + n0 + j);      // N is a multiple of 32 in this mode
+                        st1 += (x[j] + x[j + 1]) + (x[j + 2] + x[j + 3]);
+                        st2 = fmaf(x[j], x[j], st2); st2 = fmaf(x[j + 1], x[j + 1], st2);
+                        st2 = fmaf(x[j + 2], x[j + 2], st2); st2 = fmaf(x[j + 3], x[j + 3], st2);
+                        st3 = fmaf(x[j], sw.x, st3); st3 = fmaf(x[j + 1], sw.y, st3);
+                        st3 = fmaf(x[j + 2], sw.z, st3); st3 = fmaf(x[j + 3], sw.w, st3);
+                    }
                 }
-                if (!(flags & smz::GEMM_NO_STORE)) {
+                if constexpr (EPI == EPI_EXP) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) st1 += (x[j] + x[j + 1]) + (x[j + 2] + x[j + 3]);   // dead columns hold 0
+                }
+                if constexpr (EPI != EPI_HEAD) {
                 const int64_t co = g.c_off + (int64_t)m * g.ldc + n0;
                 if (out_f32) {
                     float *dst = reinterpret_cast<float *>(P.epi.C) + co;
@@ -321,7 +358,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
                 }   // !GEMM_NO_STORE
                 }   // row_ok
-                if (out_f32 && n0 + 32 <= g.N && !(flags & smz::GEMM_NO_STORE)) {   // warp-uniform: coalesced 128-byte row stores
+                if (EPI == EPI_PLAIN && out_f32 && n0 + 32 <= g.N) {   // warp-uniform: coalesced 128-byte row stores
                     __syncwarp();
                     const int m_base = m - lane;       // first row of this warp's 32 accumulator rows
                     float *base = reinterpret_cast<float *>(P.epi.C) + g.c_off + n0 + lane;
@@ -333,10 +370,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                 for (int j = 0; j < 8; j++) rcur[j] = rnext[j];
             }
-            if ((flags & smz::GEMM_ROWSTATS) && row_ok) {
-                float *so = P.epi.stat_out + ((int64_t)m * (2 * g.tiles_n) + (nt * 2 + half)) * 3;
+            if (EPI != EPI_PLAIN && row_ok) {
+                const int slots = P.epi.stat_slots > 0 ? P.epi.stat_slots : 2 * g.tiles_n;
+                float *so = P.epi.stat_out + ((g.r_off + m) * slots + (nt * 2 + half)) * 3;
                 so[0] = st1; so[1] = st2; so[2] = st3;
             }
+            if (do_exp && P.epi.guard != nullptr && !(amax <= 80.f)) atomicOr(P.epi.guard, 1);   // also catches NaN
             tc_fence_before();
             if (PAIR) mbar_arrive_remote(&tempty[as], 0); else mbar_arrive(&tempty[as]);
         }
@@ -406,10 +445,22 @@ template <bool PAIR>
 static int launch_variant(bool a_mn, bool b_mn, const CUtensorMap &ma, const CUtensorMap &mb, const Params &P, int total_tiles,
                           cudaStream_t st) {
     typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const Params);
-    const kern_t kern = a_mn ? (b_mn ? (kern_t)gemm_kernel<true, true, PAIR> : (kern_t)gemm_kernel<true, false, PAIR>)
-                             : (b_mn ? (kern_t)gemm_kernel<false, true, PAIR> : (kern_t)gemm_kernel<false, false, PAIR>);
-    const int variant = (a_mn ? 2 : 0) + (b_mn ? 1 : 0);
-    static bool attr_set[64][4] = {{false}};
+    const int f = P.epi.flags;
+    const int epi = (f & GEMM_EXP) ? EPI_EXP : (f & GEMM_ROWSTATS) ? EPI_HEAD : EPI_PLAIN;
+    kern_t kern;
+    if (epi != EPI_PLAIN) {
+        if (a_mn || b_mn) return fail(SMZ_ERR_UNSUPPORTED, "gemm: the fused head / exp epilogues exist for K-major operands only");
+        if (epi == EPI_HEAD && (!(f & GEMM_NO_STORE) || P.epi.stat_w == nullptr || P.epi.stat_out == nullptr))
+            return fail(SMZ_ERR_ARG, "gemm: GEMM_ROWSTATS needs GEMM_NO_STORE, stat_w and stat_out");
+        if (epi == EPI_EXP && (!(f & GEMM_ROWSTATS) || (f & GEMM_OUT_F32) || P.epi.stat_out == nullptr))
+            return fail(SMZ_ERR_ARG, "gemm: GEMM_EXP writes bf16 and needs GEMM_ROWSTATS + stat_out");
+        kern = epi == EPI_HEAD ? (kern_t)gemm_kernel<false, false, PAIR, EPI_HEAD> : (kern_t)gemm_kernel<false, false, PAIR, EPI_EXP>;
+    } else {
+        kern = a_mn ? (b_mn ? (kern_t)gemm_kernel<true, true, PAIR, EPI_PLAIN> : (kern_t)gemm_kernel<true, false, PAIR, EPI_PLAIN>)
+                    : (b_mn ? (kern_t)gemm_kernel<false, true, PAIR, EPI_PLAIN> : (kern_t)gemm_kernel<false, false, PAIR, EPI_PLAIN>);
+    }
+    const int variant = epi != EPI_PLAIN ? 3 + epi : (a_mn ? 2 : 0) + (b_mn ? 1 : 0);
+    static bool attr_set[64][6] = {{false}};
     int dev = 0;
     SMZ_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !attr_set[dev][variant]) {

@@ -28,6 +28,10 @@ enum : int {
                          // OUTPUT x -> stat_out[(m * 2 * tiles_n + slot) * 3 + {0,1,2}] (LayerNorm + dot folded into
                          // the producer: the consumer needs three numbers per row, not the row)
     GEMM_NO_STORE = 32,  // do not write C (only meaningful with GEMM_ROWSTATS)
+    GEMM_EXP = 64,       // attention logits: x = exp(mask(alpha * acc)) written as bf16 with zero columns up to the next
+                         // multiple of 64 (un-normalised softmax numerators; the row sums come from GEMM_ROWSTATS).
+                         // |logit| > 80 anywhere raises *guard (the caller then re-runs the exact max-subtracted path)
+    GEMM_SCALE_M = 128,  // x *= bias[r_off + m]  (row scale, e.g. 1 / softmax denominator) instead of adding a bias
 };
 
 struct GemmEpilogue {
@@ -36,8 +40,12 @@ struct GemmEpilogue {
     const void *residual;    // optional, added after bias
     float alpha;
     int flags;
-    const float *stat_w = nullptr;   // GEMM_ROWSTATS: weight vector [N]
-    float *stat_out = nullptr;       // GEMM_ROWSTATS: [M][2 * tiles_n][3]
+    const float *stat_w = nullptr;   // GEMM_ROWSTATS: weight vector [N] (optional)
+    float *stat_out = nullptr;       // GEMM_ROWSTATS: [(r_off + m)][stat_slots][3] (r_off doubles as the row offset here)
+    int stat_slots = 0;              // slots per row (>= 2 * tiles_n); 0 = 2 * tiles_n of the problem
+    int aperture = -1, ignore_self = 0;   // GEMM_EXP: VASNet's masks (vasnet.py:121-127), row / column = video-local i / j
+    int *guard = nullptr;            // GEMM_EXP: set to 1 when a logit leaves [-80, 80]
+    const int *gate = nullptr;       // when given: the whole launch is a no-op unless *gate != 0
 };
 
 constexpr int GEMM_BN = 256;

@@ -58,10 +58,13 @@ __device__ __forceinline__ float mask_logit(float e, int i, int j, int aperture,
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 softmax_kernel(const GemmProblem *__restrict__ probs, int n_probs, int total_rows, const float *__restrict__ S,
                __nv_bfloat16 *__restrict__ alpha, __nv_bfloat16 *__restrict__ P, const uint8_t *__restrict__ drop,
-               const int64_t *__restrict__ drop_off, int aperture, int ignore_self) {
+               const int64_t *__restrict__ drop_off, int aperture, int ignore_self, const int *__restrict__ gate,
+               float *__restrict__ inv_l) {
+    if (gate != nullptr && __ldg(gate) == 0) return;
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     if (r >= total_rows) return;
+    if (inv_l != nullptr && lane == 0) inv_l[r] = 1.f;     // P is normalised here: alpha.V applies no further row scale
     int lo = 0, hi = n_probs - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -271,6 +274,14 @@ __global__ void head_from_stats_kernel(const float *__restrict__ stats, int slot
     scores[r] = 1.f / (1.f + __expf(-z));
 }
 
+__global__ void rowsum_finish_kernel(const float *__restrict__ stats, int slots, int rows, float *__restrict__ inv_l) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float s = 0.f;
+    for (int k = 0; k < slots; k++) s += stats[((int64_t)r * slots + k) * 3];
+    inv_l[r] = 1.f / s;           // a fully masked row: 1/0 = inf -> NaN scores, as torch's softmax of all -inf
+}
+
 // ---- backward row kernels -------------------------------------------------------------------------
 // Column sums over rows (bias / LayerNorm-affine / k2 gradients) are accumulated per CTA in shared
 // memory and flushed with one float atomic per column and CTA.
@@ -449,6 +460,13 @@ softmax_bwd_kernel(const float *__restrict__ dP, const __nv_bfloat16 *__restrict
 
 namespace smz {
 
+int launch_rowsum_finish(const float *stats, int slots, int rows, float *inv_l, cudaStream_t st) {
+    if (rows <= 0) return SMZ_OK;
+    rowsum_finish_kernel<<<(rows + 255) / 256, 256, 0, st>>>(stats, slots, rows, inv_l);
+    SMZ_CUDA_CHECK(cudaGetLastError());
+    return SMZ_OK;
+}
+
 int launch_head_from_stats(const float *stats, int slots, const float *c, float eps, int rows, float *scores,
                            cudaStream_t st) {
     if (rows <= 0) return SMZ_OK;
@@ -499,10 +517,10 @@ int launch_cvt_bf16(const float *x, __nv_bfloat16 *y, int64_t n, cudaStream_t st
 
 int launch_softmax(const GemmProblem *d_probs, int n_probs, int total_rows, const float *S, __nv_bfloat16 *alpha,
                    __nv_bfloat16 *P, const uint8_t *drop, const int64_t *d_drop_off, int aperture, int ignore_self,
-                   cudaStream_t st) {
+                   cudaStream_t st, const int *gate, float *inv_l) {
     if (total_rows <= 0) return SMZ_OK;
     softmax_kernel<<<(total_rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, st>>>(
-        d_probs, n_probs, total_rows, S, alpha, P, drop, d_drop_off, aperture, ignore_self);
+        d_probs, n_probs, total_rows, S, alpha, P, drop, d_drop_off, aperture, ignore_self, gate, inv_l);
     SMZ_CUDA_CHECK(cudaGetLastError());
     return SMZ_OK;
 }

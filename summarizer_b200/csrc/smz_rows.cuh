@@ -16,9 +16,13 @@ int launch_cvt_bf16(const float *x, __nv_bfloat16 *y, int64_t n, cudaStream_t st
 // drop (optional): keep-mask bytes of the attention dropout, video v at drop + drop_off[v]; then
 // P = 2 * keep * alpha, else P == alpha (one buffer).  A row of P holds probs[v].pad zero columns, the
 // T probabilities, then zeros up to the next multiple of 64 (the K extent alpha.V reads).
+// gate (optional): the launch is a no-op unless *gate != 0; inv_l (optional): set to 1 for every row processed
+// (the row scale the alpha.V GEMM applies after the fused-exp logits path, see smz_vasnet.cu).
 int launch_softmax(const GemmProblem *d_probs, int n_probs, int total_rows, const float *S, __nv_bfloat16 *alpha,
                    __nv_bfloat16 *P, const uint8_t *drop, const int64_t *d_drop_off, int aperture, int ignore_self,
-                   cudaStream_t st);
+                   cudaStream_t st, const int *gate = nullptr, float *inv_l = nullptr);
+// inv_l[r] = 1 / sum_k stats[(r * slots + k) * 3]   (softmax denominators from the GEMM_ROWSTATS slots)
+int launch_rowsum_finish(const float *stats, int slots, int rows, float *inv_l, cudaStream_t st);
 
 // yn = LayerNorm(2*keep*y or y) * g + b  (vasnet.py:136-137), rows of 1024; optional mean / rstd.
 int launch_layernorm(const float *y, const uint8_t *keep, const float *g, const float *b, float eps, int rows,

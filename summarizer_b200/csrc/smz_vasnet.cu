@@ -48,7 +48,7 @@ struct Plan {
     int64_t rows_cap = 0;   // row capacity of the row-wise buffers (and stride of the stats arrays)
     int lanes = 1;          // inference with several chunks: two copies of the recycled buffers, one per stream
     int64_t lane_bytes = 0;
-    int64_t off_xb, off_qk, off_vt, off_o, off_y, off_yn, off_h, off_s, off_p, off_alpha, off_hstat, off_probs, off_dropoff,
+    int64_t off_xb, off_qk, off_vt, off_o, off_y, off_yn, off_h, off_s, off_p, off_alpha, off_hstat, off_sstat, off_invl, off_probs, off_dropoff,
         off_stats, total;
     // backward-only buffers (training)
     int64_t off_dh, off_dyn, off_dy, off_dyf, off_do, off_dqk, off_dvt, off_dp, off_ds;
@@ -112,6 +112,13 @@ int make_plan(const int32_t *cu, int n_videos, bool training, bool x_bf16, Plan 
     pl->off_p = take(LG * 2);
     pl->off_alpha = take(training ? LG * 2 : 0);
     pl->off_hstat = take(training ? 0 : R * (2 * kFeat / smz::GEMM_BN) * 3 * 4);   // fused head: [R][8 slots][3]
+    {   // fused-exp attention (inference): row-sum slots [sub rows][2 * ceil(ld / 256)][3] + guard word, 1 / denominators
+        int64_t srows = 0, slots = 0;
+        for (const Chunk &c : pl->chunks)
+            for (const Sub &s : c.subs) { if (s.rows > srows) srows = s.rows; const int64_t k = 2 * ((s.ld + 255) / 256); if (k > slots) slots = k; }
+        pl->off_sstat = take(training ? 0 : srows * slots * 12 + 64);
+        pl->off_invl = take(training ? 0 : srows * 4);
+    }
     pl->lane_bytes = o;
     pl->lanes = (!training && pl->chunks.size() > 1) ? 2 : 1;
     if (pl->lanes == 2) o += pl->lane_bytes;     // second copy of everything above
@@ -152,12 +159,14 @@ void build_problems(const Plan &pl, const int32_t *cu, std::vector<GemmProblem> 
                 a.c_off = (int64_t)sub_row * s.ld; a.ldc = s.ld;
                 a.tiles_n = (T + smz::GEMM_BN - 1) / smz::GEMM_BN;
                 a.pad = lead;
+                a.r_off = sub_row;                      // row of the video inside the sub-chunk: GEMM_ROWSTATS slots
                 tile_s += smz::gemm_tiles(T, T);
                 GemmProblem &b = (*out)[n + v];
                 b.a_row0 = sub_row; b.a_col0 = 0; b.b_row0 = 0; b.b_col0 = crow - lead;
                 b.M = T; b.N = kFeat; b.K = T + lead; b.tile0 = tile_pv;
                 b.c_off = (int64_t)crow * kFeat; b.ldc = kFeat;
                 b.tiles_n = kFeat / smz::GEMM_BN;
+                b.r_off = sub_row;                      // GEMM_SCALE_M row index
                 tile_pv += smz::gemm_tiles(T, kFeat);
                 sub_row += T;
             }
@@ -192,6 +201,10 @@ GemmProblem dense_problem(int M, int N, int K, int ldc, int ldr) {
 }
 
 }  // namespace
+
+namespace { int g_exact_softmax = 0; }
+// Testing / A-B aid: on != 0 forces the exact (fp32 logits + max-subtracted softmax) attention path for inference.
+extern "C" void smz_vasnet_set_exact_softmax(int on) { g_exact_softmax = on; }
 
 extern "C" int smz_vasnet_workspace_bytes(const int32_t *h_cu_seqlens, int n_videos, int training, int x_is_bf16,
                                           int64_t *bytes) {
@@ -312,20 +325,51 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
                 tiles_s += smz::gemm_tiles(T, T);
                 tiles_pv += smz::gemm_tiles(T, kFeat);
             }
-            smz::profile_mark(st, "gemm_logits");
-            rc = smz::gemm_bf16_tn(qk, R, 2 * kFeat, 2 * kFeat, qk, R, 2 * kFeat, 2 * kFeat, d_probs + s.v0, nv, tiles_s,
-                                   GemmProblem{}, GemmEpilogue{S, nullptr, nullptr, p->scale, smz::GEMM_OUT_F32}, st);
-            if (rc != SMZ_OK) return rc;
-        SMZ_DEBUG_STEP(st, "gemm_logits");
-            smz::profile_mark(st, "softmax");
-            rc = smz::launch_softmax(d_probs + s.v0, nv, s.rows, S, alpha, P, drop_att, d_dropoff ? d_dropoff + s.v0 : nullptr,
-                                     p->aperture, p->ignore_self, st);
-            if (rc != SMZ_OK) return rc;
-        SMZ_DEBUG_STEP(st, "softmax");
+            // Inference fast path: the logits GEMM epilogue writes exp(logit) (bf16, un-normalised) and the row sums;
+            // alpha.V then scales row i by 1 / sum_i.  Softmax is shift invariant, so skipping the max subtraction is
+            // exact as long as no |logit| exceeds 80 (fp32 / bf16 exponent range); the epilogue checks that and, if it
+            // ever fails, raises the guard word that un-gates the exact path (fp32 logits + max-subtracted softmax),
+            // launched right behind and otherwise a no-op.  Needs every video of the sub-chunk 8-row aligned.
+            bool fast = !training && !g_exact_softmax;
+            for (int v = s.v0; v < s.v1 && fast; v++) fast = ((h_cu_seqlens[v] - c.row0) & 7) == 0;
+            float *sstat = reinterpret_cast<float *>(w + pl.off_sstat + lb);
+            float *inv_l = reinterpret_cast<float *>(w + pl.off_invl + lb);
+            const int slots = 2 * ((s.ld + 255) / 256);
+            int *guard = reinterpret_cast<int *>(sstat + (int64_t)s.rows * slots * 3);
+            if (fast) {
+                smz::profile_mark(st, "gemm_logits");
+                SMZ_CUDA_CHECK(cudaMemsetAsync(sstat, 0, ((int64_t)s.rows * slots * 3 + 1) * 4, st));
+                GemmEpilogue e{P, nullptr, nullptr, p->scale, smz::GEMM_EXP | smz::GEMM_ROWSTATS};
+                e.stat_out = sstat; e.stat_slots = slots; e.aperture = p->aperture; e.ignore_self = p->ignore_self; e.guard = guard;
+                rc = smz::gemm_bf16_tn(qk, R, 2 * kFeat, 2 * kFeat, qk, R, 2 * kFeat, 2 * kFeat, d_probs + s.v0, nv, tiles_s,
+                                       GemmProblem{}, e, st);
+                if (rc != SMZ_OK) return rc;
+                SMZ_DEBUG_STEP(st, "gemm_logits_exp");
+                smz::profile_mark(st, "softmax");
+                rc = smz::launch_rowsum_finish(sstat, slots, s.rows, inv_l, st);
+                if (rc != SMZ_OK) return rc;
+            }
+            {   // exact path: always in training mode, gated by the guard word otherwise
+                const int *gate = fast ? guard : nullptr;
+                if (!fast) smz::profile_mark(st, "gemm_logits");
+                GemmEpilogue e{S, nullptr, nullptr, p->scale, smz::GEMM_OUT_F32};
+                e.gate = gate;
+                rc = smz::gemm_bf16_tn(qk, R, 2 * kFeat, 2 * kFeat, qk, R, 2 * kFeat, 2 * kFeat, d_probs + s.v0, nv, tiles_s,
+                                       GemmProblem{}, e, st);
+                if (rc != SMZ_OK) return rc;
+                SMZ_DEBUG_STEP(st, "gemm_logits");
+                if (!fast) smz::profile_mark(st, "softmax");
+                rc = smz::launch_softmax(d_probs + s.v0, nv, s.rows, S, alpha, P, drop_att, d_dropoff ? d_dropoff + s.v0 : nullptr,
+                                         p->aperture, p->ignore_self, st, gate, fast ? inv_l : nullptr);
+                if (rc != SMZ_OK) return rc;
+                SMZ_DEBUG_STEP(st, "softmax");
+            }
             smz::profile_mark(st, "gemm_pv");
-            rc = smz::gemm_bf16_tn(P, s.rows, s.ld, s.ld, vt, kFeat, R, Rpad, d_probs + n + s.v0, nv, tiles_pv, GemmProblem{},
-                                   GemmEpilogue{o, nullptr, nullptr, 1.f, 0}, st);
-            if (rc != SMZ_OK) return rc;
+            {
+                GemmEpilogue e{o, fast ? inv_l : nullptr, nullptr, 1.f, fast ? smz::GEMM_SCALE_M : 0};
+                rc = smz::gemm_bf16_tn(P, s.rows, s.ld, s.ld, vt, kFeat, R, Rpad, d_probs + n + s.v0, nv, tiles_pv, GemmProblem{}, e, st);
+                if (rc != SMZ_OK) return rc;
+            }
         SMZ_DEBUG_STEP(st, "gemm_pv");
         }
         // output projection + residual, LayerNorm, k1 + ReLU, head
