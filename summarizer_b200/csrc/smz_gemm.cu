@@ -247,18 +247,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const bool full32 = n0 + 32 <= n_store;
                 if constexpr (do_exp) {
                     const int ap = P.epi.aperture, ig = P.epi.ignore_self;
+                    if (ap < 0 && !ig && n0 + 32 <= g.N) {      // warp-uniform common case: no masks, no column tail
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const int col = n0 + j;
-                        float e = x[j];
-                        bool live = col < g.N;
-                        if (ig && col == m) live = false;                                   // vasnet.py:121-122
-                        if (ap >= 0) {                                                      // vasnet.py:124-127
-                            int d = m - col; d = d < 0 ? -d : d;
-                            if (d > ap || e * e == 0.f) live = false;
+                        for (int j = 0; j < 32; j++) {
+                            amax = fmaxf(amax, fabsf(x[j]));
+                            x[j] = __expf(x[j]);
                         }
-                        if (live) amax = fmaxf(amax, fabsf(e));
-                        x[j] = live ? __expf(e) : 0.f;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const int col = n0 + j;
+                            float e = x[j];
+                            bool live = col < g.N;
+                            if (ig && col == m) live = false;                                   // vasnet.py:121-122
+                            if (ap >= 0) {                                                      // vasnet.py:124-127
+                                int d = m - col; d = d < 0 ? -d : d;
+                                if (d > ap || e * e == 0.f) live = false;
+                            }
+                            if (live) amax = fmaxf(amax, fabsf(e));
+                            x[j] = live ? __expf(e) : 0.f;
+                        }
                     }
                 }
                 if (EPI == EPI_PLAIN && (flags & smz::GEMM_SCALE_M)) {
