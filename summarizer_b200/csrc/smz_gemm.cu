@@ -4,13 +4,17 @@
 // (vasnet.py:114-140), DSN's LSTM input projection (dsn.py:45) and the reward Gram matrix
 // (dsn.py:215-216,226-228).
 //
-// Structure (one persistent CTA per SM, 320 threads, warp-specialised):
-//   warp 0      TMA producer: 128x64 (A) and 256x64 (B) bf16 boxes, 128-byte swizzle, 4-stage
-//               mbarrier ring (48 KB per stage).
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256, K=16) into one of two
-//               256-column TMEM accumulators; tcgen05.commit releases smem stages / publishes tiles.
-//   warps 2-9   epilogue (two per TMEM lane quadrant, 128 columns each): tcgen05.ld (32 lanes x 32 columns per warp), alpha / bias / residual /
-//               ReLU in fp32, 16-byte stores; overlaps the next tile's main loop (double-buffered TMEM).
+// Structure (persistent, 320 threads per CTA, warp-specialised; default = CTA PAIRS, see Cfg<PAIR> below):
+//   warp 0      TMA producer (every CTA): its 128 A rows and its share of the B rows per 64-wide k block, bf16
+//               boxes with the 128-byte swizzle, mbarrier ring (5 x 32 KB per CTA in pair mode).
+//   warp 1      MMA issuer (leader CTA of the pair): one thread issues tcgen05.mma cta_group::2 (M=256, N=256,
+//               K=16) reading both CTAs' shared memory and accumulating in both CTAs' tensor memory (two 256-column
+//               accumulators per CTA, double buffered); tcgen05.commit multicasts "stage free" / "tile ready".
+//   warps 2-9   epilogue (two per TMEM lane quadrant, 128 columns each): tcgen05.ld 32 lanes x 32 columns, then one
+//               of three COMPILE-TIME epilogues (plain: alpha / bias or row scale / residual / ReLU / store with
+//               prefetched residual and smem-transposed fp32 stores; head: bias + ReLU + three row sums, no store;
+//               exp: masked exp + row sum + bf16 store + logit-range guard); overlaps the next tile's main loop.
+// Operands may be K-major or MN-major (k rows, m/n contiguous): the backward GEMMs read row-major activations.
 // Tiles are enumerated problem-major over a ragged batch (one problem per video for the attention
 // contractions), N fastest so that CTAs running concurrently share the A tile and the weights in L2.
 #include "smz_gemm.cuh"
