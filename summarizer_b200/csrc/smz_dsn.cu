@@ -8,10 +8,13 @@
 //                      once), multiplies it with h_{t-1} (fp32, shared memory) using fp32 FMAs, reduces the 16
 //                      partial rows of a warp with a 16-shuffle transpose-reduction, applies the gate
 //                      non-linearities in registers (cell state never leaves registers) and broadcasts its 32 new
-//                      h values to the 8 CTAs through distributed shared memory; one cluster barrier per step.
+//                      h values to the 8 CTAs through distributed shared memory with st.async, which completes
+//                      bytes on the DESTINATION CTA's mbarrier: a step waits for "1 KB of h has landed" on its
+//                      own barrier instead of a cluster-wide barrier + fence (1.27 -> 0.97 us per step).
 //   head               probs = sigmoid(y . w_out + b_out), one warp per frame.
 //   lstm_bwd_kernel    same structure with W_hh^T slices (32 units x 1024 gate columns per CTA): dh -> gate
-//                      gradients, dc carried in registers, gate gradients broadcast through DSMEM.
+//                      gradients, dc carried in registers, gate gradients broadcast through DSMEM (same st.async /
+//                      mbarrier protocol, 4 KB per step).
 //   weight gradients   dW_ih = dG^T . xb, dW_hh = dG^T . h_{t-1} as MN-major tcgen05 GEMMs after the time loop.
 #include <cooperative_groups.h>
 
@@ -40,6 +43,37 @@ __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w <<
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 __device__ __forceinline__ float tanhf_(float x) { return 2.f / (1.f + __expf(-2.f * x)) - 1.f; }
+
+// ---- DSMEM signalling: a remote store that completes bytes on the DESTINATION CTA's mbarrier -------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void bar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arm(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000LL) __trap();   // a protocol bug must not hang the GPU
+    }
+}
 
 // 16 values per lane, 32 lanes: afterwards lane L holds the warp-wide sum of value (L >> 1).
 __device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
@@ -79,12 +113,21 @@ lstm_fwd_kernel(const float *__restrict__ pre, const uint32_t *__restrict__ whh,
                 int n_videos, float *__restrict__ y, float *__restrict__ save, __nv_bfloat16 *__restrict__ hprev) {
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ __align__(16) float hbuf[2][H];
+    __shared__ __align__(8) uint64_t hbar[2];          // hbar[b]: all 256 floats of hbuf[b] have landed (1 KB per phase)
     const int cta = (int)cluster.block_rank();
     const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ul = warp * 4 + (lane >> 3);             // local unit this lane's 8-lane group finalises
     const int unit = cta * UNITS + ul;                 // hidden unit index (0..255)
-    float *remote_h = cluster.map_shared_rank(&hbuf[0][0], lane & 7);   // destination CTA of this lane's broadcast
+    // destination CTA of this lane's broadcast: its hbuf slot of `unit` and its barriers, as shared::cluster addresses
+    const uint32_t r_h = map_to_cta(smem_addr(&hbuf[0][unit]), lane & 7);
+    const uint32_t r_bar = map_to_cta(smem_addr(&hbar[0]), lane & 7);
+    if (tid == 0) {
+        bar_init(&hbar[0], 1); bar_init(&hbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t ph0 = 0, ph1 = 0;                         // wait parities of hbar[0] / hbar[1]
+    cluster.sync();
 
     int loaded_dir = -1;
     uint32_t W[WREGS];
@@ -106,6 +149,13 @@ lstm_fwd_kernel(const float *__restrict__ pre, const uint32_t *__restrict__ whh,
         float p_g = pre_col[(size_t)(row0 + t) * (2 * G4) + 2 * H], p_o = pre_col[(size_t)(row0 + t) * (2 * G4) + 3 * H];
         for (int s = 0; s < T; s++) {
             const int cur = s & 1;
+            // Step s consumes hbuf[s & 1].  No cluster barrier: every CTA's new h values arrive through st.async,
+            // which completes 1 KB on OUR mbarrier of that buffer; a CTA can only run one step ahead of the slowest
+            // one (it needs everybody's h), so the buffer being overwritten has been read by all of our warps.
+            if (s > 0) {
+                if (cur) { bar_wait(&hbar[1], ph1); ph1 ^= 1u; } else { bar_wait(&hbar[0], ph0); ph0 ^= 1u; }
+            }
+            if (tid == 0 && s + 1 < T) bar_arm(&hbar[cur ^ 1], H * 4);
             // prefetch the next step's input projections (hidden behind this step's compute)
             const int tn = dir ? t - 1 : t + 1;
             float n_i = 0.f, n_f = 0.f, n_g = 0.f, n_o = 0.f;
@@ -137,7 +187,7 @@ lstm_fwd_kernel(const float *__restrict__ pre, const uint32_t *__restrict__ whh,
             c_state = gf * c_state + gi * gg;
             const float hn = go * tanhf_(c_state);
             // every lane of the 8-lane group holds the same (h, c): lane d sends h to CTA d
-            remote_h[(cur ^ 1) * H + unit] = hn;
+            if (s + 1 < T) st_async_f32(r_h + (cur ^ 1) * H * 4, hn, r_bar + (cur ^ 1) * 8);
             const int d = lane & 7;
             const size_t row = (size_t)(row0 + t);
             if (d == 0) y[row * (2 * H) + dir * H + unit] = hn;
@@ -151,8 +201,8 @@ lstm_fwd_kernel(const float *__restrict__ pre, const uint32_t *__restrict__ whh,
             }
             p_i = n_i; p_f = n_f; p_g = n_g; p_o = n_o;
             t = tn;
-            cluster.sync();
         }
+        cluster.sync();                                // job boundary: nothing of this sequence is in flight any more
     }
 }
 
@@ -189,12 +239,20 @@ lstm_bwd_kernel(const uint32_t *__restrict__ wt, const int32_t *__restrict__ cu,
                 __nv_bfloat16 *__restrict__ dgb, float *__restrict__ d_bias) {
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ __align__(16) float dgbuf[2][G4];
+    __shared__ __align__(8) uint64_t gbar[2];          // gbar[b]: all 1024 gate gradients of dgbuf[b] have landed (4 KB)
     const int cta = (int)cluster.block_rank();
     const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int unit = cta * UNITS + warp * 4 + (lane >> 3);
     const int d = lane & 7;
-    float *remote = cluster.map_shared_rank(&dgbuf[0][0], d);
+    const uint32_t r_g = map_to_cta(smem_addr(&dgbuf[0][unit]), d);      // lane d -> CTA d
+    const uint32_t r_bar = map_to_cta(smem_addr(&gbar[0]), d);
+    if (tid == 0) {
+        bar_init(&gbar[0], 1); bar_init(&gbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t ph0 = 0, ph1 = 0;
+    cluster.sync();
 
     int loaded_dir = -1;
     uint32_t W[WREGS];
@@ -217,6 +275,10 @@ lstm_bwd_kernel(const uint32_t *__restrict__ wt, const int32_t *__restrict__ cu,
         float gi = sv[0], gf = sv[H], gg = sv[2 * H], go = sv[3 * H], cc = sv[4 * H];
         for (int s = 0; s < T; s++) {
             const int cur = s & 1;
+            if (s > 0) {                                   // same st.async / mbarrier protocol as the forward kernel
+                if (cur) { bar_wait(&gbar[1], ph1); ph1 ^= 1u; } else { bar_wait(&gbar[0], ph0); ph0 ^= 1u; }
+            }
+            if (tid == 0 && s + 1 < T) bar_arm(&gbar[cur ^ 1], G4 * 4);
             const int tp = dir ? t + 1 : t - 1;            // the step BEFORE t in forward order (next to visit)
             // prefetch the next visited step's saved activations; its cell state is this step's c_{prev}
             float n_i = 0.f, n_f = 0.f, n_g = 0.f, n_o = 0.f, n_c = 0.f;
@@ -262,8 +324,11 @@ lstm_bwd_kernel(const uint32_t *__restrict__ wt, const int32_t *__restrict__ cu,
             const float dG = dc * gi * (1.f - gg * gg);
             const float dF = dc * n_c * gf * (1.f - gf);      // n_c = c_{t-1} (0 at the sequence start)
             dc_carry = dc * gf;
-            float *dst = remote + (cur ^ 1) * G4 + unit;      // lane d -> CTA d
-            dst[0] = dI; dst[H] = dF; dst[2 * H] = dG; dst[3 * H] = dO;
+            if (s + 1 < T) {
+                const uint32_t dst = r_g + (cur ^ 1) * G4 * 4, bar = r_bar + (cur ^ 1) * 8;
+                st_async_f32(dst, dI, bar); st_async_f32(dst + H * 4, dF, bar);
+                st_async_f32(dst + 2 * H * 4, dG, bar); st_async_f32(dst + 3 * H * 4, dO, bar);
+            }
             if (d < 4) {
                 const float val = d == 0 ? dI : d == 1 ? dF : d == 2 ? dG : dO;
                 dgb[(size_t)(row0 + t) * (2 * G4) + dir * G4 + d * H + unit] = __float2bfloat16_rn(val);
@@ -271,9 +336,9 @@ lstm_bwd_kernel(const uint32_t *__restrict__ wt, const int32_t *__restrict__ cu,
             bsum[0] += dI; bsum[1] += dF; bsum[2] += dG; bsum[3] += dO;
             gi = n_i; gf = n_f; gg = n_g; go = n_o; cc = n_c;
             t = tp;
-            cluster.sync();
         }
         if (d < 4) atomicAdd(d_bias + dir * G4 + d * H + unit, d == 0 ? bsum[0] : d == 1 ? bsum[1] : d == 2 ? bsum[2] : bsum[3]);
+        cluster.sync();                                // job boundary
     }
 }
 
