@@ -57,7 +57,12 @@ def train(hps):
         weights_path = hps.weights_path[splits_file]
         pred_path = hps.pred_path[splits_file]
         model = hps.model_class(hps, splits_file)
-        mine = plan_folds([(f, fold_cost(hps, model, splits_file, f)) for f in range(n_folds)], world)[rank]
+        if (hps.extra_params or {}).get("data_parallel", False):
+            # single-split data-parallel mode: every rank trains every fold together (gradient all-reduce inside
+            # the trainer); the fold results are identical on all ranks
+            mine, world = list(range(n_folds)), 1
+        else:
+            mine = plan_folds([(f, fold_cost(hps, model, splits_file, f)) for f in range(n_folds)], world)[rank]
 
         fold_results, corr_max = {}, -1.0
         for fold in mine:
@@ -65,7 +70,10 @@ def train(hps):
             fold_results[fold] = (float(best_corr), float(best_avg_f), float(best_max_f))
             if best_corr > corr_max:
                 corr_max = best_corr
-                model.save_best_weights(weights_path if world == 1 else f"{weights_path}.rank{rank}")
+                if world > 1:
+                    model.save_best_weights(f"{weights_path}.rank{rank}")
+                elif rank == 0:
+                    model.save_best_weights(weights_path)
             hps.logger.info(f"File: {splits_file}   Fold: {fold+1}/{n_folds}   Corr: {best_corr: 0.5f}  "
                             f"Avg F-score: {best_avg_f:0.5f}  Max F-score: {best_max_f:0.5f}")
 
@@ -77,6 +85,9 @@ def train(hps):
             dist.barrier()
             if rank == 0 and os.path.exists(f"{weights_path}.rank{best_rank}"):
                 os.replace(f"{weights_path}.rank{best_rank}", weights_path)
+            dist.barrier()
+            if os.path.exists(f"{weights_path}.rank{rank}"):
+                os.remove(f"{weights_path}.rank{rank}")
         corrs_cv = [fold_results[f][0] for f in range(n_folds)]
         avg_fscores_cv = [fold_results[f][1] for f in range(n_folds)]
         max_fscores_cv = [fold_results[f][2] for f in range(n_folds)]
@@ -147,6 +158,10 @@ def main(argv=None):
     print("----------------------------------------------------------------------")
     results = train(hps)
     hps.writer.close()
+    if "WORLD_SIZE" in os.environ and int(os.environ["WORLD_SIZE"]) > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
     return results
 
 

@@ -157,6 +157,44 @@ class Trainer:
         batch, _ = self._eval_batches(test_keys)
         return self._eval_summary_device(scores.cuda(), batch)
 
+    # ---- data-parallel single-split training (BASELINE config 4 style): one video per rank and optimizer step ----
+    def _dp(self):
+        """(dist, rank, world) when ``--data_parallel`` is set and a process group exists, else (None, 0, 1).
+        This is the ONE place of the path with a real exchange step: the gradient all-reduce (NCCL over NVLink)."""
+        ep = self.hps.extra_params or {}
+        if not ep.get("data_parallel", False):
+            return None, 0, 1
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return None, 0, 1
+        return dist, dist.get_rank(), dist.get_world_size()
+
+    def _dp_sync_model(self, dist):
+        """Replicas start from rank 0's initial weights (the reference never seeds its initialisation)."""
+        for t in list(self.model.parameters()) + list(self.model.buffers()):
+            dist.broadcast(t.data, src=0)
+
+    def _dp_shuffle(self, dist, keys):
+        import random
+        box = [keys]
+        if dist.get_rank() == 0:
+            random.shuffle(box[0])
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    @staticmethod
+    def _dp_allreduce_grads(dist, params, n_active):
+        """Mean of the replicas' gradients: ONE all-reduce of the flat float32 gradient buffer per step."""
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
+        flat = torch.cat([g.reshape(-1).float() for g in grads])
+        dist.all_reduce(flat)
+        flat /= float(n_active)
+        o = 0
+        for p, g in zip(params, grads):
+            n = g.numel()
+            p.grad = flat[o:o + n].view_as(g).to(g.dtype)
+            o += n
+
     # ---- supervised loop shared by the MSE-trained scorers (vasnet.py:171-238, logistic.py:42-112) ---
     def _train_supervised(self, fold, optimizer_params=None):
         import random
@@ -167,19 +205,32 @@ class Trainer:
         params = [p for p in self.model.parameters() if p.requires_grad] if optimizer_params is None else optimizer_params
         self.optimizer = torch.optim.Adam(params, lr=self.hps.lr, weight_decay=self.hps.weight_decay) if params else None
         best_corr, best_avg_f_score, best_max_f_score = -1.0, 0.0, 0.0
+        dist, rank, world = self._dp()
+        if dist is not None:
+            self._dp_sync_model(dist)
         for epoch in range(self.hps.epochs):
             losses, dist_scores = [], {}
-            random.shuffle(train_keys)
-            for key in train_keys:
-                seq, target = self._video_tensors(key)
-                scores = self.model(seq)
-                loss = criterion(scores, target)
+            if dist is not None:
+                train_keys = self._dp_shuffle(dist, train_keys)
+            else:
+                random.shuffle(train_keys)
+            for i in range(0, len(train_keys), world):
+                group = train_keys[i:i + world]                  # one video per replica and optimizer step
+                key = group[rank] if rank < len(group) else None
                 if self.optimizer is not None:
                     self.optimizer.zero_grad()
-                    loss.backward()
+                if key is not None:
+                    seq, target = self._video_tensors(key)
+                    scores = self.model(seq)
+                    loss = criterion(scores, target)
+                    if self.optimizer is not None:
+                        loss.backward()
+                    losses.append(loss.detach())
+                    dist_scores[key] = scores.detach()
+                if self.optimizer is not None:
+                    if dist is not None:
+                        self._dp_allreduce_grads(dist, params, len(group))
                     self.optimizer.step()
-                losses.append(loss.detach())
-                dist_scores[key] = scores.detach()
             train_avg_loss = float(torch.stack(losses).mean())          # one sync per epoch, not per step
             self.log.info(f"Epoch: {f'{epoch+1}/{self.hps.epochs}':6}   Loss: {train_avg_loss:.05f}")
             self.hps.writer.add_scalar(f"{self.dataset_name}/Fold_{fold+1}/Train/Loss", train_avg_loss, epoch)

@@ -153,35 +153,54 @@ class DSNTrainer(Trainer):
         self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.hps.lr, weight_decay=self.hps.weight_decay)
         loss_BCE = torch.nn.BCELoss()
         dev = self._device()
-        baselines = {key: torch.zeros((), device=dev) for key in train_keys}      # device-resident: no sync per step
+        key_index = {key: i for i, key in enumerate(sorted(train_keys))}
+        baselines = torch.zeros(len(train_keys), device=dev)                      # device-resident: no sync per step
         reward_writers = {key: [] for key in train_keys}
         best_corr, best_avg_f_score, best_max_f_score = -1.0, 0.0, 0.0
+        dist_, rank, world = self._dp()
+        params = list(self.model.parameters())
+        if dist_ is not None:
+            self._dp_sync_model(dist_)
         for epoch in range(self.hps.epochs):
             epoch_losses, dist_scores = [], {}
-            random.shuffle(train_keys)
-            for key in train_keys:
-                seq, target = self._video_tensors(key)
-                probs = self.model(seq)                                           # (T,1,1), autograd through the device BPTT
-                dist = Bernoulli(probs)
-                loss = self.beta * (probs.mean() - self.eps) ** 2                 # summary-length penalty [Eq.11]
-                if self.sup:
-                    loss = loss + loss_BCE(probs, target)
-                actions = torch.stack([dist.sample() for _ in range(self.num_episodes)])      # (E,T,1,1)
-                rewards = compute_rewards(seq, actions.reshape(self.num_episodes, -1), self.far_sim, self.temp_dist_thre,
-                                          self._reward_ws)
-                for e in range(self.num_episodes):                                # policy gradient [Eq.10]
-                    loss = loss - dist.log_prob(actions[e]).mean() * (rewards[e] - baselines[key])
-                loss = loss / float(self.num_episodes)
+            if dist_ is not None:
+                train_keys = self._dp_shuffle(dist_, train_keys)
+            else:
+                random.shuffle(train_keys)
+            for i0 in range(0, len(train_keys), world):
+                group = train_keys[i0:i0 + world]                                  # one video per replica and step
+                key = group[rank] if rank < len(group) else None
                 self.optimizer.zero_grad()
-                loss.backward()
+                if key is not None:
+                    seq, target = self._video_tensors(key)
+                    probs = self.model(seq)                                       # (T,1,1), autograd through the device BPTT
+                    dist = Bernoulli(probs)
+                    loss = self.beta * (probs.mean() - self.eps) ** 2             # summary-length penalty [Eq.11]
+                    if self.sup:
+                        loss = loss + loss_BCE(probs, target)
+                    actions = torch.stack([dist.sample() for _ in range(self.num_episodes)])      # (E,T,1,1)
+                    rewards = compute_rewards(seq, actions.reshape(self.num_episodes, -1), self.far_sim, self.temp_dist_thre,
+                                              self._reward_ws)
+                    for e in range(self.num_episodes):                            # policy gradient [Eq.10]
+                        loss = loss - dist.log_prob(actions[e]).mean() * (rewards[e] - baselines[key_index[key]].detach())
+                    loss = loss / float(self.num_episodes)
+                    loss.backward()
+                    mean_reward = rewards.mean()
+                    delta = torch.zeros_like(baselines)                           # moving-average baseline update (dsn.py:149)
+                    delta[key_index[key]] = 0.1 * (mean_reward - baselines[key_index[key]])
+                    reward_writers[key].append(mean_reward)
+                    epoch_losses.append(loss.detach())
+                    dist_scores[key] = probs.detach()
+                else:
+                    delta = torch.zeros_like(baselines)
+                if dist_ is not None:
+                    self._dp_allreduce_grads(dist_, params, len(group))
+                    dist_.all_reduce(delta)                                       # every replica keeps every video's baseline
+                baselines = baselines + delta
                 torch.nn.utils.clip_grad_norm_(self.model.parameters(), 5.0)
                 self.optimizer.step()
-                mean_reward = rewards.mean()
-                baselines[key] = 0.9 * baselines[key] + 0.1 * mean_reward
-                reward_writers[key].append(mean_reward)
-                epoch_losses.append(loss.detach())
-                dist_scores[key] = probs.detach()
-            epoch_avg_reward = float(torch.stack([reward_writers[key][epoch] for key in train_keys]).mean())
+            seen = [k for k in train_keys if len(reward_writers[k]) > epoch]
+            epoch_avg_reward = float(torch.stack([reward_writers[key][epoch] for key in seen]).mean())
             epoch_avg_loss = float(torch.stack(epoch_losses).mean())
             self.log.info(f"Epoch: {f'{epoch+1}/{self.hps.epochs}':6}   Reward: {epoch_avg_reward:.05f}  Loss: {epoch_avg_loss:.05f}")
             self.hps.writer.add_scalar(f"{self.dataset_name}/Fold_{fold+1}/Train/Reward", epoch_avg_reward, epoch)

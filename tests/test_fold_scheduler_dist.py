@@ -51,3 +51,69 @@ def test_two_ranks_return_single_process_results(tmp_path):
     out = mgr.dict()
     mp.spawn(_worker, args=(2, str(tmp_path), 29731, out), nprocs=2, join=True)
     assert out[0] == want and out[1] == want
+
+
+# ---- data-parallel single-split training: gradient all-reduce (gloo here, NCCL on the GPU box) -------------------
+from summarizer_b200.models.logistic import LogisticRegression  # noqa: E402
+
+
+class CpuLogisticTrainer(Trainer):
+    """The shared supervised loop with a plain torch model on the CPU and a stubbed device evaluation."""
+
+    def _init_model(self):
+        torch.manual_seed(1234 + (dist.get_rank() if dist.is_initialized() else 0))    # replicas start DIFFERENT
+        return LogisticRegression()
+
+    def test(self, fold):
+        return 0.0, (0.0, 0.0)
+
+    def train(self, fold):
+        return self._train_supervised(fold)
+
+
+def make_dp_hps(root, data_parallel):
+    hps = HParameters()
+    hps.log_root, hps.tensorboard = root, False
+    hps.load_from_args(dict(model="logistic", use_cuda="no", splits_files="splits/summe_splits_overfit.json", log_level="error",
+                            epochs=2, lr=1e-2, extra_params={"data_parallel": True} if data_parallel else {}))
+    hps.model_class = CpuLogisticTrainer
+    return hps
+
+
+def _dp_worker(rank, world, root, port, out):
+    import random
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    random.seed(7)
+    hps = make_dp_hps(os.path.join(root, f"dp{rank}"), True)
+    t = hps.model_class(hps, hps.splits_files[0]).reset()
+    t.train(0)
+    out[rank] = [p.detach().clone().numpy() for p in t.model.parameters()]
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_allreduce_matches_manual_averaging(tmp_path):
+    import random
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dp_worker, args=(2, str(tmp_path), 29741, out), nprocs=2, join=True)
+    for a, b in zip(out[0], out[1]):
+        np.testing.assert_array_equal(a, b)                         # replicas stay in lock-step
+    # single process: same initial weights (rank 0's), same key order, gradients of 2 videos averaged per step
+    random.seed(7)
+    hps = make_dp_hps(str(tmp_path / "ref"), False)
+    t = hps.model_class(hps, hps.splits_files[0])
+    torch.manual_seed(1234)
+    t.model = LogisticRegression()
+    keys, _ = t._get_train_test_keys(0)
+    opt = torch.optim.Adam(t.model.parameters(), lr=hps.lr, weight_decay=hps.weight_decay)
+    for _ in range(hps.epochs):
+        random.shuffle(keys)
+        for i in range(0, len(keys), 2):
+            opt.zero_grad()
+            for k in keys[i:i + 2]:
+                seq, target = t._video_tensors(k)
+                (torch.nn.functional.mse_loss(t.model(seq), target) / len(keys[i:i + 2])).backward()
+            opt.step()
+    for a, p in zip(out[0], t.model.parameters()):
+        np.testing.assert_allclose(a, p.detach().numpy(), rtol=1e-5, atol=1e-7)
