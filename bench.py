@@ -259,7 +259,7 @@ def train_stage(dev, seconds=4.0):
 
     torch.manual_seed(0)
     vas = VASNet().to(dev).train()
-    opt = torch.optim.Adam(vas.parameters(), lr=5e-5, weight_decay=1e-5)
+    opt = torch.optim.Adam(vas.parameters(), lr=5e-5, weight_decay=1e-5, fused=True)
 
     def vas_step(x, tgt):
         loss = torch.nn.functional.mse_loss(vas(x), tgt)
@@ -269,7 +269,7 @@ def train_stage(dev, seconds=4.0):
     out["vasnet_train_tflops"] = out["vasnet_train_frames_per_s"] / sum(lens) * f_train / 1e12
 
     dsn = DSN().to(dev).train()
-    opt2 = torch.optim.Adam(dsn.parameters(), lr=5e-5, weight_decay=1e-5)
+    opt2 = torch.optim.Adam(dsn.parameters(), lr=5e-5, weight_decay=1e-5, fused=True)
     base = torch.zeros((), device=dev)
 
     def dsn_step(x, tgt):

@@ -203,7 +203,10 @@ class Trainer:
         self.draw_gtscores(fold, train_keys)
         criterion = torch.nn.MSELoss()
         params = [p for p in self.model.parameters() if p.requires_grad] if optimizer_params is None else optimizer_params
-        self.optimizer = torch.optim.Adam(params, lr=self.hps.lr, weight_decay=self.hps.weight_decay) if params else None
+        # same update rule as the reference's torch.optim.Adam (L2 term in the gradient); fused=True runs it as one
+        # multi-tensor kernel on the device
+        fused = bool(params) and all(p.is_cuda for p in params)
+        self.optimizer = torch.optim.Adam(params, lr=self.hps.lr, weight_decay=self.hps.weight_decay, fused=fused) if params else None
         best_corr, best_avg_f_score, best_max_f_score = -1.0, 0.0, 0.0
         dist, rank, world = self._dp()
         if dist is not None:

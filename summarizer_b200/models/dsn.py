@@ -150,7 +150,8 @@ class DSNTrainer(Trainer):
         train_keys, _ = self._get_train_test_keys(fold)
         self.draw_gtscores(fold, train_keys)
         self.log.debug("Parameters: {}".format(sum(p.numel() for p in self.model.parameters())))
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.hps.lr, weight_decay=self.hps.weight_decay)
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.hps.lr, weight_decay=self.hps.weight_decay,
+                                          fused=all(p.is_cuda for p in self.model.parameters()))
         loss_BCE = torch.nn.BCELoss()
         dev = self._device()
         key_index = {key: i for i, key in enumerate(sorted(train_keys))}

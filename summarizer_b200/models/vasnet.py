@@ -99,8 +99,9 @@ class VASNet(nn.Module):
         self._ws = _Workspace()
 
     # ---------------------------------------------------------------------------------------------
-    def _weights(self):
-        """bfloat16 shadow copies + the parameter struct; rebuilt when a parameter changed."""
+    def _weights(self, inference=True):
+        """bfloat16 shadow copies + the parameter struct; rebuilt when a parameter changed.  The folded head
+        constants are only derived for inference (the training path keeps the separate head kernel)."""
         ps = (self.Q.weight, self.K.weight, self.V.weight, self.attention_head_projection.weight,
               self.k1.weight, self.k1.bias, self.k2.weight, self.k2.bias, self.layer_norm.weight,
               self.layer_norm.bias)
@@ -115,15 +116,16 @@ class VASNet(nn.Module):
                     b1=self.k1.bias.float().contiguous(), w2=self.k2.weight.float().reshape(-1).contiguous(),
                     b2=self.k2.bias.float().contiguous(), ln_g=self.layer_norm.weight.float().contiguous(),
                     ln_b=self.layer_norm.bias.float().contiguous())
-                # regressor head folded into the k1 epilogue (inference): z = rstd * (sum h*gw - mean * c0) + c1
-                sh["head_gw"] = (sh["ln_g"] * sh["w2"]).contiguous()
-                sh["head_c"] = torch.stack([sh["head_gw"].sum(), (sh["ln_b"] * sh["w2"]).sum() + sh["b2"][0]]).contiguous()
             self._shadow, self._shadow_key = sh, key
         sh = self._shadow
+        if inference and "head_gw" not in sh:
+            with torch.no_grad():   # regressor head folded into the k1 epilogue: z = rstd * (sum h*gw - mean * c0) + c1
+                sh["head_gw"] = (sh["ln_g"] * sh["w2"]).contiguous()
+                sh["head_c"] = torch.stack([sh["head_gw"].sum(), (sh["ln_b"] * sh["w2"]).sum() + sh["b2"][0]]).contiguous()
         st = VasnetParams(*(sh[k].data_ptr() for k in ("wqk", "wv", "wo", "w1", "b1", "w2", "b2", "ln_g", "ln_b")),
                           float(self.scale), float(self.epsilon),
                           -1 if self.aperture is None else int(self.aperture), int(bool(self.ignore_self)),
-                          sh["head_gw"].data_ptr(), sh["head_c"].data_ptr())
+                          sh["head_gw"].data_ptr() if inference else None, sh["head_c"].data_ptr() if inference else None)
         return sh, st
 
     def score_packed(self, x, lengths):

@@ -22,8 +22,10 @@ def draw_keep_masks(lengths, device, generator=None):
     """KEEP masks (uint8, 1 = keep) of nn.Dropout(0.5) at the three sites, for a packed batch."""
     rows = int(sum(lengths))
     n_att = int(sum(t * t for t in lengths))
-    rnd = lambda n: (torch.rand(n, device=device, generator=generator) >= 0.5).to(torch.uint8)
-    return rnd(n_att), rnd(rows * 1024).view(rows, 1024), rnd(rows * 1024).view(rows, 1024)
+    n_att_pad = (n_att + 15) // 16 * 16                     # keeps the row masks 16-byte aligned (uchar4 loads)
+    keep = (torch.rand(n_att_pad + 2 * rows * 1024, device=device, generator=generator) >= 0.5).to(torch.uint8)   # one draw
+    return (keep[:n_att], keep[n_att_pad:n_att_pad + rows * 1024].view(rows, 1024),
+            keep[n_att_pad + rows * 1024:].view(rows, 1024))
 
 
 class _VasnetFunction(torch.autograd.Function):
@@ -36,7 +38,7 @@ class _VasnetFunction(torch.autograd.Function):
         cu = _cu_seqlens(lengths)
         cu_p = cu.ctypes.data_as(C.c_void_p)
         is_bf16 = int(x.dtype == torch.bfloat16)
-        sh, st = module._weights()
+        sh, st = module._weights(inference=False)
         nbytes = C.c_int64(0)
         N.check(N.lib().smz_vasnet_workspace_bytes(cu_p, len(lengths), 1, is_bf16, C.byref(nbytes)))
         ws = torch.empty(max(nbytes.value, 1024), dtype=torch.uint8, device=x.device)   # lives until backward
@@ -53,9 +55,15 @@ class _VasnetFunction(torch.autograd.Function):
         x, scores = ctx.saved_tensors
         m = ctx.module
         dev = x.device
+        shapes = dict(wqk=(2048, 1024), wv=(1024, 1024), wo=(1024, 1024), w1=(1024, 1024), b1=(1024,), w2=(1024,), b2=(1,),
+                      ln_g=(1024,), ln_b=(1024,))
+        sizes = {k: (int(torch.Size(v).numel()) + 3) // 4 * 4 for k, v in shapes.items()}    # 16-byte aligned slices
+        flat = torch.zeros(sum(sizes.values()), dtype=torch.float32, device=dev)              # one memset for all gradients
+        g, o = {}, 0
+        for k, shp in shapes.items():
+            g[k] = flat[o:o + int(torch.Size(shp).numel())].view(shp)
+            o += sizes[k]
         z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
-        g = dict(wqk=z(2048, 1024), wv=z(1024, 1024), wo=z(1024, 1024), w1=z(1024, 1024), b1=z(1024), w2=z(1024), b2=z(1),
-                 ln_g=z(1024), ln_b=z(1024))
         dx = z(x.shape[0], 1024) if ctx.needs_input_grad[0] else None
         gs = VasnetGrads(*(g[k].data_ptr() for k in ("wqk", "wv", "wo", "w1", "b1", "w2", "b2", "ln_g", "ln_b")),
                          dx.data_ptr() if dx is not None else None)
