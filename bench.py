@@ -298,6 +298,8 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL's version banner goes to STDOUT at NCCL_DEBUG=VERSION/INFO; the contract is ONE JSON line there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
