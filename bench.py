@@ -298,9 +298,19 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL's version banner goes to STDOUT at NCCL_DEBUG=VERSION/INFO; the contract is ONE JSON line there
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug_%h_%p.log")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to STDOUT when the first communicator is created; the contract is ONE JSON
+        # line there, so file descriptor 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:
