@@ -258,6 +258,45 @@ int smz_dsn_reward_workspace_bytes(int T, int n_episodes, int64_t *bytes);
 int smz_dsn_reward(const float *x, int T, const uint8_t *actions, int n_episodes, int temp_dist_thre, int far_sim,
                    float *rewards, void *ws, int64_t ws_bytes, void *stream);
 
+/* ---- SumGAN LSTM recurrences: replace the cuDNN calls behind nn.LSTM in models/sumgan.py:43 (sLSTM, 2 x 1024
+ *      bidirectional), :69 (eLSTM, 2 x 2048), :207 (cLSTM, 2 x 1024) and the step-wise decode loop :98-115 (dLSTM,
+ *      2 x 2048), forward and BPTT, batch 1.  One call = one layer over the whole sequence (both directions of a
+ *      bidirectional layer side by side).  The input projections x.W_ih^T + b, dX and the weight gradients are
+ *      whole-sequence GEMMs (smz_gemm_bf16) issued by the caller.  All pointers are device memory; gate order is
+ *      torch's (i, f, g, o); sync_ws = 256 bytes of device scratch for the grid barrier.
+ *   forward : pre [T, ldpre] float32 pre-activations (gate g of unit u at pre[t*ldpre + g*H + u]); whh bfloat16
+ *             [4H, H]; h0/c0 [H] or NULL (zeros); y[t*ldy + u] = h_t; training also fills gates (activated,
+ *             [T, ldg]) and cs [T, H]; h_last/c_last [H] or NULL.  reverse != 0 walks t = T-1 .. 0.
+ *   backward: whh_t bfloat16 [H, 4H] (= W_hh^T); dy [T, lddy] or NULL; dh_last/dc_last [H] or NULL; writes
+ *             dgates [T, ldg] (pre-activation gradients), dh0/dc0 [H] (or NULL). */
+typedef struct smz_lstm_seq {
+    int32_t T, H, reverse, ldpre, ldy, lddy, ldg, reserved;
+    const float *pre;
+    const void *whh, *whh_t;
+    const float *h0, *c0;
+    float *y, *gates, *cs, *h_last, *c_last;
+    const float *dy, *dh_last, *dc_last;
+    float *dgates, *dh0, *dc0;
+} smz_lstm_seq;
+int smz_lstm_seq_forward(const smz_lstm_seq *dirs, int n_dir, void *sync_ws, void *stream);
+int smz_lstm_seq_backward(const smz_lstm_seq *dirs, int n_dir, void *sync_ws, void *stream);
+
+/* dLSTM decode: layer 0's input at step t is layer 1's output at step t-1 (zeros at t = 0), sumgan.py:106-112.
+ *   w_* bfloat16 [4H, H], w_*_t their transposes [H, 4H] (backward only); bias0/1 float32 [4H] (b_ih + b_hh);
+ *   h_init/c_init [2, H]; hs0/hs1 [T, H] layer outputs; gates0/1 [T, 4H], cs0/1 [T, H] (training);
+ *   backward: dy [T, H] gradient of hs1 -> dgates0/1 [T, 4H], dh_init/dc_init [2, H]. */
+typedef struct smz_lstm_decode {
+    int32_t T, H;
+    const void *w_ih0, *w_hh0, *w_ih1, *w_hh1;
+    const void *w_ih0_t, *w_hh0_t, *w_ih1_t, *w_hh1_t;
+    const float *bias0, *bias1, *h_init, *c_init;
+    float *hs0, *hs1, *gates0, *gates1, *cs0, *cs1;
+    const float *dy;
+    float *dgates0, *dgates1, *dh_init, *dc_init;
+} smz_lstm_decode;
+int smz_lstm_decode_forward(const smz_lstm_decode *d, void *sync_ws, void *stream);
+int smz_lstm_decode_backward(const smz_lstm_decode *d, void *sync_ws, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,3 +96,87 @@ def dsn_reward(seq, actions, far_sim=False, temp_dist_thre=20):
     dist = sq + sq.t() - 2 * (seq @ seq.t())                                   # :227-228
     reward_rep = torch.exp(-dist[:, pick].min(1)[0].mean())                    # :229-231
     return float((reward_div + reward_rep) * 0.5)
+
+
+# ---- SumGAN (models/sumgan.py:23-258) -----------------------------------------------------------------------
+def lstm_layer(x, w_ih, w_hh, b_ih, b_hh, h0=None, c0=None, reverse=False):
+    """One direction of one torch.nn.LSTM layer with an initial state: x (T, I) -> (y (T, H), h_n (H), c_n (H))."""
+    T, H = x.shape[0], w_hh.shape[1]
+    pre = x @ w_ih.t() + b_ih + b_hh
+    h = x.new_zeros(H) if h0 is None else h0
+    c = x.new_zeros(H) if c0 is None else c0
+    out = [None] * T
+    for t in (range(T - 1, -1, -1) if reverse else range(T)):
+        g = pre[t] + w_hh @ h
+        i, f, gg, o = g[:H], g[H:2 * H], g[2 * H:3 * H], g[3 * H:]
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        out[t] = h
+    return torch.stack(out, 0), h, c
+
+
+def lstm_stack(sd, prefix, x, num_layers=2, bidirectional=False, h0=None, c0=None):
+    """torch.nn.LSTM (batch 1) from the state-dict entries ``prefix + weight_ih_l0`` ...: x (T, I) ->
+    (y (T, nd*H), h_n (L*nd, H), c_n (L*nd, H)) in nn.LSTM's layer-major, direction-minor order."""
+    nd = 2 if bidirectional else 1
+    hs, cs = [], []
+    for layer in range(num_layers):
+        ys = []
+        for d in range(nd):
+            sfx = f"_l{layer}" + ("_reverse" if d else "")
+            k = layer * nd + d
+            y, h, c = lstm_layer(x, sd[prefix + "weight_ih" + sfx], sd[prefix + "weight_hh" + sfx], sd[prefix + "bias_ih" + sfx],
+                                 sd[prefix + "bias_hh" + sfx], None if h0 is None else h0[k], None if c0 is None else c0[k], bool(d))
+            ys.append(y); hs.append(h); cs.append(c)
+        x = torch.cat(ys, 1)
+    return x, torch.stack(hs, 0), torch.stack(cs, 0)
+
+
+def sumgan_slstm(sd, x, prefix="summarizer.s_lstm."):
+    """sLSTM.forward (sumgan.py:36-46), batch 1: x (T, 1024) -> scores (T,)."""
+    y, _, _ = lstm_stack(sd, prefix + "lstm.", x, 2, True)
+    return torch.sigmoid(y @ sd[prefix + "out.weight"].t() + sd[prefix + "out.bias"]).reshape(-1)
+
+
+def sumgan_elstm(sd, x, prefix="summarizer.vae.e_lstm."):
+    """eLSTM.forward (sumgan.py:61-72), batch 1: -> (mu (2, H), logvar (2, H), c_last (2, H))."""
+    _, h, c = lstm_stack(sd, prefix + "lstm.", x, 2, False)
+    return h @ sd[prefix + "mu.weight"].t() + sd[prefix + "mu.bias"], h @ sd[prefix + "logvar.weight"].t() + sd[prefix + "logvar.bias"], c
+
+
+def sumgan_dlstm(sd, T, h, c, prefix="summarizer.vae.d_lstm."):
+    """dLSTM.forward (sumgan.py:98-115), batch 1: one-step 2-layer LSTM calls fed with their own output, the
+    reconstruction of every step, time-reversed: -> x_hat (T, 1024)."""
+    x = h.new_zeros(1, h.shape[1])
+    outs = []
+    for _ in range(T):
+        x, h, c = lstm_stack(sd, prefix + "lstm.", x, 2, False, h, c)
+        outs.append(x @ sd[prefix + "recons.weight"].t() + sd[prefix + "recons.bias"])
+    return torch.flip(torch.cat(outs, 0), (0,))
+
+
+def sumgan_clstm(sd, x, prefix="gan.c_lstm."):
+    """cLSTM.forward (sumgan.py:199-210), batch 1: -> (prob scalar tensor (1,), h_last (H,))."""
+    y, _, _ = lstm_stack(sd, prefix + "lstm.", x, 2, False)
+    h_last = y[-1]
+    return torch.sigmoid(h_last @ sd[prefix + "out.0.weight"].t() + sd[prefix + "out.0.bias"]), h_last
+
+
+def sumgan_chain(sd, x, probes):
+    """The deterministic chain the parity tests use (reparameterisation replaced by h = mu): scores -> eLSTM on the
+    weighted features -> dLSTM -> cLSTM, and a scalar probe loss that reaches every parameter.
+    probes: dict of fixed random tensors (x_hat, mu, logvar, h_last)."""
+    scores = sumgan_slstm(sd, x)
+    mu, logvar, c = sumgan_elstm(sd, x * scores[:, None])
+    x_hat = sumgan_dlstm(sd, x.shape[0], mu, c)
+    prob, h_last = sumgan_clstm(sd, x_hat)
+    loss = (x_hat * probes["x_hat"]).sum() + (mu * probes["mu"]).sum() + (logvar * probes["logvar"]).sum() \
+        + (h_last * probes["h_last"]).sum() + prob.sum() + (scores * probes["scores"]).sum()
+    return dict(scores=scores, mu=mu, logvar=logvar, c=c, x_hat=x_hat, prob=prob, h_last=h_last, loss=loss)
+
+
+def sumgan_probes(seed, T):
+    g = torch.Generator().manual_seed(30_000 + seed)
+    return dict(x_hat=torch.randn(T, 1024, generator=g), mu=torch.randn(2, 2048, generator=g),
+                logvar=torch.randn(2, 2048, generator=g), h_last=torch.randn(1024, generator=g),
+                scores=torch.randn(T, generator=g))

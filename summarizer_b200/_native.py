@@ -62,6 +62,10 @@ SIGNATURES = {
     "smz_dsn_backward": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _L, _P]),
     "smz_dsn_reward_workspace_bytes": (_I, [_I, _I, C.POINTER(C.c_int64)]),
     "smz_dsn_reward": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _L, _P]),
+    "smz_lstm_seq_forward": (_I, [_P, _I, _P, _P]),
+    "smz_lstm_seq_backward": (_I, [_P, _I, _P, _P]),
+    "smz_lstm_decode_forward": (_I, [_P, _P, _P]),
+    "smz_lstm_decode_backward": (_I, [_P, _P, _P]),
     "smz_gemm_bf16": (_I, [_I, _I, _P, _L, _P, _L, _P, _L, _I, _I, _I, C.c_float, _P, _P, _L, _I, _P]),
     "smz_gemm_bf16_tn": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, C.c_float, _P, _P, _L, _I, _P]),
 }

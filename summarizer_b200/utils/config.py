@@ -29,8 +29,8 @@ class _NullWriter:
 
 
 def _model_registry():
-    """utils/config.py:68-77.  transformer / sumgan / sumgan_att are outside the hot path and are
-    not registered: asking for them raises the reference's KeyError."""
+    """utils/config.py:68-77.  transformer / sumgan_att are outside the hot path and are not
+    registered: asking for them raises the reference's KeyError."""
     from ..models.logistic import LogisticRegressionTrainer
     from ..models.rand import RandomTrainer
     from ..models.vasnet import VASNetTrainer
@@ -40,6 +40,8 @@ def _model_registry():
         reg["dsn"] = DSNTrainer
     except ImportError:
         pass
+    from ..models.sumgan import SumGANTrainer
+    reg["sumgan"] = SumGANTrainer
     return reg
 
 
