@@ -283,6 +283,35 @@ def train_stage(dev, seconds=4.0):
         loss = loss / 5.
         opt2.zero_grad(); loss.backward(); torch.nn.utils.clip_grad_norm_(dsn.parameters(), 5.0); opt2.step()
     out["dsn_reinforce_frames_per_s"] = timed(dsn_step)
+    del vas, dsn, opt, opt2
+
+    # BASELINE config 4 (SUM-GAN-style LSTM generator/discriminator): the reference's three updates per video
+    # (sumgan.py:415-480), 195 M parameters, on SumMe-like lengths; the reference needs ~700 s per video on the CPU
+    from summarizer_b200.models.sumgan import SumGAN, SumGANTrainer
+
+    class _H:
+        lr, weight_decay = 5e-5, 1e-5
+    gan = SumGAN().to(dev).train()
+    tr = SumGANTrainer.__new__(SumGANTrainer)
+    tr.model, tr.hps, tr.sup, tr.sigma, tr.epoch_noise = gan, _H, False, 0.3, 0
+    tr.s_e_optimizer = tr._adam(list(gan.summarizer.s_lstm.parameters()) + list(gan.summarizer.vae.e_lstm.parameters()))
+    tr.d_optimizer = tr._adam(gan.summarizer.vae.d_lstm.parameters())
+    tr.c_optimizer = tr._adam(gan.gan.c_lstm.parameters())
+    tr.loss_BCE = torch.nn.BCELoss()
+    gl = [int(t) for t in rng.integers(150, 450, size=4)]
+    gv = [(v[0][:T].contiguous(), v[1][:T].contiguous()) for v, T in zip(sorted(vids, key=lambda v: -v[0].shape[0]), gl)]
+    for v in gv[:2]:
+        tr.train_step(v[0], v[1], 1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for v in gv:
+        tr.train_step(v[0], v[1], 1)
+    e1.record(); torch.cuda.synchronize()
+    out["sumgan_train_frames_per_s"] = sum(gl) / (e0.elapsed_time(e1) / 1e3)
+    out["sumgan_videos"] = gl
+    del gan, tr
+    torch.cuda.empty_cache()
     return out
 
 

@@ -117,3 +117,57 @@ def test_data_parallel_gradient_allreduce_matches_manual_averaging(tmp_path):
             opt.step()
     for a, p in zip(out[0], t.model.parameters()):
         np.testing.assert_allclose(a, p.detach().numpy(), rtol=1e-5, atol=1e-7)
+
+
+# ---- SumGANTrainer's per-phase update in data-parallel mode (BASELINE config 4): _groups + _update ----------------
+def _sumgan_update_worker(rank, world, port, out):
+    import random
+    from summarizer_b200.models.sumgan import SumGANTrainer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class _H:
+        lr, weight_decay, extra_params = 1e-2, 0.0, {"data_parallel": True}
+
+    t = SumGANTrainer.__new__(SumGANTrainer)
+    t.hps = _H
+    torch.manual_seed(5)
+    t.model = torch.nn.Linear(4, 3)
+    data = {k: torch.randn(4, generator=torch.Generator().manual_seed(i)) for i, k in enumerate("abc")}
+    opt = t._adam(t.model.parameters())
+    dp, r, w = t._dp()
+    assert dp is not None and (r, w) == (rank, world)
+    random.seed(3)
+    seen = []
+    for key, n_active in t._groups(list("abc"), dp, r, w):         # 3 videos on 2 replicas: one idle slot
+        seen.append((key, n_active))
+        loss = None if key is None else 40.0 * t.model(data[key]).pow(2).sum()
+        t._update(opt, loss, dp, n_active)
+    out[rank] = ([p.detach().clone().numpy() for p in t.model.parameters()], seen)
+    dist.destroy_process_group()
+
+
+def test_sumgan_phase_update_data_parallel(tmp_path):
+    import random
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sumgan_update_worker, args=(2, 29751, out), nprocs=2, join=True)
+    (p0, seen0), (p1, seen1) = out[0], out[1]
+    for a, b in zip(p0, p1):
+        np.testing.assert_array_equal(a, b)
+    assert [n for _, n in seen0] == [2, 1] and seen1[1][0] is None and seen0[1][0] is not None
+    order = [seen0[0][0], seen1[0][0], seen0[1][0]]
+    assert sorted(order) == list("abc")
+    # single process: averaged gradients of each group, clip at 5.0, Adam
+    torch.manual_seed(5)
+    model = torch.nn.Linear(4, 3)
+    data = {k: torch.randn(4, generator=torch.Generator().manual_seed(i)) for i, k in enumerate("abc")}
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, weight_decay=0.0)
+    for group in (order[:2], order[2:]):
+        opt.zero_grad()
+        for k in group:
+            (40.0 * model(data[k]).pow(2).sum() / len(group)).backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
+        opt.step()
+    for a, p in zip(p0, model.parameters()):
+        np.testing.assert_allclose(a, p.detach().numpy(), rtol=1e-5, atol=1e-7)
