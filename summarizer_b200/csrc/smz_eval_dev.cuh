@@ -47,6 +47,15 @@ struct FrameCursor {
     }
 };
 
+struct SmemFrames {   // upsample staged in shared memory as the score index of every frame (0xffff = zero score)
+    const unsigned short *idx;
+    const float *scores;
+    __device__ __forceinline__ float at(int f) const {
+        const unsigned i = idx[f];
+        return i == 0xffffu ? 0.f : __ldg(scores + i);
+    }
+};
+
 struct ArrayCursor {
     const float *a;
     __device__ __forceinline__ float at(int i) const { return a[i]; }
@@ -121,7 +130,8 @@ __device__ T pw_sum(Cur &cur, int start, int n) {
 // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is done with xor-shuffles (fp add is commutative, so every
 // lane ends with the same bits); the n%8 tail and n<8 blocks are summed by lane 0 and broadcast.
 // All 8 lanes of a group take the same control flow; gmask names exactly those lanes.
-static __device__ float pw_block_group(FrameCursor &cur, int start, int n, int gl, unsigned gmask, int lane0) {
+template <class Cur>
+static __device__ float pw_block_group(Cur &cur, int start, int n, int gl, unsigned gmask, int lane0) {
     float res;
     if (n < 8) {
         res = 0.f;
@@ -140,8 +150,9 @@ static __device__ float pw_block_group(FrameCursor &cur, int start, int n, int g
     return __shfl_sync(gmask, r, lane0);
 }
 
-static __device__ float pw_sum_group(FrameCursor &cur, int start, int n, int gl, unsigned gmask, int lane0) {
-    if (n <= 128) return pw_block_group(cur, start, n, gl, gmask, lane0);
+// generic depth: explicit stack (local memory), kept out of line
+template <class Cur>
+static __device__ __noinline__ float pw_sum_group_deep(Cur &cur, int start, int n, int gl, unsigned gmask, int lane0) {
     int s_start[32], s_n[32];
     float s_left[32];
     unsigned char s_stage[32];
@@ -168,6 +179,26 @@ static __device__ float pw_sum_group(FrameCursor &cur, int start, int n, int gl,
         }
     }
     return ret;
+}
+
+// the first DEPTH levels of the recursion are unrolled in registers (segments up to ~128 * 2^DEPTH frames never
+// touch the stack); left before right, so a forward-only cursor keeps moving forward
+template <int DEPTH, class Cur>
+static __device__ __forceinline__ float pw_sum_group_rec(Cur &cur, int start, int n, int gl, unsigned gmask, int lane0) {
+    if (n <= 128) return pw_block_group(cur, start, n, gl, gmask, lane0);
+    if constexpr (DEPTH == 0) {
+        return pw_sum_group_deep(cur, start, n, gl, gmask, lane0);
+    } else {
+        int n2 = n / 2; n2 -= n2 % 8;
+        const float l = pw_sum_group_rec<DEPTH - 1>(cur, start, n2, gl, gmask, lane0);
+        const float r = pw_sum_group_rec<DEPTH - 1>(cur, start + n2, n - n2, gl, gmask, lane0);
+        return __fadd_rn(l, r);
+    }
+}
+
+template <class Cur>
+static __device__ float pw_sum_group(Cur &cur, int start, int n, int gl, unsigned gmask, int lane0) {
+    return pw_sum_group_rec<3>(cur, start, n, gl, gmask, lane0);
 }
 
 __device__ __forceinline__ int warp_max(int v) {

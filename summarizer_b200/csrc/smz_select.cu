@@ -25,7 +25,11 @@ constexpr int SELECT_THREADS = 512;   // generic kernel
 constexpr int DP_THREADS = 256;       // register-DP kernel
 constexpr int POOL_THREADS = 256;     // 32 segments per CTA, 8 lanes each
 constexpr int SUMMARY_THREADS = 256;
-constexpr int kDpNeg = -(1 << 30);    // front-pad value of the DP rows: never improves a cell
+constexpr int kDpNeg = -(1 << 29) - 1;   // front-pad value of the DP rows: pad + value <= -1 never improves a cell (rows are >= 0)
+
+// |value| limit of the int32 DP: n * limit <= 2^29, so that the take test val - cand - value (dp_kernel) stays
+// inside int32 even against the pad:  2^29 + (2^29 + 1) + 2^29 < 2^31.  Values beyond it are clipped and flagged.
+__host__ __device__ inline int value_limit(int n) { return (1 << 29) / (n > 0 ? n : 1); }
 
 // ------------------------------------------------------------------------------------------
 // pool_kernel: utils/eval.py:87-94 (segment means) + utils/knapsack.py:11-15 (quantisation)
@@ -56,16 +60,95 @@ pool_kernel(const smz_video_desc *__restrict__ desc, int v0, const float *__rest
     if (gl == 0) {
         const float mean = __fdiv_rn(sum, (float)len);
         long long val = __double2ll_rz(__dmul_rn((double)mean, 1000.0));
-        const int vlim = min(INT_MAX / (n > 0 ? n : 1), 1 << 29);
+        const int vlim = value_limit(n);
         if (val > vlim || val < -vlim) { atomicOr(status + v, SMZ_STATUS_VALUE_RANGE); val = val > 0 ? vlim : -vlim; }
         if (out_mean) out_mean[d.seg_off + s] = mean;
         out_values[d.seg_off + s] = (int)val;
     }
 }
 
+// Same result, one CTA per video: the upsample (utils/eval.py:15-35) is first expanded into shared memory as one
+// 16-bit score index per frame, so that the pairwise sums read shared memory + an L1-resident score instead of
+// walking the picks cursor through global memory — ~20x fewer instructions.  2 bytes per frame keeps three CTAs
+// per SM at 30 000 frames.  Used whenever the frames fit and there are fewer than 65 535 intervals.
+constexpr int POOL_SMEM_THREADS = 512;
+
+__global__ void __launch_bounds__(POOL_SMEM_THREADS)
+pool_smem_kernel(const smz_video_desc *__restrict__ desc, int v0, const float *__restrict__ scores,
+                 const int32_t *__restrict__ picks, const int32_t *__restrict__ cps,
+                 float *__restrict__ out_mean, int32_t *__restrict__ out_values, int32_t *__restrict__ status) {
+    extern __shared__ unsigned short frames[];
+    constexpr int NT = POOL_SMEM_THREADS;
+    const int v = v0 + blockIdx.x, tid = threadIdx.x;
+    const smz_video_desc d = desc[v];
+    const int n = d.n_segs, n_frames = d.n_frames, n_picks = d.n_picks;
+    const int32_t *pk = picks + d.picks_off;
+    const float *sc = scores + d.score_off;
+    const int n_bound = n_picks + ((n_picks > 0 && __ldg(pk + n_picks - 1) != n_frames) ? 1 : 0);
+    if (tid == 0 && n_bound - 1 > d.n_scores + 1) atomicOr(status + v, SMZ_STATUS_INTERVALS);
+    {   // before picks[0], after the last boundary, zero-filled intervals: index 0xffff
+        uint32_t *w = reinterpret_cast<uint32_t *>(frames);
+        for (int f = tid; f < (n_frames + 1) / 2; f += NT) w[f] = 0xffffffffu;
+    }
+    __syncthreads();
+    for (int i = tid; i + 1 < n_bound && i < d.n_scores && i < 0xffff; i += NT) {  // interval i = [bound(i), bound(i+1))
+        const int lo = max(__ldg(pk + i), 0);
+        const int hi = min(i + 1 < n_picks ? __ldg(pk + i + 1) : n_frames, n_frames);
+        for (int f = lo; f < hi; f++) frames[f] = (unsigned short)i;
+    }
+    __syncthreads();
+    SmemFrames cur{frames, sc};
+    const int lane = tid & 31, gl = lane & 7, lane0 = lane & ~7;
+    const unsigned gmask = 0xffu << lane0;
+    const int vlim = value_limit(n);
+    for (int s = tid >> 3; s < n; s += NT / 8) {                    // uniform within an 8-lane group
+        const int start = __ldg(cps + 2 * (d.seg_off + s));
+        int end = __ldg(cps + 2 * (d.seg_off + s) + 1) + 1;
+        end = min(end, n_frames);
+        const int len = end - start;
+        const float sum = pw_sum_group(cur, start, len, gl, gmask, lane0);
+        if (gl == 0) {
+            const float mean = __fdiv_rn(sum, (float)len);
+            long long val = __double2ll_rz(__dmul_rn((double)mean, 1000.0));
+            if (val > vlim || val < -vlim) { atomicOr(status + v, SMZ_STATUS_VALUE_RANGE); val = val > 0 ? vlim : -vlim; }
+            if (out_mean) out_mean[d.seg_off + s] = mean;
+            out_values[d.seg_off + s] = (int)val;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // dp_kernel<K>: knapsack DP + OR-tools extraction (or the 'rank' greedy) -> picked[]
 // ------------------------------------------------------------------------------------------
+// Longest-first order of the videos for the dp_kernel queue (cost ~ n_segs x capacity): a counting sort over 64
+// cost buckets, so that the tail of the persistent kernel is a cheap video, not an expensive one.
+constexpr int ORDER_BUCKETS = 64;
+
+__device__ __forceinline__ int cost_bucket(const smz_video_desc &d, int max_n_segs) {
+    const int b = (int)(((int64_t)d.n_segs * ORDER_BUCKETS) / (max_n_segs + 1));
+    return ORDER_BUCKETS - 1 - min(max(b, 0), ORDER_BUCKETS - 1);             // bucket 0 = most segments
+}
+
+__global__ void order_count_kernel(const smz_video_desc *__restrict__ desc, int n_videos, int max_n_segs, int *__restrict__ counters) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < n_videos) atomicAdd(counters + 1 + cost_bucket(desc[v], max_n_segs), 1);
+}
+
+__global__ void order_fill_kernel(const smz_video_desc *__restrict__ desc, int n_videos, int max_n_segs, int *__restrict__ counters,
+                                  int *__restrict__ order) {
+    __shared__ int base[ORDER_BUCKETS];
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int b = 0; b < ORDER_BUCKETS; b++) { base[b] = run; run += counters[1 + b]; }
+    }
+    __syncthreads();
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < n_videos) {
+        const int b = cost_bucket(desc[v], max_n_segs);
+        order[base[b] + atomicAdd(counters + 1 + ORDER_BUCKETS + b, 1)] = v;
+    }
+}
+
 struct DpSmem { int dp0, dp1, wp, pk, red, total, row, pad; };
 
 __host__ __device__ inline DpSmem dp_layout(int K, int max_n_segs, int max_weight) {
@@ -84,12 +167,13 @@ __host__ __device__ inline DpSmem dp_layout(int K, int max_n_segs, int max_weigh
 }
 
 template <int K>
-__global__ void __launch_bounds__(DP_THREADS, K <= 18 ? 3 : 1)
+__global__ void __launch_bounds__(DP_THREADS, K <= 18 ? 4 : 1)
 dp_kernel(const smz_video_desc *__restrict__ desc, int n_videos, const int32_t *__restrict__ nfps,
           const int32_t *__restrict__ values, const float *__restrict__ seg_mean, int method, int max_n_segs,
           int max_weight, uint8_t *__restrict__ out_picked, int32_t *__restrict__ status,
-          uint32_t *__restrict__ ws, int64_t ws_words_per_cta) {
+          uint32_t *__restrict__ ws, int64_t ws_words_per_cta, int *__restrict__ queue, const int *__restrict__ order) {
     extern __shared__ uint32_t smem[];
+    __shared__ int s_next;
     const DpSmem L = dp_layout(K, max_n_segs, max_weight);
     int *dp0 = reinterpret_cast<int *>(smem + L.dp0);
     int *dp1 = reinterpret_cast<int *>(smem + L.dp1);
@@ -102,12 +186,17 @@ dp_kernel(const smz_video_desc *__restrict__ desc, int n_videos, const int32_t *
 
     for (int j = tid; j < L.pad; j += NT) { dp0[j - L.pad] = kDpNeg; dp1[j - L.pad] = kDpNeg; }
 
-    for (int v = blockIdx.x; v < n_videos; v += gridDim.x) {
+    // videos are handed out through an atomic queue: their cost (n_segs x capacity) varies several-fold
+    while (true) {
+        if (tid == 0) s_next = atomicAdd(queue, 1);
+        __syncthreads();
+        if (s_next >= n_videos) break;
+        const int v = order[s_next];
         const smz_video_desc d = desc[v];
         const int n = d.n_segs, cap = d.capacity;
         // ---- weights / values, sum of weights, weight-range check
         int wsum = 0, bad = 0;
-        const int vlim = min(INT_MAX / (n > 0 ? n : 1), 1 << 29);
+        const int vlim = value_limit(n);
         for (int i = tid; i < n; i += NT) {
             const int w = __ldg(nfps + d.seg_off + i);
             int p = __ldg(values + d.seg_off + i);
@@ -145,7 +234,6 @@ dp_kernel(const smz_video_desc *__restrict__ desc, int n_videos, const int32_t *
                     const int2 wp = swp[i];
                     if (wp.x <= cap) {                         // uniform: upstream's loop body is empty otherwise
                         const int *src = cur + (tid - wp.x);   // c < w lands in the kDpNeg pad
-                        const uint32_t bit = 1u << (i & 31);
 #pragma unroll
                         for (int k0 = 0; k0 < K; k0 += 9) {
                             int cand[9];
@@ -153,19 +241,23 @@ dp_kernel(const smz_video_desc *__restrict__ desc, int n_videos, const int32_t *
                             for (int k = k0; k < K && k < k0 + 9; k++) cand[k - k0] = src[k * NT];
 #pragma unroll
                             for (int k = k0; k < K && k < k0 + 9; k++) {
-                                const int c = cand[k - k0] + wp.y;
-                                if (c > val[k]) acc[k] |= bit;    // strict '>' of upstream
-                                val[k] = max(val[k], c);
+                                const int d = val[k] - cand[k - k0] - wp.y;                  // < 0 iff cand + p > val: the strict '>' of upstream
+                                val[k] = __viaddmax_s32(cand[k - k0], wp.y, val[k]);          // DPX: max(cand + p, val)
+                                acc[k] = __funnelshift_l((unsigned)d, acc[k], 1);             // take bit shifted in from the sign
                                 nxt[tid + k * NT] = val[k];
                             }
                         }
                         __syncthreads();
                         int *t = cur; cur = nxt; nxt = t;
-                    }
-                    if ((i & 31) == 31 || i == n - 1) {        // flush 32 items' take bits, coalesced
-                        uint32_t *dst = bits + (int64_t)(i >> 5) * L.row + tid;
+                    } else {
 #pragma unroll
-                        for (int k = 0; k < K; k++) { dst[k * NT] = acc[k]; acc[k] = 0u; }
+                        for (int k = 0; k < K; k++) acc[k] <<= 1;          // item not taken anywhere: a zero bit
+                    }
+                    if ((i & 31) == 31 || i == n - 1) {        // flush 32 items' take bits (item j of the word -> bit j), coalesced
+                        uint32_t *dst = bits + (int64_t)(i >> 5) * L.row + tid;
+                        const int sh = 31 - (i & 31);
+#pragma unroll
+                        for (int k = 0; k < K; k++) { dst[k * NT] = __brev(acc[k]) >> sh; acc[k] = 0u; }
                     }
                 }
                 __syncthreads();   // take bits visible to warp 0
@@ -374,7 +466,7 @@ select_generic_kernel(const smz_video_desc *__restrict__ desc, int n_videos, con
         // ---- A. segment pooling (utils/eval.py:87-94) + value quantisation (knapsack.py:11-15)
         if (values_in != nullptr) {
             // stand-alone knapsack (utils/knapsack.py:5-23): values already quantised by the caller
-            const int vlim = min(INT_MAX / (n > 0 ? n : 1), 1 << 29);
+            const int vlim = value_limit(n);
             for (int s = tid; s < n; s += NT) {
                 int val = __ldg(values_in + d.seg_off + s);
                 if (val > vlim || val < -vlim) { status |= SMZ_STATUS_VALUE_RANGE; val = val > 0 ? vlim : -vlim; }
@@ -388,7 +480,7 @@ select_generic_kernel(const smz_video_desc *__restrict__ desc, int n_videos, con
             FrameCursor cur;
             cur.init(scores + d.score_off, picks + d.picks_off, d.n_scores, d.n_picks, n_frames);
             if (cur.n_bound - 1 > d.n_scores + 1) status |= SMZ_STATUS_INTERVALS;
-            const int vlim = min(INT_MAX / (n > 0 ? n : 1), 1 << 29);
+            const int vlim = value_limit(n);
             const int gl = lane & 7, lane0 = lane & ~7;
             const unsigned gmask = 0xffu << lane0;
             for (int s0 = 0; s0 < n; s0 += NT / 8) {        // 8 lanes per segment
@@ -603,7 +695,7 @@ struct SelectPlan {
 constexpr int kDpK[] = {2, 5, 9, 18, 27, 36, 54};
 
 typedef void (*dp_fn)(const smz_video_desc *, int, const int32_t *, const int32_t *, const float *, int, int, int,
-                      uint8_t *, int32_t *, uint32_t *, int64_t);
+                      uint8_t *, int32_t *, uint32_t *, int64_t, int *, const int *);
 typedef void (*generic_fn)(const smz_video_desc *, int, const float *, const int32_t *, const int32_t *,
                            const int32_t *, const int32_t *, int, int, int, int, float *, int32_t *, uint8_t *,
                            float *, uint32_t *, int32_t *, int32_t *, uint32_t *, int64_t);
@@ -626,6 +718,8 @@ generic_fn generic_fn_for(bool bits_in_smem) {
 }
 
 }  // namespace
+
+static int64_t queue_bytes(int n_videos) { return (int64_t)(1 + 2 * ORDER_BUCKETS + 3 + n_videos) * 4 + 256; }
 
 static int select_plan(int n_videos, int max_n_segs, int max_capacity, int max_n_frames, int max_weight,
                        SelectPlan *plan) {
@@ -677,7 +771,7 @@ extern "C" int smz_select_workspace_bytes(int n_videos, int max_n_segs, int max_
     SelectPlan plan;
     int rc = select_plan(n_videos, max_n_segs, max_capacity, max_n_frames, max_seg_frames, &plan);
     if (rc != SMZ_OK) return rc;
-    *bytes = (int64_t)plan.grid * plan.ws_words_per_cta * 4;
+    *bytes = (int64_t)plan.grid * plan.ws_words_per_cta * 4 + queue_bytes(n_videos);   // + queue counter, sort counters, order
     return SMZ_OK;
 }
 
@@ -696,7 +790,10 @@ static int select_launch(const smz_video_desc *desc, int n_videos, const float *
     rc = select_plan(n_videos, max_n_segs, max_capacity, max_n_frames, max_weight, &plan);
     if (rc != SMZ_OK) return rc;
     const int64_t need = (int64_t)plan.grid * plan.ws_words_per_cta * 4;
-    SMZ_REQUIRE(need == 0 || (ws != nullptr && ws_bytes >= need), "work buffer too small: need %lld bytes", (long long)need);
+    SMZ_REQUIRE(ws != nullptr && ws_bytes >= need + queue_bytes(n_videos), "work buffer too small: need %lld bytes",
+                (long long)(need + queue_bytes(n_videos)));
+    int *queue = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(ws) + need);   // [0] queue head, [1..64] counts, [65..128] fills
+    int *order = queue + 1 + 2 * ORDER_BUCKETS + 3;
     cudaStream_t st = (cudaStream_t)stream;
     SMZ_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)n_videos, st));
     if (plan.k == 0) {
@@ -713,17 +810,28 @@ static int select_launch(const smz_video_desc *desc, int n_videos, const float *
         SMZ_REQUIRE(values != nullptr, "values output is required (it feeds the DP kernel)");
         SMZ_REQUIRE(method == SMZ_METHOD_KNAPSACK || seg_mean != nullptr, "seg_mean output is required by method 'rank'");
         const int tiles = (max_n_segs + POOL_THREADS / 8 - 1) / (POOL_THREADS / 8);
-        for (int v0 = 0; v0 < n_videos && tiles > 0; v0 += 65535) {
-            const int nv = n_videos - v0 < 65535 ? n_videos - v0 : 65535;
-            pool_kernel<<<dim3(tiles, nv), POOL_THREADS, 0, st>>>(desc, v0, scores, picks, cps, seg_mean, values, status);
+        const int64_t frame_bytes = ((int64_t)max_n_frames + 1) / 2 * 4;      // one 16-bit score index per frame
+        if (tiles > 0 && frame_bytes <= smz::max_smem_optin() - 1024 && max_n_frames < 65535) {
+            SMZ_CUDA_CHECK(cudaFuncSetAttribute((const void *)pool_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)frame_bytes));
+            pool_smem_kernel<<<n_videos, POOL_SMEM_THREADS, (size_t)frame_bytes, st>>>(desc, 0, scores, picks, cps, seg_mean,
+                                                                                     values, status);
+        } else {
+            for (int v0 = 0; v0 < n_videos && tiles > 0; v0 += 65535) {
+                const int nv = n_videos - v0 < 65535 ? n_videos - v0 : 65535;
+                pool_kernel<<<dim3(tiles, nv), POOL_THREADS, 0, st>>>(desc, v0, scores, picks, cps, seg_mean, values, status);
+            }
         }
         SMZ_CUDA_CHECK(cudaGetLastError());
         vals = values;
     }
     dp_fn fn = dp_fn_for(plan.k);
+    SMZ_CUDA_CHECK(cudaMemsetAsync(queue, 0, sizeof(int) * (1 + 2 * ORDER_BUCKETS), st));
+    order_count_kernel<<<(n_videos + 255) / 256, 256, 0, st>>>(desc, n_videos, max_n_segs, queue);
+    order_fill_kernel<<<(n_videos + 255) / 256, 256, 0, st>>>(desc, n_videos, max_n_segs, queue, order);
     fn<<<plan.grid, DP_THREADS, plan.smem_bytes, st>>>(desc, n_videos, nfps, vals, seg_mean, method, max_n_segs,
                                                       plan.pad_weight, picked, status, (uint32_t *)ws,
-                                                      plan.ws_words_per_cta);
+                                                      plan.ws_words_per_cta, queue, order);
     SMZ_CUDA_CHECK(cudaGetLastError());
     if (mask != nullptr) {
         SMZ_REQUIRE(msum != nullptr, "msum is required with mask");
