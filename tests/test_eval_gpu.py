@@ -200,6 +200,31 @@ def test_large_video_bits_in_global_workspace():
     assert np.nonzero(picked[n:2 * n])[0].tolist() == ref
 
 
+def test_long_video_register_dp_with_cursor_pooling():
+    """70 000 frames: the DP row still fits the register kernel (K = 54) but the frame staging of the pooling kernel
+    does not (>= 65 535 frames) -> the cursor-walking pool_kernel; the second video has more than 128*8 frames per
+    segment on average in its tail, so the out-of-line deep pairwise recursion runs as well."""
+    from summarizer_b200 import synthetic
+    from summarizer_b200.batch import VideoBatch
+    v = synthetic.make_video("tvsum", 601, n_frames=70000, n_users=2, with_features=False)
+    w = synthetic.make_video("tvsum", 602, n_frames=70000, n_users=2, uniform_segments=2500, with_features=False)
+    rng = np.random.default_rng(12)
+    vids, scs = [], []
+    for x in (v, w):
+        vids.append({k: x[k] for k in ("n_frames", "picks", "change_points", "n_frame_per_seg", "user_summary")})
+        scs.append(rng.random(len(x["picks"])).astype(np.float32))
+    b = VideoBatch(vids)
+    b.select(torch.from_numpy(np.concatenate(scs)))
+    b.check_status()
+    picked, off = b.picked.cpu().numpy(), 0
+    for x, sc in zip((v, w), scs):
+        seg = E.segment_scores(E.upsample(sc, 70000, x["picks"]), x["change_points"])
+        ref = E.knapsack_dp_takebits(E.knapsack_values(seg), x["n_frame_per_seg"], E.capacity_of(70000, 0.15))
+        n = len(seg)
+        assert np.nonzero(picked[off:off + n])[0].tolist() == ref
+        off += n
+
+
 def test_knapsack_ortools_signature():
     from summarizer_b200.utils.knapsack import knapsack_ortools
     rng = np.random.default_rng(12)
