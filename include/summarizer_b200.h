@@ -258,6 +258,18 @@ int smz_dsn_reward_workspace_bytes(int T, int n_episodes, int64_t *bytes);
 int smz_dsn_reward(const float *x, int T, const uint8_t *actions, int n_episodes, int temp_dist_thre, int far_sim,
                    float *rewards, void *ws, int64_t ws_bytes, void *stream);
 
+/* ---- annotator summaries as 1 bit per frame (staging form for host -> device copies) --------------
+ * evaluate_summary binarises user_summary first (utils/eval.py:148-149), so (x > 0) is all it reads.
+ * smz_host_pack_user_summary runs on HOST threads over HOST pointers (it is the copy's staging step): row u of
+ * video v, h_user + user_off + u*user_ld (n_frames floats), becomes ceil(n_frames/32) words at
+ * h_bits + h_bits_off[v] + u*ceil(n_frames/32); bit j of word w = frame 32w+j is > 0.
+ * smz_fscore_packed = smz_fscore reading those rows (device pointers); F values are bit-identical. */
+int smz_host_pack_user_summary(const smz_video_desc *h_desc, int n_videos, const float *h_user,
+                               const int64_t *h_bits_off, uint32_t *h_bits, int n_threads);
+int smz_fscore_packed(const smz_video_desc *desc, int n_videos, const uint32_t *user_bits, const int64_t *bits_off,
+                      const uint32_t *mask, const int32_t *msum, int32_t *overlap, int32_t *gsum, float *f,
+                      double *avg_f, double *max_f, void *stream);
+
 /* ---- SumGAN LSTM recurrences: replace the cuDNN calls behind nn.LSTM in models/sumgan.py:43 (sLSTM, 2 x 1024
  *      bidirectional), :69 (eLSTM, 2 x 2048), :207 (cLSTM, 2 x 1024) and the step-wise decode loop :98-115 (dLSTM,
  *      2 x 2048), forward and BPTT, batch 1.  One call = one layer over the whole sequence (both directions of a

@@ -181,6 +181,46 @@ class VideoBatch:
                                          N.ptr(self.mask), N.ptr(self.msum), N.current_stream()))
         return self
 
+    # ---- annotator summaries staged as 1 bit per frame (host -> device copies move 32x fewer bytes) -------------
+    def _bits_layout(self):
+        if not hasattr(self, "h_bits_off"):
+            words = ((self.h_desc["n_frames"].astype(np.int64) + 31) // 32) * self.h_desc["n_users"].astype(np.int64)
+            off = np.zeros(self.n_videos, dtype=np.int64)
+            if self.n_videos:
+                off[1:] = np.cumsum(words)[:-1]
+            self.h_bits_off, self.total_bit_words = off, int(words.sum())
+            self.d_bits_off = torch.from_numpy(off).to(self.device)
+        return self.h_bits_off
+
+    def pack_user_summary_host(self, h_users, out=None, n_threads=None):
+        """HOST: (x > 0) of the float32 annotator rows (flat, laid out like ``d_users``) -> int32 words, one bit per
+        frame (``evaluate_summary`` binarises exactly so, utils/eval.py:148-149).  ``out``: optional (pinned) int32
+        tensor of ``total_bit_words``; returns it.  Runs on host threads inside the caller's thread (the GIL is
+        released), typically one step ahead of the copy."""
+        self._bits_layout()
+        if h_users.dtype != torch.float32 or h_users.is_cuda or not h_users.is_contiguous():
+            raise ValueError("pack_user_summary_host: contiguous float32 host tensor expected")
+        if out is None:
+            out = torch.empty(max(self.total_bit_words, 1), dtype=torch.int32)
+        if n_threads is None:
+            import os
+            n_threads = min(os.cpu_count() or 1, 32)
+        N.check(N.lib().smz_host_pack_user_summary(self.h_desc.ctypes.data_as(ctypes.c_void_p), self.n_videos,
+                                                   ctypes.c_void_p(h_users.data_ptr()),
+                                                   self.h_bits_off.ctypes.data_as(ctypes.c_void_p),
+                                                   ctypes.c_void_p(out.data_ptr()), int(n_threads)))
+        return out
+
+    def fscore_packed(self, d_bits):
+        """fscore() against annotator rows given as device bit words (see pack_user_summary_host); same F values."""
+        self._bits_layout()
+        if d_bits.numel() < self.total_bit_words or d_bits.dtype != torch.int32 or not d_bits.is_cuda:
+            raise ValueError("fscore_packed: int32 device tensor of total_bit_words expected")
+        N.check(N.lib().smz_fscore_packed(
+            N.ptr(self.d_desc), self.n_videos, N.ptr(d_bits), N.ptr(self.d_bits_off), N.ptr(self.mask), N.ptr(self.msum),
+            N.ptr(self.overlap), N.ptr(self.gsum), N.ptr(self.f), N.ptr(self.avg_f), N.ptr(self.max_f), N.current_stream()))
+        return self
+
     def fscore(self):
         """evaluate_summary for every video (utils/eval.py:125-165) against the resident
         user summaries, using the mask of the last select()/pack_summary()."""

@@ -201,6 +201,15 @@ __global__ void upsample_kernel(const smz_video_desc *__restrict__ desc, const f
 
 }  // namespace
 
+namespace smz {
+int launch_fscore_final(const smz_video_desc *desc, int n_videos, const int32_t *msum, const int32_t *overlap,
+                        const int32_t *gsum, float *f, double *avg_f, double *max_f, cudaStream_t st) {
+    fscore_final_kernel<<<(n_videos + 127) / 128, 128, 0, st>>>(desc, n_videos, msum, overlap, gsum, f, avg_f, max_f);
+    SMZ_CUDA_CHECK(cudaGetLastError());
+    return SMZ_OK;
+}
+}  // namespace smz
+
 // ------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------
@@ -223,9 +232,7 @@ extern "C" int smz_fscore(const smz_video_desc *desc, int n_videos, int max_n_fr
         }
         SMZ_CUDA_CHECK(cudaGetLastError());
     }
-    fscore_final_kernel<<<(n_videos + 127) / 128, 128, 0, st>>>(desc, n_videos, msum, overlap, gsum, f, avg_f, max_f);
-    SMZ_CUDA_CHECK(cudaGetLastError());
-    return SMZ_OK;
+    return smz::launch_fscore_final(desc, n_videos, msum, overlap, gsum, f, avg_f, max_f, st);
 }
 
 extern "C" int smz_pack_summary(const smz_video_desc *desc, int n_videos, int max_n_frames, const float *machine,

@@ -225,6 +225,27 @@ def test_long_video_register_dp_with_cursor_pooling():
         off += n
 
 
+def test_fscore_from_host_packed_annotator_bits():
+    """smz_host_pack_user_summary + smz_fscore_packed: the 1-bit-per-frame staging form gives bit-identical F values
+    (evaluate_summary binarises with x > 0 first, utils/eval.py:148-149)."""
+    from summarizer_b200.batch import VideoBatch
+    vids, scores = _dataset_videos("tvsum", 6)
+    vids[2] = dict(vids[2]); vids[2]["user_summary"] = vids[2]["user_summary"] * np.float32(0.25)   # non-binary positives
+    vids[3] = dict(vids[3]); vids[3]["user_summary"] = vids[3]["user_summary"] - np.float32(0.5)    # negatives count as 0
+    b = VideoBatch(vids)
+    b.select(torch.from_numpy(np.concatenate(scores)))
+    b.fscore()
+    ref = [t.clone() for t in (b.overlap, b.gsum, b.f, b.avg_f, b.max_f)]
+    h_users = b.d_users.cpu()
+    h_bits = b.pack_user_summary_host(h_users, n_threads=3)
+    assert h_bits.numel() == b.total_bit_words
+    for t in (b.overlap, b.gsum, b.f, b.avg_f, b.max_f):
+        t.zero_()
+    b.fscore_packed(h_bits.cuda())
+    for r, t in zip(ref, (b.overlap, b.gsum, b.f, b.avg_f, b.max_f)):
+        assert torch.equal(r[: b.total_users if r.numel() >= b.total_users else b.n_videos], t[: b.total_users if r.numel() >= b.total_users else b.n_videos])
+
+
 def test_knapsack_ortools_signature():
     from summarizer_b200.utils.knapsack import knapsack_ortools
     rng = np.random.default_rng(12)

@@ -101,3 +101,39 @@ def test_state_dict_matches_reference_modules():
         assert all(a[k].shape == b[k].shape for k in a)
     m = VASNet()
     m.load_state_dict(ref.vasnet.VASNet().state_dict())   # a reference .pth loads unchanged
+
+
+def test_host_pack_user_summary_matches_numpy():
+    """smz_host_pack_user_summary (host threads, no GPU): bit j of word w of a row = (frame 32w+j > 0); NaN and
+    negatives are 0; ragged row lengths and strides."""
+    import ctypes
+    from summarizer_b200 import _native as N
+    shapes = [(100, 3), (4097, 2), (31, 1), (64, 4)]
+    desc = np.zeros(len(shapes), dtype=N.VIDEO_DESC)
+    rng = np.random.default_rng(0)
+    rows, off = [], 0
+    for i, (nf, nu) in enumerate(shapes):
+        ld = (nf + 3) // 4 * 4
+        desc[i]["n_frames"], desc[i]["n_users"], desc[i]["user_off"], desc[i]["user_ld"] = nf, nu, off, ld
+        a = rng.standard_normal((nu, ld)).astype(np.float32)
+        a[a < 0.3] = 0
+        a[0, :5] = np.nan
+        a[-1, -7:] = -1.0
+        rows.append(a)
+        off += nu * ld
+    flat = np.concatenate([a.reshape(-1) for a in rows])
+    words = ((desc["n_frames"].astype(np.int64) + 31) // 32) * desc["n_users"]
+    boff = np.zeros(len(shapes), np.int64)
+    boff[1:] = np.cumsum(words)[:-1]
+    for n_threads in (1, 3, 16):
+        out = np.full(int(words.sum()), 0xDEADBEEF, np.uint32)
+        N.check(N.lib().smz_host_pack_user_summary(desc.ctypes.data_as(ctypes.c_void_p), len(shapes), flat.ctypes.data_as(ctypes.c_void_p),
+                                                   boff.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), n_threads))
+        for i, a in enumerate(rows):
+            nf = int(desc[i]["n_frames"]); W = (nf + 31) // 32
+            for u in range(a.shape[0]):
+                pad = np.zeros(W * 32, bool)
+                with np.errstate(invalid="ignore"):
+                    pad[:nf] = a[u, :nf] > 0
+                ref = np.packbits(pad.reshape(W, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1)
+                assert (out[boff[i] + u * W: boff[i] + (u + 1) * W] == ref).all(), (n_threads, i, u)
