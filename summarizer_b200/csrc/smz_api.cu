@@ -1,6 +1,8 @@
 // Library-level entry points: version, error string, device check.
 #include "smz_common.cuh"
 
+#include <string.h>
+
 #include <stdlib.h>
 
 #include <map>
@@ -66,6 +68,26 @@ void profile_report() {
                 100. * kv.second.first / tot, kv.second.second, 1e3 * kv.second.first / kv.second.second);
     for (auto &x : m) cudaEventDestroy(x.ev);
     m.clear();
+}
+
+namespace {
+struct SmallBlob { unsigned char b[3584]; };
+__global__ void store_blob_kernel(const __grid_constant__ SmallBlob blob, unsigned char *__restrict__ dst, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = blob.b[i];
+}
+}  // namespace
+
+int upload_small(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return SMZ_OK;
+    if (bytes <= sizeof(SmallBlob)) {
+        SmallBlob blob;
+        memcpy(blob.b, src, bytes);
+        store_blob_kernel<<<1, 256, 0, st>>>(blob, reinterpret_cast<unsigned char *>(dst), (int)bytes);
+        SMZ_CUDA_CHECK(cudaGetLastError());
+        return SMZ_OK;
+    }
+    SMZ_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return SMZ_OK;
 }
 
 int sm_count() {

@@ -52,6 +52,10 @@ void profile_report();
 
 // Number of SMs of the current device (cached per device id).
 int sm_count();
+// Host -> device upload of a small descriptor array that is safe to capture in a CUDA graph: up to 3584 bytes travel
+// as a by-value kernel parameter (copied into the launch / graph node), so no host buffer has to outlive the call;
+// larger arrays go through cudaMemcpyAsync as before.
+int upload_small(void *dst, const void *src, size_t bytes, cudaStream_t st);
 // Max opt-in dynamic shared memory per block of the current device.
 int max_smem_optin();
 

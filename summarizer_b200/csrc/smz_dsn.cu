@@ -451,7 +451,8 @@ extern "C" int smz_dsn_forward(const void *x, int x_is_bf16, const int32_t *h_cu
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t *w = reinterpret_cast<uint8_t *>(ws);
     int32_t *d_cu = reinterpret_cast<int32_t *>(w + pl.off_cu);
-    SMZ_CUDA_CHECK(cudaMemcpyAsync(d_cu, h_cu_seqlens, (size_t)(n_videos + 1) * 4, cudaMemcpyHostToDevice, st));
+    rc = smz::upload_small(d_cu, h_cu_seqlens, (size_t)(n_videos + 1) * 4, st);
+    if (rc != SMZ_OK) return rc;
     const bf16 *xb = reinterpret_cast<const bf16 *>(x);
     if (!x_is_bf16) {
         bf16 *dst = reinterpret_cast<bf16 *>(w + pl.off_xb);

@@ -251,14 +251,16 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
     std::vector<GemmProblem> probs;
     build_problems(pl, h_cu_seqlens, &probs);
     GemmProblem *d_probs = reinterpret_cast<GemmProblem *>(w + pl.off_probs);
-    SMZ_CUDA_CHECK(cudaMemcpyAsync(d_probs, probs.data(), probs.size() * sizeof(GemmProblem), cudaMemcpyHostToDevice, st));
+    rc = smz::upload_small(d_probs, probs.data(), probs.size() * sizeof(GemmProblem), st);
+    if (rc != SMZ_OK) return rc;
     int64_t *d_dropoff = nullptr;
     if (drop_att != nullptr) {
         std::vector<int64_t> off((size_t)n);
         int64_t acc = 0;
         for (int v = 0; v < n; v++) { off[v] = acc; const int64_t T = h_cu_seqlens[v + 1] - h_cu_seqlens[v]; acc += T * T; }
         d_dropoff = reinterpret_cast<int64_t *>(w + pl.off_dropoff);
-        SMZ_CUDA_CHECK(cudaMemcpyAsync(d_dropoff, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
+        rc = smz::upload_small(d_dropoff, off.data(), off.size() * 8, st);
+        if (rc != SMZ_OK) return rc;
     }
 
     bf16 *qk = reinterpret_cast<bf16 *>(w + pl.off_qk);

@@ -195,6 +195,12 @@ class Trainer:
             p.grad = flat[o:o + n].view_as(g).to(g.dtype)
             o += n
 
+    def _invalidate_shadows(self):
+        """Drop the modules' cached bf16 / packed weight copies (they are rebuilt on the next call)."""
+        for m in self.model.modules():
+            if hasattr(m, "_shadow_key"):
+                m._shadow_key = None
+
     # ---- supervised loop shared by the MSE-trained scorers (vasnet.py:171-238, logistic.py:42-112) ---
     def _train_supervised(self, fold, optimizer_params=None):
         import random
@@ -206,11 +212,66 @@ class Trainer:
         # same update rule as the reference's torch.optim.Adam (L2 term in the gradient); fused=True runs it as one
         # multi-tensor kernel on the device
         fused = bool(params) and all(p.is_cuda for p in params)
-        self.optimizer = torch.optim.Adam(params, lr=self.hps.lr, weight_decay=self.hps.weight_decay, fused=fused) if params else None
-        best_corr, best_avg_f_score, best_max_f_score = -1.0, 0.0, 0.0
         dist, rank, world = self._dp()
+        # Batch-1 optimizer steps are launch-bound (~35 kernels of 5-20 us behind ~0.4 ms of Python / launch overhead):
+        # from the second visit of a video on, its whole step (forward, loss, backward, Adam) is replayed as ONE CUDA
+        # graph (one graph per video: T differs).  Same kernels, same arithmetic; `--cuda_graphs no` keeps it eager.
+        ep = self.hps.extra_params or {}
+        use_graphs = (fused and dist is None and getattr(self.model, "max_length", None) is None
+                      and str(ep.get("cuda_graphs", "yes")).lower() not in ("no", "0", "false"))
+        self.optimizer = torch.optim.Adam(params, lr=self.hps.lr, weight_decay=self.hps.weight_decay, fused=fused,
+                                          capturable=use_graphs) if params else None
+        best_corr, best_avg_f_score, best_max_f_score = -1.0, 0.0, 0.0
         if dist is not None:
             self._dp_sync_model(dist)
+        graphs, seen = {}, set()
+        pool = torch.cuda.graph_pool_handle() if use_graphs else None
+
+        def eager_step(key):
+            seq, target = self._video_tensors(key)
+            scores = self.model(seq)
+            loss = criterion(scores, target)
+            if self.optimizer is not None:
+                loss.backward()
+            return loss.detach(), scores.detach()
+
+        def graphed_step(key):
+            """(loss, scores) of one optimizer step on `key`, replayed from its CUDA graph once captured."""
+            nonlocal use_graphs
+            if key not in graphs:
+                if key not in seen:                              # first visit: eager (allocator, Adam state, func attributes)
+                    seen.add(key)
+                    self.optimizer.zero_grad()
+                    out = eager_step(key)
+                    self.optimizer.step()
+                    return out
+                seq, target = self._video_tensors(key)
+                try:
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    self.optimizer.zero_grad(set_to_none=True)   # gradients are (re)allocated inside the graph's pool
+                    with torch.cuda.graph(g, pool=pool):
+                        scores = self.model(seq)
+                        loss = criterion(scores, target)
+                        loss.backward()
+                        self.optimizer.step()
+                        static_out = torch.cat([loss.detach().reshape(1), scores.detach().reshape(-1)])
+                    graphs[key] = (g, static_out)
+                except Exception as e:                            # capture refused: stay eager (same kernels)
+                    self.log.warning(f"CUDA graph capture failed ({type(e).__name__}: {e}); continuing without graphs")
+                    use_graphs = False
+                    torch.cuda.synchronize()
+                    self._invalidate_shadows()
+                    self.optimizer.zero_grad(set_to_none=True)
+                    out = eager_step(key)
+                    self.optimizer.step()
+                    return out
+            g, static_out = graphs[key]
+            g.replay()
+            self._invalidate_shadows()                           # bf16 weight copies cached by the module were rebuilt in graph memory
+            snap = static_out.clone()
+            return snap[0], snap[1:].reshape(-1, 1, 1)
+
         for epoch in range(self.hps.epochs):
             losses, dist_scores = [], {}
             if dist is not None:
@@ -220,16 +281,17 @@ class Trainer:
             for i in range(0, len(train_keys), world):
                 group = train_keys[i:i + world]                  # one video per replica and optimizer step
                 key = group[rank] if rank < len(group) else None
+                if use_graphs:
+                    loss, scores = graphed_step(key)
+                    losses.append(loss)
+                    dist_scores[key] = scores
+                    continue
                 if self.optimizer is not None:
                     self.optimizer.zero_grad()
                 if key is not None:
-                    seq, target = self._video_tensors(key)
-                    scores = self.model(seq)
-                    loss = criterion(scores, target)
-                    if self.optimizer is not None:
-                        loss.backward()
-                    losses.append(loss.detach())
-                    dist_scores[key] = scores.detach()
+                    loss, scores = eager_step(key)
+                    losses.append(loss)
+                    dist_scores[key] = scores
                 if self.optimizer is not None:
                     if dist is not None:
                         self._dp_allreduce_grads(dist, params, len(group))

@@ -62,3 +62,30 @@ def test_cross_validation_run_end_to_end(tmp_path):
         assert os.path.exists(hps.pred_path[sf]) or os.path.exists(hps.pred_path[sf] + ".npz")
     sd = torch.load(hps.weights_path[hps.splits_files[0]])
     assert "attention_head_projection.weight" in sd and sd["k2.weight"].shape == (1, 1024)
+
+
+def test_graph_replayed_training_steps_match_eager(tmp_path, monkeypatch):
+    """From the second visit of a video its optimizer step is replayed as a CUDA graph (models/__init__.py
+    _train_supervised): same kernels and arithmetic.  Dropout is switched off (its random stream differs between the
+    two modes).  Adam turns the float atomics' summation-order noise into +-lr moves of the parameters whose gradient
+    is ~0, so weights are compared through what they compute: the test-video scores after 3 epochs, against an
+    eager-vs-eager control run that measures that noise."""
+    import random
+    from summarizer_b200.models import vasnet_autograd
+    monkeypatch.setattr(vasnet_autograd, "draw_keep_masks", lambda *a, **k: None)
+    scores, moved = {}, {}
+    for tag, mode in (("eager", "no"), ("eager2", "no"), ("graph", "yes")):
+        hps = make_hps(tmp_path / tag, splits_files="splits/summe_splits_overfit.json", epochs=3, test_every_epochs=5, lr=1e-4,
+                       extra_params={"cuda_graphs": mode})
+        torch.manual_seed(3); random.seed(3)
+        t = hps.model_class(hps, hps.splits_files[0]).reset()
+        init = {k: v.detach().clone() for k, v in t.model.state_dict().items()}
+        res = t.train(0)
+        assert np.isfinite(res).all()
+        moved[tag] = max(float((init[k] - v).abs().max()) for k, v in t.model.state_dict().items())
+        t.model.eval()
+        scores[tag] = torch.cat(t._score_keys(t._get_train_test_keys(0)[1]))
+    assert moved["graph"] > 1e-4 and moved["eager"] > 1e-4                     # both really trained
+    noise = float((scores["eager"] - scores["eager2"]).abs().max())
+    diff = float((scores["eager"] - scores["graph"]).abs().max())
+    assert diff <= 3 * noise + 1e-4, (diff, noise)
