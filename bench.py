@@ -244,45 +244,68 @@ def train_stage(dev, seconds=4.0):
     out = {"videos": len(lens), "frames": int(sum(lens)), "shape": "TVSum-like T in [167,1294], batch 1 per optimizer step"}
 
     def timed(step):
-        for v in vids[:3]:
-            step(*v)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n, t0 = 0, time.perf_counter()
-        e0.record()
-        while time.perf_counter() - t0 < seconds:
-            for v in vids:
-                step(*v)
-            n += 1
-        e1.record(); torch.cuda.synchronize()
-        return n * sum(lens) / (e0.elapsed_time(e1) / 1e3)
+        """frames/s of `step(x, target)` over the 16 videos, each video's step replayed as a CUDA graph (as the
+        trainers do from the second visit on, models/__init__.py StepGraphs); eager rate reported beside it."""
+        def run_pass(fn):
+            for k in range(len(vids)):
+                fn(k)
+
+        def rate(fn):
+            run_pass(fn)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n, t0 = 0, time.perf_counter()
+            e0.record()
+            while time.perf_counter() - t0 < seconds / 2:
+                run_pass(fn)
+                n += 1
+            e1.record(); torch.cuda.synchronize()
+            return n * sum(lens) / (e0.elapsed_time(e1) / 1e3)
+
+        eager = rate(lambda k: step(*vids[k]))
+        pool, graphs = torch.cuda.graph_pool_handle(), []
+        for x, tgt in vids:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                step(x, tgt)
+            graphs.append(g)
+
+        def replay(k):
+            graphs[k].replay()
+            for m in (vas, dsn):
+                m._shadow_key = None
+        return rate(replay), eager
 
     torch.manual_seed(0)
     vas = VASNet().to(dev).train()
-    opt = torch.optim.Adam(vas.parameters(), lr=5e-5, weight_decay=1e-5, fused=True)
+    dsn = DSN().to(dev).train()
+    opt = torch.optim.Adam(vas.parameters(), lr=5e-5, weight_decay=1e-5, fused=True, capturable=True)
 
     def vas_step(x, tgt):
+        opt.zero_grad(set_to_none=True)
         loss = torch.nn.functional.mse_loss(vas(x), tgt)
-        opt.zero_grad(); loss.backward(); opt.step()
-    out["vasnet_train_frames_per_s"] = timed(vas_step)
+        loss.backward(); opt.step()
+    out["vasnet_train_frames_per_s"], out["vasnet_train_frames_per_s_eager"] = timed(vas_step)
     f_train = sum(24 * T * FEAT * FEAT + 12 * T * T * FEAT + 6 * T * FEAT for T in lens)
     out["vasnet_train_tflops"] = out["vasnet_train_frames_per_s"] / sum(lens) * f_train / 1e12
 
-    dsn = DSN().to(dev).train()
-    opt2 = torch.optim.Adam(dsn.parameters(), lr=5e-5, weight_decay=1e-5, fused=True)
+    opt2 = torch.optim.Adam(dsn.parameters(), lr=5e-5, weight_decay=1e-5, fused=True, capturable=True)
     base = torch.zeros((), device=dev)
 
     def dsn_step(x, tgt):
+        opt2.zero_grad(set_to_none=True)
         probs = dsn(x)
-        dist = Bernoulli(probs)
+        dist = Bernoulli(probs, validate_args=False)
         actions = torch.stack([dist.sample() for _ in range(5)])
         rewards = compute_rewards(x, actions.reshape(5, -1))
         loss = 0.
         for e in range(5):
             loss = loss - dist.log_prob(actions[e]).mean() * (rewards[e] - base)
         loss = loss / 5.
-        opt2.zero_grad(); loss.backward(); torch.nn.utils.clip_grad_norm_(dsn.parameters(), 5.0); opt2.step()
-    out["dsn_reinforce_frames_per_s"] = timed(dsn_step)
+        loss.backward(); torch.nn.utils.clip_grad_norm_(dsn.parameters(), 5.0); opt2.step()
+    out["dsn_reinforce_frames_per_s"], out["dsn_reinforce_frames_per_s_eager"] = timed(dsn_step)
+    out["step_replay"] = "one CUDA graph per video (forward, loss, backward, clip, Adam)"
     del vas, dsn, opt, opt2
 
     # BASELINE config 4 (SUM-GAN-style LSTM generator/discriminator): the reference's three updates per video

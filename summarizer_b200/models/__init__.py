@@ -34,6 +34,47 @@ def open_dataset(path, log=None):
     raise FileNotFoundError(f"dataset {path} not found and no synthetic stand-in is defined for it")
 
 
+class StepGraphs:
+    """Per-video optimizer steps replayed as CUDA graphs.
+
+    A batch-1 training step is launch-bound (VASNet: ~35 kernels of 5-20 us behind ~0.4 ms of Python and launch
+    overhead).  ``run(key, step)`` executes ``step(key)`` eagerly on the first visit of a video (allocator warm-up,
+    optimizer state, function attributes), captures it on the second visit and replays the graph from then on — one
+    graph per video because T differs, all sharing one memory pool.  ``step`` must do the WHOLE update (zero_grad with
+    ``set_to_none=True`` first, forward, loss, backward, optimizer step, in-place updates of persistent tensors) and
+    return a tuple of tensors; replays hand back clones of them.  Same kernels and arithmetic as the eager step."""
+
+    def __init__(self, trainer, enabled):
+        self.trainer, self.enabled = trainer, bool(enabled)
+        self.graphs, self.seen = {}, set()
+        self.pool = torch.cuda.graph_pool_handle() if self.enabled else None
+
+    def run(self, key, step):
+        if not self.enabled or key not in self.seen:
+            self.seen.add(key)
+            return step(key)
+        if key not in self.graphs:
+            try:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                # the bf16 weight copies must be REBUILT INSIDE the graph: a copy cached by an eager call (e.g. test()
+                # right before) would be baked in by address and never refreshed on replay
+                self.trainer._invalidate_shadows()
+                with torch.cuda.graph(g, pool=self.pool):
+                    static = tuple(step(key))
+                self.graphs[key] = (g, static)
+            except Exception as e:                                # capture refused: stay eager (same kernels)
+                self.trainer.log.warning(f"CUDA graph capture failed ({type(e).__name__}: {e}); continuing without graphs")
+                self.enabled = False
+                torch.cuda.synchronize()
+                self.trainer._invalidate_shadows()
+                return step(key)
+        g, static = self.graphs[key]
+        g.replay()
+        self.trainer._invalidate_shadows()       # the modules' cached bf16 weight copies were rebuilt inside graph memory
+        return tuple(t.clone() for t in static)
+
+
 class Trainer:
     """Abstract class handling the training process"""
 
@@ -213,9 +254,8 @@ class Trainer:
         # multi-tensor kernel on the device
         fused = bool(params) and all(p.is_cuda for p in params)
         dist, rank, world = self._dp()
-        # Batch-1 optimizer steps are launch-bound (~35 kernels of 5-20 us behind ~0.4 ms of Python / launch overhead):
         # from the second visit of a video on, its whole step (forward, loss, backward, Adam) is replayed as ONE CUDA
-        # graph (one graph per video: T differs).  Same kernels, same arithmetic; `--cuda_graphs no` keeps it eager.
+        # graph (StepGraphs); `--cuda_graphs no` keeps it eager
         ep = self.hps.extra_params or {}
         use_graphs = (fused and dist is None and getattr(self.model, "max_length", None) is None
                       and str(ep.get("cuda_graphs", "yes")).lower() not in ("no", "0", "false"))
@@ -224,10 +264,9 @@ class Trainer:
         best_corr, best_avg_f_score, best_max_f_score = -1.0, 0.0, 0.0
         if dist is not None:
             self._dp_sync_model(dist)
-        graphs, seen = {}, set()
-        pool = torch.cuda.graph_pool_handle() if use_graphs else None
+        graphs = StepGraphs(self, use_graphs)
 
-        def eager_step(key):
+        def forward_backward(key):
             seq, target = self._video_tensors(key)
             scores = self.model(seq)
             loss = criterion(scores, target)
@@ -235,42 +274,11 @@ class Trainer:
                 loss.backward()
             return loss.detach(), scores.detach()
 
-        def graphed_step(key):
-            """(loss, scores) of one optimizer step on `key`, replayed from its CUDA graph once captured."""
-            nonlocal use_graphs
-            if key not in graphs:
-                if key not in seen:                              # first visit: eager (allocator, Adam state, func attributes)
-                    seen.add(key)
-                    self.optimizer.zero_grad()
-                    out = eager_step(key)
-                    self.optimizer.step()
-                    return out
-                seq, target = self._video_tensors(key)
-                try:
-                    torch.cuda.synchronize()
-                    g = torch.cuda.CUDAGraph()
-                    self.optimizer.zero_grad(set_to_none=True)   # gradients are (re)allocated inside the graph's pool
-                    with torch.cuda.graph(g, pool=pool):
-                        scores = self.model(seq)
-                        loss = criterion(scores, target)
-                        loss.backward()
-                        self.optimizer.step()
-                        static_out = torch.cat([loss.detach().reshape(1), scores.detach().reshape(-1)])
-                    graphs[key] = (g, static_out)
-                except Exception as e:                            # capture refused: stay eager (same kernels)
-                    self.log.warning(f"CUDA graph capture failed ({type(e).__name__}: {e}); continuing without graphs")
-                    use_graphs = False
-                    torch.cuda.synchronize()
-                    self._invalidate_shadows()
-                    self.optimizer.zero_grad(set_to_none=True)
-                    out = eager_step(key)
-                    self.optimizer.step()
-                    return out
-            g, static_out = graphs[key]
-            g.replay()
-            self._invalidate_shadows()                           # bf16 weight copies cached by the module were rebuilt in graph memory
-            snap = static_out.clone()
-            return snap[0], snap[1:].reshape(-1, 1, 1)
+        def full_step(key):                                      # what a CUDA graph replays
+            self.optimizer.zero_grad(set_to_none=True)
+            out = forward_backward(key)
+            self.optimizer.step()
+            return out
 
         for epoch in range(self.hps.epochs):
             losses, dist_scores = [], {}
@@ -282,14 +290,14 @@ class Trainer:
                 group = train_keys[i:i + world]                  # one video per replica and optimizer step
                 key = group[rank] if rank < len(group) else None
                 if use_graphs:
-                    loss, scores = graphed_step(key)
+                    loss, scores = graphs.run(key, full_step)
                     losses.append(loss)
                     dist_scores[key] = scores
                     continue
                 if self.optimizer is not None:
                     self.optimizer.zero_grad()
                 if key is not None:
-                    loss, scores = eager_step(key)
+                    loss, scores = forward_backward(key)
                     losses.append(loss)
                     dist_scores[key] = scores
                 if self.optimizer is not None:

@@ -99,7 +99,7 @@ class DSN(nn.Module):
 
 from torch.distributions import Bernoulli  # noqa: E402
 
-from . import Trainer  # noqa: E402
+from . import StepGraphs, Trainer  # noqa: E402
 
 
 def compute_rewards(seq, actions, far_sim=False, temp_dist_thre=20, workspace=None):
@@ -162,6 +162,43 @@ class DSNTrainer(Trainer):
         params = list(self.model.parameters())
         if dist_ is not None:
             self._dp_sync_model(dist_)
+        ep = self.hps.extra_params or {}
+        use_graphs = (dist_ is None and all(p.is_cuda for p in params)
+                      and str(ep.get("cuda_graphs", "yes")).lower() not in ("no", "0", "false"))
+        if use_graphs:                                            # capturable Adam keeps its step counter on the device
+            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.hps.lr, weight_decay=self.hps.weight_decay,
+                                              fused=True, capturable=True)
+        graphs = StepGraphs(self, use_graphs)
+
+        def forward_backward(key):
+            """REINFORCE loss of one video and its backward pass -> (loss, probs, mean reward, baseline delta)."""
+            seq, target = self._video_tensors(key)
+            probs = self.model(seq)                                           # (T,1,1), autograd through the device BPTT
+            dist = Bernoulli(probs, validate_args=False)
+            loss = self.beta * (probs.mean() - self.eps) ** 2                 # summary-length penalty [Eq.11]
+            if self.sup:
+                loss = loss + loss_BCE(probs, target)
+            actions = torch.stack([dist.sample() for _ in range(self.num_episodes)])      # (E,T,1,1)
+            rewards = compute_rewards(seq, actions.reshape(self.num_episodes, -1), self.far_sim, self.temp_dist_thre,
+                                      self._reward_ws)
+            base = baselines[key_index[key]].detach().clone()
+            for e in range(self.num_episodes):                                # policy gradient [Eq.10]
+                loss = loss - dist.log_prob(actions[e]).mean() * (rewards[e] - base)
+            loss = loss / float(self.num_episodes)
+            loss.backward()
+            mean_reward = rewards.mean()
+            delta = torch.zeros_like(baselines)                               # moving-average baseline update (dsn.py:149)
+            delta[key_index[key]] = 0.1 * (mean_reward - base)
+            return loss.detach(), probs.detach(), mean_reward, delta
+
+        def full_step(key):                                                   # what a CUDA graph replays
+            self.optimizer.zero_grad(set_to_none=True)
+            loss, probs, mean_reward, delta = forward_backward(key)
+            baselines.add_(delta)
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), 5.0)
+            self.optimizer.step()
+            return loss, probs, mean_reward
+
         for epoch in range(self.hps.epochs):
             epoch_losses, dist_scores = [], {}
             if dist_ is not None:
@@ -169,35 +206,26 @@ class DSNTrainer(Trainer):
             else:
                 random.shuffle(train_keys)
             for i0 in range(0, len(train_keys), world):
-                group = train_keys[i0:i0 + world]                                  # one video per replica and step
+                group = train_keys[i0:i0 + world]                  # one video per replica and step
                 key = group[rank] if rank < len(group) else None
+                if use_graphs:
+                    loss, probs, mean_reward = graphs.run(key, full_step)
+                    reward_writers[key].append(mean_reward)
+                    epoch_losses.append(loss)
+                    dist_scores[key] = probs
+                    continue
                 self.optimizer.zero_grad()
                 if key is not None:
-                    seq, target = self._video_tensors(key)
-                    probs = self.model(seq)                                       # (T,1,1), autograd through the device BPTT
-                    dist = Bernoulli(probs)
-                    loss = self.beta * (probs.mean() - self.eps) ** 2             # summary-length penalty [Eq.11]
-                    if self.sup:
-                        loss = loss + loss_BCE(probs, target)
-                    actions = torch.stack([dist.sample() for _ in range(self.num_episodes)])      # (E,T,1,1)
-                    rewards = compute_rewards(seq, actions.reshape(self.num_episodes, -1), self.far_sim, self.temp_dist_thre,
-                                              self._reward_ws)
-                    for e in range(self.num_episodes):                            # policy gradient [Eq.10]
-                        loss = loss - dist.log_prob(actions[e]).mean() * (rewards[e] - baselines[key_index[key]].detach())
-                    loss = loss / float(self.num_episodes)
-                    loss.backward()
-                    mean_reward = rewards.mean()
-                    delta = torch.zeros_like(baselines)                           # moving-average baseline update (dsn.py:149)
-                    delta[key_index[key]] = 0.1 * (mean_reward - baselines[key_index[key]])
+                    loss, probs, mean_reward, delta = forward_backward(key)
                     reward_writers[key].append(mean_reward)
-                    epoch_losses.append(loss.detach())
-                    dist_scores[key] = probs.detach()
+                    epoch_losses.append(loss)
+                    dist_scores[key] = probs
                 else:
                     delta = torch.zeros_like(baselines)
                 if dist_ is not None:
                     self._dp_allreduce_grads(dist_, params, len(group))
                     dist_.all_reduce(delta)                                       # every replica keeps every video's baseline
-                baselines = baselines + delta
+                baselines.add_(delta)
                 torch.nn.utils.clip_grad_norm_(self.model.parameters(), 5.0)
                 self.optimizer.step()
             seen = [k for k in train_keys if len(reward_writers[k]) > epoch]
