@@ -241,6 +241,8 @@ class Trainer:
         for m in self.model.modules():
             if hasattr(m, "_shadow_key"):
                 m._shadow_key = None
+            if hasattr(m, "_cache") and hasattr(m._cache, "_store"):
+                m._cache._store.clear()
 
     # ---- supervised loop shared by the MSE-trained scorers (vasnet.py:171-238, logistic.py:42-112) ---
     def _train_supervised(self, fold, optimizer_params=None):

@@ -41,11 +41,13 @@ class DSN(nn.Module):
         return (r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0, r.weight_ih_l0_reverse, r.weight_hh_l0_reverse,
                 r.bias_ih_l0_reverse, r.bias_hh_l0_reverse, o.weight, o.bias)
 
-    def _weights(self):
-        """bf16 / packed shadow copies for the kernels; rebuilt when a parameter changed."""
+    def _weights(self, training=False):
+        """bf16 / packed shadow copies for the kernels.  A training forward always rebuilds them and leaves the cache
+        dirty (fused optimizers update parameters without bumping ``Tensor._version``); inference calls reuse them
+        until a parameter's version / storage changes or a training forward happened in between."""
         ps = self._params()
         key = tuple((p.data_ptr(), p._version) for p in ps)
-        if key != self._shadow_key:
+        if training or self._shadow_key is None or key != self._shadow_key:
             wih_f, whh_f, bih_f, bhh_f, wih_b, whh_b, bih_b, bhh_b, w_out, b_out = ps
             with torch.no_grad():
                 dev = wih_f.device
@@ -56,7 +58,7 @@ class DSN(nn.Module):
                           w_out=w_out.float().reshape(-1).contiguous(), b_out=b_out.float().contiguous())
                 N.check(N.lib().smz_dsn_pack_whh(N.ptr(whh_f.float().contiguous()), N.ptr(whh_b.float().contiguous()),
                                                  N.ptr(sh["whh"]), N.ptr(sh["whh_t"]), N.current_stream()))
-            self._shadow, self._shadow_key = sh, key
+            self._shadow, self._shadow_key = sh, (None if training else key)
         sh = self._shadow
         st = DsnParams(*(sh[k].data_ptr() for k in ("w_ih", "bias", "whh", "whh_t", "w_out", "b_out")))
         return sh, st

@@ -22,7 +22,7 @@ class _DsnFunction(torch.autograd.Function):
             x = x.float()
         cu = _cu_seqlens(lengths)
         is_bf16 = int(x.dtype == torch.bfloat16)
-        sh, st = module._weights()
+        sh, st = module._weights(training=True)
         nbytes = C.c_int64(0)
         N.check(N.lib().smz_dsn_workspace_bytes(int(cu[-1]), len(lengths), 1, is_bf16, C.byref(nbytes)))
         ws = torch.empty(max(nbytes.value, 1024), dtype=torch.uint8, device=x.device)

@@ -35,18 +35,20 @@ def _off(t, elems):
 
 
 class ShadowCache:
-    """bf16 / transposed copies of parameters for the kernels, rebuilt when a parameter changed (optimizer steps
-    bump ``_version``)."""
+    """bf16 / transposed copies of parameters for the kernels.  ``fresh=True`` (training forwards) always rebuilds and
+    leaves the entry dirty: an optimizer step follows, and fused optimizers update parameters without bumping
+    ``Tensor._version``.  Inference calls reuse an entry until a version / storage changes or a training forward
+    happened in between."""
 
     def __init__(self):
         self._store = {}
 
-    def get(self, key, params, build):
+    def get(self, key, params, build, fresh=False):
         tag = tuple((p.data_ptr(), p._version) for p in params)
         ent = self._store.get(key)
-        if ent is None or ent[0] != tag:
+        if fresh or ent is None or ent[0] is None or ent[0] != tag:
             with torch.no_grad():
-                ent = (tag, build())
+                ent = (None if fresh else tag, build())
             self._store[key] = ent
         return ent[1]
 
@@ -84,9 +86,9 @@ class _LstmLayerFn(torch.autograd.Function):
         N.require_device()
         cache, key, nd, H = meta
         dirs = [flat[4 * i: 4 * i + 4] for i in range(nd)]
-        sh = cache.get(key, flat, lambda: _LayerShadow(dirs))
-        T, dev = x.shape[0], x.device
         training = any(ctx.needs_input_grad)
+        sh = cache.get(key, flat, lambda: _LayerShadow(dirs), fresh=training)
+        T, dev = x.shape[0], x.device
         xb = _bf(x)
         pre = gemm(xb, sh.w_ih, bias=sh.bias)                                     # [T, nd*4H]
         f32 = dict(dtype=torch.float32, device=dev)
@@ -182,10 +184,10 @@ class _DecodeFn(torch.autograd.Function):
         N.require_device()
         cache, key, T, H = meta
         p0, p1 = flat[:4], flat[4:]
-        sh = cache.get(key, flat, lambda: _DecodeShadow(p0, p1))
+        training = any(ctx.needs_input_grad)
+        sh = cache.get(key, flat, lambda: _DecodeShadow(p0, p1), fresh=training)
         dev = h_init.device
         f32 = dict(dtype=torch.float32, device=dev)
-        training = any(ctx.needs_input_grad)
         hi, ci = h_init.detach().float().contiguous(), c_init.detach().float().contiguous()
         hs0, hs1 = torch.empty(T, H, **f32), torch.empty(T, H, **f32)
         save = [torch.empty(T, 4 * H, **f32), torch.empty(T, 4 * H, **f32), torch.empty(T, H, **f32),

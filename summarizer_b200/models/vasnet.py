@@ -100,13 +100,17 @@ class VASNet(nn.Module):
 
     # ---------------------------------------------------------------------------------------------
     def _weights(self, inference=True):
-        """bfloat16 shadow copies + the parameter struct; rebuilt when a parameter changed.  The folded head
-        constants are only derived for inference (the training path keeps the separate head kernel)."""
+        """bfloat16 shadow copies + the parameter struct.  A training forward (``inference=False``) ALWAYS rebuilds
+        them and leaves the cache marked dirty: an optimizer step follows, and fused optimizers update the parameters
+        without bumping ``Tensor._version``, so a version key cannot be trusted across a step.  Inference calls reuse
+        the copies until a parameter's version / storage changes (``load_state_dict``, ``.cuda()``) or a training
+        forward happened in between.  The folded head constants are only derived for inference (the training path
+        keeps the separate head kernel)."""
         ps = (self.Q.weight, self.K.weight, self.V.weight, self.attention_head_projection.weight,
               self.k1.weight, self.k1.bias, self.k2.weight, self.k2.bias, self.layer_norm.weight,
               self.layer_norm.bias)
         key = tuple((p.data_ptr(), p._version) for p in ps)
-        if key != self._shadow_key:
+        if not inference or self._shadow_key is None or key != self._shadow_key:
             with torch.no_grad():
                 sh = dict(
                     wqk=torch.cat([self.Q.weight, self.K.weight], 0).to(torch.bfloat16).contiguous(),
@@ -116,7 +120,7 @@ class VASNet(nn.Module):
                     b1=self.k1.bias.float().contiguous(), w2=self.k2.weight.float().reshape(-1).contiguous(),
                     b2=self.k2.bias.float().contiguous(), ln_g=self.layer_norm.weight.float().contiguous(),
                     ln_b=self.layer_norm.bias.float().contiguous())
-            self._shadow, self._shadow_key = sh, key
+            self._shadow, self._shadow_key = sh, (key if inference else None)
         sh = self._shadow
         if inference and "head_gw" not in sh:
             with torch.no_grad():   # regressor head folded into the k1 epilogue: z = rstd * (sum h*gw - mean * c0) + c1

@@ -89,3 +89,39 @@ def test_graph_replayed_training_steps_match_eager(tmp_path, monkeypatch):
     noise = float((scores["eager"] - scores["eager2"]).abs().max())
     diff = float((scores["eager"] - scores["graph"]).abs().max())
     assert diff <= 3 * noise + 1e-4, (diff, noise)
+
+
+@pytest.mark.parametrize("family", ["vasnet", "dsn", "slstm"])
+def test_weight_copies_follow_fused_optimizer_steps(family):
+    """The kernels read bf16 / packed COPIES of the parameters.  torch's fused Adam updates parameters in place without
+    bumping Tensor._version, so a version-keyed cache would keep serving the old copies: after an optimizer step both
+    the next training forward and the next inference call must see the new weights (= what a fresh module loaded with
+    the same state dict computes)."""
+    import copy
+    torch.manual_seed(5)
+    if family == "vasnet":
+        from summarizer_b200.models.vasnet import VASNet as cls
+    elif family == "dsn":
+        from summarizer_b200.models.dsn import DSN as cls
+    else:
+        from summarizer_b200.models.sumgan import sLSTM as cls
+    m = cls().cuda().eval()                       # eval(): no dropout, so the training-path forward is deterministic
+    x = torch.rand(24, 1, 1024, device="cuda")
+    x = x / x.norm(dim=2, keepdim=True)
+    opt = torch.optim.Adam(m.parameters(), lr=3e-3, fused=True)
+    with torch.no_grad():
+        y_before = m(x).clone()
+    for _ in range(2):
+        opt.zero_grad()
+        m(x).square().mean().backward()
+        opt.step()
+    with torch.no_grad():
+        y_inf = m(x).clone()
+    y_train = m(x).detach().clone()
+    fresh = cls().cuda().eval()
+    fresh.load_state_dict(copy.deepcopy(m.state_dict()))
+    with torch.no_grad():
+        y_ref = fresh(x)
+    assert float((y_before - y_ref).abs().max()) > 1e-3            # the steps really changed the function
+    assert torch.allclose(y_inf, y_ref, atol=1e-6), float((y_inf - y_ref).abs().max())
+    assert torch.allclose(y_train, fresh(x).detach(), atol=1e-6)
