@@ -28,6 +28,10 @@ def benchmark(args, log_path):
                                                                   "extra_params": {}}, **base))
     table_results += benchmark_model("VASNet", dict({"model": "vasnet", "epochs": min(50, args.max_epochs),
                                                      "extra_params": {}}, **base))
+    table_results += benchmark_model("DSN", dict({"model": "dsn", "epochs": min(60, args.max_epochs), "extra_params": {}}, **base))
+    if getattr(args, "sumgan", False):      # 195 M parameters, three adversarial updates per video: minutes per fold
+        table_results += benchmark_model("SumGAN", dict({"model": "sumgan", "epochs": min(20, args.max_epochs),
+                                                         "extra_params": {"pretrain_vae": str(min(20, args.max_epochs))}}, **base))
     table = pd.DataFrame(table_results, columns=["Model", "File", "Correlation", "Avg F-score", "Max F-score", "Logs",
                                                  "Train+eval s"])
     show_save_results(table, log_path)
@@ -69,6 +73,7 @@ if __name__ == "__main__":
     parser.add_argument("-s", "--splits-files", type=str, default="splits/tvsum_splits.json,splits/summe_splits.json",
                         help="Comma separated list of split files")
     parser.add_argument("-c", "--use-cuda", choices=["yes", "no", "default"], default="default")
+    parser.add_argument("-g", "--sumgan", action="store_true", help="also train SumGAN (minutes per fold)")
     args, _ = parser.parse_known_args()
     print(args)
     benchmark(args, log_path)
