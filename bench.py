@@ -446,7 +446,7 @@ def run_native(args):
         st_["h_bits"] = torch.empty(st_["eb"].total_bit_words, dtype=torch.int32, pin_memory=True)
         st_["d_bits"] = torch.empty(st_["eb"].total_bit_words, dtype=torch.int32, device=dev)
     pool = ThreadPoolExecutor(max_workers=1)
-    host_threads = min(os.cpu_count() or 1, 32)
+    host_threads = max(1, min((os.cpu_count() or 1) // max(world, 1), 32))     # the ranks of one box share its cores
 
     def pack_job(k):
         sets[k]["ready"].synchronize()                             # the copy that last read this pinned buffer is done
@@ -540,7 +540,7 @@ def run_native(args):
                     "annotator_staging": ("packed on %d host threads to 1 bit/frame inside the timed region (x > 0 is all "
                                           "evaluate_summary reads)" % host_threads) if use_packed else "float32 rows as held by the reference",
                     "value_float32_rows": e2e_float, "value_host_packed": e2e_packed},
-            "gpu_launches": int((nl.value + 6) * args.steps),
+            "gpu_launches": int((nl.value + 7) * args.steps),     # + order_count, order_fill, pool, dp, summary, fscore, fscore_final
             "clocks": clocks,
         }
         if world == 1:

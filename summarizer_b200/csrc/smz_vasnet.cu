@@ -176,7 +176,7 @@ void build_problems(const Plan &pl, const int32_t *cu, std::vector<GemmProblem> 
 // Two internal streams per device: consecutive chunks run on alternating streams (each with its own copy of
 // the chunk buffers) so that the tail wave of one chunk's GEMM overlaps the next chunk's kernels.  They are
 // forked from / joined back into the caller's stream with events, so the call stays asynchronous and ordered.
-struct SideStreams { cudaStream_t s[2]; cudaEvent_t fork, join[2]; bool ok; };
+struct SideStreams { cudaStream_t s[2]; cudaEvent_t fork, join[2], ev[6]; bool ok; };
 SideStreams *side_streams() {
     static SideStreams table[64];
     int dev = 0;
@@ -188,6 +188,8 @@ SideStreams *side_streams() {
             if (cudaEventCreateWithFlags(&t.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         }
         if (cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 6; i++)
+            if (cudaEventCreateWithFlags(&t.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         t.ok = true;
     }
     return &t;
@@ -308,6 +310,14 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
             xb = dst;
         }
         // Q|K projection and V^T projection
+        // training (one video, a few tiles per GEMM): V^T runs beside Q|K on the side stream, joined before alpha.V
+        SideStreams *fs = (training && !smz::profile_enabled() && !smz::debug_sync_enabled()) ? side_streams() : nullptr;
+        cudaStream_t st_v = st;
+        if (fs != nullptr) {
+            SMZ_CUDA_CHECK(cudaEventRecord(fs->ev[0], st));                       // x (bf16) is ready
+            SMZ_CUDA_CHECK(cudaStreamWaitEvent(fs->s[0], fs->ev[0], 0));
+            st_v = fs->s[0];
+        }
         smz::profile_mark(st, "gemm_qk");
         rc = smz::gemm_bf16_tn(xb, R, kFeat, kFeat, p->wqk, 2 * kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, 2 * kFeat),
                                dense_problem(R, 2 * kFeat, kFeat, 2 * kFeat, 0), GemmEpilogue{qk, nullptr, nullptr, 1.f, 0}, st);
@@ -315,8 +325,9 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
         SMZ_DEBUG_STEP(st, "gemm_qk");
         smz::profile_mark(st, "gemm_vt");
         rc = smz::gemm_bf16_tn(p->wv, kFeat, kFeat, kFeat, xb, R, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(kFeat, R),
-                               dense_problem(kFeat, R, kFeat, (int)Rpad, 0), GemmEpilogue{vt, nullptr, nullptr, 1.f, 0}, st);
+                               dense_problem(kFeat, R, kFeat, (int)Rpad, 0), GemmEpilogue{vt, nullptr, nullptr, 1.f, 0}, st_v);
         if (rc != SMZ_OK) return rc;
+        if (fs != nullptr) SMZ_CUDA_CHECK(cudaEventRecord(fs->ev[1], st_v));
         SMZ_DEBUG_STEP(st, "gemm_vt");
         // attention, one GEMM problem per video
         for (const Sub &s : c.subs) {
@@ -367,6 +378,7 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
                 SMZ_DEBUG_STEP(st, "softmax");
             }
             smz::profile_mark(st, "gemm_pv");
+            if (fs != nullptr) SMZ_CUDA_CHECK(cudaStreamWaitEvent(st, fs->ev[1], 0));     // V^T is ready
             {
                 GemmEpilogue e{o, fast ? inv_l : nullptr, nullptr, 1.f, fast ? smz::GEMM_SCALE_M : 0};
                 rc = smz::gemm_bf16_tn(P, s.rows, s.ld, s.ld, vt, kFeat, R, Rpad, d_probs + n + s.v0, nv, tiles_pv, GemmProblem{}, e, st);
@@ -470,6 +482,19 @@ extern "C" int smz_vasnet_backward(const void *x, int x_is_bf16, const int32_t *
     const int64_t Rs = pl.rows_cap;
     const int F32ACC = smz::GEMM_OUT_F32 | smz::GEMM_RES_F32;   // C = A.B^T + C (float32)
     int64_t att_off = 0;                                         // offset of the video's attention keep-mask
+    // A batch-1 backward pass is 12 GEMMs of a few tiles each: the weight-gradient GEMMs (and dV^T, dK) do not sit on the
+    // dX chain, so they run on a side stream beside it — fork / join with events, which a CUDA-graph capture records as
+    // parallel branches.  main: head, dYn, LN, dO, dP, softmax, dQ | side: dW1, dWo, dV^T, dWv, dK | join | dWqk, dx.
+    SideStreams *ss = (!smz::profile_enabled() && !smz::debug_sync_enabled()) ? side_streams() : nullptr;
+    cudaStream_t sd = ss != nullptr ? ss->s[0] : st;
+    auto fork_to_side = [&](int e) -> int {                      // side stream continues after what main has queued so far
+        if (ss == nullptr) return SMZ_OK;
+        SMZ_CUDA_CHECK(cudaEventRecord(ss->ev[e], st));
+        SMZ_CUDA_CHECK(cudaStreamWaitEvent(sd, ss->ev[e], 0));
+        return SMZ_OK;
+    };
+    rc = fork_to_side(0);                                        // the caller's zeroed gradient buffers
+    if (rc != SMZ_OK) return rc;
 
     for (const Chunk &c : pl.chunks) {
         const int T = c.rows;
@@ -502,12 +527,14 @@ extern "C" int smz_vasnet_backward(const void *x, int x_is_bf16, const int32_t *
                                   gr->b1, st);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "head_bwd");
+        rc = fork_to_side(1);                                    // dh is ready
+        if (rc != SMZ_OK) return rc;
         // k1: dYn = dh . W1 ; dW1 += dh^T . Yn
         rc = gemm1(false, true, dh, T, kFeat, kFeat, p->w1, kFeat, kFeat, kFeat, prob(T, kFeat, kFeat, kFeat),
                    GemmEpilogue{dyn, nullptr, nullptr, 1.f, smz::GEMM_OUT_F32}, st);
         if (rc != SMZ_OK) return rc;
         rc = gemm1(true, true, dh, T, kFeat, kFeat, yn, T, kFeat, kFeat, prob(kFeat, kFeat, T, kFeat, 0, kFeat),
-                   GemmEpilogue{gr->w1, nullptr, gr->w1, 1.f, F32ACC}, st);
+                   GemmEpilogue{gr->w1, nullptr, gr->w1, 1.f, F32ACC}, sd);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "k1_bwd");
         // first LayerNorm + dropout -> dY (also the gradient of the residual branch)
@@ -515,25 +542,34 @@ extern "C" int smz_vasnet_backward(const void *x, int x_is_bf16, const int32_t *
                                        gr->ln_g, gr->ln_b, st);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "ln_bwd");
+        rc = fork_to_side(2);                                    // dY is ready
+        if (rc != SMZ_OK) return rc;
         // output projection: dO = dY . Wo ; dWo += dY^T . O
         rc = gemm1(false, true, dy, T, kFeat, kFeat, p->wo, kFeat, kFeat, kFeat, prob(T, kFeat, kFeat, kFeat),
                    GemmEpilogue{dO, nullptr, nullptr, 1.f, 0}, st);
         if (rc != SMZ_OK) return rc;
         rc = gemm1(true, true, dy, T, kFeat, kFeat, o, T, kFeat, kFeat, prob(kFeat, kFeat, T, kFeat, 0, kFeat),
-                   GemmEpilogue{gr->wo, nullptr, gr->wo, 1.f, F32ACC}, st);
+                   GemmEpilogue{gr->wo, nullptr, gr->wo, 1.f, F32ACC}, sd);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "out_bwd");
-        // attention: dP = dO . V^T (B = V^T stored [d][j]: MN-major) ; dV^T = dO^T . P
+        rc = fork_to_side(3);                                    // dO is ready
+        if (rc != SMZ_OK) return rc;
+        // attention: dP = dO . V^T (B = V^T stored [d][j]: MN-major) ; dV^T = dO^T . P ; dWv += dV^T . xb
         rc = gemm1(false, true, dO, T, kFeat, kFeat, vt, kFeat, T, Tpad, prob(T, T, kFeat, ld),
                    GemmEpilogue{dP, nullptr, nullptr, 1.f, smz::GEMM_OUT_F32}, st);
         if (rc != SMZ_OK) return rc;
         rc = gemm1(true, true, dO, T, kFeat, kFeat, P, T, T, ld, prob(kFeat, T, T, (int)Tpad),
-                   GemmEpilogue{dvt, nullptr, nullptr, 1.f, 0}, st);
+                   GemmEpilogue{dvt, nullptr, nullptr, 1.f, 0}, sd);
+        if (rc != SMZ_OK) return rc;
+        rc = gemm1(false, true, dvt, kFeat, T, Tpad, xb, T, kFeat, kFeat, prob(kFeat, kFeat, T, kFeat, 0, kFeat),
+                   GemmEpilogue{gr->wv, nullptr, gr->wv, 1.f, F32ACC}, sd);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "att_bwd1");
         rc = smz::launch_softmax_bwd(dP, alpha, drop_att ? drop_att + att_off : nullptr, T, ld, dS, st);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "softmax_bwd");
+        rc = fork_to_side(4);                                    // dS is ready
+        if (rc != SMZ_OK) return rc;
         // dQ = scale dS . K (B = K half of QK, stored [j][d]: MN-major at column 1024) ; dK = scale dS^T . Q
         {
             GemmProblem g = prob(T, kFeat, T, 2 * kFeat, 0);
@@ -541,16 +577,17 @@ extern "C" int smz_vasnet_backward(const void *x, int x_is_bf16, const int32_t *
             rc = gemm1(false, true, dS, T, T, ld, qk, T, 2 * kFeat, 2 * kFeat, g, GemmEpilogue{dqk, nullptr, nullptr, p->scale, 0}, st);
             if (rc != SMZ_OK) return rc;
             g = prob(T, kFeat, T, 2 * kFeat, kFeat);
-            rc = gemm1(true, true, dS, T, T, ld, qk, T, 2 * kFeat, 2 * kFeat, g, GemmEpilogue{dqk, nullptr, nullptr, p->scale, 0}, st);
+            rc = gemm1(true, true, dS, T, T, ld, qk, T, 2 * kFeat, 2 * kFeat, g, GemmEpilogue{dqk, nullptr, nullptr, p->scale, 0}, sd);
             if (rc != SMZ_OK) return rc;
         }
         SMZ_DEBUG_STEP(st, "att_bwd2");
-        // projections: dWqk += [dQ|dK]^T . xb ; dWv += dV^T . xb
+        if (ss != nullptr) {                                     // join: dK, dV^T and the side weight gradients are done
+            SMZ_CUDA_CHECK(cudaEventRecord(ss->ev[5], sd));
+            SMZ_CUDA_CHECK(cudaStreamWaitEvent(st, ss->ev[5], 0));
+        }
+        // projections: dWqk += [dQ|dK]^T . xb
         rc = gemm1(true, true, dqk, T, 2 * kFeat, 2 * kFeat, xb, T, kFeat, kFeat, prob(2 * kFeat, kFeat, T, kFeat, 0, kFeat),
                    GemmEpilogue{gr->wqk, nullptr, gr->wqk, 1.f, F32ACC}, st);
-        if (rc != SMZ_OK) return rc;
-        rc = gemm1(false, true, dvt, kFeat, T, Tpad, xb, T, kFeat, kFeat, prob(kFeat, kFeat, T, kFeat, 0, kFeat),
-                   GemmEpilogue{gr->wv, nullptr, gr->wv, 1.f, F32ACC}, st);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "proj_bwd");
         if (gr->dx != nullptr) {
