@@ -158,6 +158,9 @@ int smz_rank_correlation(const smz_corr_desc *desc, int n_videos, int max_n_fram
 int smz_gemm_bf16_tn(const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc, int M, int N,
                      int K, float alpha, const float *bias, const void *residual, int64_t ldr, int flags,
                      void *stream);
+/* float32 -> bfloat16 copies of up to 8 tensors in one launch (src / dst / n are HOST arrays of device pointers and
+ * element counts; 16-byte aligned segments): the parameter copies a training step refreshes. */
+int smz_cvt_bf16_multi(const float *const *src, void *const *dst, const int64_t *n, int count, void *stream);
 /* General operand storage: a_mn != 0 means A is given as [K, M] (m contiguous, lda >= M) instead of
  * [M, K]; b_mn != 0 means B is given as [K, N].  With these the autograd GEMMs of vasnet.py:209-211
  * (dX = dY.W, dW = dY^T.X) read the row-major activations directly, no transposed copies. */

@@ -68,6 +68,7 @@ SIGNATURES = {
     "smz_lstm_seq_backward": (_I, [_P, _I, _P, _P]),
     "smz_lstm_decode_forward": (_I, [_P, _P, _P]),
     "smz_lstm_decode_backward": (_I, [_P, _P, _P]),
+    "smz_cvt_bf16_multi": (_I, [_P, _P, _P, _I, _P]),
     "smz_gemm_bf16": (_I, [_I, _I, _P, _L, _P, _L, _P, _L, _I, _I, _I, C.c_float, _P, _P, _L, _I, _P]),
     "smz_gemm_bf16_tn": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, C.c_float, _P, _P, _L, _I, _P]),
 }

@@ -40,6 +40,23 @@ __global__ void cvt_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__re
     }
 }
 
+// up to 8 float32 -> bfloat16 conversions in one launch (the parameter copies of a training step): blockIdx.y = segment
+struct CvtSegments { const float *src[8]; __nv_bfloat16 *dst[8]; long long n[8]; };
+__global__ void cvt_bf16_segments_kernel(const CvtSegments seg) {
+    const float *x = seg.src[blockIdx.y];
+    __nv_bfloat16 *y = seg.dst[blockIdx.y];
+    const long long n = seg.n[blockIdx.y];
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += (long long)gridDim.x * blockDim.x * 8) {
+        if (i + 8 <= n) {
+            const float4 a = *reinterpret_cast<const float4 *>(x + i);
+            const float4 b = *reinterpret_cast<const float4 *>(x + i + 4);
+            *reinterpret_cast<uint4 *>(y + i) = make_uint4(pack2(a.x, a.y), pack2(a.z, a.w), pack2(b.x, b.y), pack2(b.z, b.w));
+        } else {
+            for (long long j = i; j < n; j++) y[j] = __float2bfloat16_rn(x[j]);
+        }
+    }
+}
+
 // vasnet.py:121-127 — masks are applied AFTER scaling: diagonal (ignore_self), then the aperture
 // band; inside the band an entry whose square is 0 is masked too (tril(e)*triu(e) == 0 quirk).
 __device__ __forceinline__ float mask_logit(float e, int i, int j, int aperture, int ignore_self) {
@@ -506,6 +523,30 @@ int launch_softmax_bwd(const float *dP, const __nv_bfloat16 *alpha, const uint8_
     SMZ_CUDA_CHECK(cudaGetLastError());
     return SMZ_OK;
 }
+
+}  // namespace smz
+
+// float32 -> bfloat16 copies of up to 8 tensors in ONE launch: src[i] (n[i] floats, 16-byte aligned) -> dst[i].  What a
+// training step uses to refresh the bf16 weight copies (replaces one torch cast kernel per parameter).
+extern "C" int smz_cvt_bf16_multi(const float *const *src, void *const *dst, const int64_t *n, int count, void *stream) {
+    SMZ_REQUIRE(src && dst && n && count >= 1 && count <= 8, "cvt_bf16_multi: 1..8 segments");
+    CvtSegments seg = {};
+    long long most = 0;
+    for (int i = 0; i < count; i++) {
+        SMZ_REQUIRE(src[i] && dst[i] && n[i] >= 0, "cvt_bf16_multi: bad segment %d", i);
+        SMZ_REQUIRE(((uintptr_t)src[i] & 15) == 0 && ((uintptr_t)dst[i] & 15) == 0, "cvt_bf16_multi: segment %d is not 16-byte aligned", i);
+        seg.src[i] = src[i]; seg.dst[i] = reinterpret_cast<__nv_bfloat16 *>(dst[i]); seg.n[i] = n[i];
+        most = n[i] > most ? n[i] : most;
+    }
+    if (most == 0) return SMZ_OK;
+    long long blocks = (most + 8 * 256 - 1) / (8 * 256);
+    if (blocks > 2048) blocks = 2048;
+    cvt_bf16_segments_kernel<<<dim3((unsigned)blocks, count), 256, 0, (cudaStream_t)stream>>>(seg);
+    SMZ_CUDA_CHECK(cudaGetLastError());
+    return SMZ_OK;
+}
+
+namespace smz {
 
 int launch_cvt_bf16(const float *x, __nv_bfloat16 *y, int64_t n, cudaStream_t st) {
     if (n <= 0) return SMZ_OK;

@@ -112,11 +112,21 @@ class VASNet(nn.Module):
         key = tuple((p.data_ptr(), p._version) for p in ps)
         if not inference or self._shadow_key is None or key != self._shadow_key:
             with torch.no_grad():
+                big = (self.Q.weight, self.K.weight, self.V.weight, self.attention_head_projection.weight, self.k1.weight)
+                if all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for t in big):
+                    # one launch: [Q;K] | V | O | k1 -> one bf16 buffer (no fp32 concatenation, no cast kernel per tensor)
+                    flat = torch.empty(5 * 1024 * 1024, dtype=torch.bfloat16, device=big[0].device)
+                    src = (C.c_void_p * 5)(*(t.data_ptr() for t in big))
+                    dst = (C.c_void_p * 5)(*(flat.data_ptr() + 2 * 1024 * 1024 * i for i in range(5)))
+                    cnt = (C.c_int64 * 5)(*([1024 * 1024] * 5))
+                    N.check(N.lib().smz_cvt_bf16_multi(src, dst, cnt, 5, N.current_stream()))
+                    w = flat.view(5 * 1024, 1024)
+                    wqk, wv, wo, w1 = w[:2048], w[2048:3072], w[3072:4096], w[4096:]
+                else:
+                    wqk = torch.cat([self.Q.weight, self.K.weight], 0).to(torch.bfloat16).contiguous()
+                    wv, wo, w1 = (t.to(torch.bfloat16).contiguous() for t in big[2:])
                 sh = dict(
-                    wqk=torch.cat([self.Q.weight, self.K.weight], 0).to(torch.bfloat16).contiguous(),
-                    wv=self.V.weight.to(torch.bfloat16).contiguous(),
-                    wo=self.attention_head_projection.weight.to(torch.bfloat16).contiguous(),
-                    w1=self.k1.weight.to(torch.bfloat16).contiguous(),
+                    wqk=wqk, wv=wv, wo=wo, w1=w1,
                     b1=self.k1.bias.float().contiguous(), w2=self.k2.weight.float().reshape(-1).contiguous(),
                     b2=self.k2.bias.float().contiguous(), ln_g=self.layer_norm.weight.float().contiguous(),
                     ln_b=self.layer_norm.bias.float().contiguous())
