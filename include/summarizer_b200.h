@@ -283,9 +283,11 @@ int smz_fscore_packed(const smz_video_desc *desc, int n_videos, const uint32_t *
  *             [4H, H]; h0/c0 [H] or NULL (zeros); y[t*ldy + u] = h_t; training also fills gates (activated,
  *             [T, ldg]) and cs [T, H]; h_last/c_last [H] or NULL.  reverse != 0 walks t = T-1 .. 0.
  *   backward: whh_t bfloat16 [H, 4H] (= W_hh^T); dy [T, lddy] or NULL; dh_last/dc_last [H] or NULL; writes
- *             dgates [T, ldg] (pre-activation gradients), dh0/dc0 [H] (or NULL). */
+ *             dgates [T, ldg] (pre-activation gradients), dh0/dc0 [H] (or NULL).
+ *   B (1..4) sequences of the same length share the weights in one launch — the per-step cost is the grid barrier and
+ *   the weight stream, so extra sequences are nearly free: sequence arrays are then [B][T][ld], state vectors [B][H]. */
 typedef struct smz_lstm_seq {
-    int32_t T, H, reverse, ldpre, ldy, lddy, ldg, reserved;
+    int32_t T, H, reverse, ldpre, ldy, lddy, ldg, B;
     const float *pre;
     const void *whh, *whh_t;
     const float *h0, *c0;
@@ -299,9 +301,10 @@ int smz_lstm_seq_backward(const smz_lstm_seq *dirs, int n_dir, void *sync_ws, vo
 /* dLSTM decode: layer 0's input at step t is layer 1's output at step t-1 (zeros at t = 0), sumgan.py:106-112.
  *   w_* bfloat16 [4H, H], w_*_t their transposes [H, 4H] (backward only); bias0/1 float32 [4H] (b_ih + b_hh);
  *   h_init/c_init [2, H]; hs0/hs1 [T, H] layer outputs; gates0/1 [T, 4H], cs0/1 [T, H] (training);
- *   backward: dy [T, H] gradient of hs1 -> dgates0/1 [T, 4H], dh_init/dc_init [2, H]. */
+ *   backward: dy [T, H] gradient of hs1 -> dgates0/1 [T, 4H], dh_init/dc_init [2, H].
+ *   With B > 1: sequence arrays [B][T][.], h_init / c_init / dh_init / dc_init [2][B][H]. */
 typedef struct smz_lstm_decode {
-    int32_t T, H;
+    int32_t T, H, B, reserved;
     const void *w_ih0, *w_hh0, *w_ih1, *w_hh1;
     const void *w_ih0_t, *w_hh0_t, *w_ih1_t, *w_hh1_t;
     const float *bias0, *bias1, *h_init, *c_init;

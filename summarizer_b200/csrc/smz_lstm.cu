@@ -27,6 +27,7 @@ constexpr int CTAS = 128;
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
 constexpr int MAX_UPW = 2;            // hidden units per warp: H / (CTAs per direction * 8)
+constexpr int MAX_B = 4;              // sequences of equal length sharing the weights in one launch
 
 struct SeqArgs { smz_lstm_seq d[2]; int n_dir; };
 
@@ -87,6 +88,43 @@ __device__ __forceinline__ void dot_gates(const bf16 *__restrict__ W, int H, int
     }
 }
 
+// batched: acc[b][g] += W[g*H + unit, 0:K] . vec_b, vec_b = vec + b*vstride (the weight chunk is loaded once for all B)
+template <int NB>
+__device__ __forceinline__ void dot_gates_b(const bf16 *__restrict__ W, int H, int K, int unit, const float *vec, int vstride,
+                                            int lane, float acc[NB][4]) {
+    const bf16 *r0 = W + (size_t)unit * K;
+    const size_t gs = (size_t)H * K;
+#pragma unroll(NB == 1 ? 4 : 2)
+    for (int c = lane * 8; c < K; c += 256) {
+        uint4 w[4];
+#pragma unroll
+        for (int g = 0; g < 4; g++) w[g] = __ldg(reinterpret_cast<const uint4 *>(r0 + g * gs + c));
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            const float4 x0 = *reinterpret_cast<const float4 *>(vec + (size_t)b * vstride + c);
+            const float4 x1 = *reinterpret_cast<const float4 *>(vec + (size_t)b * vstride + c + 4);
+#pragma unroll
+            for (int g = 0; g < 4; g++) acc[b][g] += dot8(w[g], x0, x1);
+        }
+    }
+}
+
+// batched: acc[b] += row[0:K] . vec_b
+template <int NB>
+__device__ __forceinline__ void dot_row_b(const bf16 *__restrict__ row, int K, const float *vec, int vstride, int lane,
+                                          float acc[NB]) {
+#pragma unroll(NB == 1 ? 8 : 4)
+    for (int c = lane * 8; c < K; c += 256) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(row + c));
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            const float4 x0 = *reinterpret_cast<const float4 *>(vec + (size_t)b * vstride + c);
+            const float4 x1 = *reinterpret_cast<const float4 *>(vec + (size_t)b * vstride + c + 4);
+            acc[b] += dot8(w, x0, x1);
+        }
+    }
+}
+
 // per-lane partial of row[0:K] . vec
 __device__ __forceinline__ float dot_row(const bf16 *__restrict__ row, int K, const float *vec, int lane) {
     float s0 = 0.f, s1 = 0.f;
@@ -137,49 +175,61 @@ __device__ __forceinline__ float lstm_cell_bwd(float dh, float dc_carry, float g
 // ---------------------------------------------------------------------------------------------------------
 // One layer, whole sequence, n_dir directions side by side (CTAS / n_dir CTAs each).
 // ---------------------------------------------------------------------------------------------------------
+template <int NB>
 __global__ void __launch_bounds__(THREADS, 1) lstm_seq_fwd_kernel(const SeqArgs p, unsigned int *counters) {
-    extern __shared__ float sm[];                           // h_{t-1}: H floats
+    extern __shared__ float sm[];                           // h_{t-1} of every sequence: B x H floats
     const int gd = gridDim.x / p.n_dir;
     const int dir = blockIdx.x / gd, cta = blockIdx.x % gd;
     const smz_lstm_seq &d = p.d[dir];
     const int H = d.H, T = d.T, upc = H / gd, upw = upc / WARPS;
+    constexpr int B = NB;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned int *counter = counters + dir * 32;
     const bf16 *whh = reinterpret_cast<const bf16 *>(d.whh);
     unsigned int arrivals = 0;
-    float c_state[MAX_UPW];
+    float c_state[MAX_UPW][NB];
 #pragma unroll
-    for (int u = 0; u < MAX_UPW; u++) {
-        const int unit = cta * upc + warp * upw + u;
-        c_state[u] = (u < upw && d.c0) ? d.c0[unit] : 0.f;
-    }
+    for (int u = 0; u < MAX_UPW; u++)
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+            c_state[u][b] = (u < upw && d.c0) ? d.c0[(size_t)b * H + cta * upc + warp * upw + u] : 0.f;
     for (int s = 0; s < T; s++) {
         const int t = d.reverse ? T - 1 - s : s;
-        const float *hprev = s == 0 ? d.h0 : d.y + (size_t)(d.reverse ? t + 1 : t - 1) * d.ldy;
-        stage(sm, hprev, H);
+        const int tp = d.reverse ? t + 1 : t - 1;
+        for (int b = 0; b < B; b++) {
+            const float *hprev = s == 0 ? (d.h0 ? d.h0 + (size_t)b * H : nullptr) : d.y + ((size_t)b * T + tp) * d.ldy;
+            stage(sm + b * H, hprev, H);
+        }
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < MAX_UPW; u++) {
             if (u >= upw) break;
             const int unit = cta * upc + warp * upw + u;
-            float z[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+            float acc[NB][4];
 #pragma unroll
-            for (int g = 0; g < 4; g++) z[g] = __ldg(d.pre + (size_t)t * d.ldpre + g * H + unit);
-            dot_gates(whh, H, H, unit, sm, lane, acc);
+            for (int b = 0; b < NB; b++)
 #pragma unroll
-            for (int g = 0; g < 4; g++) z[g] += warp_sum(acc[g]);
-            const Cell r = lstm_cell(z, c_state[u]);
-            c_state[u] = r.c;
-            if (lane == 0) {
-                d.y[(size_t)t * d.ldy + unit] = r.h;
-                if (d.gates) {
-                    float *gp = d.gates + (size_t)t * d.ldg + unit;
-                    gp[0] = r.i; gp[H] = r.f; gp[2 * H] = r.g; gp[3 * H] = r.o;
-                }
-                if (d.cs) d.cs[(size_t)t * H + unit] = r.c;
-                if (s == T - 1) {
-                    if (d.h_last) d.h_last[unit] = r.h;
-                    if (d.c_last) d.c_last[unit] = r.c;
+                for (int g = 0; g < 4; g++) acc[b][g] = 0.f;
+            dot_gates_b<NB>(whh, H, H, unit, sm, H, lane, acc);
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const size_t row = (size_t)b * T + t;
+                float z[4];
+#pragma unroll
+                for (int g = 0; g < 4; g++) z[g] = __ldg(d.pre + row * d.ldpre + g * H + unit) + warp_sum(acc[b][g]);
+                const Cell r = lstm_cell(z, c_state[u][b]);
+                c_state[u][b] = r.c;
+                if (lane == 0) {
+                    d.y[row * d.ldy + unit] = r.h;
+                    if (d.gates) {
+                        float *gp = d.gates + row * d.ldg + unit;
+                        gp[0] = r.i; gp[H] = r.f; gp[2 * H] = r.g; gp[3 * H] = r.o;
+                    }
+                    if (d.cs) d.cs[row * H + unit] = r.c;
+                    if (s == T - 1) {
+                        if (d.h_last) d.h_last[(size_t)b * H + unit] = r.h;
+                        if (d.c_last) d.c_last[(size_t)b * H + unit] = r.c;
+                    }
                 }
             }
         }
@@ -188,23 +238,27 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_seq_fwd_kernel(const SeqArgs 
     }
 }
 
+template <int NB>
 __global__ void __launch_bounds__(THREADS, 1) lstm_seq_bwd_kernel(const SeqArgs p, unsigned int *counters) {
-    extern __shared__ float sm[];                           // dz_t: 4H floats
+    extern __shared__ float sm[];                           // dz_t of every sequence: B x 4H floats
     const int gd = gridDim.x / p.n_dir;
     const int dir = blockIdx.x / gd, cta = blockIdx.x % gd;
     const smz_lstm_seq &d = p.d[dir];
     const int H = d.H, T = d.T, upc = H / gd, upw = upc / WARPS;
+    constexpr int B = NB;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned int *counter = counters + dir * 32;
     const bf16 *whh_t = reinterpret_cast<const bf16 *>(d.whh_t);
     unsigned int arrivals = 0;
-    float dh_rec[MAX_UPW], dc_carry[MAX_UPW];
+    float dh_rec[MAX_UPW][NB], dc_carry[MAX_UPW][NB];
 #pragma unroll
-    for (int u = 0; u < MAX_UPW; u++) {
-        const int unit = cta * upc + warp * upw + u;
-        dh_rec[u] = (u < upw && d.dh_last) ? d.dh_last[unit] : 0.f;
-        dc_carry[u] = (u < upw && d.dc_last) ? d.dc_last[unit] : 0.f;
-    }
+    for (int u = 0; u < MAX_UPW; u++)
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            const size_t k = (size_t)b * H + cta * upc + warp * upw + u;
+            dh_rec[u][b] = (u < upw && d.dh_last) ? d.dh_last[k] : 0.f;
+            dc_carry[u][b] = (u < upw && d.dc_last) ? d.dc_last[k] : 0.f;
+        }
     for (int s = 0; s < T; s++) {
         const int t = d.reverse ? s : T - 1 - s;            // the forward pass visited t at step T-1-s
         const bool first = s == T - 1;                      // t is where the forward pass started
@@ -213,34 +267,44 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_seq_bwd_kernel(const SeqArgs 
         for (int u = 0; u < MAX_UPW; u++) {
             if (u >= upw) break;
             const int unit = cta * upc + warp * upw + u;
-            const float *gp = d.gates + (size_t)t * d.ldg + unit;
-            const float c_prev = first ? (d.c0 ? d.c0[unit] : 0.f) : d.cs[(size_t)tp * H + unit];
-            const float dh = dh_rec[u] + (d.dy ? d.dy[(size_t)t * d.lddy + unit] : 0.f);
-            float dz[4];
-            dc_carry[u] = lstm_cell_bwd(dh, dc_carry[u], gp[0], gp[H], gp[2 * H], gp[3 * H], d.cs[(size_t)t * H + unit], c_prev, dz);
-            if (lane == 0) {
-                float *o = d.dgates + (size_t)t * d.ldg + unit;
-                o[0] = dz[0]; o[H] = dz[1]; o[2 * H] = dz[2]; o[3 * H] = dz[3];
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const size_t row = (size_t)b * T + t;
+                const float *gp = d.gates + row * d.ldg + unit;
+                const float c_prev = first ? (d.c0 ? d.c0[(size_t)b * H + unit] : 0.f) : d.cs[((size_t)b * T + tp) * H + unit];
+                const float dh = dh_rec[u][b] + (d.dy ? d.dy[row * d.lddy + unit] : 0.f);
+                float dz[4];
+                dc_carry[u][b] = lstm_cell_bwd(dh, dc_carry[u][b], gp[0], gp[H], gp[2 * H], gp[3 * H], d.cs[row * H + unit], c_prev, dz);
+                if (lane == 0) {
+                    float *o = d.dgates + row * d.ldg + unit;
+                    o[0] = dz[0]; o[H] = dz[1]; o[2 * H] = dz[2]; o[3 * H] = dz[3];
+                }
             }
         }
         arrivals += gd;
         group_barrier(counter, arrivals);
-        stage(sm, d.dgates + (size_t)t * d.ldg, 4 * H);
+        for (int b = 0; b < B; b++) stage(sm + b * 4 * H, d.dgates + ((size_t)b * T + t) * d.ldg, 4 * H);
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < MAX_UPW; u++) {
             if (u >= upw) break;
             const int unit = cta * upc + warp * upw + u;
-            dh_rec[u] = warp_sum(dot_row(whh_t + (size_t)unit * 4 * H, 4 * H, sm, lane));
+            float acc[NB] = {};
+            dot_row_b<NB>(whh_t + (size_t)unit * 4 * H, 4 * H, sm, 4 * H, lane, acc);
+#pragma unroll
+            for (int b = 0; b < NB; b++) dh_rec[u][b] = warp_sum(acc[b]);
         }
     }
 #pragma unroll
     for (int u = 0; u < MAX_UPW; u++) {
         if (u >= upw) break;
         const int unit = cta * upc + warp * upw + u;
-        if (lane == 0) {
-            if (d.dh0) d.dh0[unit] = dh_rec[u];
-            if (d.dc0) d.dc0[unit] = dc_carry[u];
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            if (lane == 0) {
+                if (d.dh0) d.dh0[(size_t)b * H + unit] = dh_rec[u][b];
+                if (d.dc0) d.dc0[(size_t)b * H + unit] = dc_carry[u][b];
+            }
         }
     }
 }
@@ -249,51 +313,65 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_seq_bwd_kernel(const SeqArgs 
 // dLSTM decode (sumgan.py:98-115): two stacked layers stepped together, layer 0's input at step t is layer 1's
 // output at step t-1 (zeros at t = 0).
 // ---------------------------------------------------------------------------------------------------------
+template <int NB>
 __global__ void __launch_bounds__(THREADS, 1) lstm_decode_fwd_kernel(const smz_lstm_decode d, unsigned int *counter) {
-    extern __shared__ float sm[];                           // vA, vB: 2 x H floats
+    extern __shared__ float sm[];                           // vA, vB: 2 x B x H floats
     const int H = d.H, T = d.T, upc = H / gridDim.x, upw = upc / WARPS;
+    constexpr int B = NB;
     const int cta = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float *vA = sm, *vB = sm + H;
+    float *vA = sm, *vB = sm + B * H;
     const bf16 *wih[2] = {reinterpret_cast<const bf16 *>(d.w_ih0), reinterpret_cast<const bf16 *>(d.w_ih1)};
     const bf16 *whh[2] = {reinterpret_cast<const bf16 *>(d.w_hh0), reinterpret_cast<const bf16 *>(d.w_hh1)};
     const float *bias[2] = {d.bias0, d.bias1};
     float *hs[2] = {d.hs0, d.hs1}, *gates[2] = {d.gates0, d.gates1}, *cs[2] = {d.cs0, d.cs1};
     unsigned int arrivals = 0;
-    float c_state[2][MAX_UPW];
+    float c_state[2][MAX_UPW][NB];
 #pragma unroll
     for (int l = 0; l < 2; l++)
 #pragma unroll
         for (int u = 0; u < MAX_UPW; u++)
-            c_state[l][u] = u < upw ? d.c_init[l * H + cta * upc + warp * upw + u] : 0.f;
+#pragma unroll
+            for (int b = 0; b < NB; b++)
+                c_state[l][u][b] = (u < upw) ? d.c_init[((size_t)l * B + b) * H + cta * upc + warp * upw + u] : 0.f;
     for (int t = 0; t < T; t++) {
 #pragma unroll
         for (int l = 0; l < 2; l++) {
-            // layer 0: input = top output of the previous step; layer 1: input = layer 0's output of this step
-            const float *in = l == 0 ? (t > 0 ? d.hs1 + (size_t)(t - 1) * H : nullptr) : d.hs0 + (size_t)t * H;
-            const float *rec = t > 0 ? hs[l] + (size_t)(t - 1) * H : d.h_init + l * H;
-            stage(vA, in, H);
-            stage(vB, rec, H);
+            // layer 0: input = top output of the previous step (zeros at t = 0); layer 1: input = layer 0's output of this step
+            const bool has_in = l == 1 || t > 0;
+            for (int b = 0; b < B; b++) {
+                const float *in = l == 0 ? (t > 0 ? d.hs1 + ((size_t)b * T + t - 1) * H : nullptr) : d.hs0 + ((size_t)b * T + t) * H;
+                const float *rec = t > 0 ? hs[l] + ((size_t)b * T + t - 1) * H : d.h_init + ((size_t)l * B + b) * H;
+                stage(vA + b * H, in, H);
+                stage(vB + b * H, rec, H);
+            }
             __syncthreads();
 #pragma unroll
             for (int u = 0; u < MAX_UPW; u++) {
                 if (u >= upw) break;
                 const int unit = cta * upc + warp * upw + u;
-                float z[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+                float acc[NB][4];
 #pragma unroll
-                for (int g = 0; g < 4; g++) z[g] = __ldg(bias[l] + g * H + unit);
-                if (in != nullptr) dot_gates(wih[l], H, H, unit, vA, lane, acc);
-                dot_gates(whh[l], H, H, unit, vB, lane, acc);
+                for (int b = 0; b < NB; b++)
 #pragma unroll
-                for (int g = 0; g < 4; g++) z[g] += warp_sum(acc[g]);
-                const Cell r = lstm_cell(z, c_state[l][u]);
-                c_state[l][u] = r.c;
-                if (lane == 0) {
-                    hs[l][(size_t)t * H + unit] = r.h;
-                    if (gates[l]) {
-                        float *gp = gates[l] + (size_t)t * 4 * H + unit;
-                        gp[0] = r.i; gp[H] = r.f; gp[2 * H] = r.g; gp[3 * H] = r.o;
+                    for (int g = 0; g < 4; g++) acc[b][g] = 0.f;
+                if (has_in) dot_gates_b<NB>(wih[l], H, H, unit, vA, H, lane, acc);
+                dot_gates_b<NB>(whh[l], H, H, unit, vB, H, lane, acc);
+#pragma unroll
+                for (int b = 0; b < NB; b++) {
+                        const size_t row = (size_t)b * T + t;
+                    float z[4];
+#pragma unroll
+                    for (int g = 0; g < 4; g++) z[g] = __ldg(bias[l] + g * H + unit) + warp_sum(acc[b][g]);
+                    const Cell r = lstm_cell(z, c_state[l][u][b]);
+                    c_state[l][u][b] = r.c;
+                    if (lane == 0) {
+                        hs[l][row * H + unit] = r.h;
+                        if (gates[l]) {
+                            float *gp = gates[l] + row * 4 * H + unit;
+                            gp[0] = r.i; gp[H] = r.f; gp[2 * H] = r.g; gp[3 * H] = r.o;
+                        }
+                        if (cs[l]) cs[l][row * H + unit] = r.c;
                     }
-                    if (cs[l]) cs[l][(size_t)t * H + unit] = r.c;
                 }
             }
             arrivals += gridDim.x;
@@ -302,63 +380,84 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_decode_fwd_kernel(const smz_l
     }
 }
 
+template <int NB>
 __global__ void __launch_bounds__(THREADS, 1) lstm_decode_bwd_kernel(const smz_lstm_decode d, unsigned int *counter) {
-    extern __shared__ float sm[];                           // dz: 4H floats
+    extern __shared__ float sm[];                           // dz of every sequence: B x 4H floats
     const int H = d.H, T = d.T, upc = H / gridDim.x, upw = upc / WARPS, G4 = 4 * H;
+    constexpr int B = NB;
     const int cta = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bf16 *wih0_t = reinterpret_cast<const bf16 *>(d.w_ih0_t), *whh0_t = reinterpret_cast<const bf16 *>(d.w_hh0_t);
     const bf16 *wih1_t = reinterpret_cast<const bf16 *>(d.w_ih1_t), *whh1_t = reinterpret_cast<const bf16 *>(d.w_hh1_t);
     unsigned int arrivals = 0;
-    float r0[MAX_UPW], r1[MAX_UPW], r1a[MAX_UPW], dc0[MAX_UPW], dc1[MAX_UPW];
+    float r0[MAX_UPW][NB], r1[MAX_UPW][NB], r1a[MAX_UPW][NB], dc0[MAX_UPW][NB], dc1[MAX_UPW][NB];
 #pragma unroll
-    for (int u = 0; u < MAX_UPW; u++) r0[u] = r1[u] = r1a[u] = dc0[u] = dc1[u] = 0.f;
+    for (int u = 0; u < MAX_UPW; u++)
+#pragma unroll
+        for (int b = 0; b < NB; b++) r0[u][b] = r1[u][b] = r1a[u][b] = dc0[u][b] = dc1[u][b] = 0.f;
     for (int t = T - 1; t >= 0; t--) {
         // A: top layer cells
 #pragma unroll
         for (int u = 0; u < MAX_UPW; u++) {
             if (u >= upw) break;
             const int unit = cta * upc + warp * upw + u;
-            const float *gp = d.gates1 + (size_t)t * G4 + unit;
-            const float c_prev = t > 0 ? d.cs1[(size_t)(t - 1) * H + unit] : d.c_init[H + unit];
-            const float dh = r1[u] + d.dy[(size_t)t * H + unit];
-            float dz[4];
-            dc1[u] = lstm_cell_bwd(dh, dc1[u], gp[0], gp[H], gp[2 * H], gp[3 * H], d.cs1[(size_t)t * H + unit], c_prev, dz);
-            if (lane == 0) {
-                float *o = d.dgates1 + (size_t)t * G4 + unit;
-                o[0] = dz[0]; o[H] = dz[1]; o[2 * H] = dz[2]; o[3 * H] = dz[3];
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const size_t row = (size_t)b * T + t;
+                const float *gp = d.gates1 + row * G4 + unit;
+                const float c_prev = t > 0 ? d.cs1[(row - 1) * H + unit] : d.c_init[((size_t)B + b) * H + unit];
+                const float dh = r1[u][b] + d.dy[row * H + unit];
+                float dz[4];
+                dc1[u][b] = lstm_cell_bwd(dh, dc1[u][b], gp[0], gp[H], gp[2 * H], gp[3 * H], d.cs1[row * H + unit], c_prev, dz);
+                if (lane == 0) {
+                    float *o = d.dgates1 + row * G4 + unit;
+                    o[0] = dz[0]; o[H] = dz[1]; o[2 * H] = dz[2]; o[3 * H] = dz[3];
+                }
             }
         }
         arrivals += gridDim.x;
         group_barrier(counter, arrivals);
         // B: dz1_t -> gradient of layer 0's output (its input role in layer 1) and of h1_{t-1}; layer 0 cells
-        stage(sm, d.dgates1 + (size_t)t * G4, G4);
+        for (int b = 0; b < B; b++) stage(sm + b * G4, d.dgates1 + ((size_t)b * T + t) * G4, G4);
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < MAX_UPW; u++) {
             if (u >= upw) break;
             const int unit = cta * upc + warp * upw + u;
-            const float via_in = warp_sum(dot_row(wih1_t + (size_t)unit * G4, G4, sm, lane));
-            r1a[u] = warp_sum(dot_row(whh1_t + (size_t)unit * G4, G4, sm, lane));
-            const float *gp = d.gates0 + (size_t)t * G4 + unit;
-            const float c_prev = t > 0 ? d.cs0[(size_t)(t - 1) * H + unit] : d.c_init[unit];
-            float dz[4];
-            dc0[u] = lstm_cell_bwd(via_in + r0[u], dc0[u], gp[0], gp[H], gp[2 * H], gp[3 * H], d.cs0[(size_t)t * H + unit], c_prev, dz);
-            if (lane == 0) {
-                float *o = d.dgates0 + (size_t)t * G4 + unit;
-                o[0] = dz[0]; o[H] = dz[1]; o[2 * H] = dz[2]; o[3 * H] = dz[3];
+            float via[NB] = {}, rec[NB] = {};
+            dot_row_b<NB>(wih1_t + (size_t)unit * G4, G4, sm, G4, lane, via);
+            dot_row_b<NB>(whh1_t + (size_t)unit * G4, G4, sm, G4, lane, rec);
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const size_t row = (size_t)b * T + t;
+                const float via_in = warp_sum(via[b]);
+                r1a[u][b] = warp_sum(rec[b]);
+                const float *gp = d.gates0 + row * G4 + unit;
+                const float c_prev = t > 0 ? d.cs0[(row - 1) * H + unit] : d.c_init[(size_t)b * H + unit];
+                float dz[4];
+                dc0[u][b] = lstm_cell_bwd(via_in + r0[u][b], dc0[u][b], gp[0], gp[H], gp[2 * H], gp[3 * H], d.cs0[row * H + unit], c_prev, dz);
+                if (lane == 0) {
+                    float *o = d.dgates0 + row * G4 + unit;
+                    o[0] = dz[0]; o[H] = dz[1]; o[2 * H] = dz[2]; o[3 * H] = dz[3];
+                }
             }
         }
         arrivals += gridDim.x;
         group_barrier(counter, arrivals);
         // C: dz0_t -> gradient of h0_{t-1} and (as layer 0's input, absent at t = 0) of h1_{t-1}
-        stage(sm, d.dgates0 + (size_t)t * G4, G4);
+        for (int b = 0; b < B; b++) stage(sm + b * G4, d.dgates0 + ((size_t)b * T + t) * G4, G4);
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < MAX_UPW; u++) {
             if (u >= upw) break;
             const int unit = cta * upc + warp * upw + u;
-            r0[u] = warp_sum(dot_row(whh0_t + (size_t)unit * G4, G4, sm, lane));
-            r1[u] = r1a[u] + (t > 0 ? warp_sum(dot_row(wih0_t + (size_t)unit * G4, G4, sm, lane)) : 0.f);
+            float rec[NB] = {}, via[NB] = {};
+            dot_row_b<NB>(whh0_t + (size_t)unit * G4, G4, sm, G4, lane, rec);
+            if (t > 0) dot_row_b<NB>(wih0_t + (size_t)unit * G4, G4, sm, G4, lane, via);
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                r0[u][b] = warp_sum(rec[b]);
+                r1[u][b] = r1a[u][b] + (t > 0 ? warp_sum(via[b]) : 0.f);
+            }
         }
         __syncthreads();                                    // sm is restaged right after the next barrier
     }
@@ -366,9 +465,12 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_decode_bwd_kernel(const smz_l
     for (int u = 0; u < MAX_UPW; u++) {
         if (u >= upw) break;
         const int unit = cta * upc + warp * upw + u;
-        if (lane == 0) {
-            d.dh_init[unit] = r0[u]; d.dh_init[H + unit] = r1[u];
-            d.dc_init[unit] = dc0[u]; d.dc_init[H + unit] = dc1[u];
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            if (lane == 0) {
+                d.dh_init[(size_t)b * H + unit] = r0[u][b]; d.dh_init[((size_t)B + b) * H + unit] = r1[u][b];
+                d.dc_init[(size_t)b * H + unit] = dc0[u][b]; d.dc_init[((size_t)B + b) * H + unit] = dc1[u][b];
+            }
         }
     }
 }
@@ -379,7 +481,8 @@ int check_seq(const smz_lstm_seq *dirs, int n_dir, bool backward) {
         const smz_lstm_seq &d = dirs[i];
         const int gd = CTAS / n_dir;
         SMZ_REQUIRE(d.T > 0 && d.H > 0, "lstm_seq: empty sequence");
-        SMZ_REQUIRE(d.H == dirs[0].H && d.T == dirs[0].T, "lstm_seq: directions differ in T or H");
+        SMZ_REQUIRE(d.B >= 1 && d.B <= MAX_B, "lstm_seq: 1..%d sequences per launch", MAX_B);
+        SMZ_REQUIRE(d.H == dirs[0].H && d.T == dirs[0].T && d.B == dirs[0].B, "lstm_seq: directions differ in T, H or B");
         SMZ_REQUIRE(d.H % (gd * WARPS) == 0 && d.H / (gd * WARPS) <= MAX_UPW && d.H % 256 == 0,
                     "lstm_seq: hidden size %d is not supported with %d direction(s) (1024 or 2048; 1024 when bidirectional)", d.H, n_dir);
         SMZ_REQUIRE(d.ldg % 4 == 0, "lstm_seq: ldg must be a multiple of 4");
@@ -394,6 +497,10 @@ int check_seq(const smz_lstm_seq *dirs, int n_dir, bool backward) {
     }
     return SMZ_OK;
 }
+
+#define SMZ_DISPATCH_NB(B, KERNEL, ...)                                   \
+    ((B) == 1 ? launch_coop(KERNEL<1>, __VA_ARGS__) : (B) == 2 ? launch_coop(KERNEL<2>, __VA_ARGS__) \
+     : (B) == 3 ? launch_coop(KERNEL<3>, __VA_ARGS__) : launch_coop(KERNEL<4>, __VA_ARGS__))
 
 template <typename Kern, typename Arg>
 int launch_coop(Kern kern, const Arg &arg, unsigned int *counters, int smem_bytes, cudaStream_t st) {
@@ -417,7 +524,7 @@ extern "C" int smz_lstm_seq_forward(const smz_lstm_seq *dirs, int n_dir, void *s
     a.n_dir = n_dir;
     for (int i = 0; i < n_dir; i++) a.d[i] = dirs[i];
     if (n_dir == 1) a.d[1] = dirs[0];
-    rc = launch_coop(lstm_seq_fwd_kernel, a, reinterpret_cast<unsigned int *>(sync_ws), dirs[0].H * 4, (cudaStream_t)stream);
+    rc = SMZ_DISPATCH_NB(dirs[0].B, lstm_seq_fwd_kernel, a, reinterpret_cast<unsigned int *>(sync_ws), dirs[0].B * dirs[0].H * 4, (cudaStream_t)stream);
     if (rc != SMZ_OK) return rc;
     SMZ_DEBUG_STEP((cudaStream_t)stream, "lstm_seq_forward");
     return SMZ_OK;
@@ -433,7 +540,7 @@ extern "C" int smz_lstm_seq_backward(const smz_lstm_seq *dirs, int n_dir, void *
     a.n_dir = n_dir;
     for (int i = 0; i < n_dir; i++) a.d[i] = dirs[i];
     if (n_dir == 1) a.d[1] = dirs[0];
-    rc = launch_coop(lstm_seq_bwd_kernel, a, reinterpret_cast<unsigned int *>(sync_ws), dirs[0].H * 16, (cudaStream_t)stream);
+    rc = SMZ_DISPATCH_NB(dirs[0].B, lstm_seq_bwd_kernel, a, reinterpret_cast<unsigned int *>(sync_ws), dirs[0].B * dirs[0].H * 16, (cudaStream_t)stream);
     if (rc != SMZ_OK) return rc;
     SMZ_DEBUG_STEP((cudaStream_t)stream, "lstm_seq_backward");
     return SMZ_OK;
@@ -441,6 +548,7 @@ extern "C" int smz_lstm_seq_backward(const smz_lstm_seq *dirs, int n_dir, void *
 
 static int check_decode(const smz_lstm_decode *d, bool backward) {
     SMZ_REQUIRE(d != nullptr && d->T > 0, "lstm_decode: empty sequence");
+    SMZ_REQUIRE(d->B >= 1 && d->B <= MAX_B, "lstm_decode: 1..%d sequences per launch", MAX_B);
     SMZ_REQUIRE(d->H % (CTAS * WARPS) == 0 && d->H / (CTAS * WARPS) <= MAX_UPW, "lstm_decode: hidden size %d is not supported (1024 or 2048)", d->H);
     SMZ_REQUIRE(d->h_init && d->c_init && d->hs0 && d->hs1, "lstm_decode: NULL pointer");
     if (!backward) SMZ_REQUIRE(d->w_ih0 && d->w_hh0 && d->w_ih1 && d->w_hh1 && d->bias0 && d->bias1, "lstm_decode_forward: NULL weight");
@@ -455,7 +563,7 @@ extern "C" int smz_lstm_decode_forward(const smz_lstm_decode *d, void *sync_ws, 
     SMZ_REQUIRE(sync_ws != nullptr, "lstm_decode_forward: sync_ws (256 bytes of device memory) is required");
     rc = smz_device_check();
     if (rc != SMZ_OK) return rc;
-    rc = launch_coop(lstm_decode_fwd_kernel, *d, reinterpret_cast<unsigned int *>(sync_ws), d->H * 8, (cudaStream_t)stream);
+    rc = SMZ_DISPATCH_NB(d->B, lstm_decode_fwd_kernel, *d, reinterpret_cast<unsigned int *>(sync_ws), d->B * d->H * 8, (cudaStream_t)stream);
     if (rc != SMZ_OK) return rc;
     SMZ_DEBUG_STEP((cudaStream_t)stream, "lstm_decode_forward");
     return SMZ_OK;
@@ -467,7 +575,7 @@ extern "C" int smz_lstm_decode_backward(const smz_lstm_decode *d, void *sync_ws,
     SMZ_REQUIRE(sync_ws != nullptr, "lstm_decode_backward: sync_ws (256 bytes of device memory) is required");
     rc = smz_device_check();
     if (rc != SMZ_OK) return rc;
-    rc = launch_coop(lstm_decode_bwd_kernel, *d, reinterpret_cast<unsigned int *>(sync_ws), d->H * 16, (cudaStream_t)stream);
+    rc = SMZ_DISPATCH_NB(d->B, lstm_decode_bwd_kernel, *d, reinterpret_cast<unsigned int *>(sync_ws), d->B * d->H * 16, (cudaStream_t)stream);
     if (rc != SMZ_OK) return rc;
     SMZ_DEBUG_STEP((cudaStream_t)stream, "lstm_decode_backward");
     return SMZ_OK;

@@ -16,14 +16,14 @@ from ..dense import gemm
 
 class LstmSeq(C.Structure):
     """struct smz_lstm_seq (include/summarizer_b200.h)."""
-    _fields_ = [(k, C.c_int32) for k in ("T", "H", "reverse", "ldpre", "ldy", "lddy", "ldg", "reserved")] + \
+    _fields_ = [(k, C.c_int32) for k in ("T", "H", "reverse", "ldpre", "ldy", "lddy", "ldg", "B")] + \
                [(k, C.c_void_p) for k in ("pre", "whh", "whh_t", "h0", "c0", "y", "gates", "cs", "h_last", "c_last",
                                           "dy", "dh_last", "dc_last", "dgates", "dh0", "dc0")]
 
 
 class LstmDecode(C.Structure):
     """struct smz_lstm_decode (include/summarizer_b200.h)."""
-    _fields_ = [("T", C.c_int32), ("H", C.c_int32)] + \
+    _fields_ = [("T", C.c_int32), ("H", C.c_int32), ("B", C.c_int32), ("reserved", C.c_int32)] + \
                [(k, C.c_void_p) for k in ("w_ih0", "w_hh0", "w_ih1", "w_hh1", "w_ih0_t", "w_hh0_t", "w_ih1_t", "w_hh1_t",
                                           "bias0", "bias1", "h_init", "c_init", "hs0", "hs1", "gates0", "gates1", "cs0", "cs1",
                                           "dy", "dgates0", "dgates1", "dh_init", "dc_init")]
@@ -77,9 +77,13 @@ class _LayerShadow:
         self.whh_t = [_bf(d[1].t()) for d in dirs]                                # [H, 4H]
 
 
+MAX_B = 4       # sequences of equal length per recurrence launch (csrc/smz_lstm.cu)
+
+
 class _LstmLayerFn(torch.autograd.Function):
-    """One (possibly bidirectional) LSTM layer over a whole sequence: (x [T,in], h0 [nd,H]|None, c0 [nd,H]|None)
-    -> (y [T, nd*H], h_last [nd,H], c_last [nd,H])."""
+    """One (possibly bidirectional) LSTM layer over B <= 4 sequences of the same length that share the weights:
+    (x [B,T,in], h0 [nd,B,H]|None, c0 [nd,B,H]|None) -> (y [B,T,nd*H], h_last [nd,B,H], c_last [nd,B,H]).  The per-step cost
+    of the recurrence is the grid barrier and the weight stream, so the extra sequences are nearly free."""
 
     @staticmethod
     def forward(ctx, x, h0, c0, meta, *flat):
@@ -88,24 +92,24 @@ class _LstmLayerFn(torch.autograd.Function):
         dirs = [flat[4 * i: 4 * i + 4] for i in range(nd)]
         training = any(ctx.needs_input_grad)
         sh = cache.get(key, flat, lambda: _LayerShadow(dirs), fresh=training)
-        T, dev = x.shape[0], x.device
-        xb = _bf(x)
-        pre = gemm(xb, sh.w_ih, bias=sh.bias)                                     # [T, nd*4H]
+        B, T, dev = x.shape[0], x.shape[1], x.device
+        xb = _bf(x).reshape(B * T, -1)
+        pre = gemm(xb, sh.w_ih, bias=sh.bias)                                     # [B*T, nd*4H]
         f32 = dict(dtype=torch.float32, device=dev)
-        y = torch.empty(T, nd * H, **f32)
-        gates = torch.empty(T, nd * 4 * H, **f32) if training else None
-        cs = torch.empty(nd, T, H, **f32) if training else None
-        h_last, c_last = torch.empty(nd, H, **f32), torch.empty(nd, H, **f32)
+        y = torch.empty(B, T, nd * H, **f32)
+        gates = torch.empty(B, T, nd * 4 * H, **f32) if training else None
+        cs = torch.empty(nd, B, T, H, **f32) if training else None
+        h_last, c_last = torch.empty(nd, B, H, **f32), torch.empty(nd, B, H, **f32)
         h0c = None if h0 is None else h0.detach().float().contiguous()
         c0c = None if c0 is None else c0.detach().float().contiguous()
         arr = (LstmSeq * nd)()
         for i in range(nd):
             a = arr[i]
-            a.T, a.H, a.reverse, a.ldpre, a.ldy, a.ldg = T, H, i, nd * 4 * H, nd * H, nd * 4 * H
+            a.T, a.H, a.B, a.reverse, a.ldpre, a.ldy, a.ldg = T, H, B, i, nd * 4 * H, nd * H, nd * 4 * H
             a.pre, a.whh = _off(pre, i * 4 * H), sh.whh[i].data_ptr()
-            a.h0, a.c0 = _off(h0c, i * H), _off(c0c, i * H)
-            a.y, a.gates, a.cs = _off(y, i * H), _off(gates, i * 4 * H), _off(cs, i * T * H)
-            a.h_last, a.c_last = _off(h_last, i * H), _off(c_last, i * H)
+            a.h0, a.c0 = _off(h0c, i * B * H), _off(c0c, i * B * H)
+            a.y, a.gates, a.cs = _off(y, i * H), _off(gates, i * 4 * H), _off(cs, i * B * T * H)
+            a.h_last, a.c_last = _off(h_last, i * B * H), _off(c_last, i * B * H)
         N.check(N.lib().smz_lstm_seq_forward(arr, nd, N.ptr(_sync_ws(dev)), N.current_stream()))
         ctx.meta, ctx.sh, ctx.saved = meta, sh, (xb, y, gates, cs, h0c, c0c)
         ctx.set_materialize_grads(False)
@@ -116,41 +120,45 @@ class _LstmLayerFn(torch.autograd.Function):
         cache, key, nd, H = ctx.meta
         sh = ctx.sh
         xb, y, gates, cs, h0c, c0c = ctx.saved
-        T, dev = y.shape[0], y.device
+        B, T, dev = y.shape[0], y.shape[1], y.device
         f32 = dict(dtype=torch.float32, device=dev)
-        dgates = torch.empty(T, nd * 4 * H, **f32)
-        dh0, dc0 = torch.empty(nd, H, **f32), torch.empty(nd, H, **f32)
+        dgates = torch.empty(B, T, nd * 4 * H, **f32)
+        dh0, dc0 = torch.empty(nd, B, H, **f32), torch.empty(nd, B, H, **f32)
         dy = None if dy is None else dy.float().contiguous()
         dh_last = None if dh_last is None else dh_last.float().contiguous()
         dc_last = None if dc_last is None else dc_last.float().contiguous()
         arr = (LstmSeq * nd)()
         for i in range(nd):
             a = arr[i]
-            a.T, a.H, a.reverse, a.lddy, a.ldg = T, H, i, nd * H, nd * 4 * H
+            a.T, a.H, a.B, a.reverse, a.lddy, a.ldg = T, H, B, i, nd * H, nd * 4 * H
             a.whh_t = sh.whh_t[i].data_ptr()
-            a.c0 = _off(c0c, i * H)
-            a.gates, a.cs = _off(gates, i * 4 * H), _off(cs, i * T * H)
-            a.dy, a.dh_last, a.dc_last = _off(dy, i * H), _off(dh_last, i * H), _off(dc_last, i * H)
-            a.dgates, a.dh0, a.dc0 = _off(dgates, i * 4 * H), _off(dh0, i * H), _off(dc0, i * H)
+            a.c0 = _off(c0c, i * B * H)
+            a.gates, a.cs = _off(gates, i * 4 * H), _off(cs, i * B * T * H)
+            a.dy, a.dh_last, a.dc_last = _off(dy, i * H), _off(dh_last, i * B * H), _off(dc_last, i * B * H)
+            a.dgates, a.dh0, a.dc0 = _off(dgates, i * 4 * H), _off(dh0, i * B * H), _off(dc0, i * B * H)
         N.check(N.lib().smz_lstm_seq_backward(arr, nd, N.ptr(_sync_ws(dev)), N.current_stream()))
-        dgb = dgates.to(torch.bfloat16)
-        dx = gemm(dgb, sh.w_ih, b_mn=True) if ctx.needs_input_grad[0] else None
-        dw_ih = gemm(dgb, xb, a_mn=True, b_mn=True)                               # [nd*4H, in]
-        db = dgates.sum(0)
+        dgb = dgates.to(torch.bfloat16).reshape(B * T, nd * 4 * H)
+        dx = gemm(dgb, sh.w_ih, b_mn=True).reshape(B, T, -1) if ctx.needs_input_grad[0] else None
+        dw_ih = gemm(dgb, xb, a_mn=True, b_mn=True)                               # [nd*4H, in], summed over the B sequences
+        db = dgates.sum((0, 1))
         grads = []
         for i in range(nd):
-            h_first = torch.zeros(1, H, **f32) if h0c is None else h0c[i:i + 1]
-            yi = y[:, i * H:(i + 1) * H]
-            hprev = torch.cat([h_first, yi[:-1]], 0) if i == 0 else torch.cat([yi[1:], h_first], 0)
-            dw_hh = gemm(dgb[:, i * 4 * H:(i + 1) * 4 * H], _bf(hprev), a_mn=True, b_mn=True)
+            h_first = (torch.zeros(B, H, **f32) if h0c is None else h0c[i]).unsqueeze(1)            # [B,1,H]
+            yi = y[:, :, i * H:(i + 1) * H]
+            hprev = torch.cat([h_first, yi[:, :-1]], 1) if i == 0 else torch.cat([yi[:, 1:], h_first], 1)
+            dw_hh = gemm(dgb[:, i * 4 * H:(i + 1) * 4 * H], _bf(hprev).reshape(B * T, H), a_mn=True, b_mn=True)
             dbi = db[i * 4 * H:(i + 1) * 4 * H]
             grads += [dw_ih[i * 4 * H:(i + 1) * 4 * H], dw_hh, dbi, dbi]
         ctx.saved = None
         return (dx, dh0 if ctx.needs_input_grad[1] else None, dc0 if ctx.needs_input_grad[2] else None, None, *grads)
 
 
+def _batched(x):
+    return (x.unsqueeze(0), True) if x.dim() == 2 else (x, False)
+
+
 def lstm_layer(cache, lstm, layer, x, h0=None, c0=None):
-    """One layer of ``lstm`` over x [T, in] (float32 cuda) -> (y [T, nd*H], h_last [nd,H], c_last [nd,H])."""
+    """One layer of ``lstm`` over x [B,T,in] (float32 cuda, B <= 4) -> (y [B,T,nd*H], h_last [nd,B,H], c_last [nd,B,H])."""
     dirs = layer_params(lstm, layer)
     flat = [p for d in dirs for p in d]
     meta = (cache, (id(lstm), layer), len(dirs), lstm.hidden_size)
@@ -158,15 +166,27 @@ def lstm_layer(cache, lstm, layer, x, h0=None, c0=None):
 
 
 def lstm_stack(cache, lstm, x, h0=None, c0=None):
-    """All layers of ``lstm`` (nn.LSTM semantics, batch 1): x [T, in]; h0/c0 [L*nd, H] or None.
-    Returns (y [T, nd*H], h_n [L*nd, H], c_n [L*nd, H])."""
+    """All layers of ``lstm`` (nn.LSTM semantics) over sequences of equal length: x [B,T,in] (or [T,in]); h0/c0
+    [L*nd, B, H] (or [L*nd, H]) or None.  Returns (y [B,T,nd*H], h_n [L*nd,B,H], c_n [L*nd,B,H]) (batch dimension dropped
+    when x was 2-D).  More than 4 sequences are processed in groups of 4."""
+    x, squeeze = _batched(x)
+    if squeeze:
+        h0 = None if h0 is None else h0.unsqueeze(1)
+        c0 = None if c0 is None else c0.unsqueeze(1)
     nd = 2 if lstm.bidirectional else 1
-    hs, cs = [], []
-    for layer in range(lstm.num_layers):
-        sl = slice(layer * nd, (layer + 1) * nd)
-        x, h_l, c_l = lstm_layer(cache, lstm, layer, x, None if h0 is None else h0[sl], None if c0 is None else c0[sl])
-        hs.append(h_l); cs.append(c_l)
-    return x, torch.cat(hs, 0), torch.cat(cs, 0)
+    ys, hns, cns = [], [], []
+    for b0 in range(0, x.shape[0], MAX_B):
+        xi, hs, cs = x[b0:b0 + MAX_B], [], []
+        for layer in range(lstm.num_layers):
+            sl = slice(layer * nd, (layer + 1) * nd)
+            xi, h_l, c_l = lstm_layer(cache, lstm, layer, xi, None if h0 is None else h0[sl, b0:b0 + MAX_B],
+                                      None if c0 is None else c0[sl, b0:b0 + MAX_B])
+            hs.append(h_l); cs.append(c_l)
+        ys.append(xi); hns.append(torch.cat(hs, 0)); cns.append(torch.cat(cs, 0))
+    y, h_n, c_n = torch.cat(ys, 0), torch.cat(hns, 1), torch.cat(cns, 1)
+    if squeeze:
+        return y[0], h_n[:, 0], c_n[:, 0]
+    return y, h_n, c_n
 
 
 class _DecodeShadow:
@@ -177,7 +197,8 @@ class _DecodeShadow:
 
 
 class _DecodeFn(torch.autograd.Function):
-    """dLSTM.forward's recurrence (sumgan.py:106-112): (h_init [2,H], c_init [2,H]) -> top-layer outputs [T,H]."""
+    """dLSTM.forward's recurrence (sumgan.py:106-112) for B <= 4 decodes that share the weights:
+    (h_init [2,B,H], c_init [2,B,H]) -> top-layer outputs [B,T,H]."""
 
     @staticmethod
     def forward(ctx, h_init, c_init, meta, *flat):
@@ -186,14 +207,14 @@ class _DecodeFn(torch.autograd.Function):
         p0, p1 = flat[:4], flat[4:]
         training = any(ctx.needs_input_grad)
         sh = cache.get(key, flat, lambda: _DecodeShadow(p0, p1), fresh=training)
-        dev = h_init.device
+        dev, B = h_init.device, h_init.shape[1]
         f32 = dict(dtype=torch.float32, device=dev)
         hi, ci = h_init.detach().float().contiguous(), c_init.detach().float().contiguous()
-        hs0, hs1 = torch.empty(T, H, **f32), torch.empty(T, H, **f32)
-        save = [torch.empty(T, 4 * H, **f32), torch.empty(T, 4 * H, **f32), torch.empty(T, H, **f32),
-                torch.empty(T, H, **f32)] if training else [None] * 4
+        hs0, hs1 = torch.empty(B, T, H, **f32), torch.empty(B, T, H, **f32)
+        save = [torch.empty(B, T, 4 * H, **f32), torch.empty(B, T, 4 * H, **f32), torch.empty(B, T, H, **f32),
+                torch.empty(B, T, H, **f32)] if training else [None] * 4
         d = LstmDecode()
-        d.T, d.H = T, H
+        d.T, d.H, d.B = T, H, B
         d.w_ih0, d.w_hh0, d.w_ih1, d.w_hh1 = (w.data_ptr() for w in sh.w)
         d.bias0, d.bias1, d.h_init, d.c_init = sh.bias[0].data_ptr(), sh.bias[1].data_ptr(), hi.data_ptr(), ci.data_ptr()
         d.hs0, d.hs1 = hs0.data_ptr(), hs1.data_ptr()
@@ -207,36 +228,44 @@ class _DecodeFn(torch.autograd.Function):
         cache, key, T, H = ctx.meta
         sh = ctx.sh
         hi, ci, hs0, hs1, save = ctx.saved
-        dev = hs1.device
+        dev, B = hs1.device, hs1.shape[0]
         f32 = dict(dtype=torch.float32, device=dev)
         dy = dy.float().contiguous()
-        dg0, dg1 = torch.empty(T, 4 * H, **f32), torch.empty(T, 4 * H, **f32)
-        dh_init, dc_init = torch.empty(2, H, **f32), torch.empty(2, H, **f32)
+        dg0, dg1 = torch.empty(B, T, 4 * H, **f32), torch.empty(B, T, 4 * H, **f32)
+        dh_init, dc_init = torch.empty(2, B, H, **f32), torch.empty(2, B, H, **f32)
         d = LstmDecode()
-        d.T, d.H = T, H
+        d.T, d.H, d.B = T, H, B
         d.w_ih0_t, d.w_hh0_t, d.w_ih1_t, d.w_hh1_t = (w.data_ptr() for w in sh.wt)
         d.h_init, d.c_init, d.hs0, d.hs1 = hi.data_ptr(), ci.data_ptr(), hs0.data_ptr(), hs1.data_ptr()
         d.gates0, d.gates1, d.cs0, d.cs1 = (t.data_ptr() for t in save)
         d.dy, d.dgates0, d.dgates1 = dy.data_ptr(), dg0.data_ptr(), dg1.data_ptr()
         d.dh_init, d.dc_init = dh_init.data_ptr(), dc_init.data_ptr()
         N.check(N.lib().smz_lstm_decode_backward(C.byref(d), N.ptr(_sync_ws(dev)), N.current_stream()))
-        dgb0, dgb1 = dg0.to(torch.bfloat16), dg1.to(torch.bfloat16)
-        hs0b, hs1b = _bf(hs0), _bf(hs1)
-        prev0 = _bf(torch.cat([hi[0:1], hs0[:-1]], 0))
-        prev1 = _bf(torch.cat([hi[1:2], hs1[:-1]], 0))
-        dw_ih0 = gemm(dgb0[1:], hs1b[:-1], a_mn=True, b_mn=True) if T > 1 else torch.zeros(4 * H, H, **f32)
+        rows = lambda t: _bf(t).reshape(B * T, -1)
+        dgb0, dgb1 = rows(dg0), rows(dg1)
+        in0 = rows(torch.cat([torch.zeros(B, 1, H, **f32), hs1[:, :-1]], 1))     # layer 0's input: previous top output, zeros first
+        prev0 = rows(torch.cat([hi[0].unsqueeze(1), hs0[:, :-1]], 1))
+        prev1 = rows(torch.cat([hi[1].unsqueeze(1), hs1[:, :-1]], 1))
+        dw_ih0 = gemm(dgb0, in0, a_mn=True, b_mn=True)
         dw_hh0 = gemm(dgb0, prev0, a_mn=True, b_mn=True)
-        dw_ih1 = gemm(dgb1, hs0b, a_mn=True, b_mn=True)
+        dw_ih1 = gemm(dgb1, rows(hs0), a_mn=True, b_mn=True)
         dw_hh1 = gemm(dgb1, prev1, a_mn=True, b_mn=True)
-        db0, db1 = dg0.sum(0), dg1.sum(0)
+        db0, db1 = dg0.sum((0, 1)), dg1.sum((0, 1))
         ctx.saved = None
         return dh_init, dc_init, None, dw_ih0, dw_hh0, db0, db0, dw_ih1, dw_hh1, db1, db1
 
 
 def lstm_decode(cache, lstm, seq_len, h_init, c_init):
-    """T steps of the 2-layer ``lstm`` fed with its own top-layer output (zeros first): -> [T, H]."""
+    """T steps of the 2-layer ``lstm`` fed with its own top-layer output (zeros first): h_init / c_init [2,B,H] (or [2,H])
+    -> [B,T,H] (or [T,H]).  More than 4 decodes are processed in groups of 4."""
     if lstm.num_layers != 2 or lstm.bidirectional or lstm.input_size != lstm.hidden_size:
         raise NotImplementedError("the decode kernel implements the dLSTM shape: 2 unidirectional layers, input size = hidden size")
+    squeeze = h_init.dim() == 2
+    if squeeze:
+        h_init, c_init = h_init.unsqueeze(1), c_init.unsqueeze(1)
     flat = [p for layer in (0, 1) for p in layer_params(lstm, layer)[0]]
     meta = (cache, (id(lstm), "decode"), int(seq_len), lstm.hidden_size)
-    return _DecodeFn.apply(h_init, c_init, meta, *flat)
+    outs = [_DecodeFn.apply(h_init[:, b0:b0 + MAX_B], c_init[:, b0:b0 + MAX_B], meta, *flat)
+            for b0 in range(0, h_init.shape[1], MAX_B)]
+    top = torch.cat(outs, 0)
+    return top[0] if squeeze else top

@@ -40,11 +40,8 @@ class sLSTM(nn.Module):
     def forward(self, x):
         """x: (seq_len, batch_size, input_size) -> scores: (seq_len, batch_size, 1)"""
         _require_cuda(x, "sLSTM")
-        cols = []
-        for b in range(x.shape[1]):
-            y, _, _ = lstm_stack(self._cache, self.lstm, x[:, b])
-            cols.append(torch.sigmoid(_head1(y, self.out)))
-        return torch.stack(cols, 1)
+        y, _, _ = lstm_stack(self._cache, self.lstm, x.transpose(0, 1))          # [B,T,2H], sequences share each launch
+        return torch.sigmoid(_head1(y, self.out)).transpose(0, 1)
 
 
 class eLSTM(nn.Module):
@@ -59,13 +56,12 @@ class eLSTM(nn.Module):
     def forward(self, x):
         """x: (seq_len, batch_size, input_size) -> (h_mu, h_logvar), c_last: each (num_layers, batch_size, hidden_size)"""
         _require_cuda(x, "eLSTM")
-        mus, lvs, cls = [], [], []
-        for b in range(x.shape[1]):
-            _, h_last, c_last = lstm_stack(self._cache, self.lstm, x[:, b])
-            mus.append(linear(h_last, self.mu.weight, self.mu.bias))
-            lvs.append(linear(h_last, self.logvar.weight, self.logvar.bias))
-            cls.append(c_last)
-        return (torch.stack(mus, 1), torch.stack(lvs, 1)), torch.stack(cls, 1)
+        _, h_last, c_last = lstm_stack(self._cache, self.lstm, x.transpose(0, 1))  # [L,B,H]
+        L, B, H = h_last.shape
+        flat = h_last.reshape(L * B, H)
+        h_mu = linear(flat, self.mu.weight, self.mu.bias).reshape(L, B, H)
+        h_logvar = linear(flat, self.logvar.weight, self.logvar.bias).reshape(L, B, H)
+        return (h_mu, h_logvar), c_last
 
 
 class dLSTM(nn.Module):
@@ -79,20 +75,15 @@ class dLSTM(nn.Module):
     def forward_step(self, x_prev, h_prev, c_prev):
         """Decode one sequence step: x_prev (1, B, H), h_prev/c_prev (num_layers, B, H) -> x_next, (h_next, c_next)."""
         _require_cuda(x_prev, "dLSTM")
-        xs, hs, cs = [], [], []
-        for b in range(x_prev.shape[1]):
-            y, h_n, c_n = lstm_stack(self._cache, self.lstm, x_prev[:, b], h_prev[:, b], c_prev[:, b])
-            xs.append(y); hs.append(h_n); cs.append(c_n)
-        return torch.stack(xs, 1), (torch.stack(hs, 1), torch.stack(cs, 1))
+        y, h_n, c_n = lstm_stack(self._cache, self.lstm, x_prev.transpose(0, 1), h_prev, c_prev)
+        return y.transpose(0, 1), (h_n, c_n)
 
     def forward(self, seq_len, h_0, c_0):
         """Decode entire sequence: h_0, c_0 (num_layers, B, H) -> x_hat (seq_len, B, input_size), time-reversed."""
         _require_cuda(h_0, "dLSTM")
-        outs = []
-        for b in range(h_0.shape[1]):
-            top = lstm_decode(self._cache, self.lstm, int(seq_len), h_0[:, b], c_0[:, b])     # the whole loop of :110-112
-            outs.append(linear(top, self.recons.weight, self.recons.bias))
-        x_hat = torch.stack(outs, 1)
+        top = lstm_decode(self._cache, self.lstm, int(seq_len), h_0, c_0)         # [B,T,H]: the whole loop of :110-112
+        B, T, H = top.shape
+        x_hat = linear(top.reshape(B * T, H), self.recons.weight, self.recons.bias).reshape(B, T, -1).transpose(0, 1)
         return torch.flip(x_hat, (0,))
 
 
@@ -147,11 +138,8 @@ class cLSTM(nn.Module):
     def forward(self, x):
         """x: (seq_len, B, input_size) -> probs (B, 1), h_last (B, hidden_size)"""
         _require_cuda(x, "cLSTM")
-        rows = []
-        for b in range(x.shape[1]):
-            y, _, _ = lstm_stack(self._cache, self.lstm, x[:, b])
-            rows.append(y[-1])
-        h_last = torch.stack(rows, 0)
+        y, _, _ = lstm_stack(self._cache, self.lstm, x.transpose(0, 1))          # [B,T,H]
+        h_last = y[:, -1]
         probs = torch.sigmoid(_head1(h_last, self.out[0]))
         return probs, h_last
 
@@ -296,37 +284,43 @@ class SumGANTrainer(Trainer):
         """The three updates of one video (sumgan.py:415-480).  x (T,1,1024), y (T,1,1) or None on an idle replica.
         Returns the detached scalars the reference logs, or None."""
         m, idle = self.model, x is None
+        # Sequences that go through the same network inside one phase share its recurrence launches (the weights are
+        # streamed once per step for all of them): the discriminator sees [x | x_hat | x_hat_p] as one batch of 2-3, the
+        # VAE decodes the selector-weighted and the uniformly weighted features together.  Same losses and gradients as
+        # the reference's separate calls (sumgan.py:419-421, 442-446, 463-471).
         # ---- selector and encoder
         loss_s_e = None
         if not idle:
             x_hat, (mu, logvar), scores = m.summarizer(x)
-            _, h_real = m.gan(x)
-            _, h_fake = m.gan(x_hat)
+            _, h = m.gan(torch.cat([x, x_hat], 1))
             loss_sparsity = self.loss_sparsity_sup(scores, y) if self.sup else self.loss_sparsity(scores, self.sigma)
-            loss_s_e = self.loss_recons(h_real, h_fake) + self.loss_prior(mu, logvar) + loss_sparsity
+            loss_s_e = self.loss_recons(h[0:1], h[1:2]) + self.loss_prior(mu, logvar) + loss_sparsity
         self._update(self.s_e_optimizer, loss_s_e, dp, n_active)
+
+        def both_reconstructions():
+            """x_hat from the selector's scores and x_hat_p from uniform random scores (Summarizer.forward twice)."""
+            scores = m.summarizer.s_lstm(x)
+            uniform = torch.rand_like(scores)
+            x_pair, _ = m.summarizer.vae(torch.cat([x * scores, x * uniform], 1))
+            return x_pair[:, 0:1], x_pair[:, 1:2], scores
         # ---- decoder
         loss_d = None
         if not idle:
-            x_hat, _, _ = m.summarizer(x)
-            x_hat_p, _, _ = m.summarizer(x, uniform=True)
-            _, h_real = m.gan(x)
-            probs_fake, h_fake = m.gan(x_hat)
-            probs_uniform, _ = m.gan(x_hat_p)
-            loss_d = self.loss_recons(h_real, h_fake) + self.loss_gan_generator(probs_fake, probs_uniform)
+            x_hat, x_hat_p, _ = both_reconstructions()
+            probs, h = m.gan(torch.cat([x, x_hat, x_hat_p], 1))
+            loss_d = self.loss_recons(h[0:1], h[1:2]) + self.loss_gan_generator(probs[1:2], probs[2:3])
         self._update(self.d_optimizer, loss_d, dp, n_active)
         # ---- discriminator
         loss_c = None
         if not idle:
-            x_hat, _, scores = m.summarizer(x)
-            x_hat_p, _, _ = m.summarizer(x, uniform=True)
+            x_hat, x_hat_p, scores = both_reconstructions()
+            x_in = x
             if epoch < self.epoch_noise:
-                x = torch.randn_like(x) * x
+                x_in = torch.randn_like(x) * x
                 x_hat = x_hat * torch.randn_like(x_hat)
                 x_hat_p = x_hat_p * torch.randn_like(x_hat_p)
-            probs_real, _ = m.gan(x)
-            probs_fake, _ = m.gan(x_hat)
-            probs_uniform, _ = m.gan(x_hat_p)
+            probs, _ = m.gan(torch.cat([x_in, x_hat, x_hat_p], 1))
+            probs_real, probs_fake, probs_uniform = probs[0:1], probs[1:2], probs[2:3]
             loss_c = self.loss_gan_discriminator(probs_real, probs_fake, probs_uniform)
         self._update(self.c_optimizer, loss_c, dp, n_active)
         if idle:

@@ -195,3 +195,51 @@ def test_trainer_three_phase_step_and_test(tmp_path):
     assert all(torch.isfinite(p).all() for p in m.parameters())
     avg_corr, (avg_f, max_f) = t.test(0)
     assert np.isfinite([avg_corr, avg_f, max_f]).all() and 0 <= avg_f <= max_f <= 1
+
+
+@pytest.mark.parametrize("H,bi,B", [(1024, True, 3), (2048, False, 2), (1024, False, 4)])
+def test_sequences_sharing_a_launch_match_separate_launches(H, bi, B):
+    """B sequences of equal length go through one recurrence launch per layer (weights streamed once per step for all of
+    them): outputs equal the one-sequence launches, parameter gradients equal their sum."""
+    from summarizer_b200.models.lstm_stack import ShadowCache, lstm_stack
+    torch.manual_seed(B + H)
+    lstm = nn.LSTM(1024, H, num_layers=2, bidirectional=bi).to(dev)
+    nd, T = (2 if bi else 1), 9
+    x = (torch.randn(B, T, 1024, device=dev) * 0.5)
+    h0, c0 = torch.randn(2 * nd, B, H, device=dev) * 0.3, torch.randn(2 * nd, B, H, device=dev) * 0.3
+    w = torch.randn(B, T, nd * H, device=dev)
+    xs, hs = x.clone().requires_grad_(True), h0.clone().requires_grad_(True)
+    y, hn, cn = lstm_stack(ShadowCache(), lstm, xs, hs, c0)
+    ((y * w).sum() + hn.sum() + cn.sum()).backward()
+    g_batched = {k: p.grad.clone() for k, p in lstm.named_parameters()}
+    gx, gh = xs.grad.clone(), hs.grad.clone()
+    lstm.zero_grad(set_to_none=True)
+    for b in range(B):
+        xb, hb = x[b].clone().requires_grad_(True), h0[:, b].clone().requires_grad_(True)
+        yb, hnb, cnb = lstm_stack(ShadowCache(), lstm, xb, hb, c0[:, b])
+        ((yb * w[b]).sum() + hnb.sum() + cnb.sum()).backward()
+        assert torch.allclose(yb, y[b], atol=1e-6) and torch.allclose(hnb, hn[:, b], atol=1e-6) and torch.allclose(cnb, cn[:, b], atol=1e-6)
+        assert rel(gx[b], xb.grad) < 1e-5 and rel(gh[:, b], hb.grad) < 1e-5
+    for k, p in lstm.named_parameters():
+        assert rel(g_batched[k], p.grad) < 2e-3, k           # bf16 operands of the summed-over-batch weight-gradient GEMMs
+
+
+def test_decodes_sharing_a_launch_match_separate_launches():
+    from summarizer_b200.models.lstm_stack import ShadowCache, lstm_decode
+    torch.manual_seed(9)
+    H, T, B = 2048, 7, 2
+    lstm = nn.LSTM(H, H, num_layers=2).to(dev)
+    h, c, w = torch.randn(2, B, H, device=dev) * 0.5, torch.randn(2, B, H, device=dev) * 0.5, torch.randn(B, T, H, device=dev)
+    hs, cs_ = h.clone().requires_grad_(True), c.clone().requires_grad_(True)
+    top = lstm_decode(ShadowCache(), lstm, T, hs, cs_)
+    (top * w).sum().backward()
+    g_batched = {k: p.grad.clone() for k, p in lstm.named_parameters()}
+    lstm.zero_grad(set_to_none=True)
+    for b in range(B):
+        hb, cb = h[:, b].clone().requires_grad_(True), c[:, b].clone().requires_grad_(True)
+        tb = lstm_decode(ShadowCache(), lstm, T, hb, cb)
+        (tb * w[b]).sum().backward()
+        assert torch.allclose(tb, top[b], atol=1e-6)
+        assert rel(hs.grad[:, b], hb.grad) < 1e-5 and rel(cs_.grad[:, b], cb.grad) < 1e-5
+    for k, p in lstm.named_parameters():
+        assert rel(g_batched[k], p.grad) < 2e-3, k
