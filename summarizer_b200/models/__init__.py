@@ -125,6 +125,12 @@ class Trainer:
             self._dev_cache[key] = (seq.to(self._device()), target.to(self._device()))
         return self._dev_cache[key]
 
+    def _model_input(self, seq):
+        """The cached device features, or a private copy when the model writes into its input (VASNet adds the positional
+        embedding IN PLACE to the caller's tensor when ``max_pos`` is set, vasnet.py:110,112; the reference re-reads the
+        HDF5 features every step, so the write never accumulates there)."""
+        return seq.clone() if getattr(self.model, "max_length", None) is not None else seq
+
     def _eval_batches(self, test_keys):
         """Resident evaluation inputs of a set of test keys (built once per key set)."""
         tag = tuple(test_keys)
@@ -152,7 +158,7 @@ class Trainer:
         with torch.no_grad():
             for key in keys:
                 seq, _ = self._video_tensors(key)
-                out.append(self.model(seq).reshape(-1).float())
+                out.append(self.model(self._model_input(seq)).reshape(-1).float())
         return out
 
     def test(self, fold):
@@ -270,7 +276,7 @@ class Trainer:
 
         def forward_backward(key):
             seq, target = self._video_tensors(key)
-            scores = self.model(seq)
+            scores = self.model(self._model_input(seq))
             loss = criterion(scores, target)
             if self.optimizer is not None:
                 loss.backward()

@@ -125,3 +125,16 @@ def test_weight_copies_follow_fused_optimizer_steps(family):
     assert float((y_before - y_ref).abs().max()) > 1e-3            # the steps really changed the function
     assert torch.allclose(y_inf, y_ref, atol=1e-6), float((y_inf - y_ref).abs().max())
     assert torch.allclose(y_train, fresh(x).detach(), atol=1e-6)
+
+
+def test_positional_embedding_does_not_accumulate_in_cached_features(tmp_path):
+    """--max_pos: VASNet adds the positional embedding in place to its input (reference quirk); the trainer hands it a
+    private copy so the device-resident features stay what the dataset holds."""
+    hps = make_hps(tmp_path, splits_files="splits/summe_splits_overfit.json", epochs=2, test_every_epochs=1,
+                   extra_params={"max_pos": "20000", "pos_embed": "simple"})
+    t = hps.model_class(hps, hps.splits_files[0]).reset()
+    keys, _ = t._get_train_test_keys(0)
+    before = t._video_tensors(keys[0])[0].clone()
+    res = t.train(0)
+    assert np.isfinite(res).all()
+    assert torch.equal(before, t._video_tensors(keys[0])[0])
