@@ -131,7 +131,7 @@ def test_positional_embedding_does_not_accumulate_in_cached_features(tmp_path):
     """--max_pos: VASNet adds the positional embedding in place to its input (reference quirk); the trainer hands it a
     private copy so the device-resident features stay what the dataset holds."""
     hps = make_hps(tmp_path, splits_files="splits/summe_splits_overfit.json", epochs=2, test_every_epochs=1,
-                   extra_params={"max_pos": "20000", "pos_embed": "simple"})
+                   extra_params={"max_pos": "2000", "pos_embed": "simple"})
     t = hps.model_class(hps, hps.splits_files[0]).reset()
     keys, _ = t._get_train_test_keys(0)
     before = t._video_tensors(keys[0])[0].clone()
