@@ -273,6 +273,19 @@ int smz_fscore_packed(const smz_video_desc *desc, int n_videos, const uint32_t *
                       const uint32_t *mask, const int32_t *msum, int32_t *overlap, int32_t *gsum, float *f,
                       double *avg_f, double *max_f, void *stream);
 
+/* ---- Kernel temporal segmentation (KTS, Potapov et al. ECCV 2014): produces what the datasets hold as /change_points
+ *      (datasets/README.md:24-27).  The reference ships no KTS code — it only consumes change points — so these follow
+ *      the published cpd_nonlin / cpd_auto (oracle/kts_np.py); SURVEY.md §8f NEXT-4.
+ *   smz_kts_gram: K = X X^T in float32, features [n, d] with row stride ld (device).
+ *   smz_kts: K [n, n] device float32, or NULL to compute it from `features`; max_ncp = m of cpd_nonlin, lmin / lmax the
+ *   segment length bounds; auto_select != 0 = cpd_auto's penalised choice of the number of change points (vmax,
+ *   desc_rate).  Device outputs: cps [max_ncp] (ascending, first n_cps entries valid), n_cps [1], scores [max_ncp + 1]. */
+int smz_kts_workspace_bytes(int n, int max_ncp, int from_features, int64_t *bytes);
+int smz_kts_gram(const float *features, int n, int d, int ld, float *K, void *stream);
+int smz_kts(const float *K, const float *features, int n, int d, int ld, int max_ncp, int lmin, int lmax,
+            int auto_select, double vmax, int desc_rate, int32_t *cps, int32_t *n_cps, double *scores,
+            void *ws, int64_t ws_bytes, void *stream);
+
 /* ---- SumGAN LSTM recurrences: replace the cuDNN calls behind nn.LSTM in models/sumgan.py:43 (sLSTM, 2 x 1024
  *      bidirectional), :69 (eLSTM, 2 x 2048), :207 (cLSTM, 2 x 1024) and the step-wise decode loop :98-115 (dLSTM,
  *      2 x 2048), forward and BPTT, batch 1.  One call = one layer over the whole sequence (both directions of a
