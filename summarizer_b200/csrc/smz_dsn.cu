@@ -51,6 +51,11 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
     return r;
 }
+__device__ __forceinline__ void st_async_f32x4(uint32_t remote_addr, float a, float b, float c, float d, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(remote_addr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)),
+                   "r"(__float_as_uint(d)), "r"(remote_bar) : "memory");
+}
 __device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
                  ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_bar) : "memory");
@@ -245,7 +250,8 @@ lstm_bwd_kernel(const uint32_t *__restrict__ wt, const int32_t *__restrict__ cu,
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int unit = cta * UNITS + warp * 4 + (lane >> 3);
     const int d = lane & 7;
-    const uint32_t r_g = map_to_cta(smem_addr(&dgbuf[0][unit]), d);      // lane d -> CTA d
+    // gate gradients are exchanged in [unit][gate] order: the four of one unit are ONE 16-byte st.async per destination
+    const uint32_t r_g = map_to_cta(smem_addr(&dgbuf[0][4 * unit]), d);  // lane d -> CTA d
     const uint32_t r_bar = map_to_cta(smem_addr(&gbar[0]), d);
     if (tid == 0) {
         bar_init(&gbar[0], 1); bar_init(&gbar[1], 1);
@@ -326,8 +332,7 @@ lstm_bwd_kernel(const uint32_t *__restrict__ wt, const int32_t *__restrict__ cu,
             dc_carry = dc * gf;
             if (s + 1 < T) {
                 const uint32_t dst = r_g + (cur ^ 1) * G4 * 4, bar = r_bar + (cur ^ 1) * 8;
-                st_async_f32(dst, dI, bar); st_async_f32(dst + H * 4, dF, bar);
-                st_async_f32(dst + 2 * H * 4, dG, bar); st_async_f32(dst + 3 * H * 4, dO, bar);
+                st_async_f32x4(dst, dI, dF, dG, dO, bar);
             }
             if (d < 4) {
                 const float val = d == 0 ? dI : d == 1 ? dF : d == 2 ? dG : dO;
@@ -413,11 +418,13 @@ __global__ void pack_whh_kernel(const float *__restrict__ wf, const float *__res
         const int c = 8 * lane + 2 * p;
         out_fwd[idx] = pack(row[c], row[c + 1]);
     }
-    {   // backward: (W_hh^T)[unit][gate column j]: units 4*warp+u (u<4), columns j = 32*lane + 2q, +1 (q<16); register u*16+q
+    {   // backward: (W_hh^T)[unit][.] against the gate-gradient buffer, which is ordered [unit'][gate]: position
+        // jp = 4*unit' + gate <-> row gate*H + unit' of W_hh; units 4*warp+u (u<4), positions 32*lane + 2q, +1 (q<16); register u*16+q
         const int u = k >> 4, q = k & 15;
         const int unit = cta * UNITS + warp * 4 + u;
-        const int j = 32 * lane + 2 * q;
-        out_bwd[idx] = pack(Wm[(size_t)j * H + unit], Wm[(size_t)(j + 1) * H + unit]);
+        const int jp = 32 * lane + 2 * q;
+        const int r0 = (jp & 3) * H + (jp >> 2), r1 = ((jp + 1) & 3) * H + ((jp + 1) >> 2);
+        out_bwd[idx] = pack(Wm[(size_t)r0 * H + unit], Wm[(size_t)r1 * H + unit]);
     }
 }
 }  // namespace
