@@ -534,6 +534,12 @@ def run_native(args):
 
     if rank == 0:
         hbm, tf_sus, tf_burst, which = peaks()
+        traffic = None       # DRAM bytes of the scoring stage per step, from the committed ncu capture (per video x videos)
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01n_scoring_stage_dram_traffic.json")) as fh:
+                traffic = float(json.load(fh)["dram_bytes_per_video"]) * V
+        except Exception:
+            pass
         cu = np.arange(V + 1, dtype=np.int32) * N_STEPS
         nl = ctypes.c_int64(0)
         N.check(N.lib().smz_vasnet_launch_count(cu.ctypes.data_as(ctypes.c_void_p), V, 0, 1, ctypes.byref(nl)))
@@ -552,7 +558,10 @@ def run_native(args):
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05; all launches of the VASNet scoring stage, "
                                                       "softmax/LayerNorm/head row kernels included in the time)",
                          "achieved": achieved_tf, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved_tf / tf_sus,
-                         "frac_of_burst_peak": achieved_tf / tf_burst, "traffic": None, "peak_source": which + " (sustained)",
+                         "frac_of_burst_peak": achieved_tf / tf_burst, "traffic": traffic,
+                         "traffic_source": "profiles/r01n_scoring_stage_dram_traffic.json: ncu dram__bytes_read+write of every kernel of the "
+                                           "stage on 64 videos, per video x videos (69.5 MB per video; 4.1 MB of it is the input)",
+                         "peak_source": which + " (sustained)",
                          "ms_per_launch": score_ms, "algorithmic_flops_per_launch": f_score_stage},
             "roofline_eval": {"bound": "hbm", "kernel": "fscore_kernel", "achieved": achieved_gb, "peak": hbm, "unit": "GB/s",
                               "frac": achieved_gb / hbm, "ms_per_launch": fscore_ms, "algorithmic_bytes_per_launch": b_fscore,
