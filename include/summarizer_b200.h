@@ -40,7 +40,7 @@ extern "C" {
 #define SMZ_METHOD_RANK 1     /* utils/eval.py:100-107 */
 
 /* per-video status bits written by smz_select_shots */
-#define SMZ_STATUS_VALUE_RANGE 1 /* |int(score*1000)| * n_segs does not fit the int32 DP */
+#define SMZ_STATUS_VALUE_RANGE 1 /* |int(score*1000)| * n_segs exceeds 2^29 (the int32 DP and its sign-bit take test); value clipped */
 #define SMZ_STATUS_INTERVALS 2   /* more upsample intervals than scores+1 (reference: IndexError) */
 #define SMZ_STATUS_WEIGHT_RANGE 4 /* a segment is longer than the max_seg_frames the caller declared */
 
