@@ -59,3 +59,39 @@ def test_no_oracle_import_in_product():
             if f.endswith(".py"):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_argument_validation_needs_no_gpu():
+    """Entry points reject bad arguments with SMZ_ERR_ARG (< 0) and a message before touching the device."""
+    from summarizer_b200.models.lstm_stack import LstmDecode, LstmSeq
+    L = N.lib()
+    seq = (LstmSeq * 1)()
+    seq[0].T, seq[0].H, seq[0].B = 4, 1000, 1                      # hidden size the recurrence does not implement
+    assert L.smz_lstm_seq_forward(seq, 1, None, None) < 0 and b"hidden size" in L.smz_last_error()
+    seq[0].H, seq[0].B = 1024, 9                                   # more sequences than one launch takes
+    assert L.smz_lstm_seq_forward(seq, 1, None, None) < 0 and b"sequences per launch" in L.smz_last_error()
+    assert L.smz_lstm_seq_forward(seq, 3, None, None) < 0          # one or two directions
+    dec = LstmDecode()
+    dec.T, dec.H, dec.B = 0, 2048, 1
+    assert L.smz_lstm_decode_forward(ctypes.byref(dec), None, None) < 0 and b"empty sequence" in L.smz_last_error()
+    nbytes = ctypes.c_int64(0)
+    assert L.smz_kts_workspace_bytes(100, 5, 1, ctypes.byref(nbytes)) == 0 and nbytes.value > 100 * 100 * 4
+    one = ctypes.c_void_p(16)
+    assert L.smz_kts(one, None, 10, 0, 0, 20, 1, 100, 0, 1.0, 1, one, one, one, one, 1 << 30, None) < 0
+    assert b"(m+1)*lmin" in L.smz_last_error()
+    assert L.smz_cvt_bf16_multi(None, None, None, 9, None) < 0 and b"1..8 segments" in L.smz_last_error()
+    assert L.smz_host_pack_user_summary(None, 3, None, None, None, 1) < 0
+
+
+def test_struct_sizes_match_header():
+    """ctypes mirrors of the LSTM structs against the sizes the C compiler gives the header's."""
+    import subprocess, tempfile
+    from summarizer_b200.models.lstm_stack import LstmDecode, LstmSeq
+    from summarizer_b200.models.dsn import DsnParams
+    src = '#include <stdio.h>\n#include "summarizer_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(smz_lstm_seq), sizeof(smz_lstm_decode), sizeof(smz_dsn_params), sizeof(smz_video_desc));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", os.path.join(d, "s")])
+        sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "s")]).split()]
+    assert sizes == [ctypes.sizeof(LstmSeq), ctypes.sizeof(LstmDecode), ctypes.sizeof(DsnParams), N.VIDEO_DESC.itemsize]
