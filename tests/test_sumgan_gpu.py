@@ -243,3 +243,16 @@ def test_decodes_sharing_a_launch_match_separate_launches():
         assert rel(hs.grad[:, b], hb.grad) < 1e-5 and rel(cs_.grad[:, b], cb.grad) < 1e-5
     for k, p in lstm.named_parameters():
         assert rel(g_batched[k], p.grad) < 2e-3, k
+
+
+def test_more_sequences_than_one_launch_takes(sumgan_seed11):
+    """batch 6 > 4 sequences per launch: processed in groups, same scores as one-by-one."""
+    m = sumgan_seed11.eval()
+    x = make_input(6, 8, 6).to(dev)
+    with torch.no_grad():
+        s = m(x)
+        ones = torch.cat([m(x[:, b:b + 1]) for b in range(6)], 1)
+        (mu, logvar), c = m.summarizer.vae.e_lstm(x)
+        x_hat = m.summarizer.vae.d_lstm(8, mu, c)
+    assert s.shape == (8, 6, 1) and torch.allclose(s, ones, atol=1e-6)
+    assert mu.shape == (2, 6, 2048) and c.shape == (2, 6, 2048) and x_hat.shape == (8, 6, 1024)
