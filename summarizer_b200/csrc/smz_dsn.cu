@@ -279,6 +279,7 @@ lstm_bwd_kernel(const uint32_t *__restrict__ wt, const int32_t *__restrict__ cu,
         int t = dir ? 0 : T - 1;
         const float *sv = save + ((size_t)(row0 + t) * 2 + dir) * SAVE * H + unit;
         float gi = sv[0], gf = sv[H], gg = sv[2 * H], go = sv[3 * H], cc = sv[4 * H];
+        float dzt = dz[row0 + t];
         for (int s = 0; s < T; s++) {
             const int cur = s & 1;
             if (s > 0) {                                   // same st.async / mbarrier protocol as the forward kernel
@@ -287,12 +288,12 @@ lstm_bwd_kernel(const uint32_t *__restrict__ wt, const int32_t *__restrict__ cu,
             if (tid == 0 && s + 1 < T) bar_arm(&gbar[cur ^ 1], G4 * 4);
             const int tp = dir ? t + 1 : t - 1;            // the step BEFORE t in forward order (next to visit)
             // prefetch the next visited step's saved activations; its cell state is this step's c_{prev}
-            float n_i = 0.f, n_f = 0.f, n_g = 0.f, n_o = 0.f, n_c = 0.f;
+            float n_i = 0.f, n_f = 0.f, n_g = 0.f, n_o = 0.f, n_c = 0.f, n_dz = 0.f;
             if (s + 1 < T) {
                 const float *q = save + ((size_t)(row0 + tp) * 2 + dir) * SAVE * H + unit;
                 n_i = q[0]; n_f = q[H]; n_g = q[2 * H]; n_o = q[3 * H]; n_c = q[4 * H];
+                n_dz = dz[row0 + tp];                      // the head gradient of the next visited step, off the critical path
             }
-            const float dzt = dz[row0 + t];
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int q4 = 0; q4 < 8; q4++) {
@@ -339,7 +340,7 @@ lstm_bwd_kernel(const uint32_t *__restrict__ wt, const int32_t *__restrict__ cu,
                 dgb[(size_t)(row0 + t) * (2 * G4) + dir * G4 + d * H + unit] = __float2bfloat16_rn(val);
             }
             bsum[0] += dI; bsum[1] += dF; bsum[2] += dG; bsum[3] += dO;
-            gi = n_i; gf = n_f; gg = n_g; go = n_o; cc = n_c;
+            gi = n_i; gf = n_f; gg = n_g; go = n_o; cc = n_c; dzt = n_dz;
             t = tp;
         }
         if (d < 4) atomicAdd(d_bias + dir * G4 + d * H + unit, d == 0 ? bsum[0] : d == 1 ? bsum[1] : d == 2 ? bsum[2] : bsum[3]);
