@@ -4,7 +4,8 @@
 //   cLSTM  nn.LSTM(1024, 1024, 2 layers)                     sumgan.py:189-194,207
 //   dLSTM  nn.LSTM(2048, 2048, 2 layers) called with seq_len 1 in a Python loop that feeds the top layer's
 //          output back as the next input (sumgan.py:98-115)
-// forward and BPTT, batch 1 (the trainer's shape, sumgan.py:404).
+// forward and BPTT; up to four sequences of equal length share a launch (kernels templated on that count): the trainer's
+// batch is 1 (sumgan.py:404), but inside a training phase several sequences go through the same network.
 //
 // W_hh is 8 MB (H=1024) or 32 MB (H=2048) in bf16 — far beyond one cluster's registers (the DSN kernel,
 // smz_dsn.cu) — so these recurrences are spread over 128 CTAs of a cooperative launch and the weights are streamed
@@ -70,25 +71,8 @@ __device__ __forceinline__ float dot8(const uint4 w, const float4 a, const float
     return s;
 }
 
-// acc[g] += W[g*H + unit, 0:K] . vec   for the four gates (W bf16 [4H, K] row-major, vec fp32 in shared memory);
-// per-lane partial sums, reduced by the caller.
-__device__ __forceinline__ void dot_gates(const bf16 *__restrict__ W, int H, int K, int unit, const float *vec, int lane,
-                                          float acc[4]) {
-    const bf16 *r0 = W + (size_t)unit * K;
-    const size_t gs = (size_t)H * K;
-#pragma unroll 4
-    for (int c = lane * 8; c < K; c += 256) {
-        uint4 w[4];
-#pragma unroll
-        for (int g = 0; g < 4; g++) w[g] = __ldg(reinterpret_cast<const uint4 *>(r0 + g * gs + c));
-        const float4 a = *reinterpret_cast<const float4 *>(vec + c);
-        const float4 b = *reinterpret_cast<const float4 *>(vec + c + 4);
-#pragma unroll
-        for (int g = 0; g < 4; g++) acc[g] += dot8(w[g], a, b);
-    }
-}
-
-// batched: acc[b][g] += W[g*H + unit, 0:K] . vec_b, vec_b = vec + b*vstride (the weight chunk is loaded once for all B)
+// acc[b][g] += W[g*H + unit, 0:K] . vec_b for the four gates (W bf16 [4H, K] row-major, vec_b = vec + b*vstride fp32 in
+// shared memory): per-lane partial sums, reduced by the caller; the weight chunk is loaded once for all NB sequences
 template <int NB>
 __device__ __forceinline__ void dot_gates_b(const bf16 *__restrict__ W, int H, int K, int unit, const float *vec, int vstride,
                                             int lane, float acc[NB][4]) {
@@ -109,7 +93,7 @@ __device__ __forceinline__ void dot_gates_b(const bf16 *__restrict__ W, int H, i
     }
 }
 
-// batched: acc[b] += row[0:K] . vec_b
+// acc[b] += row[0:K] . vec_b (per-lane partials)
 template <int NB>
 __device__ __forceinline__ void dot_row_b(const bf16 *__restrict__ row, int K, const float *vec, int vstride, int lane,
                                           float acc[NB]) {
@@ -123,23 +107,6 @@ __device__ __forceinline__ void dot_row_b(const bf16 *__restrict__ row, int K, c
             acc[b] += dot8(w, x0, x1);
         }
     }
-}
-
-// per-lane partial of row[0:K] . vec
-__device__ __forceinline__ float dot_row(const bf16 *__restrict__ row, int K, const float *vec, int lane) {
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll 4
-    for (int c = lane * 8; c < K; c += 512) {
-        const uint4 w0 = __ldg(reinterpret_cast<const uint4 *>(row + c));
-        const float4 a0 = *reinterpret_cast<const float4 *>(vec + c), b0 = *reinterpret_cast<const float4 *>(vec + c + 4);
-        s0 += dot8(w0, a0, b0);
-        if (c + 256 < K) {
-            const uint4 w1 = __ldg(reinterpret_cast<const uint4 *>(row + c + 256));
-            const float4 a1 = *reinterpret_cast<const float4 *>(vec + c + 256), b1 = *reinterpret_cast<const float4 *>(vec + c + 260);
-            s1 += dot8(w1, a1, b1);
-        }
-    }
-    return s0 + s1;
 }
 
 // n floats (multiple of 4, 16-byte aligned) written by other SMs -> shared memory; src == nullptr stages zeros
