@@ -525,9 +525,15 @@ def run_native(args):
         return ne * world * args.steps / (te.item() / 1e3), h_out.clone()
 
     e2e_float, out_float = e2e_run(False)
-    e2e_packed, out_packed = e2e_run(True)
-    assert torch.equal(out_float, out_packed), "packed and float32 annotator paths disagree"
-    pool.shutdown()
+    packed_note = None
+    try:
+        e2e_packed, out_packed = e2e_run(True)
+        if not torch.equal(out_float, out_packed):
+            raise RuntimeError("packed and float32 annotator paths disagree")
+    except Exception as e:                         # the float32 staging alone still gives the e2e number
+        e2e_packed, packed_note = 0.0, f"{type(e).__name__}: {e}"[:200]
+        torch.cuda.synchronize()
+    pool.shutdown(wait=False)
     use_packed = e2e_packed >= e2e_float
     e2e_value = max(e2e_packed, e2e_float)
     users_bytes = sets[0]["h_bits"].numel() * 4 if use_packed else h_users.numel() * 4
@@ -572,13 +578,20 @@ def run_native(args):
                     "pipelining": "two buffer sets: step i+1 H2D on a copy stream overlaps step i kernels",
                     "annotator_staging": ("packed on %d host threads to 1 bit/frame inside the timed region (x > 0 is all "
                                           "evaluate_summary reads)" % host_threads) if use_packed else "float32 rows as held by the reference",
-                    "value_float32_rows": e2e_float, "value_host_packed": e2e_packed},
+                    "value_float32_rows": e2e_float, "value_host_packed": e2e_packed, "host_packed_error": packed_note},
             "gpu_launches": int((nl.value + 7) * args.steps),     # + order_count, order_fill, pool, dp, summary, fscore, fscore_final
             "clocks": clocks,
         }
         if world == 1:
-            line["train"] = train_stage(dev)
-            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+            try:                                   # secondary stages never cost the headline line
+                line["train"] = train_stage(dev)
+            except Exception as e:
+                line["train"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            try:
+                line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": "videos/s", "cores": os.cpu_count(), "kind": "port",
+                                        "sample": f"failed: {type(e).__name__}: {e}"[:300]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
