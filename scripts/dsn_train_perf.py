@@ -21,12 +21,10 @@ def full(x):
     opt.zero_grad(set_to_none=True)
     probs = dsn(x)
     dist = Bernoulli(probs, validate_args=False)
-    actions = torch.stack([dist.sample() for _ in range(5)])
+    actions = dist.sample((5,))
     rewards = compute_rewards(x, actions.reshape(5, -1))
-    loss = 0.
-    for e in range(5):
-        loss = loss - dist.log_prob(actions[e]).mean() * (rewards[e] - base)
-    (loss / 5.).backward(); torch.nn.utils.clip_grad_norm_(dsn.parameters(), 5.0); opt.step()
+    loss = -(dist.log_prob(actions).reshape(5, -1).mean(1) * (rewards - base)).sum() / 5.
+    loss.backward(); torch.nn.utils.clip_grad_norm_(dsn.parameters(), 5.0); opt.step()
 
 def recurrence_only(x):
     opt.zero_grad(set_to_none=True)

@@ -180,12 +180,14 @@ class DSNTrainer(Trainer):
             loss = self.beta * (probs.mean() - self.eps) ** 2                 # summary-length penalty [Eq.11]
             if self.sup:
                 loss = loss + loss_BCE(probs, target)
-            actions = torch.stack([dist.sample() for _ in range(self.num_episodes)])      # (E,T,1,1)
+            actions = dist.sample((self.num_episodes,))                       # (E,T,1,1): the E episodes in one draw
             rewards = compute_rewards(seq, actions.reshape(self.num_episodes, -1), self.far_sim, self.temp_dist_thre,
                                       self._reward_ws)
             base = baselines[key_index[key]].detach().clone()
-            for e in range(self.num_episodes):                                # policy gradient [Eq.10]
-                loss = loss - dist.log_prob(actions[e]).mean() * (rewards[e] - base)
+            # policy gradient [Eq.10], dsn.py:134-138 for all episodes at once:
+            #   loss -= sum_e mean_t(log_prob(actions_e)) * (reward_e - baseline)
+            log_probs = dist.log_prob(actions).reshape(self.num_episodes, -1).mean(1)
+            loss = loss - (log_probs * (rewards - base)).sum()
             loss = loss / float(self.num_episodes)
             loss.backward()
             mean_reward = rewards.mean()
