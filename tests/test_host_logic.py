@@ -137,3 +137,13 @@ def test_host_pack_user_summary_matches_numpy():
                     pad[:nf] = a[u, :nf] > 0
                 ref = np.packbits(pad.reshape(W, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1)
                 assert (out[boff[i] + u * W: boff[i] + (u + 1) * W] == ref).all(), (n_threads, i, u)
+
+
+def test_step_graphs_disabled_is_plain_eager():
+    """StepGraphs with graphs off (CPU runs, --cuda_graphs no, data-parallel mode) just calls the step."""
+    from summarizer_b200.models import StepGraphs
+    calls = []
+    g = StepGraphs(trainer=None, enabled=False)
+    for key in ("a", "b", "a", "a"):
+        assert g.run(key, lambda k: (calls.append(k) or (k,))) == (key,)
+    assert calls == ["a", "b", "a", "a"] and g.graphs == {} and g.pool is None
