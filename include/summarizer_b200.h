@@ -117,6 +117,22 @@ int smz_fscore(const smz_video_desc *desc, int n_videos, int max_n_frames, int t
                const float *user_summary, const uint32_t *mask, const int32_t *msum, int32_t *overlap,
                int32_t *gsum, float *f, double *avg_f, double *max_f, void *stream);
 
+/* ---- whole evaluation path in ONE call: smz_select_shots + smz_fscore (or smz_fscore_packed) ----------------------
+ * Replaces the per-key loop of models/__init__.py:88-119 (Trainer._eval_summary: generate_summary + evaluate_summary
+ * for every test video).  The knapsack DP of a video is shared-memory bound, its F-score HBM bound; here the SAME
+ * persistent CTA that solved a video's knapsack builds its summary mask in shared memory and streams its annotator
+ * rows against it, so across the CTAs of an SM the DP of some videos overlaps the streaming of others and the stage
+ * costs about max(DP, streaming) instead of their sum; the mask never makes a round trip through global memory.
+ * Annotator rows: exactly one of user_summary (float32 rows, see smz_fscore) and user_bits + bits_off (1 bit per
+ * frame, see smz_fscore_packed).  All other arguments and outputs as in smz_select_shots / smz_fscore; results are
+ * identical to calling those two (which is what happens for videos whose DP rows do not fit the fused plan). */
+int smz_eval_batch(const smz_video_desc *desc, int n_videos, int total_users, const float *scores,
+                   const int32_t *picks, const int32_t *cps, const int32_t *nfps, int method, int max_n_segs,
+                   int max_capacity, int max_n_frames, int max_seg_frames, const float *user_summary,
+                   const uint32_t *user_bits, const int64_t *bits_off, float *seg_mean, int32_t *values,
+                   uint8_t *picked, float *summary, uint32_t *mask, int32_t *msum, int32_t *status, int32_t *overlap,
+                   int32_t *gsum, float *f, double *avg_f, double *max_f, void *ws, int64_t ws_bytes, void *stream);
+
 /* Binarise (>0), truncate/zero-pad an explicit machine summary to n_frames and pack it to the
  * bit mask smz_fscore consumes (utils/eval.py:136-145).  machine[] is indexed by summ_off /
  * summ_len like the summary output above. */

@@ -48,6 +48,8 @@ SIGNATURES = {
     "smz_select_shots": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
     "smz_knapsack": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _P]),
     "smz_fscore": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "smz_eval_batch": (_I, [_P, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                            _P, _P, _P, _P, _P, _L, _P]),
     "smz_pack_summary": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "smz_upsample": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
     "smz_rank_correlation": (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P]),

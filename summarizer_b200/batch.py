@@ -8,6 +8,7 @@ The reference re-reads the same fields from HDF5 on every call (models/__init__.
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -94,7 +95,10 @@ class VideoBatch:
         self = cls.__new__(cls)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.proportion = float(proportion)
-        self._finish(np.ascontiguousarray(desc, dtype=N.VIDEO_DESC), picks, cps, nfps, user_summary)
+        desc = np.ascontiguousarray(desc, dtype=N.VIDEO_DESC)
+        if len(desc) and int(desc["n_users"].max()) > N.FSCORE_MAX_USERS:      # fscore_kernel counts in shared memory
+            raise ValueError(f"more than {N.FSCORE_MAX_USERS} annotators in a video")
+        self._finish(desc, picks, cps, nfps, user_summary)
         return self
 
     def _to_dev(self, a, dtype):
@@ -163,6 +167,35 @@ class VideoBatch:
             self.max_seg_frames, N.ptr(self.seg_mean), N.ptr(self.values), N.ptr(self.picked),
             N.ptr(self.summary) if write_summary else None, N.ptr(self.mask), N.ptr(self.msum),
             N.ptr(self.status), N.ptr(self.ws), self.ws_bytes, N.current_stream()))
+        return self
+
+    def evaluate(self, scores, method="knapsack", write_summary=True, d_bits=None):
+        """select() followed by fscore() (or fscore_packed(d_bits)) in ONE library call (smz_eval_batch): the persistent
+        CTA that solves a video's knapsack also builds its summary mask in shared memory and streams its annotator rows
+        against it, so the shared-memory-bound DP of some videos overlaps the HBM-bound F-score of others.  Same
+        results as the two separate calls."""
+        if method not in N.SMZ_METHOD:
+            raise KeyError(f"Unknown method {method}")
+        if d_bits is None and not self.has_users:
+            raise ValueError("this batch holds no user_summary")
+        scores = self._to_dev(scores, torch.float32)
+        if scores.numel() != self.total_scores:
+            raise ValueError(f"expected {self.total_scores} scores, got {scores.numel()}")
+        bits_off = None
+        if d_bits is not None:
+            self._bits_layout()
+            if d_bits.numel() < self.total_bit_words or d_bits.dtype != torch.int32 or not d_bits.is_cuda:
+                raise ValueError("evaluate: int32 device tensor of total_bit_words expected")
+            bits_off = self.d_bits_off
+        N.check(N.lib().smz_eval_batch(
+            N.ptr(self.d_desc), self.n_videos, self.total_users,
+            N.ptr(scores), N.ptr(self.d_picks), N.ptr(self.d_cps), N.ptr(self.d_nfps), N.SMZ_METHOD[method],
+            self.max_n_segs, self.max_capacity, self.max_n_frames, self.max_seg_frames,
+            N.ptr(self.d_users) if d_bits is None else None, N.ptr(d_bits), N.ptr(bits_off),
+            N.ptr(self.seg_mean), N.ptr(self.values), N.ptr(self.picked),
+            N.ptr(self.summary) if write_summary else None, N.ptr(self.mask), N.ptr(self.msum), N.ptr(self.status),
+            N.ptr(self.overlap), N.ptr(self.gsum), N.ptr(self.f), N.ptr(self.avg_f), N.ptr(self.max_f),
+            N.ptr(self.ws), self.ws_bytes, N.current_stream()))
         return self
 
     def knapsack(self, values):

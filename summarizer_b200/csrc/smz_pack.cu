@@ -63,6 +63,15 @@ fscore_bits_kernel(const smz_video_desc *__restrict__ desc, int v0, const uint32
 
 }  // namespace
 
+namespace smz {
+int launch_fscore_bits(const smz_video_desc *desc, int n_videos, const uint32_t *user_bits, const int64_t *bits_off,
+                       const uint32_t *mask, int32_t *overlap, int32_t *gsum, cudaStream_t st) {
+    fscore_bits_kernel<<<n_videos, 256, 0, st>>>(desc, 0, user_bits, bits_off, mask, overlap, gsum);
+    SMZ_CUDA_CHECK(cudaGetLastError());
+    return SMZ_OK;
+}
+}  // namespace smz
+
 // h_desc / h_user / h_bits_off / h_bits are HOST pointers.  Row u of video v: h_user + user_off + u*user_ld
 // (n_frames floats) -> h_bits + h_bits_off[v] + u*ceil(n_frames/32) words, bit j of word w = frame 32w+j > 0.
 extern "C" int smz_host_pack_user_summary(const smz_video_desc *h_desc, int n_videos, const float *h_user,
@@ -96,7 +105,7 @@ extern "C" int smz_fscore_packed(const smz_video_desc *desc, int n_videos, const
     int rc = smz_device_check();
     if (rc != SMZ_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    fscore_bits_kernel<<<n_videos, 256, 0, st>>>(desc, 0, user_bits, bits_off, mask, overlap, gsum);
-    SMZ_CUDA_CHECK(cudaGetLastError());
+    rc = smz::launch_fscore_bits(desc, n_videos, user_bits, bits_off, mask, overlap, gsum, st);
+    if (rc != SMZ_OK) return rc;
     return smz::launch_fscore_final(desc, n_videos, msum, overlap, gsum, f, avg_f, max_f, st);
 }

@@ -11,11 +11,17 @@
 //                   word) and flushed coalesced to an L2-resident work buffer; warp 0 then walks
 //                   the OR-tools extraction loop (one L2 round trip per picked item).
 //   summary_kernel  one CTA per video: prefix of nfps -> float summary vector, bit mask, popcount.
+//   dp16_kernel<KW,MK>  the same DP on 16-bit cells, two per 32-bit shared-memory word (cells c and c + H share
+//                   word c, so a shift by any weight is ONE aligned LDS per two cells), DPX VIADDMNMX.U16x2 for
+//                   max(cand + p, val) on both halves: half the shared-memory bytes and 3 instead of 5
+//                   instructions per cell.  Exact: it only runs while every row value provably fits 16 bits and
+//                   hands the video to dp_kernel<K> (through a fallback list) otherwise.
 // Generic path: select_generic_kernel (monolithic, rows of any size up to shared memory).
 #include "smz_common.cuh"
-#include "smz_eval_dev.cuh"
+#include "smz_fscore_dev.cuh"
 
 #include <limits.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -118,6 +124,144 @@ pool_smem_kernel(const smz_video_desc *__restrict__ desc, int v0, const float *_
 }
 
 // ------------------------------------------------------------------------------------------
+// evaluation tail fused into the knapsack kernels: summary vector + mask (utils/eval.py:111-122) and
+// the per-annotator F-score (utils/eval.py:125-165) of the video the CTA has just solved
+// ------------------------------------------------------------------------------------------
+// The knapsack DP is shared-memory bound and takes ~200 us per video and CTA; the F-score streams 4*n_users*n_frames
+// bytes of annotator rows and is HBM bound.  Run as separate kernels the two add up; run by the SAME persistent CTA,
+// video after video, the CTAs of an SM are in different phases at any time, so the DP of some videos overlaps the
+// streaming of others and the stage costs about max(DP, stream) instead of the sum.  No mask round trip through
+// global memory either: the summary mask is built and consumed in shared memory.
+struct EvalTail {
+    int enabled;                    // 0: the kernels stop after out_picked
+    int n_videos_total;             // unused by the device code (kept for debugging)
+    const float *user;              // annotator rows (float32), or
+    const uint32_t *user_bits;      // ... 1 bit per frame with
+    const int64_t *bits_off;        //     per-video word offsets; both NULL: summary / mask only
+    float *summary;                 // may be NULL
+    uint32_t *mask;
+    int32_t *msum;
+    int32_t *overlap, *gsum;
+    float *f;
+    double *avg_f, *max_f;
+};
+
+__host__ __device__ inline int tail_words(int max_n_segs, int max_n_frames) {
+    return (max_n_segs + 1) + (max_n_frames + 31) / 32 + 2 * FSCORE_MAX_USERS;
+}
+
+// Called by all DP_THREADS (= FSCORE_THREADS) threads.  spk: picked flags, swp: (weight, value) per segment, both in
+// shared memory; mem: tail_words() words of shared memory that the DP no longer needs.  v: index of the video in the
+// arrays that are indexed per video (msum, avg_f, max_f).
+static_assert(DP_THREADS == FSCORE_THREADS, "the fused tail runs the F-score chunk code on the DP kernel's CTA");
+__device__ void eval_tail_video(const EvalTail &t, const smz_video_desc &d, int v, const int *spk, const int2 *swp,
+                                uint32_t *mem) {
+    __shared__ int swarp[DP_THREADS / 32];
+    __shared__ int s_msum;
+    constexpr int NT = DP_THREADS, NW = DP_THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = d.n_segs, n_frames = d.n_frames;
+    const int mwords = (n_frames + 31) >> 5;
+    int *spre = reinterpret_cast<int *>(mem);                 // n + 1
+    uint32_t *smask = mem + n + 1;                            // mwords
+    uint32_t *s_ov = smask + mwords, *s_gs = s_ov + FSCORE_MAX_USERS;
+    const int n_users = min(d.n_users, FSCORE_MAX_USERS);
+    for (int j = tid; j < mwords; j += NT) smask[j] = 0u;
+    for (int u = tid; u < n_users; u += NT) { s_ov[u] = 0u; s_gs[u] = 0u; }
+    // exclusive prefix of nfps = positions in the summary vector
+    int carry = 0;
+    for (int base = 0; base < n; base += NT) {
+        const int i = base + tid;
+        const int x = i < n ? swp[i].x : 0;
+        int incl = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) swarp[warp] = incl;
+        __syncthreads();
+        int woff = 0, tile_total = 0;
+#pragma unroll
+        for (int k = 0; k < NW; k++) { const int w = swarp[k]; if (k < warp) woff += w; tile_total += w; }
+        if (i < n) spre[i] = carry + woff + incl - x;
+        carry += tile_total;
+        __syncthreads();
+    }
+    if (tid == 0) spre[n] = carry;
+    __syncthreads();
+    for (int s = tid; s < n; s += NT) {
+        if (spk[s]) {
+            const int a = spre[s];
+            const int b = min(spre[s + 1], n_frames);
+            if (a < b) {
+                const int wa = a >> 5, wb = (b - 1) >> 5;
+                for (int wd = wa; wd <= wb; wd++) {
+                    const int lo = max(a, wd << 5) & 31;
+                    const int hi = min(b, (wd + 1) << 5) - (wd << 5);  // 1..32
+                    const uint32_t m = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+                    atomicOr(&smask[wd], m);
+                }
+            }
+        }
+    }
+    if (t.summary != nullptr) {
+        float *dst = t.summary + d.summ_off;
+        for (int s = warp; s < n; s += NW) {
+            const int a = spre[s], nf = spre[s + 1] - a;
+            const float val = spk[s] ? 1.f : 0.f;
+            for (int j = lane; j < nf; j += 32) dst[a + j] = val;
+        }
+    }
+    __syncthreads();
+    int cnt = 0;
+    for (int j = tid; j < mwords; j += NT) {
+        const uint32_t m = smask[j];
+        t.mask[d.mask_off + j] = m;
+        cnt += __popc(m);
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) swarp[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int k = 0; k < NW; k++) tot += swarp[k];
+        t.msum[v] = tot;
+        s_msum = tot;
+    }
+    if (t.user == nullptr && t.user_bits == nullptr) { __syncthreads(); return; }
+    // ---- F-score: stream the annotator rows once against the mask in shared memory
+    if (t.user != nullptr) {
+        for (int f_base = 0; f_base < n_frames; f_base += SMZ_FSCORE_CHUNK)
+            fscore_chunk_acc(d, f_base, t.user, smask, s_ov, s_gs);
+    } else {
+        const uint32_t *ub = t.user_bits + t.bits_off[v];
+        for (int u = warp; u < n_users; u += NW) {
+            const uint32_t *row = ub + (int64_t)u * mwords;
+            int ov = 0, gs = 0;
+            for (int w = lane; w < mwords; w += 32) {
+                const uint32_t x = __ldg(row + w);
+                ov += __popc(x & smask[w]);
+                gs += __popc(x);
+            }
+            ov = __reduce_add_sync(0xffffffffu, ov);
+            gs = __reduce_add_sync(0xffffffffu, gs);
+            if (lane == 0) { s_ov[u] = (uint32_t)ov; s_gs[u] = (uint32_t)gs; }
+        }
+    }
+    __syncthreads();
+    for (int u = tid; u < n_users; u += NT) {
+        t.overlap[d.ucount_off + u] = (int)s_ov[u];
+        t.gsum[d.ucount_off + u] = (int)s_gs[u];
+    }
+    if (tid == 0)
+        fscore_final_video(n_users, s_msum, reinterpret_cast<const int32_t *>(s_ov), reinterpret_cast<const int32_t *>(s_gs),
+                           t.f + d.ucount_off, t.avg_f ? t.avg_f + v : nullptr, t.max_f ? t.max_f + v : nullptr);
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
 // dp_kernel<K>: knapsack DP + OR-tools extraction (or the 'rank' greedy) -> picked[]
 // ------------------------------------------------------------------------------------------
 // Longest-first order of the videos for the dp_kernel queue (cost ~ n_segs x capacity): a counting sort over 64
@@ -151,7 +295,8 @@ __global__ void order_fill_kernel(const smz_video_desc *__restrict__ desc, int n
 
 struct DpSmem { int dp0, dp1, wp, pk, red, total, row, pad; };
 
-__host__ __device__ inline DpSmem dp_layout(int K, int max_n_segs, int max_weight) {
+// front_words: minimum size of the region in front of wp (the DP rows; the fused evaluation tail reuses it)
+__host__ __device__ inline DpSmem dp_layout(int K, int max_n_segs, int max_weight, int front_words) {
     DpSmem L;
     L.row = K * DP_THREADS;
     L.pad = (max_weight + 31) / 32 * 32;
@@ -159,6 +304,8 @@ __host__ __device__ inline DpSmem dp_layout(int K, int max_n_segs, int max_weigh
     int o = 0;
     o += L.pad; L.dp0 = o; o += L.row;      // [pad][row0][pad][row1]
     o += L.pad; L.dp1 = o; o += L.row;
+    if (o < front_words) o = front_words;
+    o = (o + 1) & ~1;                       // int2 alignment
     L.wp = o; o += 2 * max_n_segs;          // int2 (weight, value)
     L.pk = o; o += max_n_segs;              // picked flags; 'rank': order
     L.red = o; o += 32;
@@ -171,10 +318,13 @@ __global__ void __launch_bounds__(DP_THREADS, K <= 18 ? 4 : 1)
 dp_kernel(const smz_video_desc *__restrict__ desc, int n_videos, const int32_t *__restrict__ nfps,
           const int32_t *__restrict__ values, const float *__restrict__ seg_mean, int method, int max_n_segs,
           int max_weight, uint8_t *__restrict__ out_picked, int32_t *__restrict__ status,
-          uint32_t *__restrict__ ws, int64_t ws_words_per_cta, int *__restrict__ queue, const int *__restrict__ order) {
+          uint32_t *__restrict__ ws, int64_t ws_words_per_cta, int *__restrict__ queue, const int *__restrict__ order,
+          const int *__restrict__ list_count, int front_words, const EvalTail tail) {
     extern __shared__ uint32_t smem[];
     __shared__ int s_next;
-    const DpSmem L = dp_layout(K, max_n_segs, max_weight);
+    // list_count != NULL: `order` is the fallback list dp16_kernel left behind and *list_count its length
+    if (list_count != nullptr) n_videos = __ldcg(list_count);
+    const DpSmem L = dp_layout(K, max_n_segs, max_weight, front_words);
     int *dp0 = reinterpret_cast<int *>(smem + L.dp0);
     int *dp1 = reinterpret_cast<int *>(smem + L.dp1);
     int2 *swp = reinterpret_cast<int2 *>(smem + L.wp);
@@ -184,8 +334,6 @@ dp_kernel(const smz_video_desc *__restrict__ desc, int n_videos, const int32_t *
     constexpr int NT = DP_THREADS, NW = DP_THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int j = tid; j < L.pad; j += NT) { dp0[j - L.pad] = kDpNeg; dp1[j - L.pad] = kDpNeg; }
-
     // videos are handed out through an atomic queue: their cost (n_segs x capacity) varies several-fold
     while (true) {
         if (tid == 0) s_next = atomicAdd(queue, 1);
@@ -194,6 +342,7 @@ dp_kernel(const smz_video_desc *__restrict__ desc, int n_videos, const int32_t *
         const int v = order[s_next];
         const smz_video_desc d = desc[v];
         const int n = d.n_segs, cap = d.capacity;
+        for (int j = tid; j < L.pad; j += NT) { dp0[j - L.pad] = kDpNeg; dp1[j - L.pad] = kDpNeg; }   // (the tail reuses the rows)
         // ---- weights / values, sum of weights, weight-range check
         int wsum = 0, bad = 0;
         const int vlim = value_limit(n);
@@ -312,6 +461,209 @@ dp_kernel(const smz_video_desc *__restrict__ desc, int n_videos, const int32_t *
         }
         __syncthreads();
         for (int i = tid; i < n; i += NT) out_picked[d.seg_off + i] = (uint8_t)spk[i];
+        if (tail.enabled) eval_tail_video(tail, d, v, spk, swp, smem);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// dp16_kernel<KW, MK>: the knapsack DP of dp_kernel on 16-bit cells
+// ------------------------------------------------------------------------------------------
+// Row of 2H cells (H = KW * 256) stored as H words: word j = (cell j | cell j + H << 16).  The shifted read of item
+// weight w is word j - w for BOTH halves: for j >= w that is (cell j - w, cell j + H - w); for j < w the low cell does
+// not exist (the item cannot be packed below its weight: masked) and the high cell j + H - w < H is the LOW half of
+// word j + H - w — so the P words in front of the row mirror the low halves of the last P row words in their HIGH
+// halves (one extra 16-bit store for the threads that own those words).  Needs w <= P = MK * 256 for every usable
+// item; the low-cell mask is only compiled for the first MK words of a thread (k * 256 + tid < w <= MK * 256).
+// Values are unsigned 16 bit: p in [0, 32767] and no row value above 65535.  The second condition is checked
+// exactly while running: rows are non-decreasing in the cell index, so the top cell bounds the row, and an item adds
+// at most max(p): after every item the thread that owns the top cell tests top + max(p) <= 65535 (folded into the
+// barrier, BAR.RED.OR); when it fails the video goes to the fallback list and dp_kernel<K> solves it in 32 bits.
+// Take bits: per word a 2 x 16-bit shift register (item i of a group of 16 -> bit i of each half), flushed to the
+// work buffer every 16 items as [group][H] words.
+struct Dp16Smem { int row0, row1, wp, pk, total; };
+
+__host__ __device__ inline Dp16Smem dp16_layout(int KW, int MK, int max_n_segs, int front_words) {
+    Dp16Smem L;
+    const int H = KW * DP_THREADS, P = MK * DP_THREADS;
+    int o = 0;
+    o += P; L.row0 = o; o += H;             // [mirror pad][row0][mirror pad][row1]
+    o += P; L.row1 = o; o += H;
+    if (o < front_words) o = front_words;   // the fused evaluation tail reuses the rows
+    o = (o + 1) & ~1;
+    L.wp = o; o += 2 * max_n_segs;          // int2 (weight, value)
+    L.pk = o; o += max_n_segs;              // picked flags
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ uint32_t add_u16x2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("add.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t max_u16x2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("max.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+
+constexpr int dp16_min_blocks(int KW) { return KW <= 5 ? 6 : (KW <= 9 ? 5 : (KW <= 14 ? 3 : (KW <= 18 ? 2 : 1))); }
+
+template <int KW, int MK>
+__global__ void __launch_bounds__(DP_THREADS, dp16_min_blocks(KW))
+dp16_kernel(const smz_video_desc *__restrict__ desc, int n_videos, const int32_t *__restrict__ nfps,
+            const int32_t *__restrict__ values, int max_n_segs, uint8_t *__restrict__ out_picked,
+            uint32_t *__restrict__ ws, int64_t ws_words_per_cta, int *__restrict__ queue, const int *__restrict__ order,
+            int *__restrict__ fallback, int front_words, const EvalTail tail) {
+    extern __shared__ uint32_t smem[];
+    __shared__ int s_next;
+    constexpr int NT = DP_THREADS, NW = DP_THREADS / 32;
+    constexpr int H = KW * NT, P = MK * NT;
+    __shared__ int sred[6 * NW];
+    const Dp16Smem L = dp16_layout(KW, MK, max_n_segs, front_words);
+    uint32_t *row0 = smem + L.row0, *row1 = smem + L.row1;
+    int2 *swp = reinterpret_cast<int2 *>(smem + L.wp);
+    int *spk = reinterpret_cast<int *>(smem + L.pk);
+    uint32_t *bits = ws + (int64_t)blockIdx.x * ws_words_per_cta;   // [item / 16][H]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    while (true) {
+        if (tid == 0) s_next = atomicAdd(queue, 1);
+        __syncthreads();
+        if (s_next >= n_videos) break;
+        const int v = order[s_next];
+        const smz_video_desc d = desc[v];
+        const int n = d.n_segs, cap = d.capacity;
+        // ---- weights / values and what decides the path: sum of weights, value / weight ranges of the usable items
+        int wsum = 0, bad = 0, maxw = 0, maxp = 0, minp = 0, psum = 0;
+        const int vlim = value_limit(n);
+        for (int i = tid; i < n; i += NT) {
+            const int w = __ldg(nfps + d.seg_off + i);
+            const int p = __ldg(values + d.seg_off + i);
+            if (p > vlim || p < -vlim || w < 0) bad = 1;        // dp_kernel flags and clips these
+            swp[i] = make_int2(w, p);
+            spk[i] = 0;
+            wsum += w;
+            if (w <= cap) { maxw = max(maxw, w); maxp = max(maxp, p); minp = min(minp, p); psum += min(max(p, 0), 32767); }
+        }
+        wsum = __reduce_add_sync(0xffffffffu, wsum);
+        psum = __reduce_add_sync(0xffffffffu, psum);
+        bad = __reduce_or_sync(0xffffffffu, bad);
+        maxw = __reduce_max_sync(0xffffffffu, maxw);
+        maxp = __reduce_max_sync(0xffffffffu, maxp);
+        minp = __reduce_min_sync(0xffffffffu, minp);
+        if (lane == 0) {
+            sred[warp] = wsum; sred[NW + warp] = bad; sred[2 * NW + warp] = maxw;
+            sred[3 * NW + warp] = maxp; sred[4 * NW + warp] = minp; sred[5 * NW + warp] = psum;
+        }
+        __syncthreads();
+        wsum = 0; bad = 0; maxw = 0; maxp = 0; minp = 0; psum = 0;
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            wsum += sred[k]; bad |= sred[NW + k]; maxw = max(maxw, sred[2 * NW + k]);
+            maxp = max(maxp, sred[3 * NW + k]); minp = min(minp, sred[4 * NW + k]); psum += sred[5 * NW + k];
+        }
+        // 0: nothing packed, 1: everything packed (KnapsackSolver::ReduceCapacities), 2: 16-bit DP, 3: dp_kernel<K>
+        int mode;
+        if (bad) mode = 3;
+        else if (n == 0) mode = 0;
+        else if (wsum <= cap) mode = 1;
+        else if (cap <= 0) mode = 0;
+        else {
+            // exact conditions (cells, pad, value range) + a guess that spares a doomed attempt: the optimum is at
+            // least about the average value density times the capacity
+            const bool fits = cap < 2 * H && maxw <= (P < H ? P : H) && minp >= 0 && maxp <= 32767;
+            const bool hopeless = (long long)psum * cap > 45000ll * wsum;
+            mode = (fits && !hopeless) ? 2 : 3;
+        }
+        if (mode == 1)
+            for (int i = tid; i < n; i += NT) spk[i] = 1;
+        if (mode == 2) {
+            uint32_t val[KW], acc[KW];
+            uint32_t *cur = row0, *nxt = row1;
+#pragma unroll
+            for (int k = 0; k < KW; k++) { val[k] = 0u; acc[k] = 0u; cur[tid + k * NT] = 0u; }
+            for (int j = tid; j < P; j += NT) { row0[j - P] = 0u; row1[j - P] = 0u; }
+            __syncthreads();
+            const uint32_t top_limit = 65535u - (uint32_t)maxp;
+            int aborted = 0;
+            for (int i = 0; i < n; i++) {
+                const int2 wp = swp[i];
+                if (wp.x <= cap) {                             // uniform: upstream's loop body is empty otherwise
+                    const uint32_t *src = cur + (tid - wp.x);  // word j - w; j < w lands in the mirror pad
+                    const uint32_t pp = (uint32_t)wp.y * 0x10001u;
+                    uint32_t cand[KW];
+#pragma unroll
+                    for (int k = 0; k < KW; k++) cand[k] = src[k * NT];
+#pragma unroll
+                    for (int k = 0; k < KW; k++) {
+                        uint32_t nv;
+                        if (k < MK) {
+                            uint32_t t = add_u16x2(cand[k], pp);
+                            if (tid + k * NT < wp.x) t &= 0xffff0000u;      // cell j < w: the item does not fit
+                            nv = max_u16x2(t, val[k]);
+                        } else {
+                            nv = __viaddmax_u16x2(cand[k], pp, val[k]);       // DPX: max(cand + p, val) on both halves
+                        }
+                        // improved halves differ by 1..32767: + 0x7fff sets bit 15 of exactly those (no carry between halves)
+                        const uint32_t y = nv - val[k] + 0x7fff7fffu;
+                        acc[k] = (acc[k] >> 1) | (y & 0x80008000u);
+                        val[k] = nv;
+                        nxt[tid + k * NT] = nv;
+                        if (k >= KW - MK)                                    // words [H - P, H): mirror the low half
+                            reinterpret_cast<unsigned short *>(nxt + (tid + k * NT - H))[1] = (unsigned short)nv;
+                    }
+                    aborted = __syncthreads_or(tid == NT - 1 && (val[KW - 1] >> 16) > top_limit && i + 1 < n);
+                    uint32_t *t = cur; cur = nxt; nxt = t;
+                    if (aborted) break;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < KW; k++) acc[k] >>= 1;             // item not taken anywhere: zero bits
+                }
+                if ((i & 15) == 15 || i == n - 1) {           // flush 16 items' take bits (item j of the group -> bit j), coalesced
+                    uint32_t *dst = bits + (int64_t)(i >> 4) * H + tid;
+                    const int sh = 15 - (i & 15);
+                    const uint32_t m = (0xffffu >> sh) * 0x10001u;
+#pragma unroll
+                    for (int k = 0; k < KW; k++) { dst[k * NT] = (acc[k] >> sh) & m; acc[k] = 0u; }
+                }
+            }
+            if (aborted) mode = 3;
+            __syncthreads();   // take bits visible to warp 0
+            // KnapsackDynamicProgrammingSolver::Solve extraction loop (see dp_kernel)
+            if (mode == 2 && warp == 0) {
+                int remaining = cap, num = n;
+                while (remaining > 0 && num > 0) {
+                    const int j = remaining >= H ? remaining - H : remaining;
+                    const int hs = remaining >= H ? 16 : 0;
+                    const int last = (num - 1) >> 4;
+                    int sel = -1;
+                    for (int g0 = 0; g0 <= last; g0 += 32) {
+                        const int g = g0 + lane;
+                        uint32_t wv = 0u;
+                        if (g <= last) {
+                            wv = (__ldcg(bits + (int64_t)g * H + j) >> hs) & 0xffffu;
+                            const int nb = num - (g << 4);
+                            if (nb < 16) wv &= (1u << nb) - 1u;
+                        }
+                        const int c = wv ? (g << 4) + 31 - __clz(wv) : -1;
+                        sel = max(sel, warp_max(c));
+                    }
+                    sel = max(sel, 0);
+                    remaining -= swp[sel].x;
+                    num = sel;
+                    if (remaining >= 0 && lane == 0) spk[sel] = 1;
+                }
+            }
+        }
+        if (mode == 3) {
+            if (tid == 0) { const int k = atomicAdd(fallback, 1); fallback[1 + k] = v; }
+        } else {
+            __syncthreads();
+            for (int i = tid; i < n; i += NT) out_picked[d.seg_off + i] = (uint8_t)spk[i];
+            if (tail.enabled) eval_tail_video(tail, d, v, spk, swp, smem);
+        }
         __syncthreads();
     }
 }
@@ -690,12 +1042,22 @@ struct SelectPlan {
     int grid;
     int64_t ws_words_per_cta;
     int pad_weight;      // max weight the dp rows' front pad is sized for
+    int kw16, mk16;      // words per thread / masked words of dp16_kernel; kw16 == 0: no 16-bit pass
+    int smem16_bytes, grid16;
+    int64_t ws16_words_per_cta;
+    int front_words;     // > 0: the DP kernels' shared memory also holds the fused evaluation tail (summary + F-score)
+    int64_t ws_bits_bytes() const {
+        const int64_t a = (int64_t)grid * ws_words_per_cta, b = kw16 ? (int64_t)grid16 * ws16_words_per_cta : 0;
+        return (a > b ? a : b) * 4;      // the two DP passes run one after the other and share the take-bit buffer
+    }
 };
 
 constexpr int kDpK[] = {2, 5, 9, 18, 27, 36, 54};
 
 typedef void (*dp_fn)(const smz_video_desc *, int, const int32_t *, const int32_t *, const float *, int, int, int,
-                      uint8_t *, int32_t *, uint32_t *, int64_t, int *, const int *);
+                      uint8_t *, int32_t *, uint32_t *, int64_t, int *, const int *, const int *, int, const EvalTail);
+typedef void (*dp16_fn)(const smz_video_desc *, int, const int32_t *, const int32_t *, int, uint8_t *, uint32_t *, int64_t,
+                        int *, const int *, int *, int, const EvalTail);
 typedef void (*generic_fn)(const smz_video_desc *, int, const float *, const int32_t *, const int32_t *,
                            const int32_t *, const int32_t *, int, int, int, int, float *, int32_t *, uint8_t *,
                            float *, uint32_t *, int32_t *, int32_t *, uint32_t *, int64_t);
@@ -713,13 +1075,47 @@ dp_fn dp_fn_for(int k) {
     }
 }
 
+dp16_fn dp16_fn_for(int kw, int mk) {
+#define SMZ_DP16_CASE(KW, MK) if (kw == KW && mk == MK) return dp16_kernel<KW, MK>;
+    SMZ_DP16_CASE(1, 1) SMZ_DP16_CASE(3, 2) SMZ_DP16_CASE(3, 3) SMZ_DP16_CASE(5, 2) SMZ_DP16_CASE(5, 5)
+    SMZ_DP16_CASE(9, 2) SMZ_DP16_CASE(9, 9) SMZ_DP16_CASE(14, 2) SMZ_DP16_CASE(14, 14) SMZ_DP16_CASE(18, 2)
+    SMZ_DP16_CASE(18, 18) SMZ_DP16_CASE(27, 2) SMZ_DP16_CASE(27, 27)
+#undef SMZ_DP16_CASE
+    return nullptr;
+}
+
 generic_fn generic_fn_for(bool bits_in_smem) {
     return bits_in_smem ? (generic_fn)select_generic_kernel<true> : (generic_fn)select_generic_kernel<false>;
 }
 
 }  // namespace
 
-static int64_t queue_bytes(int n_videos) { return (int64_t)(1 + 2 * ORDER_BUCKETS + 3 + n_videos) * 4 + 256; }
+// int32 words behind the take-bit buffer: [0] dp16 queue head, [1..64] bucket counts, [65..128] bucket fills,
+// [129] dp_kernel queue head, [130] fallback count, [131, 131 + n) fallback list, then order[n]
+constexpr int kQueueHead32 = 1 + 2 * ORDER_BUCKETS, kFallback = kQueueHead32 + 1, kQueueInts = kFallback + 1;
+static int64_t queue_bytes(int n_videos) { return (int64_t)(kQueueInts + 2 * (int64_t)n_videos) * 4 + 256; }
+
+// cudaFuncSetAttribute + occupancy query once per (device, kernel, dynamic shared memory): the plan is rebuilt on every
+// call and these two driver calls would otherwise dominate its host time
+static int cached_occupancy(const void *fn, int threads, int smem_bytes, int *per_sm) {
+    struct Entry { int dev; const void *fn; int smem, per_sm; };
+    static Entry table[96];
+    static int used = 0;
+    int dev = 0;
+    SMZ_CUDA_CHECK(cudaGetDevice(&dev));
+    int attr = -1;                       // largest dynamic size this kernel's attribute was raised to on this device
+    for (int i = 0; i < used; i++) {
+        if (table[i].dev != dev || table[i].fn != fn) continue;
+        if (table[i].smem == smem_bytes) { *per_sm = table[i].per_sm; return SMZ_OK; }
+        if (table[i].smem > attr) attr = table[i].smem;
+    }
+    if (smem_bytes > attr)               // only ever raised, so launches planned from older entries stay valid
+        SMZ_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    SMZ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fn, threads, smem_bytes));
+    if (used < 96) table[used++] = Entry{dev, fn, smem_bytes, *per_sm};     // callers hold the GIL / own the stream
+    else SMZ_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes > attr ? smem_bytes : attr));
+    return SMZ_OK;
+}
 
 static int select_plan(int n_videos, int max_n_segs, int max_capacity, int max_n_frames, int max_weight,
                        SelectPlan *plan) {
@@ -730,19 +1126,40 @@ static int select_plan(int n_videos, int max_n_segs, int max_capacity, int max_n
     const int need = ncell > max_n_segs ? ncell : max_n_segs;
     plan->pad_weight = max_weight < max_capacity ? max_weight : max_capacity;   // heavier items are never read
     plan->k = 0;
+    plan->kw16 = plan->mk16 = plan->smem16_bytes = plan->grid16 = 0;
+    plan->ws16_words_per_cta = 0;
+    plan->front_words = 0;
     for (int k : kDpK)
         if (k * DP_THREADS >= need) { plan->k = k; break; }
     int per_sm = 0;
     if (plan->k > 0) {
-        plan->smem_bytes = dp_layout(plan->k, max_n_segs, plan->pad_weight).total * 4;
+        // with the evaluation tail when it fits next to the rows (it reuses them), without it otherwise
+        const int fw = getenv("SMZ_NO_FUSED_TAIL") ? 0 : tail_words(max_n_segs, max_n_frames);
+        plan->smem_bytes = dp_layout(plan->k, max_n_segs, plan->pad_weight, fw).total * 4;
+        if (plan->smem_bytes <= optin) plan->front_words = fw;
+        else plan->smem_bytes = dp_layout(plan->k, max_n_segs, plan->pad_weight, 0).total * 4;
         if (plan->smem_bytes > optin) plan->k = 0;
     }
     if (plan->k > 0) {
         dp_fn fn = dp_fn_for(plan->k);
         plan->bits_in_smem = false;
-        SMZ_CUDA_CHECK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes));
-        SMZ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, DP_THREADS, plan->smem_bytes));
+        { const int rc = cached_occupancy((const void *)fn, DP_THREADS, plan->smem_bytes, &per_sm); if (rc != SMZ_OK) return rc; }
         plan->ws_words_per_cta = (int64_t)((max_n_segs + 31) / 32) * plan->k * DP_THREADS;
+        // 16-bit pass in front of it (same cell count: 2 * kw16 * 256 >= k * 256)
+        const int kw = (plan->k + 1) / 2;
+        const int mk = (kw >= 2 && plan->pad_weight <= 2 * DP_THREADS) ? 2 : kw;
+        dp16_fn fn16 = getenv("SMZ_NO_DP16") ? nullptr : dp16_fn_for(kw, mk);
+        const int smem16 = dp16_layout(kw, mk, max_n_segs, plan->front_words).total * 4;
+        if (fn16 != nullptr && smem16 <= optin) {
+            int per_sm16 = 0;
+            { const int rc = cached_occupancy((const void *)fn16, DP_THREADS, smem16, &per_sm16); if (rc != SMZ_OK) return rc; }
+            if (per_sm16 >= 1) {
+                plan->kw16 = kw; plan->mk16 = mk; plan->smem16_bytes = smem16;
+                const int g16 = smz::sm_count() * per_sm16;
+                plan->grid16 = n_videos < g16 ? n_videos : g16;
+                plan->ws16_words_per_cta = (int64_t)((max_n_segs + 15) / 16) * kw * DP_THREADS;
+            }
+        }
     } else {
         const int with_bits = select_layout(max_n_segs, max_capacity, max_n_frames, true).total * 4;
         const int without = select_layout(max_n_segs, max_capacity, max_n_frames, false).total * 4;
@@ -753,8 +1170,7 @@ static int select_plan(int n_videos, int max_n_segs, int max_capacity, int max_n
                              "select_shots: DP rows for capacity %d, %d segments and %d frames need %d B of shared "
                              "memory (> %d B per CTA)", max_capacity, max_n_segs, max_n_frames, without, optin);
         generic_fn fn = generic_fn_for(plan->bits_in_smem);
-        SMZ_CUDA_CHECK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes));
-        SMZ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, SELECT_THREADS, plan->smem_bytes));
+        { const int rc = cached_occupancy((const void *)fn, SELECT_THREADS, plan->smem_bytes, &per_sm); if (rc != SMZ_OK) return rc; }
         plan->ws_words_per_cta = plan->bits_in_smem ? 0 : (int64_t)max_n_segs * ((ncell + 31) / 32);
     }
     if (per_sm < 1) per_sm = 1;
@@ -771,7 +1187,7 @@ extern "C" int smz_select_workspace_bytes(int n_videos, int max_n_segs, int max_
     SelectPlan plan;
     int rc = select_plan(n_videos, max_n_segs, max_capacity, max_n_frames, max_seg_frames, &plan);
     if (rc != SMZ_OK) return rc;
-    *bytes = (int64_t)plan.grid * plan.ws_words_per_cta * 4 + queue_bytes(n_videos);   // + queue counter, sort counters, order
+    *bytes = plan.ws_bits_bytes() + queue_bytes(n_videos);   // + queue counters, sort counters, fallback list, order
     return SMZ_OK;
 }
 
@@ -779,7 +1195,9 @@ static int select_launch(const smz_video_desc *desc, int n_videos, const float *
                          const int32_t *cps, const int32_t *nfps, const int32_t *values_in, int method,
                          int max_n_segs, int max_capacity, int max_n_frames, int max_weight, float *seg_mean,
                          int32_t *values, uint8_t *picked, float *summary, uint32_t *mask, int32_t *msum,
-                         int32_t *status, void *ws, int64_t ws_bytes, void *stream) {
+                         int32_t *status, void *ws, int64_t ws_bytes, void *stream, const EvalTail *fscore_tail = nullptr,
+                         bool *fscore_done = nullptr) {
+    if (fscore_done) *fscore_done = false;
     if (n_videos == 0) return SMZ_OK;
     SMZ_REQUIRE(n_videos > 0, "n_videos < 0");
     SMZ_REQUIRE(desc && nfps && picked && status, "NULL pointer (desc, nfps, picked and status are required)");
@@ -789,11 +1207,12 @@ static int select_launch(const smz_video_desc *desc, int n_videos, const float *
     SelectPlan plan;
     rc = select_plan(n_videos, max_n_segs, max_capacity, max_n_frames, max_weight, &plan);
     if (rc != SMZ_OK) return rc;
-    const int64_t need = (int64_t)plan.grid * plan.ws_words_per_cta * 4;
+    const int64_t need = plan.ws_bits_bytes();
     SMZ_REQUIRE(ws != nullptr && ws_bytes >= need + queue_bytes(n_videos), "work buffer too small: need %lld bytes",
                 (long long)(need + queue_bytes(n_videos)));
-    int *queue = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(ws) + need);   // [0] queue head, [1..64] counts, [65..128] fills
-    int *order = queue + 1 + 2 * ORDER_BUCKETS + 3;
+    int *queue = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(ws) + need);   // layout: see queue_bytes
+    int *fallback = queue + kFallback;
+    int *order = queue + kQueueInts + n_videos;
     cudaStream_t st = (cudaStream_t)stream;
     SMZ_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)n_videos, st));
     if (plan.k == 0) {
@@ -812,8 +1231,7 @@ static int select_launch(const smz_video_desc *desc, int n_videos, const float *
         const int tiles = (max_n_segs + POOL_THREADS / 8 - 1) / (POOL_THREADS / 8);
         const int64_t frame_bytes = ((int64_t)max_n_frames + 1) / 2 * 4;      // one 16-bit score index per frame
         if (tiles > 0 && frame_bytes <= smz::max_smem_optin() - 1024 && max_n_frames < 65535) {
-            SMZ_CUDA_CHECK(cudaFuncSetAttribute((const void *)pool_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)frame_bytes));
+            { int unused = 0; const int rc2 = cached_occupancy((const void *)pool_smem_kernel, POOL_SMEM_THREADS, (int)frame_bytes, &unused); if (rc2 != SMZ_OK) return rc2; }
             pool_smem_kernel<<<n_videos, POOL_SMEM_THREADS, (size_t)frame_bytes, st>>>(desc, 0, scores, picks, cps, seg_mean,
                                                                                      values, status);
         } else {
@@ -826,18 +1244,37 @@ static int select_launch(const smz_video_desc *desc, int n_videos, const float *
         vals = values;
     }
     dp_fn fn = dp_fn_for(plan.k);
-    SMZ_CUDA_CHECK(cudaMemsetAsync(queue, 0, sizeof(int) * (1 + 2 * ORDER_BUCKETS), st));
+    // evaluation tail inside the DP kernels: summary vector + mask (+ the F-score when the caller asked for it)
+    EvalTail tail = {};
+    if (plan.front_words > 0 && mask != nullptr) {
+        SMZ_REQUIRE(msum != nullptr, "msum is required with mask");
+        if (fscore_tail != nullptr) { tail = *fscore_tail; if (fscore_done) *fscore_done = true; }
+        tail.enabled = 1; tail.summary = summary; tail.mask = mask; tail.msum = msum;
+    }
+    SMZ_CUDA_CHECK(cudaMemsetAsync(queue, 0, sizeof(int) * kQueueInts, st));
     order_count_kernel<<<(n_videos + 255) / 256, 256, 0, st>>>(desc, n_videos, max_n_segs, queue);
     order_fill_kernel<<<(n_videos + 255) / 256, 256, 0, st>>>(desc, n_videos, max_n_segs, queue, order);
-    fn<<<plan.grid, DP_THREADS, plan.smem_bytes, st>>>(desc, n_videos, nfps, vals, seg_mean, method, max_n_segs,
-                                                      plan.pad_weight, picked, status, (uint32_t *)ws,
-                                                      plan.ws_words_per_cta, queue, order);
+    if (method == SMZ_METHOD_KNAPSACK && plan.kw16 > 0) {
+        // 16-bit pass over every video, then the 32-bit kernel over whatever it handed back (usually nothing)
+        dp16_fn fn16 = dp16_fn_for(plan.kw16, plan.mk16);
+        fn16<<<plan.grid16, DP_THREADS, plan.smem16_bytes, st>>>(desc, n_videos, nfps, vals, max_n_segs, picked,
+                                                                 (uint32_t *)ws, plan.ws16_words_per_cta, queue, order, fallback,
+                                                                 plan.front_words, tail);
+        fn<<<plan.grid, DP_THREADS, plan.smem_bytes, st>>>(desc, n_videos, nfps, vals, seg_mean, method, max_n_segs,
+                                                          plan.pad_weight, picked, status, (uint32_t *)ws,
+                                                          plan.ws_words_per_cta, queue + kQueueHead32, fallback + 1, fallback,
+                                                          plan.front_words, tail);
+    } else {
+        fn<<<plan.grid, DP_THREADS, plan.smem_bytes, st>>>(desc, n_videos, nfps, vals, seg_mean, method, max_n_segs,
+                                                          plan.pad_weight, picked, status, (uint32_t *)ws,
+                                                          plan.ws_words_per_cta, queue, order, nullptr, plan.front_words, tail);
+    }
     SMZ_CUDA_CHECK(cudaGetLastError());
-    if (mask != nullptr) {
+    if (mask != nullptr && !tail.enabled) {
         SMZ_REQUIRE(msum != nullptr, "msum is required with mask");
         const int sm_bytes = (max_n_segs + 1 + (max_n_frames + 31) / 32) * 4;
         SMZ_REQUIRE(sm_bytes <= smz::max_smem_optin(), "summary: %d B of shared memory needed", sm_bytes);
-        SMZ_CUDA_CHECK(cudaFuncSetAttribute((const void *)summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes));
+        { int unused = 0; const int rc2 = cached_occupancy((const void *)summary_kernel, SUMMARY_THREADS, sm_bytes, &unused); if (rc2 != SMZ_OK) return rc2; }
         summary_kernel<<<n_videos, SUMMARY_THREADS, sm_bytes, st>>>(desc, 0, nfps, picked, max_n_segs, max_n_frames,
                                                                    summary, mask, msum);
         SMZ_CUDA_CHECK(cudaGetLastError());
@@ -865,4 +1302,50 @@ extern "C" int smz_knapsack(const smz_video_desc *desc, int n_videos, const int3
     return select_launch(desc, n_videos, nullptr, nullptr, nullptr, nfps, values, SMZ_METHOD_KNAPSACK, max_n_segs,
                          max_capacity, max_n_frames, max_seg_frames, nullptr, nullptr, picked, nullptr, mask, msum,
                          status, ws, ws_bytes, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// smz_eval_batch: shot selection + F-score of a whole batch in one pass
+// ------------------------------------------------------------------------------------------
+namespace smz {
+int launch_fscore_counts(const smz_video_desc *desc, int n_videos, int max_n_frames, const float *user_summary,
+                         const uint32_t *mask, int32_t *overlap, int32_t *gsum, cudaStream_t st);
+int launch_fscore_bits(const smz_video_desc *desc, int n_videos, const uint32_t *user_bits, const int64_t *bits_off,
+                       const uint32_t *mask, int32_t *overlap, int32_t *gsum, cudaStream_t st);
+int launch_fscore_final(const smz_video_desc *desc, int n_videos, const int32_t *msum, const int32_t *overlap,
+                        const int32_t *gsum, float *f, double *avg_f, double *max_f, cudaStream_t st);
+}  // namespace smz
+
+extern "C" int smz_eval_batch(const smz_video_desc *desc, int n_videos, int total_users, const float *scores,
+                              const int32_t *picks, const int32_t *cps, const int32_t *nfps, int method,
+                              int max_n_segs, int max_capacity, int max_n_frames, int max_seg_frames,
+                              const float *user_summary, const uint32_t *user_bits, const int64_t *bits_off,
+                              float *seg_mean, int32_t *values, uint8_t *picked, float *summary, uint32_t *mask,
+                              int32_t *msum, int32_t *status, int32_t *overlap, int32_t *gsum, float *f, double *avg_f,
+                              double *max_f, void *ws, int64_t ws_bytes, void *stream) {
+    if (n_videos == 0) return SMZ_OK;
+    SMZ_REQUIRE(n_videos > 0 && total_users >= 0, "negative size");
+    SMZ_REQUIRE(desc && scores && picks && cps && nfps && mask && msum && picked && status, "NULL pointer");
+    SMZ_REQUIRE((user_summary != nullptr) != (user_bits != nullptr), "exactly one of user_summary / user_bits");
+    SMZ_REQUIRE(user_bits == nullptr || bits_off != nullptr, "bits_off is required with user_bits");
+    SMZ_REQUIRE(overlap && gsum && f, "NULL output pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    EvalTail tail = {};
+    tail.user = user_summary; tail.user_bits = user_bits; tail.bits_off = bits_off;
+    tail.overlap = overlap; tail.gsum = gsum; tail.f = f; tail.avg_f = avg_f; tail.max_f = max_f;
+    bool fused = false;
+    int rc = select_launch(desc, n_videos, scores, picks, cps, nfps, nullptr, method, max_n_segs, max_capacity, max_n_frames,
+                           max_seg_frames, seg_mean, values, picked, summary, mask, msum, status, ws, ws_bytes, stream,
+                           &tail, &fused);
+    if (rc != SMZ_OK || fused) return rc;
+    // rows that do not fit the register-DP plan (very long videos): the stand-alone F-score kernels behind the selection
+    if (user_summary != nullptr) {
+        SMZ_CUDA_CHECK(cudaMemsetAsync(overlap, 0, sizeof(int32_t) * (size_t)total_users, st));
+        SMZ_CUDA_CHECK(cudaMemsetAsync(gsum, 0, sizeof(int32_t) * (size_t)total_users, st));
+        rc = smz::launch_fscore_counts(desc, n_videos, max_n_frames, user_summary, mask, overlap, gsum, st);
+    } else {
+        rc = smz::launch_fscore_bits(desc, n_videos, user_bits, bits_off, mask, overlap, gsum, st);
+    }
+    if (rc != SMZ_OK) return rc;
+    return smz::launch_fscore_final(desc, n_videos, msum, overlap, gsum, f, avg_f, max_f, st);
 }

@@ -3,9 +3,9 @@
 cross-validation means, TensorBoard hparams, predictions over the whole dataset.
 
 Multi-GPU (one process per GPU, ``torchrun --nproc-per-node N main.py ...``): the (split file, fold) jobs are
-independent (main.py:14,26), so they are dealt to the ranks longest-first and run with NO data-path
-collective; rank 0 gathers the per-fold results (and the best fold's weights) through torch.distributed and
-returns the same ``results`` list as a single-process run."""
+independent (main.py:14,26), so ALL of them — across split files — are dealt to the ranks longest-first and run
+with NO data-path collective; rank 0 gathers the per-fold results (and the best fold's weights) through
+torch.distributed and returns the same ``results`` list as a single-process run."""
 import argparse
 import os
 import sys
@@ -47,68 +47,99 @@ def fold_cost(hps, model, splits_file, fold):
     return float(hps.epochs) * sum(int(np.shape(model.dataset[k]["features"])[0]) for k in keys)
 
 
+def _cpu_state(state_dict):
+    """Detached host copy of a state dict (``state_dict()`` aliases the live parameters, which the next fold resets)."""
+    return {k: v.detach().to("cpu", copy=True) for k, v in state_dict.items()}
+
+
 def train(hps):
-    """Training.  Returns [(splits_file, mean corr, mean avg F, mean max F), ...] (main.py:10-72)."""
+    """Training.  Returns [(splits_file, mean corr, mean avg F, mean max F), ...] (main.py:10-72).
+
+    One process: the reference's loop.  Several ranks (fold-parallel): ALL (split file, fold) jobs of the run are
+    dealt to the ranks at once, longest first (SumMe + TVSum = 10 jobs, the TVSum folds ~3x heavier), every rank
+    trains its jobs with no collective, then the per-fold results are gathered and, per split file, the rank that
+    owns the best fold (highest correlation, first fold on ties as main.py:33-35) ships that fold's weights to
+    rank 0 through the process group — no files, no dependence on a shared log directory."""
     dist, rank, world = _dist()
+    data_parallel = bool((hps.extra_params or {}).get("data_parallel", False))
+    if data_parallel:
+        world = 1            # every rank trains every fold together (gradient all-reduce inside the trainer)
+    models = {sf: hps.model_class(hps, sf) for sf in hps.splits_files}
+    jobs = [(i, f) for i, sf in enumerate(hps.splits_files) for f in range(len(hps.splits_of_file[sf]))]
+    if world > 1:
+        costs = [((i, f), fold_cost(hps, models[hps.splits_files[i]], hps.splits_files[i], f)) for i, f in jobs]
+        mine = plan_folds(costs, world)[rank]
+    else:
+        mine = jobs
+
+    fold_results = {}                      # (file index, fold) -> (corr, avg F, max F)
+    best = {}                              # file index -> (corr, fold, host copy of the weights)
+    for i, fold in mine:
+        sf = hps.splits_files[i]
+        n_folds = len(hps.splits_of_file[sf])
+        if fold == 0 or world > 1:
+            hps.logger.info(f"Start training on {sf}" + (f" (rank {rank})" if world > 1 else ""))
+        model = models[sf]
+        best_corr, best_avg_f, best_max_f = model.reset().train(fold)
+        fold_results[(i, fold)] = (float(best_corr), float(best_avg_f), float(best_max_f))
+        if best_corr > best.get(i, (-1.0,))[0]:
+            if world > 1:
+                if model.best_weights is None:
+                    raise Exception("best_weights property is empty, can't save model's weights")
+                best[i] = (float(best_corr), fold, _cpu_state(model.best_weights))
+            else:
+                best[i] = (float(best_corr), fold, None)
+                if rank == 0:
+                    model.save_best_weights(hps.weights_path[sf])
+        hps.logger.info(f"File: {sf}   Fold: {fold+1}/{n_folds}   Corr: {best_corr: 0.5f}  "
+                        f"Avg F-score: {best_avg_f:0.5f}  Max F-score: {best_max_f:0.5f}")
+
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (fold_results, {i: b[:2] for i, b in best.items()}))
+        fold_results = {k: r for g, _ in gathered for k, r in g.items()}
+        for i, sf in enumerate(hps.splits_files):
+            cand = [(-b[i][0], b[i][1], r) for r, (_, b) in enumerate(gathered) if i in b]
+            if not cand:
+                raise RuntimeError(f"{sf}: no rank reported a trained fold")
+            _, _, owner = min(cand)                               # highest correlation, then the first fold
+            box = [best[i][2] if rank == owner else None]
+            if owner != 0:                                        # owner -> rank 0
+                dist.broadcast_object_list(box, src=owner)
+            if rank == 0:
+                if box[0] is None:
+                    raise RuntimeError(f"{sf}: the best fold's weights did not arrive from rank {owner}")
+                torch.save(box[0], hps.weights_path[sf])
+
     results = []
-    for splits_file in hps.splits_files:
-        hps.logger.info(f"Start training on {splits_file}")
-        n_folds = len(hps.splits_of_file[splits_file])
-        weights_path = hps.weights_path[splits_file]
-        pred_path = hps.pred_path[splits_file]
-        model = hps.model_class(hps, splits_file)
-        if (hps.extra_params or {}).get("data_parallel", False):
-            # single-split data-parallel mode: every rank trains every fold together (gradient all-reduce inside
-            # the trainer); the fold results are identical on all ranks
-            mine, world = list(range(n_folds)), 1
-        else:
-            mine = plan_folds([(f, fold_cost(hps, model, splits_file, f)) for f in range(n_folds)], world)[rank]
-
-        fold_results, corr_max = {}, -1.0
-        for fold in mine:
-            best_corr, best_avg_f, best_max_f = model.reset().train(fold)
-            fold_results[fold] = (float(best_corr), float(best_avg_f), float(best_max_f))
-            if best_corr > corr_max:
-                corr_max = best_corr
-                if world > 1:
-                    model.save_best_weights(f"{weights_path}.rank{rank}")
-                elif rank == 0:
-                    model.save_best_weights(weights_path)
-            hps.logger.info(f"File: {splits_file}   Fold: {fold+1}/{n_folds}   Corr: {best_corr: 0.5f}  "
-                            f"Avg F-score: {best_avg_f:0.5f}  Max F-score: {best_max_f:0.5f}")
-
-        if world > 1:   # gather the fold results on every rank; rank 0 adopts the best fold's weights
-            gathered = [None] * world
-            dist.all_gather_object(gathered, (fold_results, corr_max))
-            fold_results = {f: r for g, _ in gathered for f, r in g.items()}
-            best_rank = int(np.argmax([c for _, c in gathered]))
-            dist.barrier()
-            if rank == 0 and os.path.exists(f"{weights_path}.rank{best_rank}"):
-                os.replace(f"{weights_path}.rank{best_rank}", weights_path)
-            dist.barrier()
-            if os.path.exists(f"{weights_path}.rank{rank}"):
-                os.remove(f"{weights_path}.rank{rank}")
-        corrs_cv = [fold_results[f][0] for f in range(n_folds)]
-        avg_fscores_cv = [fold_results[f][1] for f in range(n_folds)]
-        max_fscores_cv = [fold_results[f][2] for f in range(n_folds)]
-
-        hps.logger.info(f"File: {splits_file}   Cross-validation Corr: {np.mean(corrs_cv): 0.5f}  "
+    for i, sf in enumerate(hps.splits_files):
+        n_folds = len(hps.splits_of_file[sf])
+        weights_path, pred_path = hps.weights_path[sf], hps.pred_path[sf]
+        missing = [f for f in range(n_folds) if (i, f) not in fold_results]
+        if missing:
+            raise RuntimeError(f"{sf}: folds {missing} were not trained by any rank")
+        corrs_cv = [fold_results[(i, f)][0] for f in range(n_folds)]
+        avg_fscores_cv = [fold_results[(i, f)][1] for f in range(n_folds)]
+        max_fscores_cv = [fold_results[(i, f)][2] for f in range(n_folds)]
+        hps.logger.info(f"File: {sf}   Cross-validation Corr: {np.mean(corrs_cv): 0.5f}  "
                         f"Avg F-score: {np.mean(avg_fscores_cv):0.5f}  Max F-score: {np.mean(max_fscores_cv):0.5f}")
-        hps.logger.info(f"File: {splits_file}   Best weights: {weights_path}")
         if rank == 0:
+            if not os.path.exists(weights_path):
+                raise FileNotFoundError(f"{sf}: best weights {weights_path} were not written")
+            hps.logger.info(f"File: {sf}   Best weights: {weights_path}")
             hparam_dict = hps.get_full_hps_dict()
-            hparam_dict["dataset"] = hps.dataset_name_of_file[splits_file]
+            hparam_dict["dataset"] = hps.dataset_name_of_file[sf]
             metric_dict = {f"F-score_max/Fold_{f+1}": s for f, s in enumerate(max_fscores_cv)}   # main.py:56-58 keeps the last
             metric_dict["Correlation/CV_Average"] = np.mean(corrs_cv)
             metric_dict["F-score_avg/CV_Average"] = np.mean(avg_fscores_cv)
             metric_dict["F-score_max/CV_Average"] = np.mean(max_fscores_cv)
             hps.writer.add_hparams(hparam_dict, metric_dict)
-            if os.path.exists(weights_path):
-                model.reset().load_weights(weights_path)
-                model.best_weights = model.model.state_dict()
-                model.predict_dataset(pred_path)
-                hps.logger.info(f"File: {splits_file}   Machine predictions: {pred_path}")
-        results.append((splits_file, np.mean(corrs_cv), np.mean(avg_fscores_cv), np.mean(max_fscores_cv)))
+            model = models[sf]
+            model.reset().load_weights(weights_path)
+            model.best_weights = model.model.state_dict()
+            model.predict_dataset(pred_path)
+            hps.logger.info(f"File: {sf}   Machine predictions: {pred_path}")
+        results.append((sf, np.mean(corrs_cv), np.mean(avg_fscores_cv), np.mean(max_fscores_cv)))
     return results
 
 
@@ -144,9 +175,12 @@ def main(argv=None):
     if "WORLD_SIZE" in os.environ and int(os.environ["WORLD_SIZE"]) > 1:
         import torch.distributed as dist
         local = int(os.environ.get("LOCAL_RANK", 0))
+        # fold-parallel runs only gather small Python objects (and one state dict): a host-side gloo group is enough
+        # and spares the NCCL communicator set-up; --data_parallel all-reduces gradients and needs NCCL
         if torch.cuda.is_available():
             torch.cuda.set_device(local)
             hps_init["cuda_device"] = local
+        if torch.cuda.is_available() and hps_init["extra_params"].get("data_parallel", False):
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         else:
             dist.init_process_group("gloo")

@@ -9,12 +9,14 @@ from . import Trainer
 class LogisticRegression(nn.Module):
     def __init__(self, input_size=1024):
         super().__init__()
-        self.linear = nn.Linear(input_size, 1)
-        self.sigmoid = nn.Sigmoid()
+        self.input_size = input_size
+        self.perceptron = nn.Linear(input_size, 1)           # reference attribute names: state-dict keys perceptron.*
+        self.sig = nn.Sigmoid()
 
     def forward(self, x):
         """x: (seq_len, batch_size, input_size) -> (seq_len, batch_size, 1)"""
-        return self.sigmoid(self.linear(x))
+        assert x.shape[2] == self.input_size, f"Input size of {self.input_size} expected, {x.shape[2]} given."
+        return self.sig(self.perceptron(x))
 
 
 class LogisticRegressionTrainer(Trainer):

@@ -240,13 +240,28 @@ class SumGANTrainer(Trainer):
 
     def _update(self, optimizer, loss, dp, n_active):
         """zero_grad of THIS optimizer, backward, clip over ALL parameters (stale gradients of the other
-        sub-networks enter the norm exactly as in sumgan.py:433-436), step."""
+        sub-networks enter the norm exactly as in sumgan.py:433-436), step.
+
+        Data-parallel: only the stepping optimizer's gradients are all-reduced; the stale gradients of the other
+        sub-networks are local to each replica (every rank saw a different video), so a locally computed clip
+        coefficient would differ per rank and the replicas would drift apart.  The squared total norm is therefore
+        averaged over the ranks and ONE shared coefficient is applied everywhere."""
         optimizer.zero_grad()
         if loss is not None:
             loss.backward()
-        if dp is not None:
+        if dp is None:
+            nn.utils.clip_grad_norm_(self.model.parameters(), 5.0)
+        else:
             self._dp_allreduce_grads(dp, [p for g in optimizer.param_groups for p in g["params"]], n_active)
-        nn.utils.clip_grad_norm_(self.model.parameters(), 5.0)
+            grads = [p.grad for p in self.model.parameters() if p.grad is not None]
+            if grads:
+                sq = torch.stack([g.float().pow(2).sum() for g in grads]).sum()
+            else:
+                sq = torch.zeros((), device=next(self.model.parameters()).device)
+            dp.all_reduce(sq)
+            coef = torch.clamp(5.0 / (torch.sqrt(sq / dp.get_world_size()) + 1e-6), max=1.0)
+            for g in grads:
+                g.mul_(coef.to(g.dtype))
         optimizer.step()
 
     def _groups(self, train_keys, dp, rank, world):
@@ -279,6 +294,16 @@ class SumGANTrainer(Trainer):
             if epoch % 10 == 0 or epoch == self.pretrain_vae - 1:
                 avg = float(torch.stack(losses).mean()) if losses else float("nan")
                 self.log.info(f"Pretrain: {epoch+1:3}/{self.pretrain_vae:3}   Lvae: {avg:.05f}")
+
+    def _pretrain_epochs(self):
+        return self.pretrain_vae
+
+    def _make_optimizers(self):
+        """sumgan.py:366-380: selector + encoder, decoder, discriminator each with their own Adam."""
+        m = self.model
+        self.s_e_optimizer = self._adam(list(m.summarizer.s_lstm.parameters()) + list(m.summarizer.vae.e_lstm.parameters()))
+        self.d_optimizer = self._adam(m.summarizer.vae.d_lstm.parameters())
+        self.c_optimizer = self._adam(m.gan.c_lstm.parameters())
 
     def train_step(self, x, y, epoch, dp=None, n_active=1):
         """The three updates of one video (sumgan.py:415-480).  x (T,1,1024), y (T,1,1) or None on an idle replica.
@@ -335,12 +360,9 @@ class SumGANTrainer(Trainer):
         dp, rank, world = self._dp()
         if dp is not None:
             self._dp_sync_model(dp)
-        if self.pretrain_vae > 0:
+        if self._pretrain_epochs() > 0:
             self.pretrain(fold)
-        m = self.model
-        self.s_e_optimizer = self._adam(list(m.summarizer.s_lstm.parameters()) + list(m.summarizer.vae.e_lstm.parameters()))
-        self.d_optimizer = self._adam(m.summarizer.vae.d_lstm.parameters())
-        self.c_optimizer = self._adam(m.gan.c_lstm.parameters())
+        self._make_optimizers()
         self.loss_BCE = nn.BCELoss()
         best_corr, best_avg_f_score, best_max_f_score = -1.0, 0.0, 0.0
         tags = ("Lse", "Ld", "Lc", "D_x", "D_x_hat", "D_x_hat_p")

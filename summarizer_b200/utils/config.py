@@ -29,8 +29,8 @@ class _NullWriter:
 
 
 def _model_registry():
-    """utils/config.py:68-77.  transformer / sumgan_att are outside the hot path and are not
-    registered: asking for them raises the reference's KeyError."""
+    """utils/config.py:68-77.  transformer / sumgan_att are plain-torch passthrough modules (outside the hot path,
+    SURVEY.md §2.1; part of the drop-in surface, §8b)."""
     from ..models.logistic import LogisticRegressionTrainer
     from ..models.rand import RandomTrainer
     from ..models.vasnet import VASNetTrainer
@@ -41,7 +41,11 @@ def _model_registry():
     except ImportError:
         pass
     from ..models.sumgan import SumGANTrainer
+    from ..models.sumgan_att import SumGANAttTrainer
+    from ..models.transformer import TransformerTrainer
     reg["sumgan"] = SumGANTrainer
+    reg["sumgan_att"] = SumGANAttTrainer
+    reg["transformer"] = TransformerTrainer
     return reg
 
 
@@ -88,10 +92,23 @@ class HParameters:
 
     def _init(self):
         log_dir = str(int(datetime.datetime.now().timestamp())) + "_" + self.model_class.__name__
+        # several ranks of one run share ONE log directory: rank 0's name is broadcast (each rank building its own from
+        # its wall clock only agreed when all of them started within the same second); only rank 0 writes TensorBoard
+        rank = 0
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                rank = dist.get_rank()
+                box = [log_dir]
+                dist.broadcast_object_list(box, src=0)
+                log_dir = box[0]
+        except ImportError:
+            pass
+        self.rank = rank
         self.log_path = os.path.join(self.log_root, log_dir)
         os.makedirs(self.log_path, exist_ok=True)
         self.writer = _NullWriter()
-        if self.tensorboard:
+        if self.tensorboard and rank == 0:
             try:
                 from torch.utils.tensorboard import SummaryWriter
                 self.writer = SummaryWriter(self.log_path)
@@ -106,6 +123,11 @@ class HParameters:
             self.use_cuda = False
         if self.use_cuda:
             torch.cuda.set_device(self.cuda_device)
+        elif not getattr(self, "allow_cpu", False):
+            # Trainer.test() evaluates with the sm_100a kernels: there is no CPU path to fall back to, so say so now
+            # rather than at the first test() (tests that only exercise host logic set allow_cpu)
+            raise RuntimeError("summarizer_b200 runs on an sm_100 (B200) device: no CUDA device is available or "
+                               "--use-cuda no was given, and there is no CPU fallback")
 
         shorthands = {
             "minimal": ["splits/tvsum_splits_overfit.json"],
@@ -136,7 +158,8 @@ class HParameters:
         for h in list(self.logger.handlers):
             self.logger.removeHandler(h)
         fmt = logging.Formatter("%(asctime)s::%(levelname)s: %(message)s", "%H:%M:%S")
-        for h in (logging.StreamHandler(), logging.FileHandler(os.path.join(self.log_path, "train.log"))):
+        log_name = "train.log" if self.rank == 0 else f"train.rank{self.rank}.log"
+        for h in (logging.StreamHandler(), logging.FileHandler(os.path.join(self.log_path, log_name))):
             h.setFormatter(fmt)
             self.logger.addHandler(h)
         self.logger.setLevel(getattr(logging, str(self.log_level).upper()))

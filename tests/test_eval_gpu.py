@@ -291,3 +291,93 @@ def test_sweep_shaped_invariants_and_sample():
                                                    30000, nfps[so:so + ns], picks[int(d["picks_off"]):int(d["picks_off"]) + 2000])
         assert np.nonzero(picked[so:so + ns])[0].tolist() == parts["picks"]
         assert np.array_equal(summ[i].cpu().numpy(), ref_sum)
+
+
+# ------------------------------------------------------------------------------------------------
+# 16-bit knapsack DP (dp16_kernel) and its hand-over to the 32-bit kernel; sliced two-stream evaluation
+# ------------------------------------------------------------------------------------------------
+def _knapsack_batch(cases):
+    """cases: list of (values int array, weights int array, capacity) -> picked index lists from smz_knapsack."""
+    from summarizer_b200 import _native as N
+    from summarizer_b200.batch import VideoBatch
+    desc = np.zeros(len(cases), dtype=N.VIDEO_DESC)
+    so = 0
+    for i, (vals, w, cap) in enumerate(cases):
+        desc[i]["seg_off"], desc[i]["n_segs"], desc[i]["capacity"] = so, len(w), cap
+        so += len(w)
+    nfps = np.concatenate([np.asarray(c[1], np.int32) for c in cases])
+    b = VideoBatch.from_packed(desc, np.zeros(1, np.int32), np.zeros(2, np.int32), nfps, None, 0.15)
+    b.knapsack(torch.from_numpy(np.concatenate([np.asarray(c[0], np.int32) for c in cases])))
+    torch.cuda.synchronize()
+    picked, st, out, so = b.picked.cpu().numpy(), b.status.cpu().numpy(), [], 0
+    for vals, w, cap in cases:
+        out.append(np.nonzero(picked[so:so + len(w)])[0].tolist()); so += len(w)
+    return out, st
+
+
+def test_dp16_matches_oracle_on_every_hand_over_condition():
+    """Random instances built to hit each branch of dp16_kernel: plain 16-bit runs, values above 32767, negative values,
+    row values that outgrow 16 bits half way (abort -> 32-bit redo), weights above the mirror pad, zero weights, zero
+    values (item-0 quirk), everything-fits and nothing-fits shortcuts.  Bit-exact against the C oracle."""
+    rng = np.random.default_rng(21)
+    cases = []
+    for kind in range(12):
+        for rep in range(6):
+            n = int(rng.integers(1, 200))
+            w = rng.integers(1, 300, n)
+            vals = rng.integers(0, 1001, n)
+            cap = int(rng.integers(1, 4500))
+            if kind == 1: vals = rng.integers(0, 40000, n)                   # p > 32767 somewhere: 32-bit path
+            if kind == 2: vals = rng.integers(-500, 1000, n)                 # negative values: 32-bit path
+            if kind == 3: vals = rng.integers(2000, 6000, n); cap = 4400     # overflows 16 bits while running: abort
+            if kind == 4: w = rng.integers(1, 2500, n)                       # items heavier than 512: masked variant
+            if kind == 5: w = rng.integers(0, 3, n); cap = int(rng.integers(1, 40))   # zero weights, tiny capacity
+            if kind == 6: vals = np.zeros(n, np.int64)                       # all-zero values: default id 0 quirk
+            if kind == 7: cap = int(w.sum()) + 3                             # everything fits
+            if kind == 8: w = rng.integers(5000, 6000, n)                    # nothing fits
+            if kind == 9: vals = rng.integers(0, 3, n) * 500; w = np.full(n, 60)   # tie-heavy uniform segments
+            if kind == 10: vals = rng.integers(300, 700, n); w = rng.integers(30, 301, n); cap = 4500   # sweep-like
+            if kind == 11: vals = rng.integers(30000, 32768, n); cap = int(rng.integers(1, 600))        # top-cell check at the limit
+            cases.append((vals, w, cap))
+    got, st = _knapsack_batch(cases)
+    assert not st[: len(cases)].any()
+    for i, (vals, w, cap) in enumerate(cases):
+        assert got[i] == c_oracle.knapsack(vals, w, cap), (i, i // 6)
+
+
+def test_dp16_and_32bit_kernels_agree_on_a_dataset(monkeypatch):
+    from summarizer_b200.batch import VideoBatch
+    vids, scores = _dataset_videos("tvsum", 16)
+    sc = torch.from_numpy(np.concatenate(scores))
+    b = VideoBatch(vids)
+    b.select(sc); torch.cuda.synchronize()
+    a = b.picked.clone()
+    monkeypatch.setenv("SMZ_NO_DP16", "1")
+    b.picked.zero_()
+    b.select(sc); torch.cuda.synchronize()
+    assert torch.equal(a, b.picked)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_evaluate_fused_tail_equals_select_then_fscore(fused, monkeypatch):
+    if not fused:
+        monkeypatch.setenv("SMZ_NO_FUSED_TAIL", "1")
+    from summarizer_b200.batch import VideoBatch
+    vids, scores = _dataset_videos("tvsum", 13)
+    sc = torch.from_numpy(np.concatenate(scores)).cuda()
+    b = VideoBatch(vids)
+    b.select(sc).fscore(); torch.cuda.synchronize()
+    names = ("picked", "summary", "mask", "msum", "overlap", "gsum", "f", "avg_f", "max_f", "status")
+    ref = {k: getattr(b, k).clone() for k in names}
+    for k in names:
+        getattr(b, k).fill_(0 if k != "status" else 7)
+    b.evaluate(sc); b.check_status(); torch.cuda.synchronize()
+    for k in names:
+        assert torch.equal(ref[k], getattr(b, k)), k
+    # annotator rows as bits
+    h_bits = b.pack_user_summary_host(b.d_users.cpu(), n_threads=2)
+    for k in ("overlap", "gsum", "f", "avg_f", "max_f"):
+        getattr(b, k).zero_()
+    b.evaluate(sc, d_bits=h_bits.cuda()); torch.cuda.synchronize()
+    for k in names:
+        assert torch.equal(ref[k], getattr(b, k)), k

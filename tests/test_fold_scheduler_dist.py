@@ -20,8 +20,12 @@ class StubTrainer(Trainer):
 
     def train(self, fold):
         self._get_train_test_keys(fold)
+        with torch.no_grad():
+            self.model.weight.fill_(float(fold))                   # the weights remember which fold produced them
         self.best_weights = self.model.state_dict()
-        return 0.1 * (fold + 1), 0.2 + 0.01 * fold, 0.5 + 0.01 * fold
+        # best fold: 3 for SumMe; 1 for TVSum, tied with fold 4, which must lose against the earlier fold
+        corr = {"summe": [0.1, 0.2, 0.3, 0.9, 0.5], "tvsum": [0.1, 0.9, 0.3, 0.4, 0.9]}[self.dataset_name][fold]
+        return corr, 0.2 + 0.01 * fold, 0.5 + 0.01 * fold
 
     def predict_dataset(self, pred_path):
         open(pred_path + ".npz", "wb").close()
@@ -29,28 +33,39 @@ class StubTrainer(Trainer):
 
 def make_hps(root):
     hps = HParameters()
-    hps.log_root, hps.tensorboard = root, False
-    hps.load_from_args(dict(model="random", use_cuda="no", splits_files="summe", log_level="error", extra_params={}))
+    hps.log_root, hps.tensorboard, hps.allow_cpu = root, False, True
+    hps.load_from_args(dict(model="random", use_cuda="no", splits_files="splits/summe_splits.json,splits/tvsum_splits.json",
+                            log_level="error", extra_params={}))
     hps.model_class = StubTrainer
     return hps
+
+
+def _best_fold_of_saved_weights(hps):
+    return [int(torch.load(hps.weights_path[sf])["weight"][0, 0].item()) for sf in hps.splits_files]
 
 
 def _worker(rank, world, root, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    res = train(make_hps(os.path.join(root, f"r{rank}")))
-    out[rank] = [(os.path.basename(f), float(c), float(a), float(m)) for f, c, a, m in res]
+    hps = make_hps(root)
+    res = train(hps)
+    out[rank] = ([(os.path.basename(f), float(c), float(a), float(m)) for f, c, a, m in res], hps.log_path,
+                 _best_fold_of_saved_weights(hps) if rank == 0 else None)
     dist.destroy_process_group()
 
 
 def test_two_ranks_return_single_process_results(tmp_path):
-    single = train(make_hps(str(tmp_path / "single")))
+    hps1 = make_hps(str(tmp_path / "single"))
+    single = train(hps1)
     want = [(os.path.basename(f), float(c), float(a), float(m)) for f, c, a, m in single]
-    assert want[0][1] == np.mean([0.1 * (f + 1) for f in range(5)])
+    assert [w[0] for w in want] == ["summe_splits.json", "tvsum_splits.json"]
+    assert _best_fold_of_saved_weights(hps1) == [3, 1]             # first fold reaching the maximum (main.py:33-35)
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(2, str(tmp_path), 29731, out), nprocs=2, join=True)
-    assert out[0] == want and out[1] == want
+    mp.spawn(_worker, args=(2, str(tmp_path / "two"), 29731, out), nprocs=2, join=True)
+    assert out[0][0] == want and out[1][0] == want
+    assert out[0][1] == out[1][1]                                  # ONE log directory for the run (rank 0's, broadcast)
+    assert out[0][2] == [3, 1]                                     # the owning rank shipped the best fold's weights to rank 0
 
 
 # ---- data-parallel single-split training: gradient all-reduce (gloo here, NCCL on the GPU box) -------------------
@@ -73,7 +88,7 @@ class CpuLogisticTrainer(Trainer):
 
 def make_dp_hps(root, data_parallel):
     hps = HParameters()
-    hps.log_root, hps.tensorboard = root, False
+    hps.log_root, hps.tensorboard, hps.allow_cpu = root, False, True
     hps.load_from_args(dict(model="logistic", use_cuda="no", splits_files="splits/summe_splits_overfit.json", log_level="error",
                             epochs=2, lr=1e-2, extra_params={"data_parallel": True} if data_parallel else {}))
     hps.model_class = CpuLogisticTrainer
@@ -171,3 +186,36 @@ def test_sumgan_phase_update_data_parallel(tmp_path):
         opt.step()
     for a, p in zip(p0, model.parameters()):
         np.testing.assert_allclose(a, p.detach().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def _sumgan_two_optimizer_worker(rank, world, port, out):
+    """Two sub-networks with their own optimizers, gradients far above the clip threshold, a different video per rank:
+    the stale gradients of the sub-network that is NOT stepping are rank-local and enter the clip norm."""
+    from summarizer_b200.models.sumgan import SumGANTrainer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class _H:
+        lr, weight_decay, extra_params = 1e-2, 0.0, {"data_parallel": True}
+
+    t = SumGANTrainer.__new__(SumGANTrainer)
+    t.hps = _H
+    torch.manual_seed(11)
+    t.model = torch.nn.ModuleDict({"a": torch.nn.Linear(4, 4), "b": torch.nn.Linear(4, 2)})
+    opt_a, opt_b = t._adam(t.model["a"].parameters()), t._adam(t.model["b"].parameters())
+    dp, r, w = t._dp()
+    x = torch.randn(3, 4, generator=torch.Generator().manual_seed(100 + rank))      # every rank sees another video
+    for step in range(4):
+        for opt in (opt_a, opt_b):
+            loss = 300.0 * t.model["b"](torch.relu(t.model["a"](x))).pow(2).sum()   # both sub-networks get gradients
+            t._update(opt, loss, dp, world)
+    out[rank] = [p.detach().clone().numpy() for p in t.model.parameters()]
+    dist.destroy_process_group()
+
+
+def test_sumgan_clip_is_shared_across_replicas_with_stale_local_gradients(tmp_path):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sumgan_two_optimizer_worker, args=(2, 29761, out), nprocs=2, join=True)
+    for a, b in zip(out[0], out[1]):
+        np.testing.assert_array_equal(a, b)

@@ -18,6 +18,7 @@ def make_hps(tmp_path, **kw):
     hps = HParameters()
     hps.log_root = str(tmp_path)
     hps.tensorboard = False
+    hps.allow_cpu = True
     args = dict(model="vasnet", use_cuda="no", splits_files="summe", log_level="error", extra_params={})
     args.update(kw)
     hps.load_from_args(args)
