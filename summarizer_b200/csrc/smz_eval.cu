@@ -30,17 +30,19 @@ using namespace smzdev;
 // ------------------------------------------------------------------------------------------
 // fscore kernels
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FSCORE_THREADS)
-fscore_kernel(const smz_video_desc *__restrict__ desc, int v0, const float *__restrict__ user,
+// grid (frame range, video): a CTA streams `span` frames (a multiple of SMZ_FSCORE_CHUNK) of all annotator rows.  Large
+// batches give every CTA a whole video (one warp reduction per row and video), small ones split videos for parallelism.
+__global__ void __launch_bounds__(FSCORE_THREADS, 6)
+fscore_kernel(const smz_video_desc *__restrict__ desc, int v0, int span, const float *__restrict__ user,
               const uint32_t *__restrict__ mask, int32_t *__restrict__ overlap, int32_t *__restrict__ gsum) {
     __shared__ uint32_t s_ov[FSCORE_MAX_USERS], s_gs[FSCORE_MAX_USERS];
     const smz_video_desc d = desc[v0 + blockIdx.y];
-    const int f_base = blockIdx.x * SMZ_FSCORE_CHUNK;
+    const int f_base = blockIdx.x * span;
     if (f_base >= d.n_frames) return;
     const int n_users = min(d.n_users, FSCORE_MAX_USERS);      // the C ABI callers reject larger counts up front
     for (int u = threadIdx.x; u < n_users; u += FSCORE_THREADS) { s_ov[u] = 0u; s_gs[u] = 0u; }
     __syncthreads();
-    fscore_chunk_acc(d, f_base, user, mask + d.mask_off, s_ov, s_gs);
+    fscore_rows_acc<FSCORE_UNROLL>(d, f_base, f_base + span, user, mask + d.mask_off, s_ov, s_gs);
     __syncthreads();
     for (int u = threadIdx.x; u < n_users; u += FSCORE_THREADS) {
         if (s_ov[u]) atomicAdd(overlap + d.ucount_off + u, (int)s_ov[u]);
@@ -100,9 +102,15 @@ int launch_fscore_counts(const smz_video_desc *desc, int n_videos, int max_n_fra
                          const uint32_t *mask, int32_t *overlap, int32_t *gsum, cudaStream_t st) {
     const int chunks = (max_n_frames + SMZ_FSCORE_CHUNK - 1) / SMZ_FSCORE_CHUNK;
     if (chunks > 0) {
+        // chunks per CTA: as many as still leave ~4 waves of CTAs (6 resident per SM)
+        int64_t per = ((int64_t)n_videos * chunks) / ((int64_t)smz::sm_count() * 6 * 4);
+        if (per < 1) per = 1;
+        if (per > chunks) per = chunks;
+        const int ranges = (int)((chunks + per - 1) / per);
         for (int v0 = 0; v0 < n_videos; v0 += 65535) {
             const int nv = n_videos - v0 < 65535 ? n_videos - v0 : 65535;
-            fscore_kernel<<<dim3(chunks, nv), FSCORE_THREADS, 0, st>>>(desc, v0, user_summary, mask, overlap, gsum);
+            fscore_kernel<<<dim3(ranges, nv), FSCORE_THREADS, 0, st>>>(desc, v0, (int)per * SMZ_FSCORE_CHUNK, user_summary, mask,
+                                                                     overlap, gsum);
         }
         SMZ_CUDA_CHECK(cudaGetLastError());
     }

@@ -123,6 +123,83 @@ pool_smem_kernel(const smz_video_desc *__restrict__ desc, int v0, const float *_
     }
 }
 
+// Same result again for the common dataset layout — picks on a regular grid, picks[i] = i * stride
+// (datasets/README.md:36-41: every 15th frame): the upsample needs no per-frame table at all, frame f belongs to
+// interval min(f / stride, last), the division is one multiply-high by a per-video constant, and the scores sit in
+// shared memory (4 bytes per STEP, 8 KB for 2 000 steps: many CTAs per SM).  ~6 instructions per frame instead of ~55.
+// Videos whose picks are not such a grid take the cursor walk over global memory (pool_kernel's path) in the same CTA.
+constexpr int POOL_REG_THREADS = 256;
+
+struct RegularFrames {   // upsample of a regular pick grid: scores staged in shared memory (zero-filled past n_scores)
+    const float *sc;
+    uint32_t magic;      // floor(2^32 / stride) + 1: f / stride == umulhi(f, magic) for f, stride < 65536
+    int last;            // index of the last interval
+    __device__ __forceinline__ float at(int f) const { return sc[min((int)__umulhi((uint32_t)f, magic), last)]; }
+};
+
+__global__ void __launch_bounds__(POOL_REG_THREADS)
+pool_regular_kernel(const smz_video_desc *__restrict__ desc, int v0, const float *__restrict__ scores,
+                    const int32_t *__restrict__ picks, const int32_t *__restrict__ cps, int max_intervals,
+                    float *__restrict__ out_mean, int32_t *__restrict__ out_values, int32_t *__restrict__ status) {
+    extern __shared__ float s_sc[];          // max_intervals scores, then 4 * max_n_segs ints (segment lists)
+    __shared__ int s_class[4];
+    constexpr int NT = POOL_REG_THREADS;
+    const int v = v0 + blockIdx.x, tid = threadIdx.x;
+    const smz_video_desc d = desc[v];
+    const int n = d.n_segs, n_frames = d.n_frames, n_picks = d.n_picks;
+    const int32_t *pk = picks + d.picks_off;
+    const float *sc = scores + d.score_off;
+    const int n_bound = n_picks + ((n_picks > 0 && __ldg(pk + n_picks - 1) != n_frames) ? 1 : 0);
+    const int n_int = n_bound - 1;                                   // intervals [bound(i), bound(i+1))
+    if (tid == 0 && n_int > d.n_scores + 1) atomicOr(status + v, SMZ_STATUS_INTERVALS);
+    const int stride = n_picks >= 2 ? __ldg(pk + 1) - __ldg(pk) : n_frames;
+    int ok = n_picks >= 1 && n_int >= 1 && n_int <= max_intervals && stride >= 1 && stride < 65536 && n_frames < 65536;
+    for (int i = tid; i < n_picks && ok; i += NT) ok = __ldg(pk + i) == i * stride;
+    for (int i = tid; i < n_int && i < max_intervals; i += NT) s_sc[i] = i < d.n_scores ? __ldg(sc + i) : 0.f;
+    ok = __syncthreads_and(ok);
+    const int lane = tid & 31, gl = lane & 7, lane0 = lane & ~7;
+    const unsigned gmask = 0xffu << lane0;
+    const int vlim = value_limit(n);
+    RegularFrames reg{s_sc, (uint32_t)(0x100000000ull / (uint32_t)max(stride, 1)) + 1u, n_int - 1};
+    FrameCursor cur;
+    if (!ok) cur.init(sc, pk, d.n_scores, n_picks, n_frames);
+    // Segments are handed to the 8-lane groups sorted by the SHAPE of their pairwise-summation tree (one block up to
+    // 128 frames, two up to 256, four up to 512, deeper beyond): the four groups of a warp then run the same code path
+    // instead of four different ones one after the other.
+    int *s_list = reinterpret_cast<int *>(s_sc + max_intervals);    // 4 lists of up to n segment indices
+    if (tid < 4) s_class[tid] = 0;
+    __syncthreads();
+    for (int s = tid; s < n; s += NT) {
+        const int start = __ldg(cps + 2 * (d.seg_off + s));
+        const int len = min(__ldg(cps + 2 * (d.seg_off + s) + 1) + 1, n_frames) - start;
+        const int c = len <= 128 ? 0 : (len <= 256 ? 1 : (len <= 512 ? 2 : 3));
+        s_list[c * n + atomicAdd(&s_class[c], 1)] = s;
+    }
+    __syncthreads();
+    const int c0 = s_class[0], c1 = c0 + s_class[1], c2 = c1 + s_class[2];
+    for (int t = tid >> 3; t < n; t += NT / 8) {                    // uniform within an 8-lane group
+        const int s = t < c0 ? s_list[t] : (t < c1 ? s_list[n + t - c0] : (t < c2 ? s_list[2 * n + t - c1] : s_list[3 * n + t - c2]));
+        const int start = __ldg(cps + 2 * (d.seg_off + s));
+        int end = __ldg(cps + 2 * (d.seg_off + s) + 1) + 1;
+        end = min(end, n_frames);
+        const int len = end - start;
+        float sum;
+        if (ok) {
+            sum = pw_sum_group(reg, start, len, gl, gmask, lane0);
+        } else {
+            cur.seek(start + (len >= 8 ? gl : 0));
+            sum = pw_sum_group(cur, start, len, gl, gmask, lane0);
+        }
+        if (gl == 0) {
+            const float mean = __fdiv_rn(sum, (float)len);
+            long long val = __double2ll_rz(__dmul_rn((double)mean, 1000.0));
+            if (val > vlim || val < -vlim) { atomicOr(status + v, SMZ_STATUS_VALUE_RANGE); val = val > 0 ? vlim : -vlim; }
+            if (out_mean) out_mean[d.seg_off + s] = mean;
+            out_values[d.seg_off + s] = (int)val;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // evaluation tail fused into the knapsack kernels: summary vector + mask (utils/eval.py:111-122) and
 // the per-annotator F-score (utils/eval.py:125-165) of the video the CTA has just solved
@@ -233,8 +310,7 @@ __device__ void eval_tail_video(const EvalTail &t, const smz_video_desc &d, int 
     if (t.user == nullptr && t.user_bits == nullptr) { __syncthreads(); return; }
     // ---- F-score: stream the annotator rows once against the mask in shared memory
     if (t.user != nullptr) {
-        for (int f_base = 0; f_base < n_frames; f_base += SMZ_FSCORE_CHUNK)
-            fscore_chunk_acc(d, f_base, t.user, smask, s_ov, s_gs);
+        fscore_rows_acc<FSCORE_UNROLL>(d, 0, n_frames, t.user, smask, s_ov, s_gs);
     } else {
         const uint32_t *ub = t.user_bits + t.bits_off[v];
         for (int u = warp; u < n_users; u += NW) {
@@ -481,7 +557,7 @@ dp_kernel(const smz_video_desc *__restrict__ desc, int n_videos, const int32_t *
 // barrier, BAR.RED.OR); when it fails the video goes to the fallback list and dp_kernel<K> solves it in 32 bits.
 // Take bits: per word a 2 x 16-bit shift register (item i of a group of 16 -> bit i of each half), flushed to the
 // work buffer every 16 items as [group][H] words.
-struct Dp16Smem { int row0, row1, wp, pk, total; };
+struct Dp16Smem { int row0, row1, wp, dpi, pk, total; };
 
 __host__ __device__ inline Dp16Smem dp16_layout(int KW, int MK, int max_n_segs, int front_words) {
     Dp16Smem L;
@@ -492,6 +568,7 @@ __host__ __device__ inline Dp16Smem dp16_layout(int KW, int MK, int max_n_segs, 
     if (o < front_words) o = front_words;   // the fused evaluation tail reuses the rows
     o = (o + 1) & ~1;
     L.wp = o; o += 2 * max_n_segs;          // int2 (weight, value)
+    L.dpi = o; o += 2 * max_n_segs;         // int2 (weight, value) as the DP loop sees them
     L.pk = o; o += max_n_segs;              // picked flags
     L.total = o;
     return L;
@@ -524,6 +601,7 @@ dp16_kernel(const smz_video_desc *__restrict__ desc, int n_videos, const int32_t
     const Dp16Smem L = dp16_layout(KW, MK, max_n_segs, front_words);
     uint32_t *row0 = smem + L.row0, *row1 = smem + L.row1;
     int2 *swp = reinterpret_cast<int2 *>(smem + L.wp);
+    int2 *sdp = reinterpret_cast<int2 *>(smem + L.dpi);
     int *spk = reinterpret_cast<int *>(smem + L.pk);
     uint32_t *bits = ws + (int64_t)blockIdx.x * ws_words_per_cta;   // [item / 16][H]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -543,6 +621,7 @@ dp16_kernel(const smz_video_desc *__restrict__ desc, int n_videos, const int32_t
             const int p = __ldg(values + d.seg_off + i);
             if (p > vlim || p < -vlim || w < 0) bad = 1;        // dp_kernel flags and clips these
             swp[i] = make_int2(w, p);
+            sdp[i] = w <= cap ? make_int2(w, p) : make_int2(0, 0);
             spk[i] = 0;
             wsum += w;
             if (w <= cap) { maxw = max(maxw, w); maxp = max(maxp, p); minp = min(minp, p); psum += min(max(p, 0), 32767); }
@@ -581,54 +660,63 @@ dp16_kernel(const smz_video_desc *__restrict__ desc, int n_videos, const int32_t
             for (int i = tid; i < n; i += NT) spk[i] = 1;
         if (mode == 2) {
             uint32_t val[KW], acc[KW];
-            uint32_t *cur = row0, *nxt = row1;
 #pragma unroll
-            for (int k = 0; k < KW; k++) { val[k] = 0u; acc[k] = 0u; cur[tid + k * NT] = 0u; }
+            for (int k = 0; k < KW; k++) { val[k] = 0u; acc[k] = 0u; row0[tid + k * NT] = 0u; }
             for (int j = tid; j < P; j += NT) { row0[j - P] = 0u; row1[j - P] = 0u; }
             __syncthreads();
             const uint32_t top_limit = 65535u - (uint32_t)maxp;
             int aborted = 0;
-            for (int i = 0; i < n; i++) {
-                const int2 wp = swp[i];
-                if (wp.x <= cap) {                             // uniform: upstream's loop body is empty otherwise
-                    const uint32_t *src = cur + (tid - wp.x);  // word j - w; j < w lands in the mirror pad
-                    const uint32_t pp = (uint32_t)wp.y * 0x10001u;
-                    uint32_t cand[KW];
-#pragma unroll
-                    for (int k = 0; k < KW; k++) cand[k] = src[k * NT];
-#pragma unroll
-                    for (int k = 0; k < KW; k++) {
-                        uint32_t nv;
-                        if (k < MK) {
-                            uint32_t t = add_u16x2(cand[k], pp);
-                            if (tid + k * NT < wp.x) t &= 0xffff0000u;      // cell j < w: the item does not fit
-                            nv = max_u16x2(t, val[k]);
-                        } else {
-                            nv = __viaddmax_u16x2(cand[k], pp, val[k]);       // DPX: max(cand + p, val) on both halves
-                        }
-                        // improved halves differ by 1..32767: + 0x7fff sets bit 15 of exactly those (no carry between halves)
-                        const uint32_t y = nv - val[k] + 0x7fff7fffu;
-                        acc[k] = (acc[k] >> 1) | (y & 0x80008000u);
-                        val[k] = nv;
-                        nxt[tid + k * NT] = nv;
-                        if (k >= KW - MK)                                    // words [H - P, H): mirror the low half
-                            reinterpret_cast<unsigned short *>(nxt + (tid + k * NT - H))[1] = (unsigned short)nv;
-                    }
-                    aborted = __syncthreads_or(tid == NT - 1 && (val[KW - 1] >> 16) > top_limit && i + 1 < n);
-                    uint32_t *t = cur; cur = nxt; nxt = t;
-                    if (aborted) break;
-                } else {
-#pragma unroll
-                    for (int k = 0; k < KW; k++) acc[k] >>= 1;             // item not taken anywhere: zero bits
-                }
-                if ((i & 15) == 15 || i == n - 1) {           // flush 16 items' take bits (item j of the group -> bit j), coalesced
-                    uint32_t *dst = bits + (int64_t)(i >> 4) * H + tid;
-                    const int sh = 15 - (i & 15);
-                    const uint32_t m = (0xffffu >> sh) * 0x10001u;
-#pragma unroll
-                    for (int k = 0; k < KW; k++) { dst[k * NT] = (acc[k] >> sh) & m; acc[k] = 0u; }
-                }
+            // One item: row CUR -> row NXT.  sdp[] is the DP's view of the items: (w, p), (0, 0) for an item heavier than
+            // the capacity (upstream's loop body is empty for it; with w = p = 0 every cell compares against itself and
+            // nothing is taken, so the row ping-pong keeps its parity), w < 0 = stop marker left by the top-cell check.
+#define SMZ_DP16_STEP(CUR, NXT, I)                                                                                   \
+            {                                                                                                        \
+                const int2 wp = sdp[I];                                                                              \
+                if (wp.x < 0) { aborted = 1; break; }                                                                \
+                const uint32_t *src = (CUR) + (tid - wp.x);       /* word j - w; j < w lands in the mirror pad */    \
+                const uint32_t pp = (uint32_t)wp.y * 0x10001u;                                                       \
+                uint32_t cand[KW];                                                                                   \
+                _Pragma("unroll") for (int k = 0; k < KW; k++) cand[k] = src[k * NT];                                \
+                _Pragma("unroll") for (int k = 0; k < KW; k++) {                                                     \
+                    uint32_t nv;                                                                                     \
+                    if (k < MK) {                                                                                    \
+                        uint32_t t = add_u16x2(cand[k], pp);                                                         \
+                        if (tid + k * NT < wp.x) t &= 0xffff0000u;     /* cell j < w: the item does not fit */       \
+                        nv = max_u16x2(t, val[k]);                                                                   \
+                    } else {                                                                                         \
+                        nv = __viaddmax_u16x2(cand[k], pp, val[k]);     /* DPX: max(cand + p, val), both halves */   \
+                    }                                                                                                \
+                    /* improved halves differ by 1..32767: + 0x7fff sets bit 15 of exactly those (no carries) */     \
+                    const uint32_t y = nv - val[k] + 0x7fff7fffu;                                                    \
+                    acc[k] = (acc[k] >> 1) | (y & 0x80008000u);                                                      \
+                    val[k] = nv;                                                                                     \
+                    (NXT)[tid + k * NT] = nv;                                                                        \
+                    if (k >= KW - MK)                                   /* words [H - P, H): mirror the low half */  \
+                        reinterpret_cast<unsigned short *>((NXT) + (tid + k * NT - H))[1] = (unsigned short)nv;      \
+                }                                                                                                    \
+                if (tid == NT - 1 && val[KW - 1] > ((top_limit << 16) | 0xffffu) && (I) + 1 < n) sdp[(I) + 1].x = -1; \
+                __syncthreads();                                                                                     \
             }
+            // flush `cnt` items' take bits of group G (item j of the group -> bit j of each half), coalesced
+#define SMZ_DP16_FLUSH(G, CNT)                                                                                        \
+            {                                                                                                        \
+                uint32_t *dst = bits + (int64_t)(G) * H + tid;                                                       \
+                const int sh = 16 - (CNT);                                                                           \
+                const uint32_t m = (0xffffu >> sh) * 0x10001u;                                                       \
+                _Pragma("unroll") for (int k = 0; k < KW; k++) { dst[k * NT] = (acc[k] >> sh) & m; acc[k] = 0u; }    \
+            }
+            int i = 0;
+            for (; i + 1 < n; i += 2) {                     // two items per trip: the rows (and the registers) ping-pong
+                SMZ_DP16_STEP(row0, row1, i)
+                SMZ_DP16_STEP(row1, row0, i + 1)
+                if ((i & 15) == 14) SMZ_DP16_FLUSH(i >> 4, 16)
+            }
+            if (!aborted && i < n) {
+                do { SMZ_DP16_STEP(row0, row1, i) } while (0);
+            }
+            if (!aborted && (n & 15)) SMZ_DP16_FLUSH((n - 1) >> 4, n & 15)
+#undef SMZ_DP16_STEP
+#undef SMZ_DP16_FLUSH
             if (aborted) mode = 3;
             __syncthreads();   // take bits visible to warp 0
             // KnapsackDynamicProgrammingSolver::Solve extraction loop (see dp_kernel)
@@ -1230,7 +1318,15 @@ static int select_launch(const smz_video_desc *desc, int n_videos, const float *
         SMZ_REQUIRE(method == SMZ_METHOD_KNAPSACK || seg_mean != nullptr, "seg_mean output is required by method 'rank'");
         const int tiles = (max_n_segs + POOL_THREADS / 8 - 1) / (POOL_THREADS / 8);
         const int64_t frame_bytes = ((int64_t)max_n_frames + 1) / 2 * 4;      // one 16-bit score index per frame
-        if (tiles > 0 && frame_bytes <= smz::max_smem_optin() - 1024 && max_n_frames < 65535) {
+        int max_intervals = max_n_frames + 1 < 12288 ? max_n_frames + 1 : 12288;          // staged scores per CTA, with the
+        if (max_intervals + 4 * max_n_segs > 12288) max_intervals = 12288 - 4 * max_n_segs > 0 ? 12288 - 4 * max_n_segs : 0;   // segment lists <= 48 KB
+        if (tiles > 0 && max_n_segs <= 2048 && !getenv("SMZ_NO_POOL_REGULAR")) {
+            for (int v0 = 0; v0 < n_videos; v0 += 65535) {
+                const int nv = n_videos - v0 < 65535 ? n_videos - v0 : 65535;
+                pool_regular_kernel<<<nv, POOL_REG_THREADS, ((size_t)max_intervals + 4 * (size_t)max_n_segs) * sizeof(float), st>>>(
+                    desc, v0, scores, picks, cps, max_intervals, seg_mean, values, status);
+            }
+        } else if (tiles > 0 && frame_bytes <= smz::max_smem_optin() - 1024 && max_n_frames < 65535) {
             { int unused = 0; const int rc2 = cached_occupancy((const void *)pool_smem_kernel, POOL_SMEM_THREADS, (int)frame_bytes, &unused); if (rc2 != SMZ_OK) return rc2; }
             pool_smem_kernel<<<n_videos, POOL_SMEM_THREADS, (size_t)frame_bytes, st>>>(desc, 0, scores, picks, cps, seg_mean,
                                                                                      values, status);

@@ -16,20 +16,27 @@ from ..rankcorr import CorrBatch
 from ..utils.eval import evaluate_scores, evaluate_summary, generate_scores, generate_summary  # noqa: F401 (reference surface)
 
 
+def h5_file(path, mode):
+    """``h5py.File`` when h5py is installed, else this package's own HDF5 reader / writer (utils/hdf5.py): same
+    ``keys() / [] / create_group / create_dataset`` subset, same bytes on disk."""
+    try:
+        import h5py
+        return h5py.File(path, mode)
+    except ImportError:
+        from ..utils import hdf5
+        return hdf5.File(path, mode)
+
+
 def open_dataset(path, log=None):
-    """``h5py.File(path, "r")`` when the file and h5py exist (models/__init__.py:15); otherwise the seeded
-    synthetic dataset of the same shape (SumMe-/TVSum-shaped) — the real files are not
-    distributable and this image has no h5py."""
+    """``h5py.File(path, "r")`` as models/__init__.py:15 (through the built-in HDF5 reader when h5py is not installed);
+    when the file does not exist, the seeded synthetic dataset of the same shape (SumMe-/TVSum-shaped)
+    — the real files are not distributable."""
     if os.path.exists(path):
-        try:
-            import h5py
-            return h5py.File(path, "r")
-        except ImportError:
-            pass
+        return h5_file(path, "r")
     for name in ("summe", "tvsum"):
         if name in os.path.basename(path).lower():
             if log is not None:
-                log.warning(f"{path}: not readable here (file or h5py missing) -> seeded synthetic {name}-shaped dataset")
+                log.warning(f"{path}: file not found -> seeded synthetic {name}-shaped dataset")
             return synthetic.make_dataset(name)
     raise FileNotFoundError(f"dataset {path} not found and no synthetic stand-in is defined for it")
 
@@ -345,8 +352,10 @@ class Trainer:
             self.hps.writer.add_histogram(f"{self.dataset_name}/Fold_{fold+1}/Train/final_scores", scores, i)
 
     def predict_dataset(self, pred_path):
-        """Predict on all videos of the dataset (models/__init__.py:142-177).  Written as HDF5 when h5py is
-        importable, otherwise as an .npz with the same group/key/field names joined by '/'."""
+        """Predict on all videos of the dataset (models/__init__.py:142-177): ``<pred_path>`` is an HDF5 file with one
+        group per dataset file (its basename) holding, per video key, ``scores``, ``user_summary``,
+        ``machine_summary`` and ``machine_scores`` — written with h5py when it is installed, else with the built-in
+        writer (utils/hdf5.py); summary.py:40-43 reads it back either way."""
         self.model.load_state_dict(self.best_weights)
         self.model.eval()
         keys = list(self.dataset.keys())
@@ -357,21 +366,16 @@ class Trainer:
         machine_scores = batch.upsample(packed)
         batch.check_status()
         group = os.path.basename(self.hps.dataset_of_file[self.splits_file])
-        out, fo = {}, 0
-        for i, key in enumerate(keys):
-            n_frames = int(batch.h_desc[i]["n_frames"])
-            out[f"{group}/{key}/scores"] = scores[i].cpu().numpy()
-            out[f"{group}/{key}/user_summary"] = np.asarray(self.dataset[key]["user_summary"][...])
-            out[f"{group}/{key}/machine_summary"] = batch.summary_of(i).cpu().numpy()
-            out[f"{group}/{key}/machine_scores"] = machine_scores[fo:fo + n_frames].cpu().numpy()
-            fo += n_frames
-        try:
-            import h5py
-            with h5py.File(pred_path, "w") as f:
-                for name, arr in out.items():
-                    f.create_dataset(name, data=arr)
-        except ImportError:
-            np.savez_compressed(pred_path + ".npz", **out)
+        with h5_file(pred_path, "w") as f:
+            d, fo = f.create_group(group), 0
+            for i, key in enumerate(keys):
+                n_frames = int(batch.h_desc[i]["n_frames"])
+                k = d.create_group(key)
+                k.create_dataset("scores", data=scores[i].cpu().numpy())
+                k.create_dataset("user_summary", data=np.asarray(self.dataset[key]["user_summary"][...]))
+                k.create_dataset("machine_summary", data=batch.summary_of(i).cpu().numpy())
+                k.create_dataset("machine_scores", data=machine_scores[fo:fo + n_frames].cpu().numpy())
+                fo += n_frames
 
     def save_best_weights(self, weights_path):
         if self.best_weights is None:

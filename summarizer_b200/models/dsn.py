@@ -135,6 +135,11 @@ class DSNTrainer(Trainer):
         self._reward_ws = _Workspace()
         return DSN()
 
+    def _draw_actions(self, dist):
+        """The frame selections of all episodes of a step (dsn.py:124-126 draws them one ``dist.sample()`` at a time):
+        (num_episodes, T, 1, 1) float 0/1.  A method so that tests can replay the reference's draws."""
+        return dist.sample((self.num_episodes,))
+
     def compute_reward(self, seq, actions, far_sim=False, temp_dist_thre=20):
         """One episode (reference signature, dsn.py:185): seq (T,1,1024), actions (T,1,1) -> scalar tensor."""
         return compute_rewards(seq.reshape(-1, 1024), actions.reshape(1, -1), far_sim, temp_dist_thre, self._reward_ws)[0]
@@ -180,7 +185,7 @@ class DSNTrainer(Trainer):
             loss = self.beta * (probs.mean() - self.eps) ** 2                 # summary-length penalty [Eq.11]
             if self.sup:
                 loss = loss + loss_BCE(probs, target)
-            actions = dist.sample((self.num_episodes,))                       # (E,T,1,1): the E episodes in one draw
+            actions = self._draw_actions(dist)                                # (E,T,1,1): the E episodes in one draw
             rewards = compute_rewards(seq, actions.reshape(self.num_episodes, -1), self.far_sim, self.temp_dist_thre,
                                       self._reward_ws)
             base = baselines[key_index[key]].detach().clone()

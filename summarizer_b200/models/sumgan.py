@@ -18,6 +18,26 @@ from ..dense import linear
 from .lstm_stack import ShadowCache, lstm_decode, lstm_stack
 
 
+class NoiseSource:
+    """Where the trainer's random tensors come from (sumgan.py:134 reparameterisation noise, :177 uniform scores,
+    :466-468 discriminator input noise).  Default: torch's generator of the tensor's device.  ``begin(phase)`` is
+    called at the start of every phase ("pretrain", "p1" selector/encoder, "p2" decoder, "p3" discriminator) and
+    ``role`` names the draw inside it ("eps" / "eps_p": VAE noise of x_hat / x_hat_p, "uniform", "noise_x",
+    "noise_x_hat", "noise_x_hat_p"), so that tests can replay the reference's draws one for one."""
+
+    def begin(self, phase):
+        pass
+
+    def randn_like(self, t, role):
+        return torch.randn_like(t)
+
+    def rand_like(self, t, role):
+        return torch.rand_like(t)
+
+
+noise = NoiseSource()
+
+
 def _require_cuda(x, what):
     if not x.is_cuda:
         raise N.NativeError(f"summarizer_b200.{what} runs on a CUDA (sm_100a) device only; move the input with .cuda()")
@@ -94,15 +114,18 @@ class VAE(nn.Module):
         self.e_lstm = eLSTM(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers)
         self.d_lstm = dLSTM(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers)
 
-    def reparameterize(self, mu, logvar):
+    def reparameterize(self, mu, logvar, roles=None):
         std = torch.exp(0.5 * logvar)
-        eps = torch.randn_like(std)
+        if roles is None:
+            eps = noise.randn_like(std, "eps")
+        else:       # sequences batched along dim 1 draw their noise separately, in the reference's order
+            eps = torch.cat([noise.randn_like(std[:, b:b + 1], r) for b, r in enumerate(roles)], 1)
         return mu + eps * std
 
-    def forward(self, x):
+    def forward(self, x, roles=None):
         """x: (seq_len, B, input_size) -> x_hat (seq_len, B, input_size), (h_mu, h_logvar)"""
         (h_mu, h_logvar), c = self.e_lstm(x)
-        h = self.reparameterize(h_mu, h_logvar)
+        h = self.reparameterize(h_mu, h_logvar, roles)
         x_hat = self.d_lstm(x.size(0), h, c)
         return x_hat, (h_mu, h_logvar)
 
@@ -119,7 +142,7 @@ class Summarizer(nn.Module):
         """-> x_hat (seq_len, B, input_size), (h_mu, h_logvar), scores (seq_len, B, 1)"""
         if uniform:
             seq_len, batch_size, _ = x.size()
-            scores = torch.rand((seq_len, batch_size, 1)).to(x.device)
+            scores = noise.rand_like(x[:, :, :1], "uniform")
         else:
             scores = self.s_lstm(x)
         x_weighted = x * scores
@@ -285,6 +308,7 @@ class SumGANTrainer(Trainer):
             losses = []
             for key, n_active in self._groups(train_keys, dp, rank, world):
                 loss_vae = None
+                noise.begin("pretrain")
                 if key is not None:
                     x, _ = self._video_tensors(key)
                     x_hat, (mu, logvar) = self.model.summarizer.vae(x)
@@ -315,6 +339,7 @@ class SumGANTrainer(Trainer):
         # the reference's separate calls (sumgan.py:419-421, 442-446, 463-471).
         # ---- selector and encoder
         loss_s_e = None
+        noise.begin("p1")
         if not idle:
             x_hat, (mu, logvar), scores = m.summarizer(x)
             _, h = m.gan(torch.cat([x, x_hat], 1))
@@ -325,11 +350,12 @@ class SumGANTrainer(Trainer):
         def both_reconstructions():
             """x_hat from the selector's scores and x_hat_p from uniform random scores (Summarizer.forward twice)."""
             scores = m.summarizer.s_lstm(x)
-            uniform = torch.rand_like(scores)
-            x_pair, _ = m.summarizer.vae(torch.cat([x * scores, x * uniform], 1))
+            uniform = noise.rand_like(scores, "uniform")
+            x_pair, _ = m.summarizer.vae(torch.cat([x * scores, x * uniform], 1), roles=("eps", "eps_p"))
             return x_pair[:, 0:1], x_pair[:, 1:2], scores
         # ---- decoder
         loss_d = None
+        noise.begin("p2")
         if not idle:
             x_hat, x_hat_p, _ = both_reconstructions()
             probs, h = m.gan(torch.cat([x, x_hat, x_hat_p], 1))
@@ -337,13 +363,14 @@ class SumGANTrainer(Trainer):
         self._update(self.d_optimizer, loss_d, dp, n_active)
         # ---- discriminator
         loss_c = None
+        noise.begin("p3")
         if not idle:
             x_hat, x_hat_p, scores = both_reconstructions()
             x_in = x
             if epoch < self.epoch_noise:
-                x_in = torch.randn_like(x) * x
-                x_hat = x_hat * torch.randn_like(x_hat)
-                x_hat_p = x_hat_p * torch.randn_like(x_hat_p)
+                x_in = noise.randn_like(x, "noise_x") * x
+                x_hat = x_hat * noise.randn_like(x_hat, "noise_x_hat")
+                x_hat_p = x_hat_p * noise.randn_like(x_hat_p, "noise_x_hat_p")
             probs, _ = m.gan(torch.cat([x_in, x_hat, x_hat_p], 1))
             probs_real, probs_fake, probs_uniform = probs[0:1], probs[1:2], probs[2:3]
             loss_c = self.loss_gan_discriminator(probs_real, probs_fake, probs_uniform)

@@ -135,6 +135,26 @@ def make_dataset(dataset, n_videos=None, **kw):
     return ArrayDataset({f"video_{i}": make_video(dataset, i, **kw) for i in range(1, n_videos + 1)}, name=dataset)
 
 
+def write_dataset_h5(dataset, path):
+    """Writes an ``ArrayDataset`` as an HDF5 file with the schema of datasets/README.md:5-42 (one group per video key,
+    scalars as 0-d datasets, ``video_name`` as a string) — with h5py when it is installed, else with utils/hdf5.py."""
+    try:
+        import h5py
+        opener = h5py.File
+    except ImportError:
+        from .utils import hdf5
+        opener = hdf5.File
+    with opener(path, "w") as f:
+        for key in dataset.keys():
+            g = f.create_group(key)
+            for name in dict.keys(dataset[key]):
+                val = dataset[key].raw(name)
+                g.create_dataset(name, data=np.bytes_(val) if isinstance(val, str) else val)
+            if "video_name" not in dataset[key]:
+                g.create_dataset("video_name", data=np.bytes_(f"{dataset.name}_{key}"))
+    return path
+
+
 # ----------------------------------------------------------------------------------------------
 # sweep (config 5): 10k videos x 2000 steps (30 000 frames), 20 annotators — generated ON the device
 # ----------------------------------------------------------------------------------------------

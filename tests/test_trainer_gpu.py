@@ -57,9 +57,26 @@ def test_cross_validation_run_end_to_end(tmp_path):
     for _, corr, avg_f, max_f in results:
         assert np.isfinite([corr, avg_f, max_f]).all() and 0 <= avg_f <= max_f <= 1
     import os
+    from oracle import c_oracle
+    from summarizer_b200.models import h5_file, open_dataset
     for sf in hps.splits_files:
         assert os.path.exists(hps.weights_path[sf])
-        assert os.path.exists(hps.pred_path[sf]) or os.path.exists(hps.pred_path[sf] + ".npz")
+        # <split>_preds.h5 (models/__init__.py:142-177): group = dataset file name, per key the four fields; the stored
+        # machine summary is what the oracle's generate_summary makes of the stored scores
+        ds = open_dataset(hps.dataset_of_file[sf])
+        with h5_file(hps.pred_path[sf], "r") as f:
+            g = f[os.path.basename(hps.dataset_of_file[sf])]
+            assert sorted(g.keys()) == sorted(ds.keys())
+            for key in list(ds.keys())[:6]:
+                k, d = g[key], ds[key]
+                assert sorted(k.keys()) == ["machine_scores", "machine_summary", "scores", "user_summary"]
+                sc = k["scores"][...]
+                assert sc.dtype == np.float32 and sc.shape == (d["picks"][...].shape[0],)
+                assert np.array_equal(k["user_summary"][...], d["user_summary"][...])
+                ref_sum, _ = c_oracle.generate_summary(sc, d["change_points"][...], int(d["n_frames"][()]),
+                                                       d["n_frame_per_seg"][...], d["picks"][...])
+                assert np.array_equal(k["machine_summary"][...], ref_sum)
+                assert k["machine_scores"][...].shape == (int(d["n_frames"][()]),)
     sd = torch.load(hps.weights_path[hps.splits_files[0]])
     assert "attention_head_projection.weight" in sd and sd["k2.weight"].shape == (1, 1024)
 
