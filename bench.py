@@ -414,7 +414,7 @@ def run_native(args):
     f_score_stage = V * flops_vasnet_fwd(N_STEPS)
 
     def step(ev=None):
-        scores = model.score_packed(feats, lengths)
+        scores = model.score_packed(feats, lengths, check=False)     # range status: read once, behind the timed region
         if ev is not None:
             ev[0].record(stream)
         # shot selection + F-score in one library call: the persistent CTA that solved a video's knapsack (shared-memory
@@ -427,6 +427,8 @@ def run_native(args):
     for _ in range(args.warmup):
         step()
     batch.check_status()
+    if not model.check_status():
+        raise RuntimeError("the fast scoring path left its checked value range on the synthetic sweep")
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -442,6 +444,8 @@ def run_native(args):
     t_end.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    if not model.check_status():
+        raise RuntimeError("the fast scoring path left its checked value range inside the timed region")
     ms = t_start.elapsed_time(t_end)
     score_ms = float(np.mean([e[3].elapsed_time(e[0]) for e in evs]))
     eval_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
@@ -473,6 +477,7 @@ def run_native(args):
     h_users = torch.empty(sets[0]["eb"].d_users.shape, dtype=torch.float32, pin_memory=True); h_users.copy_(sets[0]["eb"].d_users)
     h_feats = torch.empty((ne * N_STEPS, FEAT), dtype=torch.bfloat16, pin_memory=True); h_feats.copy_(feats[: ne * N_STEPS])
     h_out = torch.empty((2, 2, ne), dtype=torch.float64, pin_memory=True)
+    h_status = torch.zeros((2, 1), dtype=torch.int32, pin_memory=True)
     copy_stream = torch.cuda.Stream(device=dev)
     for st_ in sets:
         st_["done"].record(stream)
@@ -509,9 +514,10 @@ def run_native(args):
                 st_["eb"].d_users.copy_(h_users, non_blocking=True)
             st_["ready"].record(copy_stream)
         stream.wait_event(st_["ready"])
-        sc = model.score_packed(st_["d_feats"], le)
+        sc = model.score_packed(st_["d_feats"], le, check=False)
         st_["eb"].evaluate(sc, d_bits=st_["d_bits"] if packed else None)
         h_out[i & 1, 0].copy_(st_["eb"].avg_f[:ne], non_blocking=True); h_out[i & 1, 1].copy_(st_["eb"].max_f[:ne], non_blocking=True)
+        h_status[i & 1].copy_(model._status, non_blocking=True)   # the scorer's range status travels with the step's results
         st_["done"].record(stream)
 
     def e2e_run(packed):
@@ -535,6 +541,8 @@ def run_native(args):
         te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        if int(h_status.max()) != 0:
+            raise RuntimeError("the fast scoring path left its checked value range in the e2e loop")
         return ne * world * args.steps / (te.item() / 1e3), h_out.clone()
 
     e2e_float, out_float = e2e_run(False)
@@ -591,7 +599,7 @@ def run_native(args):
                               "eval_path_frac_serial": (b_eval / ((select_ms + fscore_ms) / 1e3) / 1e9) / hbm},
             "e2e": {"value": e2e_value, "unit": "videos/s",
                     "h2d_bytes_per_step": int(h_feats.numel() * 2 + users_bytes),
-                    "d2h_bytes_per_step": int(2 * ne * 8), "videos_per_step": ne,
+                    "d2h_bytes_per_step": int(2 * ne * 8 + 4), "videos_per_step": ne,
                     "pipelining": "two buffer sets: step i+1 H2D on a copy stream overlaps step i kernels",
                     "annotator_staging": ("packed on %d host threads to 1 bit/frame inside the timed region (x > 0 is all "
                                           "evaluate_summary reads)" % host_threads) if use_packed else "float32 rows as held by the reference",

@@ -171,6 +171,9 @@ int smz_rank_correlation(const smz_corr_desc *desc, int n_videos, int max_n_fram
 #define SMZ_GEMM_RELU 2
 #define SMZ_GEMM_RES_F32 4
 #define SMZ_GEMM_BIAS_M 8
+#define SMZ_GEMM_OUT_F16 2048   /* C is float16 (IEEE half) instead of bfloat16 */
+#define SMZ_GEMM_A_F16 4096     /* A holds float16 instead of bfloat16 (the formats of A and B are independent) */
+#define SMZ_GEMM_B_F16 8192     /* B holds float16 */
 int smz_gemm_bf16_tn(const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc, int M, int N,
                      int K, float alpha, const float *bias, const void *residual, int64_t ldr, int flags,
                      void *stream);
@@ -194,6 +197,8 @@ int smz_gemm_bf16(int a_mn, int b_mn, const void *A, int64_t lda, const void *B,
  *   LayerNorm the reference applies twice, vasnet.py:54,137,143)
  * scale multiplies the logits (vasnet.py:34,119); aperture < 0 = global attention, else the band
  * |i-j| <= aperture of vasnet.py:124-127; ignore_self masks the diagonal (vasnet.py:121-122). */
+#define SMZ_VASNET_STATUS_LOGIT_RANGE 1   /* an attention logit left [-80, 80] */
+#define SMZ_VASNET_STATUS_F16_RANGE 2     /* a float16 activation (V, attention output, y) exceeded the float16 range */
 typedef struct smz_vasnet_params {
     const void *wqk, *wv, *wo, *w1;
     const float *b1, *w2, *b2, *ln_g, *ln_b;
@@ -203,6 +208,23 @@ typedef struct smz_vasnet_params {
      * (float32, device).  When both are given the regressor head (vasnet.py:143-145) is folded into the k1
      * GEMM epilogue and the hidden activations never reach memory; NULL keeps the separate head kernel. */
     const float *head_gw, *head_c;
+    /* optional (inference, fast path): the first LayerNorm (vasnet.py:137) folded into k1,
+     *   W1 . LN(y) + b1 = rstd * (W1g . y - mean * ln_c) + b1f
+     * with w1g [1024,1024] = float16(k1.weight * ln_g[None, :]), ln_c [1024] = row sums of w1g (of the float16
+     * values, float32) and b1f [1024] = k1.weight . ln_b + k1.bias (float32).  Then the output projection writes y as
+     * float16 with its per-row sum / sum of squares and no LayerNorm kernel runs; NULL keeps the separate kernel. */
+    const void *w1g;
+    const float *ln_c, *b1f;
+    /* optional (inference), all required together with head_gw .. b1f for the FAST path: float16 copies of [Wq; Wk; Wv]
+     * ([3072,1024]) and of the output projection, and a device status word.  The fast path computes softmax without the
+     * max subtraction (exp and row sums in the logits epilogue) and keeps V, the attention output, y and their weights
+     * in float16 (3 more mantissa bits than bf16: the golden-vector error drops 5-10x).  Both are exact reformulations
+     * inside a value range the kernels check: a violation ORs SMZ_VASNET_STATUS_* into *status (never cleared by the
+     * library), the scores of that call are void, and the caller repeats the call with status = NULL (the wide-range
+     * path: bf16 everywhere, fp32 logits, max-subtracted softmax, LayerNorm kernel).  The host reads the word
+     * whenever it next synchronises — no launch waits on it. */
+    const void *wqkv16, *wo16;
+    int32_t *status;
 } smz_vasnet_params;
 
 /* x: packed features [sum T, 1024] (float32, or bfloat16 when x_is_bf16), video v owns rows
@@ -213,12 +235,11 @@ typedef struct smz_vasnet_params {
  * NULL = no dropout at that site): drop_att packed per video [T*T], drop_y / drop_h [sum T, 1024]. */
 int smz_vasnet_workspace_bytes(const int32_t *h_cu_seqlens, int n_videos, int training, int x_is_bf16,
                                int64_t *bytes);
-/* Inference computes attention as exp(logit) / row sum straight out of the logits GEMM epilogue and falls back,
- * on the device, to the max-subtracted softmax when a |logit| exceeds 80.  on != 0 forces the fallback path for
- * every call of this process (testing / A-B aid). */
+/* on != 0 forces the exact inference path for every call of this process, status word or not (testing / A-B aid). */
 void smz_vasnet_set_exact_softmax(int on);
+/* kernels one forward call launches (reporting); training: 1 = training, 0 = fast inference, 2 = exact inference */
 int smz_vasnet_launch_count(const int32_t *h_cu_seqlens, int n_videos, int training, int x_is_bf16,
-                            int64_t *launches);   /* kernels one forward call launches (reporting) */
+                            int64_t *launches);
 int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h_cu_seqlens, int n_videos,
                        const smz_vasnet_params *p, int training, const uint8_t *drop_att, const uint8_t *drop_y,
                        const uint8_t *drop_h, float *scores, void *ws, int64_t ws_bytes, void *stream);

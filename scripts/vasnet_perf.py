@@ -14,11 +14,11 @@ def run(n_videos, T, dtype, iters=5):
     x = (x / x.norm(dim=1, keepdim=True)).to(dtype)
     lengths = [T] * n_videos
     for _ in range(2):
-        s = m.score_packed(x, lengths)
+        s = m.score_packed(x, lengths, check=False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record()
     for _ in range(iters):
-        s = m.score_packed(x, lengths)
+        s = m.score_packed(x, lengths, check=False)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     fl = n_videos * flops_fwd(T)

@@ -10,8 +10,8 @@ m = VASNet().cuda().eval()
 nv, T = 64, 2000
 x = torch.rand(nv * T, 1024, device="cuda"); x = (x / x.norm(dim=1, keepdim=True)).bfloat16()
 for _ in range(2):
-    m.score_packed(x, [T] * nv)
+    m.score_packed(x, [T] * nv, check=False)
 N.lib().smz_profile_report()          # discard warm-up
 for _ in range(5):
-    m.score_packed(x, [T] * nv)
+    m.score_packed(x, [T] * nv, check=False)
 N.lib().smz_profile_report()

@@ -160,7 +160,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ------------------------------------------------------------------ MMA issuer (leader CTA only)
         if (lane == 0 && rank == 0) {
             Cursor c;
-            const uint32_t idesc = make_idesc_bf16(TILE_M, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+            // operand format fields ([7,10) A, [10,13) B): 1 = bf16 (make_idesc_bf16's default), 0 = f16
+            const uint32_t idesc = (make_idesc_bf16(TILE_M, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u))
+                                   & ~(((P.epi.flags & smz::GEMM_A_F16) ? (1u << 7) : 0u) | ((P.epi.flags & smz::GEMM_B_F16) ? (1u << 10) : 0u));
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int tile = first_tile; tile < P.total_tiles; tile += tile_step, ++it) {
@@ -204,7 +206,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int as = it & 1;
             const int m = mt * TILE_M + rank * BM + row;
             const bool row_ok = m < g.M;
-            const float bias_m = (P.epi.bias != nullptr && (flags & smz::GEMM_BIAS_M) && !(flags & smz::GEMM_SCALE_M) && row_ok) ? __ldg(P.epi.bias + m) : 0.f;
+            const float bias_m = (P.epi.bias != nullptr && (flags & smz::GEMM_BIAS_M) && !(flags & (smz::GEMM_SCALE_M | smz::GEMM_SCALE_STATS)) && row_ok) ? __ldg(P.epi.bias + m) : 0.f;
             const bool out_f32 = flags & smz::GEMM_OUT_F32;
             const bool res_f32 = flags & smz::GEMM_RES_F32;
             const bool c_vec = ((g.c_off | (int64_t)g.ldc) & 7) == 0 && (reinterpret_cast<uintptr_t>(P.epi.C) & 15) == 0;
@@ -234,6 +236,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + b));
             }
             res_fetch(nt * BN + half * (BN / 2), rcur);
+            // per-row constants, fetched while the MMAs of this tile are still running
+            float row_scale = 1.f, ln_mean = 0.f, ln_rstd = 1.f;
+            if (EPI == EPI_PLAIN && row_ok && (flags & smz::GEMM_SCALE_M)) row_scale = __ldg(P.epi.bias + g.r_off + m);
+            if (EPI == EPI_PLAIN && row_ok && (flags & smz::GEMM_SCALE_STATS)) {
+                const float *sp = P.epi.bias + (g.r_off + m) * P.epi.stat_slots * 3;
+                float ssum = 0.f;
+                for (int k = 0; k < P.epi.stat_slots; k++) ssum += __ldg(sp + 3 * k);
+                row_scale = 1.f / ssum;       // a fully masked row: 1/0 = inf -> NaN scores, as torch's softmax of all -inf
+            }
+            if (EPI == EPI_HEAD && row_ok && (flags & smz::GEMM_LN_FOLD)) {
+                const float *sp = P.epi.ln_stats + (g.r_off + m) * P.epi.ln_slots * 3;
+                float s1 = 0.f, s2 = 0.f;
+                for (int k = 0; k < P.epi.ln_slots; k++) { s1 += __ldg(sp + 3 * k); s2 += __ldg(sp + 3 * k + 1); }
+                const float inv_w = 1.f / (float)P.epi.ln_width;
+                ln_mean = s1 * inv_w;
+                ln_rstd = rsqrtf(fmaxf(s2 * inv_w - ln_mean * ln_mean, 0.f) + P.epi.ln_eps);
+            }
             mbar_wait(&tfull[as], ((uint32_t)it >> 1) & 1u);
             tc_fence_after();
             for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
@@ -273,12 +292,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                     }
                 }
-                if (EPI == EPI_PLAIN && (flags & smz::GEMM_SCALE_M)) {
-                    const float sc = __ldg(P.epi.bias + g.r_off + m);
+                if (EPI == EPI_PLAIN && (flags & (smz::GEMM_SCALE_M | smz::GEMM_SCALE_STATS))) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) x[j] *= sc;
+                    for (int j = 0; j < 32; j++) x[j] *= row_scale;
                 }
-                if (EPI != EPI_EXP && P.epi.bias != nullptr && !(flags & smz::GEMM_SCALE_M)) {
+                if (EPI == EPI_HEAD && (flags & smz::GEMM_LN_FOLD)) {       // N is a multiple of 32 in this mode
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 cc = ld_f4(P.epi.ln_c + n0 + j);
+                        x[j] = ln_rstd * fmaf(-ln_mean, cc.x, x[j]); x[j + 1] = ln_rstd * fmaf(-ln_mean, cc.y, x[j + 1]);
+                        x[j + 2] = ln_rstd * fmaf(-ln_mean, cc.z, x[j + 2]); x[j + 3] = ln_rstd * fmaf(-ln_mean, cc.w, x[j + 3]);
+                    }
+                }
+                if (EPI != EPI_EXP && P.epi.bias != nullptr && !(flags & (smz::GEMM_SCALE_M | smz::GEMM_SCALE_STATS))) {
                     if (flags & smz::GEMM_BIAS_M) {
 #pragma unroll
                         for (int j = 0; j < 32; j++) x[j] += bias_m;
@@ -326,6 +352,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                     for (int j = 0; j < 32; j++) x[j] = fmaxf(x[j], 0.f);
                 }
+                const bool f16 = EPI == EPI_PLAIN && (flags & smz::GEMM_OUT_F16) && n0 >= P.epi.f16_col0;     // warp-uniform
+                if (f16 && !(flags & smz::GEMM_LN_STATS)) {     // range check (with GEMM_LN_STATS the sum of squares does it)
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) amax = fmaxf(amax, fmaxf(fabsf(x[j]), fabsf(x[j + 1])));
+                }
+                if (EPI == EPI_PLAIN && (flags & smz::GEMM_LN_STATS)) {      // N is a multiple of 32 in this mode
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        st1 += (x[j] + x[j + 1]) + (x[j + 2] + x[j + 3]);
+                        st2 = fmaf(x[j], x[j], st2); st2 = fmaf(x[j + 1], x[j + 1], st2);
+                        st2 = fmaf(x[j + 2], x[j + 2], st2); st2 = fmaf(x[j + 3], x[j + 3], st2);
+                    }
+                }
                 if constexpr (EPI == EPI_HEAD) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -360,9 +399,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if (full32 && c_vec) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8)
-                            *reinterpret_cast<uint4 *>(dst + j) =
+                            *reinterpret_cast<uint4 *>(dst + j) = f16 ?
+                                make_uint4(pack_f16x2(x[j], x[j + 1]), pack_f16x2(x[j + 2], x[j + 3]),
+                                           pack_f16x2(x[j + 4], x[j + 5]), pack_f16x2(x[j + 6], x[j + 7])) :
                                 make_uint4(pack_bf16x2(x[j], x[j + 1]), pack_bf16x2(x[j + 2], x[j + 3]),
                                            pack_bf16x2(x[j + 4], x[j + 5]), pack_bf16x2(x[j + 6], x[j + 7]));
+                    } else if (f16) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) if (n0 + j < g.N) reinterpret_cast<__half *>(dst)[j] = __float2half_rn(x[j]);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; j++) if (n0 + j < g.N) dst[j] = __float2bfloat16_rn(x[j]);
@@ -382,12 +426,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                 for (int j = 0; j < 8; j++) rcur[j] = rnext[j];
             }
-            if (EPI != EPI_PLAIN && row_ok) {
+            if ((EPI != EPI_PLAIN || (flags & smz::GEMM_LN_STATS)) && row_ok) {
                 const int slots = P.epi.stat_slots > 0 ? P.epi.stat_slots : 2 * g.tiles_n;
                 float *so = P.epi.stat_out + ((g.r_off + m) * slots + (nt * 2 + half)) * 3;
                 so[0] = st1; so[1] = st2; so[2] = st3;
             }
-            if (do_exp && P.epi.guard != nullptr && !(amax <= 80.f)) atomicOr(P.epi.guard, 1);   // also catches NaN
+            if (do_exp && P.epi.guard != nullptr && !(amax <= 80.f)) atomicOr(P.epi.guard, P.epi.guard_bit);   // also catches NaN
+            // float16 range: sum x^2 < 60000^2 bounds every |x| of the slot (conservative: tripping it costs a repeat on the
+            // exact path, never a wrong result)
+            if (EPI == EPI_PLAIN && (flags & smz::GEMM_OUT_F16) && P.epi.guard != nullptr && row_ok &&
+                !(((flags & smz::GEMM_LN_STATS) ? st2 : amax * amax) <= 3.6e9f))
+                atomicOr(P.epi.guard, P.epi.guard_bit);
             tc_fence_before();
             if (PAIR) mbar_arrive_remote(&tempty[as], 0); else mbar_arrive(&tempty[as]);
         }

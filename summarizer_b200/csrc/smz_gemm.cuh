@@ -32,6 +32,17 @@ enum : int {
                          // multiple of 64 (un-normalised softmax numerators; the row sums come from GEMM_ROWSTATS).
                          // |logit| > 80 anywhere raises *guard (the caller then re-runs the exact max-subtracted path)
     GEMM_SCALE_M = 128,  // x *= bias[r_off + m]  (row scale, e.g. 1 / softmax denominator) instead of adding a bias
+    GEMM_SCALE_STATS = 256,  // x *= 1 / sum_k bias[((r_off + m) * stat_slots + k) * 3]: the row scale straight from the
+                         // GEMM_ROWSTATS slots of the producer (softmax denominators: no kernel in between)
+    GEMM_LN_STATS = 512, // plain epilogue + per row and (n-tile, column half) slot: sum x, sum x^2 of the OUTPUT x
+                         // -> stat_out[((r_off + m) * stat_slots + slot) * 3 + {0,1}] (LayerNorm statistics for the consumer)
+    GEMM_OUT_F16 = 2048, // columns >= f16_col0 of C are float16 (IEEE half) instead of bf16: 3 more mantissa bits for an
+                         // activation whose range is checked — |x| > 60000 raises guard_bit in *guard
+    GEMM_A_F16 = 4096,   // the A operand holds float16 instead of bf16 (tcgen05 kind::f16 takes either format per operand)
+    GEMM_B_F16 = 8192,   // the B operand holds float16
+    GEMM_LN_FOLD = 1024, // head epilogue whose A operand is the un-normalised LayerNorm input y (bf16 / f16) and whose B is
+                         // W * diag(gamma): x = rstd_m * (acc - mean_m * ln_c[n]) + bias[n], mean / rstd of row m from the
+                         // GEMM_LN_STATS slots in ln_stats (ln_slots per row, rows of ln_width elements, eps ln_eps)
 };
 
 struct GemmEpilogue {
@@ -44,8 +55,14 @@ struct GemmEpilogue {
     float *stat_out = nullptr;       // GEMM_ROWSTATS: [(r_off + m)][stat_slots][3] (r_off doubles as the row offset here)
     int stat_slots = 0;              // slots per row (>= 2 * tiles_n); 0 = 2 * tiles_n of the problem
     int aperture = -1, ignore_self = 0;   // GEMM_EXP: VASNet's masks (vasnet.py:121-127), row / column = video-local i / j
-    int *guard = nullptr;            // GEMM_EXP: set to 1 when a logit leaves [-80, 80]
+    int *guard = nullptr;            // GEMM_EXP: |= guard_bit when a logit leaves [-80, 80]; GEMM_OUT_F16: when |x| > 60000
+    int guard_bit = 1;
+    int f16_col0 = 0;                // GEMM_OUT_F16: first float16 column (a multiple of 32)
     const int *gate = nullptr;       // when given: the whole launch is a no-op unless *gate != 0
+    const float *ln_stats = nullptr; // GEMM_LN_FOLD: [(m)][ln_slots][3] sums written by a GEMM_LN_STATS producer
+    const float *ln_c = nullptr;     // GEMM_LN_FOLD: [N] row sums of the B operand (W * diag(gamma)) as the tensor core sees it
+    int ln_slots = 0, ln_width = 0;
+    float ln_eps = 0.f;
 };
 
 constexpr int GEMM_BN = 256;

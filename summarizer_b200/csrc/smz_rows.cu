@@ -1,6 +1,7 @@
 // Row-wise kernels of the scorers: softmax with VASNet's masks (vasnet.py:121-130), LayerNorm
 // (vasnet.py:137,143), regressor head k2 + sigmoid (vasnet.py:144-145), fp32 -> bf16 conversion.
 // One warp per row, 128-bit accesses, fp32 arithmetic.  All of them are L2/HBM-bandwidth bound.
+#include <cuda_fp16.h>
 #include "smz_rows.cuh"
 
 #include <math.h>
@@ -40,6 +41,26 @@ __global__ void cvt_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__re
     }
 }
 
+// float32 -> float16 with a range check: |x| > 60000 (or NaN) ORs `bit` into *guard
+__global__ void cvt_f16_kernel(const float *__restrict__ x, __half *__restrict__ y, int64_t n, int *__restrict__ guard, int bit) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    float amax = 0.f;
+    if (i + 8 <= n) {
+        const float4 a = *reinterpret_cast<const float4 *>(x + i);
+        const float4 b = *reinterpret_cast<const float4 *>(x + i + 4);
+        amax = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                     fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+        if (!(a.x == a.x && a.y == a.y && a.z == a.z && a.w == a.w && b.x == b.x && b.y == b.y && b.z == b.z && b.w == b.w)) amax = INFINITY;
+        const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+        const __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+        *reinterpret_cast<uint4 *>(y + i) = make_uint4(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1),
+                                                       *reinterpret_cast<const uint32_t *>(&h2), *reinterpret_cast<const uint32_t *>(&h3));
+    } else {
+        for (int64_t j = i; j < n; j++) { y[j] = __float2half_rn(x[j]); amax = (x[j] == x[j]) ? fmaxf(amax, fabsf(x[j])) : INFINITY; }
+    }
+    if (guard != nullptr && !(amax <= 60000.f)) atomicOr(guard, bit);
+}
+
 // up to 8 float32 -> bfloat16 conversions in one launch (the parameter copies of a training step): blockIdx.y = segment
 struct CvtSegments { const float *src[8]; __nv_bfloat16 *dst[8]; long long n[8]; };
 __global__ void cvt_bf16_segments_kernel(const CvtSegments seg) {
@@ -76,12 +97,13 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 softmax_kernel(const GemmProblem *__restrict__ probs, int n_probs, int total_rows, const float *__restrict__ S,
                __nv_bfloat16 *__restrict__ alpha, __nv_bfloat16 *__restrict__ P, const uint8_t *__restrict__ drop,
                const int64_t *__restrict__ drop_off, int aperture, int ignore_self, const int *__restrict__ gate,
-               float *__restrict__ inv_l) {
+               float *__restrict__ sum_slots, int n_slots) {
     if (gate != nullptr && __ldg(gate) == 0) return;
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     if (r >= total_rows) return;
-    if (inv_l != nullptr && lane == 0) inv_l[r] = 1.f;     // P is normalised here: alpha.V applies no further row scale
+    if (sum_slots != nullptr)       // P is normalised here: the row-sum slots alpha.V scales by (GEMM_SCALE_STATS) become {1, 0, ...}
+        for (int k = lane; k < n_slots; k += 32) sum_slots[((int64_t)r * n_slots + k) * 3] = k == 0 ? 1.f : 0.f;
     int lo = 0, hi = n_probs - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -291,14 +313,6 @@ __global__ void head_from_stats_kernel(const float *__restrict__ stats, int slot
     scores[r] = 1.f / (1.f + __expf(-z));
 }
 
-__global__ void rowsum_finish_kernel(const float *__restrict__ stats, int slots, int rows, float *__restrict__ inv_l) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= rows) return;
-    float s = 0.f;
-    for (int k = 0; k < slots; k++) s += stats[((int64_t)r * slots + k) * 3];
-    inv_l[r] = 1.f / s;           // a fully masked row: 1/0 = inf -> NaN scores, as torch's softmax of all -inf
-}
-
 // ---- backward row kernels -------------------------------------------------------------------------
 // Column sums over rows (bias / LayerNorm-affine / k2 gradients) are accumulated per CTA in shared
 // memory and flushed with one float atomic per column and CTA.
@@ -477,13 +491,6 @@ softmax_bwd_kernel(const float *__restrict__ dP, const __nv_bfloat16 *__restrict
 
 namespace smz {
 
-int launch_rowsum_finish(const float *stats, int slots, int rows, float *inv_l, cudaStream_t st) {
-    if (rows <= 0) return SMZ_OK;
-    rowsum_finish_kernel<<<(rows + 255) / 256, 256, 0, st>>>(stats, slots, rows, inv_l);
-    SMZ_CUDA_CHECK(cudaGetLastError());
-    return SMZ_OK;
-}
-
 int launch_head_from_stats(const float *stats, int slots, const float *c, float eps, int rows, float *scores,
                            cudaStream_t st) {
     if (rows <= 0) return SMZ_OK;
@@ -556,12 +563,20 @@ int launch_cvt_bf16(const float *x, __nv_bfloat16 *y, int64_t n, cudaStream_t st
     return SMZ_OK;
 }
 
+int launch_cvt_f16(const float *x, void *y, int64_t n, int *guard, int bit, cudaStream_t st) {
+    if (n <= 0) return SMZ_OK;
+    const int64_t blocks = (n + 8 * 256 - 1) / (8 * 256);
+    cvt_f16_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, reinterpret_cast<__half *>(y), n, guard, bit);
+    SMZ_CUDA_CHECK(cudaGetLastError());
+    return SMZ_OK;
+}
+
 int launch_softmax(const GemmProblem *d_probs, int n_probs, int total_rows, const float *S, __nv_bfloat16 *alpha,
                    __nv_bfloat16 *P, const uint8_t *drop, const int64_t *d_drop_off, int aperture, int ignore_self,
-                   cudaStream_t st, const int *gate, float *inv_l) {
+                   cudaStream_t st, const int *gate, float *sum_slots, int n_slots) {
     if (total_rows <= 0) return SMZ_OK;
     softmax_kernel<<<(total_rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, st>>>(
-        d_probs, n_probs, total_rows, S, alpha, P, drop, d_drop_off, aperture, ignore_self, gate, inv_l);
+        d_probs, n_probs, total_rows, S, alpha, P, drop, d_drop_off, aperture, ignore_self, gate, sum_slots, n_slots);
     SMZ_CUDA_CHECK(cudaGetLastError());
     return SMZ_OK;
 }

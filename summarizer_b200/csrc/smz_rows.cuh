@@ -10,19 +10,20 @@ namespace smz {
 constexpr int kFeat = 1024;   // feature / hidden width of VASNet (vasnet.py:18)
 
 int launch_cvt_bf16(const float *x, __nv_bfloat16 *y, int64_t n, cudaStream_t st);
+// float32 -> float16 with a range check: |x| > 60000 or NaN ORs `bit` into *guard (the VASNet fast path's feature copy)
+int launch_cvt_f16(const float *x, void *y, int64_t n, int *guard, int bit, cudaStream_t st);
 
 // alpha = softmax(mask(S)) over the keys of each row (vasnet.py:121-130).  `probs` are the problems of
 // the logits GEMM (M = N = T, c_off / ldc locate the video's block in S); alpha/P use the same offsets.
 // drop (optional): keep-mask bytes of the attention dropout, video v at drop + drop_off[v]; then
 // P = 2 * keep * alpha, else P == alpha (one buffer).  A row of P holds probs[v].pad zero columns, the
 // T probabilities, then zeros up to the next multiple of 64 (the K extent alpha.V reads).
-// gate (optional): the launch is a no-op unless *gate != 0; inv_l (optional): set to 1 for every row processed
-// (the row scale the alpha.V GEMM applies after the fused-exp logits path, see smz_vasnet.cu).
+// gate (optional): the launch is a no-op unless *gate != 0; sum_slots (optional, [rows][n_slots][3]): the row-sum
+// slots of the fused-exp logits path are overwritten with {1, 0, ...} for every row processed, so that the alpha.V
+// GEMM's GEMM_SCALE_STATS row scale becomes 1 (see smz_vasnet.cu).
 int launch_softmax(const GemmProblem *d_probs, int n_probs, int total_rows, const float *S, __nv_bfloat16 *alpha,
                    __nv_bfloat16 *P, const uint8_t *drop, const int64_t *d_drop_off, int aperture, int ignore_self,
-                   cudaStream_t st, const int *gate = nullptr, float *inv_l = nullptr);
-// inv_l[r] = 1 / sum_k stats[(r * slots + k) * 3]   (softmax denominators from the GEMM_ROWSTATS slots)
-int launch_rowsum_finish(const float *stats, int slots, int rows, float *inv_l, cudaStream_t st);
+                   cudaStream_t st, const int *gate = nullptr, float *sum_slots = nullptr, int n_slots = 0);
 
 // yn = LayerNorm(2*keep*y or y) * g + b  (vasnet.py:136-137), rows of 1024; optional mean / rstd.
 int launch_layernorm(const float *y, const uint8_t *keep, const float *g, const float *b, float eps, int rows,

@@ -1318,8 +1318,9 @@ static int select_launch(const smz_video_desc *desc, int n_videos, const float *
         SMZ_REQUIRE(method == SMZ_METHOD_KNAPSACK || seg_mean != nullptr, "seg_mean output is required by method 'rank'");
         const int tiles = (max_n_segs + POOL_THREADS / 8 - 1) / (POOL_THREADS / 8);
         const int64_t frame_bytes = ((int64_t)max_n_frames + 1) / 2 * 4;      // one 16-bit score index per frame
-        int max_intervals = max_n_frames + 1 < 12288 ? max_n_frames + 1 : 12288;          // staged scores per CTA, with the
-        if (max_intervals + 4 * max_n_segs > 12288) max_intervals = 12288 - 4 * max_n_segs > 0 ? 12288 - 4 * max_n_segs : 0;   // segment lists <= 48 KB
+        constexpr int kPoolWords = 12288 - 16;       // 48 KB less the kernel's static shared memory (s_class)
+        int max_intervals = max_n_frames + 1 < kPoolWords ? max_n_frames + 1 : kPoolWords;  // staged scores per CTA, with the
+        if (max_intervals + 4 * max_n_segs > kPoolWords) max_intervals = kPoolWords - 4 * max_n_segs > 0 ? kPoolWords - 4 * max_n_segs : 0;   // segment lists <= 48 KB
         if (tiles > 0 && max_n_segs <= 2048 && !getenv("SMZ_NO_POOL_REGULAR")) {
             for (int v0 = 0; v0 < n_videos; v0 += 65535) {
                 const int nv = n_videos - v0 < 65535 ? n_videos - v0 : 65535;

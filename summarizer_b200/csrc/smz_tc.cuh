@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -180,6 +181,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    __half2 t = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&t);
 }
 

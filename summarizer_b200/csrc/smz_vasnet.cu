@@ -4,7 +4,9 @@
 //   xb  = bf16(x)                                              (skipped when the features are bf16)
 //   QK  = xb . [Wq;Wk]^T                      [R, 2048] bf16    vasnet.py:114-115, one packed GEMM
 //   Vt  = Wv . xb^T                           [1024, R] bf16    vasnet.py:116, produced transposed so that
-//                                                               alpha.V is a K-major GEMM too
+//                                                               alpha.V is a K-major GEMM too (training; inference
+//                                                               packs Q|K|V into ONE [R, 3072] GEMM and alpha.V reads
+//                                                               V in place as an MN-major B operand)
 //   per attention sub-chunk (logits stay L2-resident):
 //     S   = scale * Q_v . K_v^T               [T, T]   fp32     vasnet.py:118-119, one GEMM problem per video
 //     P   = dropout(softmax(mask(S)))         [T, ld]  bf16     vasnet.py:121-130 (zero padded columns)
@@ -14,7 +16,14 @@
 //   H   = relu(Yn . W1^T + b1)                fp32              vasnet.py:140-141
 //   s   = sigmoid(LayerNorm(dropout(H)) . w2 + b2)              vasnet.py:142-145
 // In training mode the whole batch is one chunk and every intermediate stays in the work buffer for
-// smz_vasnet_backward.
+// smz_vasnet_backward.  Inference fuses the row-wise steps into the GEMM epilogues: the softmax is exp + row sums in
+// the logits epilogue and a 1 / row-sum scale in the alpha.V epilogue; the first LayerNorm is folded into k1
+// (W1.LN(y) = rstd (W1 diag(g) y - mean W1 g) + W1 b: the output projection emits bf16 y plus per-row sum / sum of
+// squares slots, k1 runs on y with W1 diag(g) and un-does the mean / applies rstd in its epilogue); the regressor head
+// is three more row sums of the k1 epilogue.  Per chunk: QKV, (logits, alpha.V) per sub-chunk, out, k1, head — no
+// row kernel reads a [R, 1024] activation.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "smz_gemm.cuh"
@@ -31,7 +40,12 @@ typedef __nv_bfloat16 bf16;
 // attention problems (one T=2000 video is only 128 logits tiles / 64 alpha.V tiles for 148 SMs): 16k rows
 // (8 sweep videos) give >= 512 tiles per launch; the spilled intermediates cost < 25 % of HBM bandwidth.
 constexpr int kRowChunk = 32768;                // rows per chunk of the row-wise GEMMs (1000+ tiles: < 4 % wave tail)
-constexpr int64_t kLogitBudget = 34ll << 20;    // fp32 logits in flight per sub-chunk (8 x 2000 x 2048)
+// logits in flight per sub-chunk (elements).  Development knob: SMZ_VASNET_LOGIT_MELEMS overrides (in Mi elements).
+int64_t logit_budget() {
+    static int64_t v = -1;
+    if (v < 0) { const char *e = getenv("SMZ_VASNET_LOGIT_MELEMS"); v = (e != nullptr && atoi(e) > 0) ? ((int64_t)atoi(e) << 20) : (34ll << 20); }
+    return v;
+}
 
 inline int64_t up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
@@ -48,7 +62,7 @@ struct Plan {
     int64_t rows_cap = 0;   // row capacity of the row-wise buffers (and stride of the stats arrays)
     int lanes = 1;          // inference with several chunks: two copies of the recycled buffers, one per stream
     int64_t lane_bytes = 0;
-    int64_t off_xb, off_qk, off_vt, off_o, off_y, off_yn, off_h, off_s, off_p, off_alpha, off_hstat, off_sstat, off_invl, off_probs, off_dropoff,
+    int64_t off_xb, off_qk, off_vt, off_o, off_y, off_yn, off_h, off_s, off_p, off_alpha, off_hstat, off_sstat, off_lnstat, off_probs, off_dropoff,
         off_stats, total;
     // backward-only buffers (training)
     int64_t off_dh, off_dyn, off_dy, off_dyf, off_do, off_dqk, off_dvt, off_dp, off_ds;
@@ -82,7 +96,7 @@ int make_plan(const int32_t *cu, int n_videos, bool training, bool x_bf16, Plan 
                 const int T = cu[u + 1] - cu[u];
                 const int nm = T > maxT ? T : maxT;
                 const int64_t elems = (int64_t)(s.rows + T) * up(nm + 7, 64);
-                if (s.rows > 0 && elems > kLogitBudget) break;
+                if (s.rows > 0 && elems > logit_budget()) break;
                 maxT = nm; s.rows += T; ++u;
             }
             s.v1 = u; s.ld = (int)up(maxT + 7, 64);   // + up to 7 leading pad columns, see build_problems
@@ -102,8 +116,8 @@ int make_plan(const int32_t *cu, int n_videos, bool training, bool x_bf16, Plan 
     int64_t o = 0;
     auto take = [&](int64_t bytes) { const int64_t at = o; o += up(bytes, 1024); return at; };
     pl->off_xb = take(x_bf16 ? 0 : R * kFeat * 2);
-    pl->off_qk = take(R * 2 * kFeat * 2);
-    pl->off_vt = take(VT * 2);
+    pl->off_qk = take(R * (training ? 2 : 3) * kFeat * 2);      // inference: Q | K | V packed, [R, 3072]
+    pl->off_vt = take(training ? VT * 2 : 0);
     pl->off_o = take(R * kFeat * 2);
     pl->off_y = take(R * kFeat * 4);
     pl->off_yn = take(R * kFeat * 2);
@@ -117,8 +131,8 @@ int make_plan(const int32_t *cu, int n_videos, bool training, bool x_bf16, Plan 
         for (const Chunk &c : pl->chunks)
             for (const Sub &s : c.subs) { if (s.rows > srows) srows = s.rows; const int64_t k = 2 * ((s.ld + 255) / 256); if (k > slots) slots = k; }
         pl->off_sstat = take(training ? 0 : srows * slots * 12 + 64);
-        pl->off_invl = take(training ? 0 : srows * 4);
     }
+    pl->off_lnstat = take(training ? 0 : R * (2 * kFeat / smz::GEMM_BN) * 3 * 4);  // LayerNorm-1 sums of the out-proj epilogue
     pl->lane_bytes = o;
     pl->lanes = (!training && pl->chunks.size() > 1) ? 2 : 1;
     if (pl->lanes == 2) o += pl->lane_bytes;     // second copy of everything above
@@ -141,6 +155,7 @@ int make_plan(const int32_t *cu, int n_videos, bool training, bool x_bf16, Plan 
 
 // host-side GEMM problem tables: [0, n) logits problems, [n, 2n) alpha.V problems
 void build_problems(const Plan &pl, const int32_t *cu, std::vector<GemmProblem> *out) {
+    const bool packed_v = !pl.training;       // inference: V lives in columns [2048, 3072) of the packed Q|K|V rows
     const int n = pl.n_videos;
     out->assign((size_t)2 * n, GemmProblem{});
     for (const Chunk &c : pl.chunks)
@@ -152,7 +167,9 @@ void build_problems(const Plan &pl, const int32_t *cu, std::vector<GemmProblem> 
                 // TMA needs 16-byte aligned coordinates along the contiguous dimension: the video's columns
                 // of V^T start at crow, so alpha.V reads V^T from crow - lead and P carries `lead` zero
                 // columns in front (written by the softmax kernel).
-                const int lead = crow & 7;
+                // Inference reads V [T, 1024] in place as an MN-major B operand (k = frame = TMA row coordinate, no
+                // alignment constraint): no lead there.
+                const int lead = packed_v ? 0 : (crow & 7);
                 GemmProblem &a = (*out)[v];
                 a.a_row0 = crow; a.a_col0 = 0; a.b_row0 = crow; a.b_col0 = kFeat;
                 a.M = T; a.N = T; a.K = kFeat; a.tile0 = tile_s;
@@ -163,10 +180,11 @@ void build_problems(const Plan &pl, const int32_t *cu, std::vector<GemmProblem> 
                 tile_s += smz::gemm_tiles(T, T);
                 GemmProblem &b = (*out)[n + v];
                 b.a_row0 = sub_row; b.a_col0 = 0; b.b_row0 = 0; b.b_col0 = crow - lead;
+                if (packed_v) { b.b_row0 = crow; b.b_col0 = 2 * kFeat; }
                 b.M = T; b.N = kFeat; b.K = T + lead; b.tile0 = tile_pv;
                 b.c_off = (int64_t)crow * kFeat; b.ldc = kFeat;
                 b.tiles_n = kFeat / smz::GEMM_BN;
-                b.r_off = sub_row;                      // GEMM_SCALE_M row index
+                b.r_off = sub_row;                      // GEMM_SCALE_STATS row index
                 tile_pv += smz::gemm_tiles(T, kFeat);
                 sub_row += T;
             }
@@ -223,10 +241,16 @@ extern "C" int smz_vasnet_launch_count(const int32_t *h_cu_seqlens, int n_videos
                                        int64_t *launches) {
     SMZ_REQUIRE(launches != nullptr, "launches is NULL");
     Plan pl;
-    int rc = make_plan(h_cu_seqlens, n_videos, training != 0, x_is_bf16 != 0, &pl);
+    int rc = make_plan(h_cu_seqlens, n_videos, training == 1, x_is_bf16 != 0, &pl);
     if (rc != SMZ_OK) return rc;
     int64_t n = 0;
-    for (const Chunk &c : pl.chunks) n += (x_is_bf16 ? 0 : 1) + 6 + 3 * (int64_t)c.subs.size();
+    // training (1): [cvt] QK Vt out layernorm k1 head per chunk; logits, softmax, alpha.V per sub-chunk
+    // inference (0, the fast path taken with params.status): [cvt] QKV out k1 head per chunk; fused-exp logits, alpha.V per sub-chunk
+    // exact inference (2, no status word): [cvt] QKV out layernorm k1 head per chunk; logits, softmax, alpha.V per sub-chunk
+    for (const Chunk &c : pl.chunks) {
+        const int64_t subs = (int64_t)c.subs.size(), cvt = x_is_bf16 ? 0 : 1;
+        n += training == 1 ? cvt + 6 + 3 * subs : (training == 2 ? cvt + 5 + 3 * subs : cvt + 4 + 2 * subs);
+    }
     *launches = n;
     return SMZ_OK;
 }
@@ -295,16 +319,24 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
         if (ss != nullptr) st = ss->s[lane_id];
         const int64_t lb = (int64_t)lane_id * pl.lane_bytes;   // byte offset of this lane's buffer copy
         auto lane = [&](auto *ptr) { return reinterpret_cast<decltype(ptr)>(reinterpret_cast<uint8_t *>(ptr) + lb); };
+        const int qld = training ? 2 * kFeat : 3 * kFeat;        // row length of the packed projection buffer
         qk = lane(qk0) + rb * 2 * kFeat; vt = lane(vt0) + c.vt_off; o = lane(o0) + rb * kFeat; y = lane(y0) + rb * kFeat;
         yn = lane(yn0) + rb * kFeat; h = lane(h0) + rb * kFeat; S = lane(S0) + c.lg_off; P = lane(P0) + c.lg_off;
         alpha = lane(alpha0) + c.lg_off;
         stats = training ? stats0 + rb : nullptr;
+        // Fast inference path (the caller passed a status word and float16 weights), see the attention block below:
+        // float16 wherever the value range can be checked on the fly (tcgen05 kind::f16 wants A and B in the SAME
+        // 16-bit format, so each GEMM is all-bf16 or all-float16; the output format is the epilogue's choice).
+        const bool fast = !training && !g_exact_softmax && p->status != nullptr && p->wqkv16 != nullptr && p->wo16 != nullptr &&
+                          p->head_gw != nullptr && p->head_c != nullptr && p->w1g != nullptr && p->ln_c != nullptr && p->b1f != nullptr;
         const bf16 *xb;
         if (x_is_bf16) {
             xb = reinterpret_cast<const bf16 *>(x) + (int64_t)c.row0 * kFeat;
         } else {
             bf16 *dst = reinterpret_cast<bf16 *>(w + pl.off_xb + lb) + rb * kFeat;
-            rc = smz::launch_cvt_bf16(reinterpret_cast<const float *>(x) + (int64_t)c.row0 * kFeat, dst, (int64_t)R * kFeat, st);
+            const float *src = reinterpret_cast<const float *>(x) + (int64_t)c.row0 * kFeat;
+            rc = fast ? smz::launch_cvt_f16(src, dst, (int64_t)R * kFeat, p->status, SMZ_VASNET_STATUS_F16_RANGE, st)   // float16 features
+                      : smz::launch_cvt_bf16(src, dst, (int64_t)R * kFeat, st);
             if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "cvt");
             xb = dst;
@@ -319,16 +351,37 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
             st_v = fs->s[0];
         }
         smz::profile_mark(st, "gemm_qk");
-        rc = smz::gemm_bf16_tn(xb, R, kFeat, kFeat, p->wqk, 2 * kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, 2 * kFeat),
-                               dense_problem(R, 2 * kFeat, kFeat, 2 * kFeat, 0), GemmEpilogue{qk, nullptr, nullptr, 1.f, 0}, st);
-        if (rc != SMZ_OK) return rc;
-        SMZ_DEBUG_STEP(st, "gemm_qk");
-        smz::profile_mark(st, "gemm_vt");
-        rc = smz::gemm_bf16_tn(p->wv, kFeat, kFeat, kFeat, xb, R, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(kFeat, R),
-                               dense_problem(kFeat, R, kFeat, (int)Rpad, 0), GemmEpilogue{vt, nullptr, nullptr, 1.f, 0}, st_v);
-        if (rc != SMZ_OK) return rc;
-        if (fs != nullptr) SMZ_CUDA_CHECK(cudaEventRecord(fs->ev[1], st_v));
-        SMZ_DEBUG_STEP(st, "gemm_vt");
+        const bool wqkv_packed = reinterpret_cast<const bf16 *>(p->wv) == reinterpret_cast<const bf16 *>(p->wqk) + 2 * kFeat * kFeat;
+        if (fast && !x_is_bf16) {
+            // float32 features: their float16 copy against float16 [Wq; Wk; Wv]; Q | K | V leave as bf16 (the logits
+            // epilogue's exp output needs the bf16 range, and alpha.V must match its format)
+            GemmEpilogue e{qk, nullptr, nullptr, 1.f, smz::GEMM_A_F16 | smz::GEMM_B_F16};
+            rc = smz::gemm_bf16_tn(xb, R, kFeat, kFeat, p->wqkv16, 3 * kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, 3 * kFeat),
+                                   dense_problem(R, 3 * kFeat, kFeat, 3 * kFeat, 0), e, st);
+            if (rc != SMZ_OK) return rc;
+            SMZ_DEBUG_STEP(st, "gemm_qkv");
+        } else if (!training && wqkv_packed) {
+            // inference: one [R, 3072] GEMM against [Wq; Wk; Wv] (the caller's bf16 copies are one buffer)
+            rc = smz::gemm_bf16_tn(xb, R, kFeat, kFeat, p->wqk, 3 * kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, 3 * kFeat),
+                                   dense_problem(R, 3 * kFeat, kFeat, 3 * kFeat, 0), GemmEpilogue{qk, nullptr, nullptr, 1.f, 0}, st);
+            if (rc != SMZ_OK) return rc;
+            SMZ_DEBUG_STEP(st, "gemm_qkv");
+        } else {
+            rc = smz::gemm_bf16_tn(xb, R, kFeat, kFeat, p->wqk, 2 * kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, 2 * kFeat),
+                                   dense_problem(R, 2 * kFeat, kFeat, qld, 0), GemmEpilogue{qk, nullptr, nullptr, 1.f, 0}, st);
+            if (rc != SMZ_OK) return rc;
+            SMZ_DEBUG_STEP(st, "gemm_qk");
+            smz::profile_mark(st, "gemm_vt");
+            if (training)       // V^T [1024, R]
+                rc = smz::gemm_bf16_tn(p->wv, kFeat, kFeat, kFeat, xb, R, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(kFeat, R),
+                                       dense_problem(kFeat, R, kFeat, (int)Rpad, 0), GemmEpilogue{vt, nullptr, nullptr, 1.f, 0}, st_v);
+            else                // V into columns [2048, 3072) of the packed rows
+                rc = smz::gemm_bf16_tn(xb, R, kFeat, kFeat, p->wv, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
+                                       dense_problem(R, kFeat, kFeat, qld, 0), GemmEpilogue{qk + 2 * kFeat, nullptr, nullptr, 1.f, 0}, st_v);
+            if (rc != SMZ_OK) return rc;
+            if (fs != nullptr) SMZ_CUDA_CHECK(cudaEventRecord(fs->ev[1], st_v));
+            SMZ_DEBUG_STEP(st, "gemm_vt");
+        }
         // attention, one GEMM problem per video
         for (const Sub &s : c.subs) {
             const int nv = s.v1 - s.v0;
@@ -338,49 +391,49 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
                 tiles_s += smz::gemm_tiles(T, T);
                 tiles_pv += smz::gemm_tiles(T, kFeat);
             }
-            // Inference fast path: the logits GEMM epilogue writes exp(logit) (bf16, un-normalised) and the row sums;
-            // alpha.V then scales row i by 1 / sum_i.  Softmax is shift invariant, so skipping the max subtraction is
-            // exact as long as no |logit| exceeds 80 (fp32 / bf16 exponent range); the epilogue checks that and, if it
-            // ever fails, raises the guard word that un-gates the exact path (fp32 logits + max-subtracted softmax),
-            // launched right behind and otherwise a no-op.  Needs every video of the sub-chunk 8-row aligned.
-            bool fast = !training && !g_exact_softmax;
-            for (int v = s.v0; v < s.v1 && fast; v++) fast = ((h_cu_seqlens[v] - c.row0) & 7) == 0;
+            // Inference fast path (the caller passed a status word and float16 weights): the logits GEMM epilogue writes
+            // exp(logit) (bf16, un-normalised) and the row sums; alpha.V (bf16 P x bf16 V -> float16 O) then scales row
+            // i by 1 / sum_i straight from the row-sum slots (GEMM_SCALE_STATS).  Softmax is shift invariant, so skipping the max subtraction is exact as long as no
+            // |logit| exceeds 80 (fp32 / bf16 exponent range); the epilogue checks that and, if it ever fails, raises
+            // SMZ_VASNET_STATUS_LOGIT_RANGE in *status: the scores of the call are then void and the caller repeats it
+            // on the exact path (no status word: fp32 logits + max-subtracted softmax).  No gated launches in between:
+            // an empty launch of the persistent GEMM costs ~5 us, two per sub-chunk were 4 % of the sweep.
+            const bool inference = !training;
             float *sstat = reinterpret_cast<float *>(w + pl.off_sstat + lb);
-            float *inv_l = reinterpret_cast<float *>(w + pl.off_invl + lb);
             const int slots = 2 * ((s.ld + 255) / 256);
-            int *guard = reinterpret_cast<int *>(sstat + (int64_t)s.rows * slots * 3);
             if (fast) {
                 smz::profile_mark(st, "gemm_logits");
-                SMZ_CUDA_CHECK(cudaMemsetAsync(sstat, 0, ((int64_t)s.rows * slots * 3 + 1) * 4, st));
+                bool ragged = false;    // a video narrower than the widest leaves slots unwritten: they must read 0
+                for (int v = s.v0; v < s.v1; v++) ragged |= 2 * ((h_cu_seqlens[v + 1] - h_cu_seqlens[v] + 255) / 256) != slots;
+                if (ragged) SMZ_CUDA_CHECK(cudaMemsetAsync(sstat, 0, (int64_t)s.rows * slots * 3 * 4, st));
                 GemmEpilogue e{P, nullptr, nullptr, p->scale, smz::GEMM_EXP | smz::GEMM_ROWSTATS};
-                e.stat_out = sstat; e.stat_slots = slots; e.aperture = p->aperture; e.ignore_self = p->ignore_self; e.guard = guard;
-                rc = smz::gemm_bf16_tn(qk, R, 2 * kFeat, 2 * kFeat, qk, R, 2 * kFeat, 2 * kFeat, d_probs + s.v0, nv, tiles_s,
-                                       GemmProblem{}, e, st);
+                e.stat_out = sstat; e.stat_slots = slots; e.aperture = p->aperture; e.ignore_self = p->ignore_self;
+                e.guard = p->status; e.guard_bit = SMZ_VASNET_STATUS_LOGIT_RANGE;
+                rc = smz::gemm_bf16_tn(qk, R, qld, qld, qk, R, qld, qld, d_probs + s.v0, nv, tiles_s, GemmProblem{}, e, st);
                 if (rc != SMZ_OK) return rc;
                 SMZ_DEBUG_STEP(st, "gemm_logits_exp");
-                smz::profile_mark(st, "softmax");
-                rc = smz::launch_rowsum_finish(sstat, slots, s.rows, inv_l, st);
-                if (rc != SMZ_OK) return rc;
-            }
-            {   // exact path: always in training mode, gated by the guard word otherwise
-                const int *gate = fast ? guard : nullptr;
-                if (!fast) smz::profile_mark(st, "gemm_logits");
+            } else {   // exact path
+                smz::profile_mark(st, "gemm_logits");
                 GemmEpilogue e{S, nullptr, nullptr, p->scale, smz::GEMM_OUT_F32};
-                e.gate = gate;
-                rc = smz::gemm_bf16_tn(qk, R, 2 * kFeat, 2 * kFeat, qk, R, 2 * kFeat, 2 * kFeat, d_probs + s.v0, nv, tiles_s,
-                                       GemmProblem{}, e, st);
+                rc = smz::gemm_bf16_tn(qk, R, qld, qld, qk, R, qld, qld, d_probs + s.v0, nv, tiles_s, GemmProblem{}, e, st);
                 if (rc != SMZ_OK) return rc;
                 SMZ_DEBUG_STEP(st, "gemm_logits");
-                if (!fast) smz::profile_mark(st, "softmax");
+                smz::profile_mark(st, "softmax");
                 rc = smz::launch_softmax(d_probs + s.v0, nv, s.rows, S, alpha, P, drop_att, d_dropoff ? d_dropoff + s.v0 : nullptr,
-                                         p->aperture, p->ignore_self, st, gate, fast ? inv_l : nullptr);
+                                         p->aperture, p->ignore_self, st);
                 if (rc != SMZ_OK) return rc;
                 SMZ_DEBUG_STEP(st, "softmax");
             }
             smz::profile_mark(st, "gemm_pv");
             if (fs != nullptr) SMZ_CUDA_CHECK(cudaStreamWaitEvent(st, fs->ev[1], 0));     // V^T is ready
-            {
-                GemmEpilogue e{o, fast ? inv_l : nullptr, nullptr, 1.f, fast ? smz::GEMM_SCALE_M : 0};
+            if (inference) {    // B = V in place: rows = frames (k), columns [2048, 3072) of the packed Q|K|V rows (MN-major)
+                GemmEpilogue e{o, fast ? sstat : nullptr, nullptr, 1.f, fast ? (smz::GEMM_SCALE_STATS | smz::GEMM_OUT_F16) : 0};
+                e.stat_slots = slots;
+                if (fast) { e.guard = p->status; e.guard_bit = SMZ_VASNET_STATUS_F16_RANGE; }
+                rc = smz::gemm_bf16(false, true, P, s.rows, s.ld, s.ld, qk, R, qld, qld, d_probs + n + s.v0, nv, tiles_pv, GemmProblem{}, e, st);
+                if (rc != SMZ_OK) return rc;
+            } else {
+                GemmEpilogue e{o, nullptr, nullptr, 1.f, 0};
                 rc = smz::gemm_bf16_tn(P, s.rows, s.ld, s.ld, vt, kFeat, R, Rpad, d_probs + n + s.v0, nv, tiles_pv, GemmProblem{}, e, st);
                 if (rc != SMZ_OK) return rc;
             }
@@ -389,7 +442,20 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
         // output projection + residual, LayerNorm, k1 + ReLU, head
         const void *res = x_is_bf16 ? (const void *)(reinterpret_cast<const bf16 *>(x) + (int64_t)c.row0 * kFeat)
                                     : (const void *)(reinterpret_cast<const float *>(x) + (int64_t)c.row0 * kFeat);
+        const bool fused_head = !training && p->head_gw != nullptr && p->head_c != nullptr;
+        // fast path: O, Wo, y, W1 diag(g) all float16, the first LayerNorm folded into k1
+        const bool fused_ln = fast;
+        float *lnstat = reinterpret_cast<float *>(w + pl.off_lnstat + lb);
+        constexpr int kLnSlots = 2 * kFeat / smz::GEMM_BN;
         smz::profile_mark(st, "gemm_out");
+        if (fused_ln) {     // y leaves as float16 (it is k1's A operand) together with the LayerNorm sums of its float32 values
+            GemmEpilogue e{yn, nullptr, res, 1.f, (x_is_bf16 ? 0 : smz::GEMM_RES_F32) | smz::GEMM_LN_STATS | smz::GEMM_OUT_F16 | smz::GEMM_A_F16 | smz::GEMM_B_F16};
+            e.stat_out = lnstat; e.guard = p->status; e.guard_bit = SMZ_VASNET_STATUS_F16_RANGE;
+            rc = smz::gemm_bf16_tn(o, R, kFeat, kFeat, p->wo16, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
+                                   dense_problem(R, kFeat, kFeat, kFeat, kFeat), e, st);
+            if (rc != SMZ_OK) return rc;
+            SMZ_DEBUG_STEP(st, "gemm_out");
+        } else {
         rc = smz::gemm_bf16_tn(o, R, kFeat, kFeat, p->wo, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
                                dense_problem(R, kFeat, kFeat, kFeat, kFeat),
                                GemmEpilogue{y, nullptr, res, 1.f, smz::GEMM_OUT_F32 | (x_is_bf16 ? 0 : smz::GEMM_RES_F32)}, st);
@@ -400,15 +466,18 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
                                    stats, stats ? stats + Rs : nullptr, st);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "layernorm");
-        const bool fused_head = !training && p->head_gw != nullptr && p->head_c != nullptr;
+        }
         smz::profile_mark(st, "gemm_k1");
         if (fused_head) {
             // inference: H never reaches memory — the k1 epilogue reduces relu(h) to the three row sums the second
             // LayerNorm + k2 dot need (GEMM_ROWSTATS), a one-thread-per-frame kernel finishes the score
             float *hstat = reinterpret_cast<float *>(w + pl.off_hstat + lb);
-            GemmEpilogue e{h, p->b1, nullptr, 1.f, smz::GEMM_RELU | smz::GEMM_OUT_F32 | smz::GEMM_ROWSTATS | smz::GEMM_NO_STORE};
+            GemmEpilogue e{h, fused_ln ? p->b1f : p->b1, nullptr, 1.f,
+                           smz::GEMM_RELU | smz::GEMM_OUT_F32 | smz::GEMM_ROWSTATS | smz::GEMM_NO_STORE |
+                           (fused_ln ? (smz::GEMM_LN_FOLD | smz::GEMM_A_F16 | smz::GEMM_B_F16) : 0)};
             e.stat_w = p->head_gw; e.stat_out = hstat;
-            rc = smz::gemm_bf16_tn(yn, R, kFeat, kFeat, p->w1, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
+            if (fused_ln) { e.ln_stats = lnstat; e.ln_c = p->ln_c; e.ln_slots = kLnSlots; e.ln_width = kFeat; e.ln_eps = p->eps; }
+            rc = smz::gemm_bf16_tn(yn, R, kFeat, kFeat, fused_ln ? p->w1g : p->w1, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
                                    dense_problem(R, kFeat, kFeat, kFeat, 0), e, st);
             if (rc != SMZ_OK) return rc;
             SMZ_DEBUG_STEP(st, "gemm_k1");

@@ -23,7 +23,9 @@ class VasnetParams(C.Structure):
     _fields_ = [("wqk", C.c_void_p), ("wv", C.c_void_p), ("wo", C.c_void_p), ("w1", C.c_void_p),
                 ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("ln_g", C.c_void_p),
                 ("ln_b", C.c_void_p), ("scale", C.c_float), ("eps", C.c_float), ("aperture", C.c_int32),
-                ("ignore_self", C.c_int32), ("head_gw", C.c_void_p), ("head_c", C.c_void_p)]
+                ("ignore_self", C.c_int32), ("head_gw", C.c_void_p), ("head_c", C.c_void_p),
+                ("w1g", C.c_void_p), ("ln_c", C.c_void_p), ("b1f", C.c_void_p), ("wqkv16", C.c_void_p), ("wo16", C.c_void_p),
+                ("status", C.c_void_p)]
 
 
 def _cu_seqlens(lengths):
@@ -96,10 +98,11 @@ class VASNet(nn.Module):
 
         self._shadow = None
         self._shadow_key = None
+        self._status = None
         self._ws = _Workspace()
 
     # ---------------------------------------------------------------------------------------------
-    def _weights(self, inference=True):
+    def _weights(self, inference=True, fast=True):
         """bfloat16 shadow copies + the parameter struct.  A training forward (``inference=False``) ALWAYS rebuilds
         them and leaves the cache marked dirty: an optimizer step follows, and fused optimizers update the parameters
         without bumping ``Tensor._version``, so a version key cannot be trusted across a step.  Inference calls reuse
@@ -136,22 +139,58 @@ class VASNet(nn.Module):
             with torch.no_grad():   # regressor head folded into the k1 epilogue: z = rstd * (sum h*gw - mean * c0) + c1
                 sh["head_gw"] = (sh["ln_g"] * sh["w2"]).contiguous()
                 sh["head_c"] = torch.stack([sh["head_gw"].sum(), (sh["ln_b"] * sh["w2"]).sum() + sh["b2"][0]]).contiguous()
+                # first LayerNorm folded into k1: W1.LN(y) + b1 = rstd * (W1g.y - mean * rowsum(W1g)) + (W1.ln_b + b1)
+                w1 = self.k1.weight.float()
+                sh["w1g"] = (w1 * sh["ln_g"][None, :]).to(torch.float16).contiguous()       # float16: y is handed over as float16
+                sh["ln_c"] = sh["w1g"].float().sum(1).contiguous()
+                sh["b1f"] = (w1 @ sh["ln_b"] + sh["b1"]).contiguous()
+                # float16 weights of the fast path; it is only offered when float16 holds them well (no overflow, the
+                # largest entries far above the subnormal range)
+                mats = (self.Q.weight, self.K.weight, self.V.weight, self.attention_head_projection.weight, w1 * sh["ln_g"][None, :])
+                amax = torch.stack([t.detach().abs().max() for t in mats]).float()
+                sh["f16_ok"] = bool(((amax < 6e4) & (amax > 1e-3)).all().item())
+                sh["wqkv16"] = torch.cat([t.detach() for t in mats[:3]], 0).to(torch.float16).contiguous()
+                sh["wo16"] = mats[3].detach().to(torch.float16).contiguous()
         st = VasnetParams(*(sh[k].data_ptr() for k in ("wqk", "wv", "wo", "w1", "b1", "w2", "b2", "ln_g", "ln_b")),
                           float(self.scale), float(self.epsilon),
                           -1 if self.aperture is None else int(self.aperture), int(bool(self.ignore_self)),
-                          sh["head_gw"].data_ptr() if inference else None, sh["head_c"].data_ptr() if inference else None)
+                          *((sh[k].data_ptr() if inference else None) for k in ("head_gw", "head_c", "w1g", "ln_c", "b1f")),
+                          *((sh[k].data_ptr() if (inference and fast and sh["f16_ok"]) else None) for k in ("wqkv16", "wo16")),
+                          self._status_word(sh["ln_g"].device).data_ptr() if (inference and fast and sh["f16_ok"]) else None)
         return sh, st
 
-    def score_packed(self, x, lengths):
+    def _status_word(self, device):
+        """Device word the fast inference path ORs SMZ_VASNET_STATUS_* into (include/summarizer_b200.h)."""
+        if self._status is None or self._status.device != device:
+            self._status = torch.zeros(1, dtype=torch.int32, device=device)
+        return self._status
+
+    def check_status(self):
+        """True when every fast-path call since the last check stayed inside the checked value ranges (synchronises).
+        ``score_packed(check=True)`` does this itself; callers that pipeline several ``check=False`` calls ask once at
+        the end and, on False, repeat them with ``exact=True``."""
+        if self._status is None:
+            return True
+        bad = int(self._status.item())
+        if bad:
+            self._status.zero_()
+        return bad == 0
+
+    def score_packed(self, x, lengths, check=True, exact=False):
         """Inference over a ragged batch: ``x`` packed [sum T, 1024] (float32 or bfloat16, device),
-        ``lengths`` the per-video frame counts.  Returns float32 scores [sum T]."""
+        ``lengths`` the per-video frame counts.  Returns float32 scores [sum T].
+
+        The fast path (softmax without the max subtraction, float16 LayerNorm input) is exact inside value ranges the
+        kernels check on the fly; ``check=True`` reads the status word after the call (one synchronisation, as the
+        reference's own ``.cpu()`` per video) and repeats the call on the exact path if a range was left.
+        ``check=False`` leaves that to a later ``check_status()``; ``exact=True`` takes the exact path directly."""
         N.require_device()
         if x.dtype not in (torch.float32, torch.bfloat16):
             x = x.float()
         x = x.contiguous()
         cu = _cu_seqlens(lengths)
         assert x.shape == (int(cu[-1]), self.input_size)
-        _, st = self._weights()
+        _, st = self._weights(fast=not exact)
         nbytes = C.c_int64(0)
         cu_p = cu.ctypes.data_as(C.c_void_p)
         is_bf16 = int(x.dtype == torch.bfloat16)
@@ -160,6 +199,8 @@ class VASNet(nn.Module):
         scores = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
         N.check(N.lib().smz_vasnet_forward(N.ptr(x), is_bf16, cu_p, len(lengths), C.byref(st), 0, None, None, None,
                                            N.ptr(scores), N.ptr(ws), ws.numel(), N.current_stream()))
+        if check and not exact and not self.check_status():
+            return self.score_packed(x, lengths, exact=True)
         return scores
 
     def forward(self, x):

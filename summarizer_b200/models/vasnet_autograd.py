@@ -70,7 +70,7 @@ class _VasnetFunction(torch.autograd.Function):
         sh = ctx.shadow   # the bf16 weights the forward used
         st = VasnetParams(*(sh[k].data_ptr() for k in ("wqk", "wv", "wo", "w1", "b1", "w2", "b2", "ln_g", "ln_b")),
                           float(m.scale), float(m.epsilon), -1 if m.aperture is None else int(m.aperture),
-                          int(bool(m.ignore_self)), None, None)
+                          int(bool(m.ignore_self)), *([None] * 8))
         m_att, m_y, m_h = ctx.masks if ctx.masks is not None else (None, None, None)
         cu = ctx.cu
         N.check(N.lib().smz_vasnet_backward(N.ptr(x), int(x.dtype == torch.bfloat16), cu.ctypes.data_as(C.c_void_p),

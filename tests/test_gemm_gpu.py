@@ -11,6 +11,7 @@ from summarizer_b200 import _native as N
 pytestmark = pytest.mark.gpu
 
 OUT_F32, RELU, RES_F32, BIAS_M = 1, 2, 4, 8
+OUT_F16, A_F16, B_F16 = 2048, 4096, 8192
 
 
 def gemm(a, b, alpha=1.0, bias=None, residual=None, flags=0, ldc=None):
@@ -18,7 +19,7 @@ def gemm(a, b, alpha=1.0, bias=None, residual=None, flags=0, ldc=None):
     Nn = b.shape[0]
     ldc = Nn if ldc is None else ldc
     out = torch.full((M, ldc), float("nan"), device=a.device,
-                     dtype=torch.float32 if flags & OUT_F32 else torch.bfloat16)
+                     dtype=torch.float32 if flags & OUT_F32 else (torch.float16 if flags & OUT_F16 else torch.bfloat16))
     N.check(N.lib().smz_gemm_bf16_tn(N.ptr(a), a.stride(0), N.ptr(b), b.stride(0), N.ptr(out), ldc, M, Nn, K,
                                      C.c_float(alpha), N.ptr(bias), N.ptr(residual),
                                      0 if residual is None else residual.stride(0), flags, N.current_stream()))
@@ -130,3 +131,23 @@ def test_gemm_mn_major_operands(a_mn, b_mn, M, Nn, K):
     N.check(N.lib().smz_gemm_bf16(int(a_mn), int(b_mn), N.ptr(a), a.stride(0), N.ptr(b), b.stride(0), N.ptr(out), Nn,
                                   M, Nn, K, C.c_float(1.0), None, N.ptr(out), Nn, OUT_F32 | RES_F32, N.current_stream()))
     assert torch.allclose(out, want + acc, atol=tol, rtol=1e-3), describe_mismatch(out, want + acc, tol)
+
+
+@pytest.mark.parametrize("a16,b16,out16", [(True, True, True), (False, False, True), (True, True, False)])
+def test_gemm_float16_operands(a16, b16, out16):
+    """tcgen05 kind::f16 with float16 operands (both operands in the same format: the hardware rejects a bf16 x f16 mix
+    as an illegal instruction) and / or float16 output, which keeps 11 significant bits."""
+    N.require_device()
+    M, Nn, K = 515, 768, 320
+    g = torch.Generator(device="cuda"); g.manual_seed(99)
+    a = torch.randn(M, K, generator=g, device="cuda").to(torch.float16 if a16 else torch.bfloat16)
+    b = torch.randn(Nn, K, generator=g, device="cuda").to(torch.float16 if b16 else torch.bfloat16)
+    flags = (A_F16 if a16 else 0) | (B_F16 if b16 else 0)
+    want = ref(a, b)
+    got = gemm(a, b, flags=flags | OUT_F32)
+    assert torch.allclose(got, want, rtol=0, atol=1e-3 * K ** 0.5), describe_mismatch(got, want, 1e-3 * K ** 0.5)
+    got = gemm(a, b, flags=flags | (OUT_F16 if out16 else 0))
+    assert got.dtype == (torch.float16 if out16 else torch.bfloat16)
+    rel = 2.0 ** (-11 if out16 else -8)
+    assert ((got.float() - want).abs() <= rel * want.abs() + 1e-3 * K ** 0.5).all()
+    assert ((got.float() - want).abs() / want.abs().clamp_min(1.0)).max().item() < 1.01 * rel + 2e-3

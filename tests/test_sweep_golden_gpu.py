@@ -33,12 +33,12 @@ def test_vasnet_t2000_bf16_packed_matches_reference():
         y = m.score_packed(x, [S.T] * S.N_VIDEOS).reshape(S.N_VIDEOS, S.T)
     want = torch.from_numpy(GOLDEN["vas/y"]).cuda()
     rel = rel_err(y, want)
-    # bf16 operands, fp32 accumulation: north_star's 1e-2 on 99.9 % of the 34 000 frames (measured: median 5e-4, p99 4e-3,
-    # 3e-5 of the frames between 1e-2 and 1.2e-2 — the smallest scores, where d(sigmoid)/sigmoid = (1 - s) dz is largest)
+    # north_star's 1e-2 on EVERY one of the 34 000 frames (bf16 features and Q | K | V, float16 attention output / y /
+    # their weights, fp32 accumulation)
     frac_over = (rel > 1e-2).float().mean().item()
     print(f"vasnet T=2000 bf16: rel err median {rel.median().item():.2e} p99 {torch.quantile(rel[:1_000_000], 0.99).item():.2e} "
           f"max {rel.max().item():.2e}; frames over 1e-2: {frac_over:.2e}")
-    assert torch.quantile(rel, 0.999).item() < 1e-2 and rel.max().item() < 1.5e-2
+    assert rel.max().item() < 1e-2
     # per-video MSE loss against a ramp target: 1e-2 relative
     target = torch.linspace(0, 1, S.T, device="cuda")
     l_got, l_want = ((y - target) ** 2).mean(1), ((want - target) ** 2).mean(1)
@@ -46,7 +46,7 @@ def test_vasnet_t2000_bf16_packed_matches_reference():
     # a video scored alone gives the same result as inside the packed, chunked batch (same kernels, other tiling)
     with torch.no_grad():
         alone = m.score_packed(x[: S.T], [S.T])
-    assert rel_err(alone, want[0]).max().item() < 2e-2
+    assert rel_err(alone, want[0]).max().item() < 1e-2
 
 
 def test_dsn_t2000_bf16_packed_matches_reference():
