@@ -74,6 +74,12 @@ def flops_vasnet_fwd(T, D=FEAT):
     return 10 * T * D * D + 4 * T * T * D + 2 * T * D
 
 
+def flops_vasnet_fwd_executed(T, D=FEAT):
+    """What the fast inference path multiplies: the K projection and the output projection are folded into the Q / V
+    weights (Wq^T Wk, Wo Wv), so 6 T D^2 instead of 10 T D^2 (smz_vasnet.cu, fast_chunk)."""
+    return 6 * T * D * D + 4 * T * T * D + 2 * T * D
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -586,7 +592,12 @@ def run_native(args):
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05; all launches of the VASNet scoring stage, "
                                                       "softmax/LayerNorm/head row kernels included in the time)",
                          "achieved": achieved_tf, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved_tf / tf_sus,
-                         "frac_of_burst_peak": achieved_tf / tf_burst, "traffic": traffic,
+                         "frac_of_burst_peak": achieved_tf / tf_burst,
+                         "executed_flops_per_launch": V * flops_vasnet_fwd_executed(N_STEPS),
+                         "frac_executed": achieved_tf * flops_vasnet_fwd_executed(N_STEPS) / flops_vasnet_fwd(N_STEPS) / tf_sus,
+                         "flops_note": "achieved / frac count the ALGORITHMIC flops of the reference's forward (SURVEY 8d: 10TD^2 + "
+                                       "4T^2D); the fast path executes 6TD^2 + 4T^2D (K and output projections folded into the "
+                                       "weights) - frac_executed is the tensor-pipe utilisation", "traffic": traffic,
                          "traffic_source": "profiles/r01n_scoring_stage_dram_traffic.json: ncu dram__bytes_read+write of every kernel of the "
                                            "stage on 64 videos, per video x videos (69.5 MB per video; 4.1 MB of it is the input)",
                          "peak_source": which + " (sustained)",

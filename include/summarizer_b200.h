@@ -198,7 +198,7 @@ int smz_gemm_bf16(int a_mn, int b_mn, const void *A, int64_t lda, const void *B,
  * scale multiplies the logits (vasnet.py:34,119); aperture < 0 = global attention, else the band
  * |i-j| <= aperture of vasnet.py:124-127; ignore_self masks the diagonal (vasnet.py:121-122). */
 #define SMZ_VASNET_STATUS_LOGIT_RANGE 1   /* an attention logit left [-80, 80] */
-#define SMZ_VASNET_STATUS_F16_RANGE 2     /* a float16 activation (V, attention output, y) exceeded the float16 range */
+#define SMZ_VASNET_STATUS_F16_RANGE 2     /* a float16 value (features, x.(Wq^T Wk), y) exceeded the float16 range */
 typedef struct smz_vasnet_params {
     const void *wqk, *wv, *wo, *w1;
     const float *b1, *w2, *b2, *ln_g, *ln_b;
@@ -208,22 +208,23 @@ typedef struct smz_vasnet_params {
      * (float32, device).  When both are given the regressor head (vasnet.py:143-145) is folded into the k1
      * GEMM epilogue and the hidden activations never reach memory; NULL keeps the separate head kernel. */
     const float *head_gw, *head_c;
-    /* optional (inference, fast path): the first LayerNorm (vasnet.py:137) folded into k1,
-     *   W1 . LN(y) + b1 = rstd * (W1g . y - mean * ln_c) + b1f
-     * with w1g [1024,1024] = float16(k1.weight * ln_g[None, :]), ln_c [1024] = row sums of w1g (of the float16
-     * values, float32) and b1f [1024] = k1.weight . ln_b + k1.bias (float32).  Then the output projection writes y as
-     * float16 with its per-row sum / sum of squares and no LayerNorm kernel runs; NULL keeps the separate kernel. */
+    /* optional (inference), all required together with head_gw / head_c for the FAST path (smz_vasnet.cu, fast_chunk):
+     * the forward with its linear maps folded where no non-linearity sits between them —
+     *   logits_ij = x_i^T (Wq^T Wk) x_j,   c_i = sum_j alpha_ij (Wo Wv) x_j,   W1 . LN(y) + b1 = rstd * (W1g . y - mean * ln_c) + b1f
+     * — exact in real arithmetic, 22 % fewer multiply-adds, no K / output projection and no LayerNorm kernel.
+     *   w1g  [1024,1024] float16(k1.weight * ln_g[None, :]);  ln_c [1024] row sums of w1g (of the float16 values, float32);
+     *   b1f  [1024] = k1.weight . ln_b + k1.bias (float32);
+     *   wgv  [2048,1024] bfloat16: rows 0..1023 = Wo Wv, rows 1024..2047 = Wk^T Wq (products formed in float32) — used
+     *        with bfloat16 features;  wgv16: the same in float16 — used with float32 features (copied to float16);
+     *   status: device word.  Softmax runs without the max subtraction (exp and row sums in the logits epilogue) and
+     *        y / W1g (and, for float32 features, x / G / the folded weights) are float16: exact reformulations inside a
+     *        value range the kernels check.  A violation ORs SMZ_VASNET_STATUS_* into *status (never cleared by the
+     *        library), the scores of that call are void, and the caller repeats the call with status = NULL (the
+     *        wide-range path: the literal chain in bf16 / fp32, max-subtracted softmax, LayerNorm kernel).  The host
+     *        reads the word whenever it next synchronises — no launch waits on it. */
     const void *w1g;
     const float *ln_c, *b1f;
-    /* optional (inference), all required together with head_gw .. b1f for the FAST path: float16 copies of [Wq; Wk; Wv]
-     * ([3072,1024]) and of the output projection, and a device status word.  The fast path computes softmax without the
-     * max subtraction (exp and row sums in the logits epilogue) and keeps V, the attention output, y and their weights
-     * in float16 (3 more mantissa bits than bf16: the golden-vector error drops 5-10x).  Both are exact reformulations
-     * inside a value range the kernels check: a violation ORs SMZ_VASNET_STATUS_* into *status (never cleared by the
-     * library), the scores of that call are void, and the caller repeats the call with status = NULL (the wide-range
-     * path: bf16 everywhere, fp32 logits, max-subtracted softmax, LayerNorm kernel).  The host reads the word
-     * whenever it next synchronises — no launch waits on it. */
-    const void *wqkv16, *wo16;
+    const void *wgv, *wgv16;
     int32_t *status;
 } smz_vasnet_params;
 

@@ -12,7 +12,7 @@ for name, seed, T, B, kw, sharpen in VASNET_CASES:
         continue
     packed = x.permute(1, 0, 2).reshape(B * T, 1024)
     want = torch.from_numpy(g[f"{name}/y"]).cuda().permute(1, 0, 2).reshape(-1)
-    for mode in ("fast", "exact"):
-        y = m.score_packed(packed, [T] * B, exact=(mode == "exact"))
+    for mode in ("fast", "fast-bf16-x", "exact"):
+        y = m.score_packed(packed.bfloat16() if "bf16" in mode else packed, [T] * B, exact=(mode == "exact"))
         rel = ((y - want).abs() / want.abs().clamp_min(1e-6))
-        print(f"{name:14s} {mode:6s} p50 {rel.median().item():.2e} p95 {torch.quantile(rel, 0.95).item():.2e} max {rel.max().item():.2e}  abs max {(y-want).abs().max().item():.2e}")
+        print(f"{name:14s} {mode:11s} p50 {rel.median().item():.2e} p95 {torch.quantile(rel, 0.95).item():.2e} max {rel.max().item():.2e}  abs max {(y-want).abs().max().item():.2e}")

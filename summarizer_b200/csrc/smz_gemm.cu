@@ -210,12 +210,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const bool out_f32 = flags & smz::GEMM_OUT_F32;
             const bool res_f32 = flags & smz::GEMM_RES_F32;
             const bool c_vec = ((g.c_off | (int64_t)g.ldc) & 7) == 0 && (reinterpret_cast<uintptr_t>(P.epi.C) & 15) == 0;
-            const bool r_vec = ((g.r_off | (int64_t)g.ldr) & 7) == 0 && (reinterpret_cast<uintptr_t>(P.epi.residual) & 15) == 0;
+            const int64_t res_off = (flags & smz::GEMM_RES_AT_C) ? g.c_off : g.r_off;
+            const int res_ld = (flags & smz::GEMM_RES_AT_C) ? g.ldc : g.ldr;
+            const bool r_vec = ((res_off | (int64_t)res_ld) & 7) == 0 && (reinterpret_cast<uintptr_t>(P.epi.residual) & 15) == 0;
             // The residual of the NEXT 32-column chunk is fetched while the current one is processed (and the
             // first one while the MMAs of this tile are still running): its ~1 us L2/HBM latency would otherwise
             // serialise 8 times per tile and make the epilogue, not the tensor pipe, the pace of the kernel.
             const char *res_row = P.epi.residual == nullptr ? nullptr
-                : reinterpret_cast<const char *>(P.epi.residual) + (g.r_off + (int64_t)m * g.ldr) * (res_f32 ? 4 : 2);
+                : reinterpret_cast<const char *>(P.epi.residual) + (res_off + (int64_t)m * res_ld) * (res_f32 ? 4 : 2);
             auto res_vec_ok = [&](int n0) { return res_row != nullptr && row_ok && r_vec && n0 + 32 <= g.N; };
             auto res_fetch = [&](int n0, uint4 (&buf)[8]) {
                 if (!res_vec_ok(n0)) return;
@@ -240,9 +242,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             float row_scale = 1.f, ln_mean = 0.f, ln_rstd = 1.f;
             if (EPI == EPI_PLAIN && row_ok && (flags & smz::GEMM_SCALE_M)) row_scale = __ldg(P.epi.bias + g.r_off + m);
             if (EPI == EPI_PLAIN && row_ok && (flags & smz::GEMM_SCALE_STATS)) {
-                const float *sp = P.epi.bias + (g.r_off + m) * P.epi.stat_slots * 3;
+                const int ns = P.epi.scale_slots > 0 ? P.epi.scale_slots : P.epi.stat_slots;
+                const float *sp = P.epi.bias + (g.r_off + m) * ns * 3;
                 float ssum = 0.f;
-                for (int k = 0; k < P.epi.stat_slots; k++) ssum += __ldg(sp + 3 * k);
+                for (int k = 0; k < ns; k++) ssum += __ldg(sp + 3 * k);
                 row_scale = 1.f / ssum;       // a fully masked row: 1/0 = inf -> NaN scores, as torch's softmax of all -inf
             }
             if (EPI == EPI_HEAD && row_ok && (flags & smz::GEMM_LN_FOLD)) {

@@ -40,6 +40,8 @@ enum : int {
                          // activation whose range is checked — |x| > 60000 raises guard_bit in *guard
     GEMM_A_F16 = 4096,   // the A operand holds float16 instead of bf16 (tcgen05 kind::f16 takes either format per operand)
     GEMM_B_F16 = 8192,   // the B operand holds float16
+    GEMM_RES_AT_C = 16384,   // the residual array has C's layout: its element offset / leading dimension are c_off / ldc (r_off is
+                         // then free to carry the row offset of the per-row statistics)
     GEMM_LN_FOLD = 1024, // head epilogue whose A operand is the un-normalised LayerNorm input y (bf16 / f16) and whose B is
                          // W * diag(gamma): x = rstd_m * (acc - mean_m * ln_c[n]) + bias[n], mean / rstd of row m from the
                          // GEMM_LN_STATS slots in ln_stats (ln_slots per row, rows of ln_width elements, eps ln_eps)
@@ -54,6 +56,7 @@ struct GemmEpilogue {
     const float *stat_w = nullptr;   // GEMM_ROWSTATS: weight vector [N] (optional)
     float *stat_out = nullptr;       // GEMM_ROWSTATS: [(r_off + m)][stat_slots][3] (r_off doubles as the row offset here)
     int stat_slots = 0;              // slots per row (>= 2 * tiles_n); 0 = 2 * tiles_n of the problem
+    int scale_slots = 0;             // GEMM_SCALE_STATS: slots per row of the array read through `bias` (0 = stat_slots)
     int aperture = -1, ignore_self = 0;   // GEMM_EXP: VASNet's masks (vasnet.py:121-127), row / column = video-local i / j
     int *guard = nullptr;            // GEMM_EXP: |= guard_bit when a logit leaves [-80, 80]; GEMM_OUT_F16: when |x| > 60000
     int guard_bit = 1;

@@ -37,13 +37,14 @@ using smz::kFeat;
 typedef __nv_bfloat16 bf16;
 
 // Chunk sizes trade L2 residency of the intermediates against wave quantisation of the per-video
-// attention problems (one T=2000 video is only 128 logits tiles / 64 alpha.V tiles for 148 SMs): 16k rows
-// (8 sweep videos) give >= 512 tiles per launch; the spilled intermediates cost < 25 % of HBM bandwidth.
+// attention problems (one T=2000 video is only 64 logits tiles / 32 alpha.V tiles for 74 CTA pairs): a sub-chunk
+// of 16 sweep videos gives 512 alpha.V tiles = 6.9 waves (8 videos: 3.5 waves, 13 % of the launch idle in the tail;
+// measured 1.5 % of the sweep).
 constexpr int kRowChunk = 32768;                // rows per chunk of the row-wise GEMMs (1000+ tiles: < 4 % wave tail)
 // logits in flight per sub-chunk (elements).  Development knob: SMZ_VASNET_LOGIT_MELEMS overrides (in Mi elements).
 int64_t logit_budget() {
     static int64_t v = -1;
-    if (v < 0) { const char *e = getenv("SMZ_VASNET_LOGIT_MELEMS"); v = (e != nullptr && atoi(e) > 0) ? ((int64_t)atoi(e) << 20) : (34ll << 20); }
+    if (v < 0) { const char *e = getenv("SMZ_VASNET_LOGIT_MELEMS"); v = (e != nullptr && atoi(e) > 0) ? ((int64_t)atoi(e) << 20) : (68ll << 20); }
     return v;
 }
 
@@ -126,11 +127,11 @@ int make_plan(const int32_t *cu, int n_videos, bool training, bool x_bf16, Plan 
     pl->off_p = take(LG * 2);
     pl->off_alpha = take(training ? LG * 2 : 0);
     pl->off_hstat = take(training ? 0 : R * (2 * kFeat / smz::GEMM_BN) * 3 * 4);   // fused head: [R][8 slots][3]
-    {   // fused-exp attention (inference): row-sum slots [sub rows][2 * ceil(ld / 256)][3] + guard word, 1 / denominators
-        int64_t srows = 0, slots = 0;
+    {   // fused-exp attention (inference): row-sum slots [chunk rows][2 * ceil(ld / 256)][3]
+        int64_t slots = 0;
         for (const Chunk &c : pl->chunks)
-            for (const Sub &s : c.subs) { if (s.rows > srows) srows = s.rows; const int64_t k = 2 * ((s.ld + 255) / 256); if (k > slots) slots = k; }
-        pl->off_sstat = take(training ? 0 : srows * slots * 12 + 64);
+            for (const Sub &s : c.subs) { const int64_t k = 2 * ((s.ld + 255) / 256); if (k > slots) slots = k; }
+        pl->off_sstat = take(training ? 0 : R * slots * 12 + 64);
     }
     pl->off_lnstat = take(training ? 0 : R * (2 * kFeat / smz::GEMM_BN) * 3 * 4);  // LayerNorm-1 sums of the out-proj epilogue
     pl->lane_bytes = o;
@@ -154,7 +155,10 @@ int make_plan(const int32_t *cu, int n_videos, bool training, bool x_bf16, Plan 
 }
 
 // host-side GEMM problem tables: [0, n) logits problems, [n, 2n) alpha.V problems
-void build_problems(const Plan &pl, const int32_t *cu, std::vector<GemmProblem> *out) {
+// fast (inference with folded weights): the packed projection rows are [V' | G] (V' = x.(Wo Wv)^T in columns [0, 1024),
+// G = x.(Wq^T Wk) in [1024, 2048)); logits = G . x^T reads the features as its B operand; alpha.V' reads V' in place
+// (MN-major) and r_off carries the chunk-local row of the video for the row statistics (the residual sits at c_off).
+void build_problems(const Plan &pl, const int32_t *cu, bool fast, std::vector<GemmProblem> *out) {
     const bool packed_v = !pl.training;       // inference: V lives in columns [2048, 3072) of the packed Q|K|V rows
     const int n = pl.n_videos;
     out->assign((size_t)2 * n, GemmProblem{});
@@ -171,20 +175,20 @@ void build_problems(const Plan &pl, const int32_t *cu, std::vector<GemmProblem> 
                 // alignment constraint): no lead there.
                 const int lead = packed_v ? 0 : (crow & 7);
                 GemmProblem &a = (*out)[v];
-                a.a_row0 = crow; a.a_col0 = 0; a.b_row0 = crow; a.b_col0 = kFeat;
+                a.a_row0 = crow; a.a_col0 = fast ? kFeat : 0; a.b_row0 = crow; a.b_col0 = fast ? 0 : kFeat;
                 a.M = T; a.N = T; a.K = kFeat; a.tile0 = tile_s;
                 a.c_off = (int64_t)sub_row * s.ld; a.ldc = s.ld;
                 a.tiles_n = (T + smz::GEMM_BN - 1) / smz::GEMM_BN;
                 a.pad = lead;
-                a.r_off = sub_row;                      // row of the video inside the sub-chunk: GEMM_ROWSTATS slots
+                a.r_off = fast ? crow : sub_row;        // GEMM_ROWSTATS slots: row of the video inside the chunk / sub-chunk
                 tile_s += smz::gemm_tiles(T, T);
                 GemmProblem &b = (*out)[n + v];
                 b.a_row0 = sub_row; b.a_col0 = 0; b.b_row0 = 0; b.b_col0 = crow - lead;
-                if (packed_v) { b.b_row0 = crow; b.b_col0 = 2 * kFeat; }
+                if (packed_v) { b.b_row0 = crow; b.b_col0 = fast ? 0 : 2 * kFeat; }
                 b.M = T; b.N = kFeat; b.K = T + lead; b.tile0 = tile_pv;
                 b.c_off = (int64_t)crow * kFeat; b.ldc = kFeat;
                 b.tiles_n = kFeat / smz::GEMM_BN;
-                b.r_off = sub_row;                      // GEMM_SCALE_STATS row index
+                b.r_off = fast ? crow : sub_row;        // fast: row of the softmax row sums (read) and LayerNorm sums (written)
                 tile_pv += smz::gemm_tiles(T, kFeat);
                 sub_row += T;
             }
@@ -220,6 +224,92 @@ GemmProblem dense_problem(int M, int N, int K, int ldc, int ldr) {
     return g;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// FAST inference path: the reference's forward (vasnet.py:114-145) with its linear maps folded where no non-linearity
+// sits between them — exact in real arithmetic, and 22 % fewer multiply-adds than the literal chain:
+//   logits_ij = (Wq x_i).(Wk x_j) = (x_i^T M) x_j          M   = Wq^T Wk     (the K projection disappears)
+//   c_i = Wo sum_j a_ij Wv x_j   = sum_j a_ij (Wvo x_j)    Wvo = Wo Wv       (the output projection disappears)
+//   W1 LN(y) + b1 = rstd (W1 diag(g) y - mean W1 g) + (W1 b + b1)            (the LayerNorm kernel disappears)
+// and the row-wise steps fused into GEMM epilogues.  Per chunk of <= 32 768 frames:
+//   [V' | G] = x . [Wvo ; M^T]^T                  one [R, 2048] GEMM
+//   P        = exp(scale * G . x^T) (masked), row sums        logits epilogue, no max subtraction (range-checked)
+//   y        = (P . V') / rowsum + x, row sum / sum of squares of y, float16      alpha.V' epilogue, V' read in place (MN-major)
+//   score    = head(relu(rstd (W1g . y - mean c) + b1f))      k1 epilogue reduces relu(h) to three row sums + a per-row kernel
+// 16-bit formats: bf16 features as given (float32 features are copied to float16 and then G / M / the logits operands
+// are float16 too); V', P bf16 (alpha.V' must match P, whose un-normalised exponentials need the bf16 range); y, W1g
+// float16.  tcgen05 kind::f16 wants both operands of one GEMM in the same format.  Every float16 value and every logit
+// is range-checked on the fly (SMZ_VASNET_STATUS_* in *status); a violation voids the call and the caller repeats it
+// on the wide-range path below (the literal chain, bf16 / fp32, max-subtracted softmax).  No launch is gated on the
+// status word: an empty launch of the persistent GEMM costs ~5 us, two per sub-chunk were 4 % of the sweep.
+int fast_chunk(const Plan &pl, const Chunk &c, const int32_t *cu, const smz_vasnet_params *p, const void *xb, const void *res,
+               bool x_bf16, bf16 *gv, bf16 *P, bf16 *y16, float *sstat, float *lnstat, float *hstat, const GemmProblem *d_probs,
+               float *scores, cudaStream_t st) {
+    const int R = c.rows, n = pl.n_videos;
+    const int f16 = x_bf16 ? 0 : (smz::GEMM_A_F16 | smz::GEMM_B_F16);
+    int rc;
+    smz::profile_mark(st, "gemm_proj");
+    {
+        GemmEpilogue e{gv, nullptr, nullptr, 1.f, f16 | (x_bf16 ? 0 : smz::GEMM_OUT_F16)};
+        e.f16_col0 = kFeat; e.guard = p->status; e.guard_bit = SMZ_VASNET_STATUS_F16_RANGE;     // V' bf16 | G float16 (float32 features)
+        rc = smz::gemm_bf16_tn(xb, R, kFeat, kFeat, x_bf16 ? p->wgv : p->wgv16, 2 * kFeat, kFeat, kFeat, nullptr, 1,
+                               smz::gemm_tiles(R, 2 * kFeat), dense_problem(R, 2 * kFeat, kFeat, 2 * kFeat, 0), e, st);
+        if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "gemm_proj");
+    }
+    int slots = 0;
+    for (const Sub &s : c.subs) { const int k = 2 * ((s.ld + 255) / 256); if (k > slots) slots = k; }
+    bool ragged = false;    // a video narrower than the widest leaves row-sum slots unwritten: they must read 0
+    for (int v = c.v0; v < c.v1; v++) ragged |= 2 * ((cu[v + 1] - cu[v] + 255) / 256) != slots;
+    if (ragged) SMZ_CUDA_CHECK(cudaMemsetAsync(sstat, 0, (int64_t)R * slots * 3 * 4, st));
+    constexpr int kLnSlots = 2 * kFeat / smz::GEMM_BN;
+    for (const Sub &s : c.subs) {
+        const int nv = s.v1 - s.v0;
+        int tiles_s = 0, tiles_pv = 0;
+        for (int v = s.v0; v < s.v1; v++) {
+            const int T = cu[v + 1] - cu[v];
+            tiles_s += smz::gemm_tiles(T, T);
+            tiles_pv += smz::gemm_tiles(T, kFeat);
+        }
+        smz::profile_mark(st, "gemm_logits");
+        {   // softmax is shift invariant: exp without the max subtraction is exact while |logit| <= 80 (checked)
+            GemmEpilogue e{P, nullptr, nullptr, p->scale, smz::GEMM_EXP | smz::GEMM_ROWSTATS | f16};
+            e.stat_out = sstat; e.stat_slots = slots; e.aperture = p->aperture; e.ignore_self = p->ignore_self;
+            e.guard = p->status; e.guard_bit = SMZ_VASNET_STATUS_LOGIT_RANGE;
+            rc = smz::gemm_bf16_tn(gv, R, 2 * kFeat, 2 * kFeat, xb, R, kFeat, kFeat, d_probs + s.v0, nv, tiles_s, GemmProblem{}, e, st);
+            if (rc != SMZ_OK) return rc;
+            SMZ_DEBUG_STEP(st, "gemm_logits_exp");
+        }
+        smz::profile_mark(st, "gemm_pv");
+        {   // y = P . V' / rowsum + x  (float16) and the LayerNorm sums of its float32 values
+            GemmEpilogue e{y16, sstat, res, 1.f, smz::GEMM_SCALE_STATS | smz::GEMM_RES_AT_C | (x_bf16 ? 0 : smz::GEMM_RES_F32) |
+                                                 smz::GEMM_LN_STATS | smz::GEMM_OUT_F16};
+            e.scale_slots = slots; e.stat_out = lnstat; e.stat_slots = kLnSlots;
+            e.guard = p->status; e.guard_bit = SMZ_VASNET_STATUS_F16_RANGE;
+            rc = smz::gemm_bf16(false, true, P, s.rows, s.ld, s.ld, gv, R, 2 * kFeat, 2 * kFeat, d_probs + n + s.v0, nv, tiles_pv,
+                                GemmProblem{}, e, st);
+            if (rc != SMZ_OK) return rc;
+            SMZ_DEBUG_STEP(st, "gemm_pv");
+        }
+    }
+    smz::profile_mark(st, "gemm_k1");
+    {
+        GemmEpilogue e{hstat, p->b1f, nullptr, 1.f, smz::GEMM_RELU | smz::GEMM_OUT_F32 | smz::GEMM_ROWSTATS | smz::GEMM_NO_STORE |
+                                                   smz::GEMM_LN_FOLD | smz::GEMM_A_F16 | smz::GEMM_B_F16};
+        e.stat_w = p->head_gw; e.stat_out = hstat;
+        e.ln_stats = lnstat; e.ln_c = p->ln_c; e.ln_slots = kLnSlots; e.ln_width = kFeat; e.ln_eps = p->eps;
+        rc = smz::gemm_bf16_tn(y16, R, kFeat, kFeat, p->w1g, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
+                               dense_problem(R, kFeat, kFeat, kFeat, 0), e, st);
+        if (rc != SMZ_OK) return rc;
+        SMZ_DEBUG_STEP(st, "gemm_k1");
+    }
+    smz::profile_mark(st, "head");
+    rc = smz::launch_head_from_stats(hstat, kLnSlots, p->head_c, p->eps, R, scores, st);
+    if (rc != SMZ_OK) return rc;
+    SMZ_DEBUG_STEP(st, "head");
+    smz::profile_mark(st, "");
+    return SMZ_OK;
+}
+
 }  // namespace
 
 namespace { int g_exact_softmax = 0; }
@@ -245,11 +335,11 @@ extern "C" int smz_vasnet_launch_count(const int32_t *h_cu_seqlens, int n_videos
     if (rc != SMZ_OK) return rc;
     int64_t n = 0;
     // training (1): [cvt] QK Vt out layernorm k1 head per chunk; logits, softmax, alpha.V per sub-chunk
-    // inference (0, the fast path taken with params.status): [cvt] QKV out k1 head per chunk; fused-exp logits, alpha.V per sub-chunk
+    // inference (0, the fast path taken with params.status): [cvt] proj k1 head per chunk; fused-exp logits, alpha.V' per sub-chunk
     // exact inference (2, no status word): [cvt] QKV out layernorm k1 head per chunk; logits, softmax, alpha.V per sub-chunk
     for (const Chunk &c : pl.chunks) {
         const int64_t subs = (int64_t)c.subs.size(), cvt = x_is_bf16 ? 0 : 1;
-        n += training == 1 ? cvt + 6 + 3 * subs : (training == 2 ? cvt + 5 + 3 * subs : cvt + 4 + 2 * subs);
+        n += training == 1 ? cvt + 6 + 3 * subs : (training == 2 ? cvt + 5 + 3 * subs : cvt + 3 + 2 * subs);
     }
     *launches = n;
     return SMZ_OK;
@@ -274,8 +364,11 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
     uint8_t *w = reinterpret_cast<uint8_t *>(ws);
     const int n = n_videos;
 
+    // Fast inference path (the caller passed a status word and the folded weights), see fast_chunk() below
+    const bool fast = !training && !g_exact_softmax && p->status != nullptr && (x_is_bf16 ? p->wgv : p->wgv16) != nullptr &&
+                      p->head_gw != nullptr && p->head_c != nullptr && p->w1g != nullptr && p->ln_c != nullptr && p->b1f != nullptr;
     std::vector<GemmProblem> probs;
-    build_problems(pl, h_cu_seqlens, &probs);
+    build_problems(pl, h_cu_seqlens, fast, &probs);
     GemmProblem *d_probs = reinterpret_cast<GemmProblem *>(w + pl.off_probs);
     rc = smz::upload_small(d_probs, probs.data(), probs.size() * sizeof(GemmProblem), st);
     if (rc != SMZ_OK) return rc;
@@ -324,11 +417,6 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
         yn = lane(yn0) + rb * kFeat; h = lane(h0) + rb * kFeat; S = lane(S0) + c.lg_off; P = lane(P0) + c.lg_off;
         alpha = lane(alpha0) + c.lg_off;
         stats = training ? stats0 + rb : nullptr;
-        // Fast inference path (the caller passed a status word and float16 weights), see the attention block below:
-        // float16 wherever the value range can be checked on the fly (tcgen05 kind::f16 wants A and B in the SAME
-        // 16-bit format, so each GEMM is all-bf16 or all-float16; the output format is the epilogue's choice).
-        const bool fast = !training && !g_exact_softmax && p->status != nullptr && p->wqkv16 != nullptr && p->wo16 != nullptr &&
-                          p->head_gw != nullptr && p->head_c != nullptr && p->w1g != nullptr && p->ln_c != nullptr && p->b1f != nullptr;
         const bf16 *xb;
         if (x_is_bf16) {
             xb = reinterpret_cast<const bf16 *>(x) + (int64_t)c.row0 * kFeat;
@@ -341,6 +429,15 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
         SMZ_DEBUG_STEP(st, "cvt");
             xb = dst;
         }
+        if (fast) {
+            const void *res = x_is_bf16 ? (const void *)(reinterpret_cast<const bf16 *>(x) + (int64_t)c.row0 * kFeat)
+                                        : (const void *)(reinterpret_cast<const float *>(x) + (int64_t)c.row0 * kFeat);
+            rc = fast_chunk(pl, c, h_cu_seqlens, p, xb, res, x_is_bf16 != 0, qk, P, yn, reinterpret_cast<float *>(w + pl.off_sstat + lb),
+                            reinterpret_cast<float *>(w + pl.off_lnstat + lb), reinterpret_cast<float *>(w + pl.off_hstat + lb),
+                            d_probs, scores + c.row0, st);
+            if (rc != SMZ_OK) return rc;
+            continue;
+        }
         // Q|K projection and V^T projection
         // training (one video, a few tiles per GEMM): V^T runs beside Q|K on the side stream, joined before alpha.V
         SideStreams *fs = (training && !smz::profile_enabled() && !smz::debug_sync_enabled()) ? side_streams() : nullptr;
@@ -352,15 +449,7 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
         }
         smz::profile_mark(st, "gemm_qk");
         const bool wqkv_packed = reinterpret_cast<const bf16 *>(p->wv) == reinterpret_cast<const bf16 *>(p->wqk) + 2 * kFeat * kFeat;
-        if (fast && !x_is_bf16) {
-            // float32 features: their float16 copy against float16 [Wq; Wk; Wv]; Q | K | V leave as bf16 (the logits
-            // epilogue's exp output needs the bf16 range, and alpha.V must match its format)
-            GemmEpilogue e{qk, nullptr, nullptr, 1.f, smz::GEMM_A_F16 | smz::GEMM_B_F16};
-            rc = smz::gemm_bf16_tn(xb, R, kFeat, kFeat, p->wqkv16, 3 * kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, 3 * kFeat),
-                                   dense_problem(R, 3 * kFeat, kFeat, 3 * kFeat, 0), e, st);
-            if (rc != SMZ_OK) return rc;
-            SMZ_DEBUG_STEP(st, "gemm_qkv");
-        } else if (!training && wqkv_packed) {
+        if (!training && wqkv_packed) {
             // inference: one [R, 3072] GEMM against [Wq; Wk; Wv] (the caller's bf16 copies are one buffer)
             rc = smz::gemm_bf16_tn(xb, R, kFeat, kFeat, p->wqk, 3 * kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, 3 * kFeat),
                                    dense_problem(R, 3 * kFeat, kFeat, 3 * kFeat, 0), GemmEpilogue{qk, nullptr, nullptr, 1.f, 0}, st);
@@ -391,28 +480,8 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
                 tiles_s += smz::gemm_tiles(T, T);
                 tiles_pv += smz::gemm_tiles(T, kFeat);
             }
-            // Inference fast path (the caller passed a status word and float16 weights): the logits GEMM epilogue writes
-            // exp(logit) (bf16, un-normalised) and the row sums; alpha.V (bf16 P x bf16 V -> float16 O) then scales row
-            // i by 1 / sum_i straight from the row-sum slots (GEMM_SCALE_STATS).  Softmax is shift invariant, so skipping the max subtraction is exact as long as no
-            // |logit| exceeds 80 (fp32 / bf16 exponent range); the epilogue checks that and, if it ever fails, raises
-            // SMZ_VASNET_STATUS_LOGIT_RANGE in *status: the scores of the call are then void and the caller repeats it
-            // on the exact path (no status word: fp32 logits + max-subtracted softmax).  No gated launches in between:
-            // an empty launch of the persistent GEMM costs ~5 us, two per sub-chunk were 4 % of the sweep.
             const bool inference = !training;
-            float *sstat = reinterpret_cast<float *>(w + pl.off_sstat + lb);
-            const int slots = 2 * ((s.ld + 255) / 256);
-            if (fast) {
-                smz::profile_mark(st, "gemm_logits");
-                bool ragged = false;    // a video narrower than the widest leaves slots unwritten: they must read 0
-                for (int v = s.v0; v < s.v1; v++) ragged |= 2 * ((h_cu_seqlens[v + 1] - h_cu_seqlens[v] + 255) / 256) != slots;
-                if (ragged) SMZ_CUDA_CHECK(cudaMemsetAsync(sstat, 0, (int64_t)s.rows * slots * 3 * 4, st));
-                GemmEpilogue e{P, nullptr, nullptr, p->scale, smz::GEMM_EXP | smz::GEMM_ROWSTATS};
-                e.stat_out = sstat; e.stat_slots = slots; e.aperture = p->aperture; e.ignore_self = p->ignore_self;
-                e.guard = p->status; e.guard_bit = SMZ_VASNET_STATUS_LOGIT_RANGE;
-                rc = smz::gemm_bf16_tn(qk, R, qld, qld, qk, R, qld, qld, d_probs + s.v0, nv, tiles_s, GemmProblem{}, e, st);
-                if (rc != SMZ_OK) return rc;
-                SMZ_DEBUG_STEP(st, "gemm_logits_exp");
-            } else {   // exact path
+            {   // fp32 logits + max-subtracted softmax (dropout in training mode)
                 smz::profile_mark(st, "gemm_logits");
                 GemmEpilogue e{S, nullptr, nullptr, p->scale, smz::GEMM_OUT_F32};
                 rc = smz::gemm_bf16_tn(qk, R, qld, qld, qk, R, qld, qld, d_probs + s.v0, nv, tiles_s, GemmProblem{}, e, st);
@@ -427,9 +496,7 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
             smz::profile_mark(st, "gemm_pv");
             if (fs != nullptr) SMZ_CUDA_CHECK(cudaStreamWaitEvent(st, fs->ev[1], 0));     // V^T is ready
             if (inference) {    // B = V in place: rows = frames (k), columns [2048, 3072) of the packed Q|K|V rows (MN-major)
-                GemmEpilogue e{o, fast ? sstat : nullptr, nullptr, 1.f, fast ? (smz::GEMM_SCALE_STATS | smz::GEMM_OUT_F16) : 0};
-                e.stat_slots = slots;
-                if (fast) { e.guard = p->status; e.guard_bit = SMZ_VASNET_STATUS_F16_RANGE; }
+                GemmEpilogue e{o, nullptr, nullptr, 1.f, 0};
                 rc = smz::gemm_bf16(false, true, P, s.rows, s.ld, s.ld, qk, R, qld, qld, d_probs + n + s.v0, nv, tiles_pv, GemmProblem{}, e, st);
                 if (rc != SMZ_OK) return rc;
             } else {
@@ -443,19 +510,7 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
         const void *res = x_is_bf16 ? (const void *)(reinterpret_cast<const bf16 *>(x) + (int64_t)c.row0 * kFeat)
                                     : (const void *)(reinterpret_cast<const float *>(x) + (int64_t)c.row0 * kFeat);
         const bool fused_head = !training && p->head_gw != nullptr && p->head_c != nullptr;
-        // fast path: O, Wo, y, W1 diag(g) all float16, the first LayerNorm folded into k1
-        const bool fused_ln = fast;
-        float *lnstat = reinterpret_cast<float *>(w + pl.off_lnstat + lb);
-        constexpr int kLnSlots = 2 * kFeat / smz::GEMM_BN;
         smz::profile_mark(st, "gemm_out");
-        if (fused_ln) {     // y leaves as float16 (it is k1's A operand) together with the LayerNorm sums of its float32 values
-            GemmEpilogue e{yn, nullptr, res, 1.f, (x_is_bf16 ? 0 : smz::GEMM_RES_F32) | smz::GEMM_LN_STATS | smz::GEMM_OUT_F16 | smz::GEMM_A_F16 | smz::GEMM_B_F16};
-            e.stat_out = lnstat; e.guard = p->status; e.guard_bit = SMZ_VASNET_STATUS_F16_RANGE;
-            rc = smz::gemm_bf16_tn(o, R, kFeat, kFeat, p->wo16, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
-                                   dense_problem(R, kFeat, kFeat, kFeat, kFeat), e, st);
-            if (rc != SMZ_OK) return rc;
-            SMZ_DEBUG_STEP(st, "gemm_out");
-        } else {
         rc = smz::gemm_bf16_tn(o, R, kFeat, kFeat, p->wo, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
                                dense_problem(R, kFeat, kFeat, kFeat, kFeat),
                                GemmEpilogue{y, nullptr, res, 1.f, smz::GEMM_OUT_F32 | (x_is_bf16 ? 0 : smz::GEMM_RES_F32)}, st);
@@ -466,18 +521,14 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
                                    stats, stats ? stats + Rs : nullptr, st);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "layernorm");
-        }
         smz::profile_mark(st, "gemm_k1");
         if (fused_head) {
             // inference: H never reaches memory — the k1 epilogue reduces relu(h) to the three row sums the second
             // LayerNorm + k2 dot need (GEMM_ROWSTATS), a one-thread-per-frame kernel finishes the score
             float *hstat = reinterpret_cast<float *>(w + pl.off_hstat + lb);
-            GemmEpilogue e{h, fused_ln ? p->b1f : p->b1, nullptr, 1.f,
-                           smz::GEMM_RELU | smz::GEMM_OUT_F32 | smz::GEMM_ROWSTATS | smz::GEMM_NO_STORE |
-                           (fused_ln ? (smz::GEMM_LN_FOLD | smz::GEMM_A_F16 | smz::GEMM_B_F16) : 0)};
+            GemmEpilogue e{h, p->b1, nullptr, 1.f, smz::GEMM_RELU | smz::GEMM_OUT_F32 | smz::GEMM_ROWSTATS | smz::GEMM_NO_STORE};
             e.stat_w = p->head_gw; e.stat_out = hstat;
-            if (fused_ln) { e.ln_stats = lnstat; e.ln_c = p->ln_c; e.ln_slots = kLnSlots; e.ln_width = kFeat; e.ln_eps = p->eps; }
-            rc = smz::gemm_bf16_tn(yn, R, kFeat, kFeat, fused_ln ? p->w1g : p->w1, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
+            rc = smz::gemm_bf16_tn(yn, R, kFeat, kFeat, p->w1, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
                                    dense_problem(R, kFeat, kFeat, kFeat, 0), e, st);
             if (rc != SMZ_OK) return rc;
             SMZ_DEBUG_STEP(st, "gemm_k1");

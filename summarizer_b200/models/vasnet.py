@@ -24,7 +24,7 @@ class VasnetParams(C.Structure):
                 ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("ln_g", C.c_void_p),
                 ("ln_b", C.c_void_p), ("scale", C.c_float), ("eps", C.c_float), ("aperture", C.c_int32),
                 ("ignore_self", C.c_int32), ("head_gw", C.c_void_p), ("head_c", C.c_void_p),
-                ("w1g", C.c_void_p), ("ln_c", C.c_void_p), ("b1f", C.c_void_p), ("wqkv16", C.c_void_p), ("wo16", C.c_void_p),
+                ("w1g", C.c_void_p), ("ln_c", C.c_void_p), ("b1f", C.c_void_p), ("wgv", C.c_void_p), ("wgv16", C.c_void_p),
                 ("status", C.c_void_p)]
 
 
@@ -144,19 +144,22 @@ class VASNet(nn.Module):
                 sh["w1g"] = (w1 * sh["ln_g"][None, :]).to(torch.float16).contiguous()       # float16: y is handed over as float16
                 sh["ln_c"] = sh["w1g"].float().sum(1).contiguous()
                 sh["b1f"] = (w1 @ sh["ln_b"] + sh["b1"]).contiguous()
-                # float16 weights of the fast path; it is only offered when float16 holds them well (no overflow, the
-                # largest entries far above the subnormal range)
-                mats = (self.Q.weight, self.K.weight, self.V.weight, self.attention_head_projection.weight, w1 * sh["ln_g"][None, :])
-                amax = torch.stack([t.detach().abs().max() for t in mats]).float()
-                sh["f16_ok"] = bool(((amax < 6e4) & (amax > 1e-3)).all().item())
-                sh["wqkv16"] = torch.cat([t.detach() for t in mats[:3]], 0).to(torch.float16).contiguous()
-                sh["wo16"] = mats[3].detach().to(torch.float16).contiguous()
+                # folded projections of the fast path (products in float32): rows 0..1023 = Wo Wv, 1024..2047 = Wk^T Wq.
+                # The fast path is only offered when 16-bit floats hold them well (no overflow, the largest entries far
+                # above the float16 subnormal range)
+                wq, wk, wv, wo = (t.detach().float() for t in (self.Q.weight, self.K.weight, self.V.weight,
+                                                               self.attention_head_projection.weight))
+                gv = torch.cat([wo @ wv, wk.t() @ wq], 0)
+                amax = torch.stack([gv[:1024].abs().max(), gv[1024:].abs().max(), (w1 * sh["ln_g"][None, :]).abs().max()])
+                sh["fast_ok"] = bool((torch.isfinite(amax) & (amax < 6e4) & (amax > 1e-3)).all().item())
+                sh["wgv"] = gv.to(torch.bfloat16).contiguous()
+                sh["wgv16"] = gv.to(torch.float16).contiguous()
         st = VasnetParams(*(sh[k].data_ptr() for k in ("wqk", "wv", "wo", "w1", "b1", "w2", "b2", "ln_g", "ln_b")),
                           float(self.scale), float(self.epsilon),
                           -1 if self.aperture is None else int(self.aperture), int(bool(self.ignore_self)),
                           *((sh[k].data_ptr() if inference else None) for k in ("head_gw", "head_c", "w1g", "ln_c", "b1f")),
-                          *((sh[k].data_ptr() if (inference and fast and sh["f16_ok"]) else None) for k in ("wqkv16", "wo16")),
-                          self._status_word(sh["ln_g"].device).data_ptr() if (inference and fast and sh["f16_ok"]) else None)
+                          *((sh[k].data_ptr() if (inference and fast and sh["fast_ok"]) else None) for k in ("wgv", "wgv16")),
+                          self._status_word(sh["ln_g"].device).data_ptr() if (inference and fast and sh["fast_ok"]) else None)
         return sh, st
 
     def _status_word(self, device):
