@@ -74,6 +74,11 @@ int main() {
     report("logits 16x2000 EXP + row sums", fl_att, time_it([&] { GemmEpilogue e{P, nullptr, nullptr, 0.06f, smz::GEMM_EXP | smz::GEMM_ROWSTATS}; e.stat_out = stat; e.stat_slots = 16; e.guard = guard; rc |= smz::gemm_bf16_tn(qkv, R, 3 * D, 3 * D, qkv, R, 3 * D, 3 * D, dpr, NV, tl, GemmProblem{}, e, st); }));
     report("pv     16x2000 MN-major V plain", fl_att, time_it([&] { rc |= smz::gemm_bf16(false, true, P, R, LD, LD, qkv, R, 3 * D, 3 * D, dpr + NV, NV, tp, GemmProblem{}, GemmEpilogue{o, nullptr, nullptr, 1.f, 0}, st); }));
     report("pv     16x2000 MN-major V SCALE_STATS", fl_att, time_it([&] { GemmEpilogue e{o, stat, nullptr, 1.f, smz::GEMM_SCALE_STATS}; e.stat_slots = 16; rc |= smz::gemm_bf16(false, true, P, R, LD, LD, qkv, R, 3 * D, 3 * D, dpr + NV, NV, tp, GemmProblem{}, e, st); }));
+    // ---- the folded fast path (smz_vasnet.cu, fast_chunk)
+    float *lnstat; CK(cudaMalloc(&lnstat, (size_t)R * 8 * 3 * 4));
+    report("proj  N=2048 plain bf16", 2.0 * R * 2048 * D, time_it([&] { rc |= smz::gemm_bf16_tn(x, R, D, D, w, 2048, D, D, nullptr, 1, smz::gemm_tiles(R, 2048), dense(R, 2048, D, 3072, 0), GemmEpilogue{qkv, nullptr, nullptr, 1.f, 0}, st); }));
+    report("pv'   SCALE_STATS + res + LN_STATS + f16", fl_att, time_it([&] { GemmEpilogue e{o, stat, x, 1.f, smz::GEMM_SCALE_STATS | smz::GEMM_RES_AT_C | smz::GEMM_LN_STATS | smz::GEMM_OUT_F16}; e.scale_slots = 16; e.stat_out = lnstat; e.stat_slots = 8; e.guard = guard; rc |= smz::gemm_bf16(false, true, P, R, LD, LD, qkv, R, 3 * D, 3 * D, dpr + NV, NV, tp, GemmProblem{}, e, st); }));
+    report("k1    head + LN_FOLD (f16 operands)", 2.0 * R * D * D, time_it([&] { GemmEpilogue e{f32, vec, nullptr, 1.f, smz::GEMM_RELU | smz::GEMM_OUT_F32 | smz::GEMM_ROWSTATS | smz::GEMM_NO_STORE | smz::GEMM_LN_FOLD | smz::GEMM_A_F16 | smz::GEMM_B_F16}; e.stat_w = vec; e.stat_out = stat; e.ln_stats = lnstat; e.ln_c = vec; e.ln_slots = 8; e.ln_width = 1024; e.ln_eps = 1e-6f; rc |= smz::gemm_bf16_tn(x, R, D, D, w, D, D, D, nullptr, 1, smz::gemm_tiles(R, D), dense(R, D, D, D, 0), e, st); }));
     printf("rc %d %s\n", rc, rc ? smz_last_error() : "");
     return rc;
 }

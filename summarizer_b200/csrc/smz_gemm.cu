@@ -100,7 +100,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     float *stg_all = reinterpret_cast<float *>(smem + STAGES * (A_STAGE + B_STAGE) + BAR_BYTES);
 
     if (P.epi.gate != nullptr && __ldg(P.epi.gate) == 0) return;  // gated launch (fallback path not needed): every CTA leaves
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;     // warp index, provably uniform
     const int rank = PAIR ? (int)cluster_ctarank() : 0;           // 0 = leader CTA of the pair
     const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -120,7 +120,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (every CTA)
-        if (lane == 0) {
+        // whole warp in the loop, one elected lane issues (see the MMA issuer below)
+        {
             Cursor c;
             int stage = 0; uint32_t phase = 0;
             for (int tile = first_tile; tile < P.total_tiles; tile += tile_step) {
@@ -134,35 +135,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int a_k = A_MN ? c.cur.a_row0 : c.cur.a_col0, b_k = B_MN ? c.cur.b_row0 : c.cur.b_col0;
                 for (int kb = 0; kb < nkb; kb++) {
                     mbar_wait(&empty[stage], phase ^ 1u);
-                    // the bytes of BOTH CTAs are accounted on the leader's barrier, which the MMA thread waits on
-                    if (!PAIR) mbar_arrive_expect_tx(&full[stage], A_STAGE + B_STAGE);
-                    else if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (A_STAGE + B_STAGE));
-                    else mbar_arrive_remote(&full[stage], 0);
-                    if (A_MN) {
+                    if (elect_one()) {
+                        // the bytes of BOTH CTAs are accounted on the leader's barrier, which the MMA thread waits on
+                        if (!PAIR) mbar_arrive_expect_tx(&full[stage], A_STAGE + B_STAGE);
+                        else if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (A_STAGE + B_STAGE));
+                        else mbar_arrive_remote(&full[stage], 0);
+                        if (A_MN) {
 #pragma unroll
-                        for (int j = 0; j < BM / 64; j++)
-                            tma_load<PAIR>(sA + stage * A_STAGE + j * 8192, &tmA, &full[stage], a_mn + 64 * j, a_k + kb * BK);
-                    } else {
-                        tma_load<PAIR>(sA + stage * A_STAGE, &tmA, &full[stage], a_k + kb * BK, a_mn);
-                    }
-                    if (B_MN) {
+                            for (int j = 0; j < BM / 64; j++)
+                                tma_load<PAIR>(sA + stage * A_STAGE + j * 8192, &tmA, &full[stage], a_mn + 64 * j, a_k + kb * BK);
+                        } else {
+                            tma_load<PAIR>(sA + stage * A_STAGE, &tmA, &full[stage], a_k + kb * BK, a_mn);
+                        }
+                        if (B_MN) {
 #pragma unroll
-                        for (int j = 0; j < B_ROWS / 64; j++)
-                            tma_load<PAIR>(sB + stage * B_STAGE + j * 8192, &tmB, &full[stage], b_mn + 64 * j, b_k + kb * BK);
-                    } else {
-                        tma_load<PAIR>(sB + stage * B_STAGE, &tmB, &full[stage], b_k + kb * BK, b_mn);
+                            for (int j = 0; j < B_ROWS / 64; j++)
+                                tma_load<PAIR>(sB + stage * B_STAGE + j * 8192, &tmB, &full[stage], b_mn + 64 * j, b_k + kb * BK);
+                        } else {
+                            tma_load<PAIR>(sB + stage * B_STAGE, &tmB, &full[stage], b_k + kb * BK, b_mn);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-        if (lane == 0 && rank == 0) {
+        // The whole warp walks the loop and waits on the barriers; one elected lane issues.  With a single-lane branch
+        // around the loop the compiler must treat every descriptor as divergent and wraps each tcgen05.mma in an
+        // ELECT / R2UR waterfall loop: ~110 dependent instructions per k block against 512 cycles of tensor work,
+        // which held the tensor pipe at 65-75 % (profiles/r02c).
+        if (rank == 0) {
             Cursor c;
             // operand format fields ([7,10) A, [10,13) B): 1 = bf16 (make_idesc_bf16's default), 0 = f16
             const uint32_t idesc = (make_idesc_bf16(TILE_M, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u))
                                    & ~(((P.epi.flags & smz::GEMM_A_F16) ? (1u << 7) : 0u) | ((P.epi.flags & smz::GEMM_B_F16) ? (1u << 10) : 0u));
+            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int tile = first_tile; tile < P.total_tiles; tile += tile_step, ++it) {
@@ -175,17 +184,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 for (int kb = 0; kb < nkb; kb++) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sA + stage * A_STAGE), b_addr = smem_u32(sB + stage * B_STAGE);
+                    const uint32_t a_addr = a_base + stage * A_STAGE, b_addr = b_base + stage * B_STAGE;
                     const uint64_t adesc = A_MN ? make_mnmajor_sw128_desc(a_addr) : make_kmajor_sw128_desc(a_addr);
                     const uint64_t bdesc = B_MN ? make_mnmajor_sw128_desc(b_addr) : make_kmajor_sw128_desc(b_addr);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; k++)   // per K=16 slice: +32 B inside the swizzle atom (K-major), +2 KB (MN-major)
-                        umma_bf16<PAIR>(d_tmem, adesc + (A_MN ? 128 : 2) * k, bdesc + (B_MN ? 128 : 2) * k, idesc,
-                                        (uint32_t)((kb | k) != 0));
-                    umma_commit<PAIR>(&empty[stage]);       // PAIR: multicast to the same barrier of both CTAs
+                        for (int k = 0; k < BK / 16; k++)   // per K=16 slice: +32 B inside the swizzle atom (K-major), +2 KB (MN-major)
+                            umma_bf16<PAIR>(d_tmem, adesc + (A_MN ? 128 : 2) * k, bdesc + (B_MN ? 128 : 2) * k, idesc,
+                                            (uint32_t)((kb | k) != 0));
+                        umma_commit<PAIR>(&empty[stage]);       // PAIR: multicast to the same barrier of both CTAs
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit<PAIR>(&tfull[as]);
+                if (elect_one()) umma_commit<PAIR>(&tfull[as]);
+                __syncwarp();
             }
         }
     } else {
@@ -400,9 +413,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 } else {
                     __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(P.epi.C) + co;
                     if (full32 && c_vec) {
+                        // 16-bit tiles leave through the pad as well (below): 8 rows x 64 contiguous bytes per store
+                        // instruction instead of 32 rows x 16 bytes (half-used sectors on 32 different lines)
+                        uint4 *pad = reinterpret_cast<uint4 *>(reinterpret_cast<uint32_t *>(stg) + lane * 20);
 #pragma unroll
                         for (int j = 0; j < 32; j += 8)
-                            *reinterpret_cast<uint4 *>(dst + j) = f16 ?
+                            pad[j >> 3] = f16 ?
                                 make_uint4(pack_f16x2(x[j], x[j + 1]), pack_f16x2(x[j + 2], x[j + 3]),
                                            pack_f16x2(x[j + 4], x[j + 5]), pack_f16x2(x[j + 6], x[j + 7])) :
                                 make_uint4(pack_bf16x2(x[j], x[j + 1]), pack_bf16x2(x[j + 2], x[j + 3]),
@@ -424,6 +440,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll 8
                     for (int r = 0; r < 32; r++)
                         if (m_base + r < g.M) base[(int64_t)(m_base + r) * g.ldc] = stg[r * 33 + lane];
+                    __syncwarp();
+                }
+                if (EPI != EPI_HEAD && !out_f32 && n0 + 32 <= n_store && c_vec) {   // warp-uniform: 16-bit rows, 64 contiguous bytes each
+                    __syncwarp();
+                    const int m_base = m - lane;
+                    const int sub = lane >> 2, part = lane & 3;
+                    __nv_bfloat16 *base = reinterpret_cast<__nv_bfloat16 *>(P.epi.C) + g.c_off + n0 + part * 8;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int r = 8 * i + sub;
+                        const uint4 w4 = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(stg) + r * 20 + part * 4);
+                        if (m_base + r < g.M) *reinterpret_cast<uint4 *>(base + (int64_t)(m_base + r) * g.ldc) = w4;
+                    }
                     __syncwarp();
                 }
 #pragma unroll

@@ -86,6 +86,14 @@ __device__ __forceinline__ void tma_load(void *smem_dst, const CUtensorMap *m, u
 }
 
 // ---- tcgen05 ---------------------------------------------------------------------------------
+// one lane of the (converged) warp: the tcgen05 / TMA issue idiom — the WHOLE warp runs the role's loop, so every loop
+// variable is warp-uniform and lives in the uniform datapath; only the issue itself is predicated on the elected lane
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
