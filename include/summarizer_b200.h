@@ -126,6 +126,10 @@ int smz_fscore(const smz_video_desc *desc, int n_videos, int max_n_frames, int t
  * Annotator rows: exactly one of user_summary (float32 rows, see smz_fscore) and user_bits + bits_off (1 bit per
  * frame, see smz_fscore_packed).  All other arguments and outputs as in smz_select_shots / smz_fscore; results are
  * identical to calling those two (which is what happens for videos whose DP rows do not fit the fused plan). */
+/* DEVICE: float32 annotator rows -> 1 bit per frame (x > 0), the layout of smz_host_pack_user_summary: pack once, then
+ * evaluate any number of score sets with smz_fscore_packed / smz_eval_batch(user_bits) at 1/32 of the bytes. */
+int smz_pack_user_bits(const smz_video_desc *desc, int n_videos, const float *user_summary, const int64_t *bits_off,
+                       uint32_t *user_bits, void *stream);
 int smz_eval_batch(const smz_video_desc *desc, int n_videos, int total_users, const float *scores,
                    const int32_t *picks, const int32_t *cps, const int32_t *nfps, int method, int max_n_segs,
                    int max_capacity, int max_n_frames, int max_seg_frames, const float *user_summary,

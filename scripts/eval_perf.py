@@ -39,6 +39,8 @@ def timed(fn, reps=5):
 out = {"videos": n, "scores": mode, "no_dp16": bool(os.environ.get("SMZ_NO_DP16"))}
 out["select_ms"] = timed(lambda: b.select(scores))
 out["fscore_ms"] = timed(lambda: b.fscore())
+pk = b.pack_user_bits()
+out["pack_ms"] = timed(lambda: b.pack_user_bits(pk))
 ref = {k: getattr(b, k).clone() for k in ("picked", "mask", "msum", "overlap", "avg_f")}
 out["evaluate_ms"] = timed(lambda: b.evaluate(scores))
 torch.cuda.synchronize()

@@ -66,6 +66,7 @@ SIGNATURES = {
     "smz_dsn_reward": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _L, _P]),
     "smz_host_pack_user_summary": (_I, [_P, _I, _P, _P, _P, _I]),
     "smz_fscore_packed": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "smz_pack_user_bits": (_I, [_P, _I, _P, _P, _P, _P]),
     "smz_kts_workspace_bytes": (_I, [_I, _I, _I, C.POINTER(C.c_int64)]),
     "smz_kts_gram": (_I, [_P, _I, _I, _I, _P, _P]),
     "smz_kts": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, C.c_double, _I, _P, _P, _P, _P, _L, _P]),

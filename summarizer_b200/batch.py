@@ -244,6 +244,18 @@ class VideoBatch:
                                                    ctypes.c_void_p(out.data_ptr()), int(n_threads)))
         return out
 
+    def pack_user_bits(self, out=None):
+        """DEVICE: the resident float32 annotator rows -> int32 words, one bit per frame (same layout and bits as
+        ``pack_user_summary_host``).  HBM-bound streaming kernel (smz_pack_user_bits)."""
+        if not self.has_users:
+            raise ValueError("this batch holds no user_summary")
+        self._bits_layout()
+        if out is None:
+            out = torch.empty(max(self.total_bit_words, 1), dtype=torch.int32, device=self.device)
+        N.check(N.lib().smz_pack_user_bits(N.ptr(self.d_desc), self.n_videos, N.ptr(self.d_users), N.ptr(self.d_bits_off),
+                                           N.ptr(out), N.current_stream()))
+        return out
+
     def fscore_packed(self, d_bits):
         """fscore() against annotator rows given as device bit words (see pack_user_summary_host); same F values."""
         self._bits_layout()

@@ -59,4 +59,5 @@ int upload_small(void *dst, const void *src, size_t bytes, cudaStream_t st);
 // Max opt-in dynamic shared memory per block of the current device.
 int max_smem_optin();
 
+
 }  // namespace smz

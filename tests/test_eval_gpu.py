@@ -246,6 +246,25 @@ def test_fscore_from_host_packed_annotator_bits():
         assert torch.equal(r[: b.total_users if r.numel() >= b.total_users else b.n_videos], t[: b.total_users if r.numel() >= b.total_users else b.n_videos])
 
 
+@pytest.mark.gpu
+def test_device_pack_equals_host_pack():
+    """smz_pack_user_bits (bulk-copy streaming kernel) produces the words smz_host_pack_user_summary does: aligned and
+    unaligned rows, ragged lengths (chunk tails), non-binary / negative annotations, more chunks than ring stages."""
+    from summarizer_b200 import synthetic
+    from summarizer_b200.batch import VideoBatch
+    vids, _ = _dataset_videos("tvsum", 5)
+    vids[1] = dict(vids[1]); vids[1]["user_summary"] = vids[1]["user_summary"] * np.float32(0.25)
+    vids[2] = dict(vids[2]); vids[2]["user_summary"] = vids[2]["user_summary"] - np.float32(0.5)
+    for nf, nu in ((5, 1), (1024, 2), (1025, 3), (33000, 7), (4097, 21)):
+        v = synthetic.make_video("summe", 700 + nf, n_frames=nf, n_users=nu, with_features=False)
+        vids.append({k: v[k] for k in ("n_frames", "picks", "change_points", "n_frame_per_seg", "user_summary")})
+    for pad in (True, False):
+        b = VideoBatch(vids, pad_user_rows=pad)
+        want = b.pack_user_summary_host(b.d_users.cpu(), n_threads=2)
+        got = b.pack_user_bits(torch.full((b.total_bit_words,), -1, dtype=torch.int32, device="cuda"))
+        assert torch.equal(got.cpu(), want), f"pad_user_rows={pad}"
+
+
 def test_knapsack_ortools_signature():
     from summarizer_b200.utils.knapsack import knapsack_ortools
     rng = np.random.default_rng(12)
