@@ -206,12 +206,103 @@ def cpu_baseline(seconds):
         incumbent = {"value": reps * len(xs) / (e0.elapsed_time(e1) / 1e3), "unit": "videos/s (scoring only)",
                      "what": "oracle/models_torch.py VASNet forward in float32 torch on this B200 (stock ATen/cuBLAS kernels, "
                              "one 2000-frame video per call, as the reference's per-video loop)"}
+        with torch.no_grad():
+            # the same-precision incumbent: the same restatement in bfloat16, 16 videos per call (torch.bmm attention)
+            bsd = {k: v.to(torch.bfloat16) for k, v in dsd.items()}
+            xb = torch.stack([xs[i % len(xs)] for i in range(16)]).to(torch.bfloat16)
+
+            def batched(x3):
+                K = x3 @ bsd["K.weight"].t(); Q = x3 @ bsd["Q.weight"].t(); V = x3 @ bsd["V.weight"].t()
+                a = torch.softmax(torch.bmm(Q, K.transpose(1, 2)) * scale, dim=2)
+                y = torch.bmm(a, V) @ bsd["attention_head_projection.weight"].t() + x3
+                ln = lambda t: torch.nn.functional.layer_norm(t, (FEAT,), bsd["layer_norm.weight"], bsd["layer_norm.bias"], eps)
+                h = ln(torch.relu(ln(y) @ bsd["k1.weight"].t() + bsd["k1.bias"]))
+                return torch.sigmoid(h @ bsd["k2.weight"].t() + bsd["k2.bias"])
+            for _ in range(2):
+                batched(xb)
+            torch.cuda.synchronize()
+            e0.record()
+            for r in range(reps):
+                batched(xb)
+            e1.record(); torch.cuda.synchronize()
+            incumbent["bf16_batched"] = {"value": reps * 16 / (e0.elapsed_time(e1) / 1e3), "unit": "videos/s (scoring only)",
+                                         "what": "the same forward in bfloat16 torch, 16 videos per call (cuBLAS bf16 GEMMs / bmm, "
+                                                 "ATen softmax / LayerNorm): the same-precision stock incumbent"}
       except Exception as e:                      # a reported extra, never a reason to lose the bench line
         incumbent = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     return {"value": n / dt, "unit": "videos/s", "cores": cores, "kind": "port", "stock_torch_on_this_gpu": incumbent,
             "sample": f"{n} sweep-shaped videos (2000 x 1024 fp32 features, 30000 frames, 20 users) in {dt:.1f}s: "
                       "VASNet forward in float32 torch on all host threads (oracle/models_torch.py) + "
                       "oracle/ref_port.py eval (numpy+Python loops as the reference, C restatement of the OR-tools DP)"}
+
+
+def _torch_train_arm(device, seconds):
+    """frames/s of the reference's per-video training steps in stock float32 torch on `device` ("cpu": all host
+    threads; "cuda": stock ATen / cuBLAS / cuDNN kernels): VASNet forward + MSE + backward + Adam (vasnet.py:193-212,
+    oracle/models_torch.py restatement under autograd) and DSN forward (nn.LSTM, as dsn.py:37-50) + 5 REINFORCE
+    episodes with the diversity / representativeness reward (dsn.py:96-149,165-236) + backward + clip + Adam, on the
+    same 16 TVSum-like lengths as the native `train` stage."""
+    import torch
+    from torch.distributions import Bernoulli
+    from oracle import models_torch
+    from summarizer_b200.models.vasnet import VASNet
+    dev = torch.device(device)
+    rng = np.random.default_rng(2)
+    lens = [int(t) for t in rng.integers(167, 1295, size=16)]
+    g = torch.Generator().manual_seed(3)
+    vids = []
+    for T in lens:
+        x = torch.randn(T, FEAT, generator=g).abs_()
+        vids.append(((x / x.norm(dim=1, keepdim=True)).to(dev), torch.rand(T, generator=g).to(dev)))
+    sync = torch.cuda.synchronize if dev.type == "cuda" else (lambda: None)
+
+    def rate(step, budget):
+        step(*vids[0]); sync()
+        n, frames, t0 = 0, 0, time.perf_counter()
+        while time.perf_counter() - t0 < budget:
+            x, tgt = vids[n % len(vids)]
+            step(x, tgt); sync()
+            frames += x.shape[0]; n += 1
+        return frames / (time.perf_counter() - t0), n
+
+    torch.manual_seed(0)
+    m = VASNet()
+    sd = {k: v.detach().clone().to(dev).requires_grad_(True) for k, v in m.state_dict().items()}
+    opt = torch.optim.Adam(list(sd.values()), lr=5e-5, weight_decay=1e-5)
+
+    def vas_step(x, tgt):
+        opt.zero_grad(set_to_none=True)
+        y = models_torch.vasnet_forward(sd, x, scale=float(m.scale), eps=float(m.epsilon))
+        torch.nn.functional.mse_loss(y, tgt).backward()
+        opt.step()
+    vas_rate, vas_n = rate(vas_step, seconds / 2)
+
+    lstm = torch.nn.LSTM(FEAT, 256, bidirectional=True).to(dev)
+    fc = torch.nn.Linear(512, 1).to(dev)
+    params = list(lstm.parameters()) + list(fc.parameters())
+    opt2 = torch.optim.Adam(params, lr=5e-5, weight_decay=1e-5)
+
+    def dsn_step(x, tgt):
+        opt2.zero_grad(set_to_none=True)
+        h, _ = lstm(x.unsqueeze(1))
+        probs = torch.sigmoid(fc(h)).reshape(-1)
+        dist = Bernoulli(probs)
+        cost = 0.
+        for _ in range(5):
+            actions = dist.sample()
+            reward = models_torch.dsn_reward(x, actions)
+            cost = cost - dist.log_prob(actions).mean() * reward
+        (cost / 5).backward()
+        torch.nn.utils.clip_grad_norm_(params, 5.0)
+        opt2.step()
+    try:
+        dsn_rate, dsn_n = rate(dsn_step, seconds / 2)
+    except Exception as e:
+        dsn_rate, dsn_n = None, f"{type(e).__name__}: {e}"[:160]
+    return {"vasnet_train_frames_per_s": vas_rate, "vasnet_steps": vas_n, "dsn_reinforce_frames_per_s": dsn_rate,
+            "dsn_steps": dsn_n, "device": device,
+            "what": "stock float32 torch (oracle/models_torch.py VASNet under autograd; nn.LSTM DSN + restated reward), "
+                    "one video per optimizer step, same lengths as the native train stage"}
 
 
 def run_reference(args):
@@ -252,6 +343,10 @@ def run_reference(args):
                                        "(the reference is pure Python + un-installable OR-tools, so the port is timed)"},
             "e2e": {"value": value, "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    try:                                           # the frames/s fwd+bwd half of the metric, same box, CPU arm
+        line["train"] = _torch_train_arm("cpu", min(args.cpu_seconds, 12.0))
+    except Exception as e:
+        line["train"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     print(json.dumps(line), flush=True)
 
 
@@ -376,6 +471,152 @@ def train_stage(dev, seconds=4.0):
     del gan, tr
     torch.cuda.empty_cache()
     return out
+
+
+def strong_stage(args, model, dev, rank, world, barrier, dist):
+    """Strong scaling of the sweep: ONE 10 000-video sweep split over the ranks (V / N videos each, no
+    data-path collective).  Returns videos/s of the whole job, max-over-ranks device time."""
+    import torch
+    from summarizer_b200 import synthetic
+    Vs = max(1, args.videos // world)
+    batch = synthetic.make_sweep_batch(Vs, dev, seed=6000 + 100000 * rank)
+    feats = make_features(Vs, dev, seed=177 + rank)
+    lengths = [N_STEPS] * Vs
+    stream = torch.cuda.current_stream()
+
+    def step():
+        batch.evaluate(model.score_packed(feats, lengths, check=False))
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    batch.check_status()
+    ok = model.check_status()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    del batch, feats
+    torch.cuda.empty_cache()
+    return {"scaling": "strong", "videos_total": Vs * world, "videos_per_gpu": Vs, "value": Vs * world * args.steps / (t.item() / 1e3),
+            "unit": "videos/s", "ms_per_step": t.item() / args.steps, "range_ok": bool(ok)}
+
+
+def train_dp_stage(dev, rank, world, dist, seconds=3.0):
+    """BASELINE config 4 style data parallelism on the VASNet trainer: one video per rank and optimizer step, the
+    replicas' gradients averaged with ONE NCCL all-reduce of a persistent flat float32 buffer (the parameters' .grad
+    are views into it), Adam on every rank.  frames/s of the whole job and the all-reduce's device time."""
+    import torch
+    from summarizer_b200.models.vasnet import VASNet
+    rng = np.random.default_rng(2)
+    lens = [int(t) for t in rng.integers(167, 1295, size=16)]
+    g = torch.Generator(device=dev); g.manual_seed(3 + rank)
+    vids = []
+    for T in lens:
+        x = torch.randn(T, 1, FEAT, generator=g, device=dev).abs_()
+        vids.append((x / x.norm(dim=2, keepdim=True), torch.rand(T, 1, 1, generator=g, device=dev)))
+    torch.manual_seed(0)
+    vas = VASNet().to(dev).train()
+    params = [p for p in vas.parameters() if p.requires_grad]
+    for p in params:
+        dist.broadcast(p.data, src=0)
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+    o = 0
+    for p in params:
+        p.grad = flat[o:o + p.numel()].view_as(p); o += p.numel()
+    opt = torch.optim.Adam(params, lr=5e-5, weight_decay=1e-5, fused=True)
+    ar0, ar1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ar_ms = []
+
+    def step(k, timed_ar=False):
+        x, tgt = vids[k % len(vids)]
+        flat.zero_()
+        torch.nn.functional.mse_loss(vas(x), tgt).backward()
+        if timed_ar:
+            ar0.record()
+        dist.all_reduce(flat)
+        flat.div_(world)
+        if timed_ar:
+            ar1.record()
+        opt.step()
+        vas._shadow_key = None
+        return x.shape[0]
+    for k in range(4):
+        step(k)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_steps = 64                      # fixed on every rank: the loop holds a collective
+    e0.record()
+    frames = 0
+    for k in range(n_steps):
+        frames += step(k, timed_ar=(k % 16 == 15))
+        if k % 16 == 15:
+            torch.cuda.synchronize(); ar_ms.append(ar0.elapsed_time(ar1))
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    same = flat.clone(); dist.all_reduce(same, op=dist.ReduceOp.MAX)
+    replicas_equal = bool(torch.equal(same, flat))         # after the averaged all-reduce every rank holds the same gradient
+    out = {"model": "VASNet", "videos_per_step": world, "steps": n_steps, "frames_per_s": frames * world / (t.item() / 1e3),
+           "ms_per_step": t.item() / n_steps, "allreduce_ms": float(np.median(ar_ms)), "allreduce_mb": flat.numel() * 4 / 1e6,
+           "gradients_equal_across_ranks": replicas_equal, "what": "eager step: forward + MSE + backward (smz kernels), one "
+           "NCCL all-reduce of the flat gradient buffer, fused Adam; every rank a different video"}
+    del vas, opt, flat
+    return out
+
+
+def cv_stage(dev, rank, world):
+    """BASELINE config 3: VASNet 5-fold cross-validation on the SumMe- and TVSum-shaped synthetic datasets (10 fold
+    jobs), fold-parallel over the ranks (summarizer_b200.main.train: all jobs dealt longest-first, no data-path
+    collective), measured IN this process so that interpreter / CUDA start-up (19 s of the 20 s a cold
+    `python main.py` takes) is not what is timed."""
+    import tempfile
+    import torch
+    from summarizer_b200 import main as M
+    from summarizer_b200.utils.config import HParameters
+    tmp = tempfile.mkdtemp(prefix="smz_bench_cv_")
+    hps = HParameters()
+    hps.load_from_args({"use_cuda": "yes", "cuda_device": dev.index, "model": "vasnet", "epochs": 20, "test_every_epochs": 10,
+                        "splits_files": "splits/tvsum_splits.json,splits/summe_splits.json", "log_level": "error",
+                        "log_root": tmp, "tensorboard": False, "extra_params": {}})
+    # the synthetic stand-in datasets are generated once, outside the timed region (a real run opens the HDF5 files)
+    from summarizer_b200 import synthetic
+    cache = {n: synthetic.make_dataset(n) for n in ("tvsum", "summe")}
+    orig = synthetic.make_dataset
+    synthetic.make_dataset = lambda name, *a, **k: cache[name]
+    try:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        results = M.train(hps)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    finally:
+        synthetic.make_dataset = orig
+    return {"config": "VASNet 5-fold CV on both synthetic datasets (10 fold jobs), 20 epochs, test every 10", "wall_s": dt,
+            "n_gpus": world, "cv": [[os.path.basename(sf), float(c), float(a), float(m)] for sf, c, a, m in results]}
+
+
+def h2d_ceiling(dev, world, dist, nbytes=512 << 20, reps=6):
+    """Plain pinned host -> device copy bandwidth of this box with ALL ranks copying at once (GB/s per rank, min over ranks)."""
+    import torch
+    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d.copy_(h, non_blocking=True); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        d.copy_(h, non_blocking=True)
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return reps * nbytes / (t.item() / 1e3) / 1e9
 
 
 def run_native(args):
@@ -563,6 +804,20 @@ def run_native(args):
     pool.shutdown(wait=False)
     use_packed = e2e_packed >= e2e_float
     e2e_value = max(e2e_packed, e2e_float)
+    try:
+        h2d_gbs = h2d_ceiling(dev, world, dist)
+    except Exception:
+        h2d_gbs = None
+    extra = {}
+    if world > 1:
+        for name, fn in (("strong", lambda: strong_stage(args, model, dev, rank, world, barrier, dist)),
+                         ("train_dp", lambda: train_dp_stage(dev, rank, world, dist)),
+                         ("cv_fold_parallel", lambda: cv_stage(dev, rank, world))):
+            try:                                   # secondary stages never cost the headline line; every rank takes part
+                extra[name] = fn()
+            except Exception as e:
+                extra[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                torch.cuda.synchronize()
     users_bytes = sets[0]["h_bits"].numel() * 4 if use_packed else h_users.numel() * 4
 
     if rank == 0:
@@ -614,16 +869,25 @@ def run_native(args):
                     "pipelining": "two buffer sets: step i+1 H2D on a copy stream overlaps step i kernels",
                     "annotator_staging": ("packed on %d host threads to 1 bit/frame inside the timed region (x > 0 is all "
                                           "evaluate_summary reads)" % host_threads) if use_packed else "float32 rows as held by the reference",
-                    "value_float32_rows": e2e_float, "value_host_packed": e2e_packed, "host_packed_error": packed_note},
+                    "value_float32_rows": e2e_float, "value_host_packed": e2e_packed, "host_packed_error": packed_note,
+                    "h2d_gbs_per_rank_all_ranks_copying": h2d_gbs,
+                    "h2d_ceiling_videos_per_s": (h2d_gbs * 1e9 * world / ((h_feats.numel() * 2 + users_bytes) / ne)) if h2d_gbs else None,
+                    "frac_of_h2d_ceiling": (e2e_value / (h2d_gbs * 1e9 * world / ((h_feats.numel() * 2 + users_bytes) / ne))) if h2d_gbs else None},
             # evaluation: order_count, order_fill, pool, dp16 (+ fused summary / F-score tail), dp (fallback list)
             "gpu_launches": int((nl.value + 5) * args.steps),
             "clocks": clocks,
         }
+        line.update(extra)
         if world == 1:
             try:                                   # secondary stages never cost the headline line
                 line["train"] = train_stage(dev)
+                line["train"]["stock_torch_on_this_gpu"] = _torch_train_arm("cuda", 4.0)
             except Exception as e:
-                line["train"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                line.setdefault("train", {})["error"] = f"{type(e).__name__}: {e}"[:300]
+            try:
+                line["cv_fold_parallel"] = cv_stage(dev, rank, world)
+            except Exception as e:
+                line["cv_fold_parallel"] = {"error": f"{type(e).__name__}: {e}"[:300]}
             try:
                 line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
             except Exception as e:
