@@ -589,14 +589,18 @@ def cv_stage(dev, rank, world):
     orig = synthetic.make_dataset
     synthetic.make_dataset = lambda name, *a, **k: cache[name]
     try:
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        results = M.train(hps)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        walls = []
+        for _ in range(2):      # the first pass also pays this process's one-time costs (module loading, allocator growth)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            results = M.train(hps)
+            torch.cuda.synchronize()
+            walls.append(time.perf_counter() - t0)
+        dt = walls[1]
     finally:
         synthetic.make_dataset = orig
     return {"config": "VASNet 5-fold CV on both synthetic datasets (10 fold jobs), 20 epochs, test every 10", "wall_s": dt,
+            "wall_s_first_pass": walls[0],
             "n_gpus": world, "cv": [[os.path.basename(sf), float(c), float(a), float(m)] for sf, c, a, m in results]}
 
 

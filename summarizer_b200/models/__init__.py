@@ -54,7 +54,11 @@ class StepGraphs:
     def __init__(self, trainer, enabled):
         self.trainer, self.enabled = trainer, bool(enabled)
         self.graphs, self.seen = {}, set()
-        self.pool = torch.cuda.graph_pool_handle() if self.enabled else None
+        # ONE graph memory pool per trainer, reused fold after fold: a fresh pool per fold meant a round of cudaMalloc /
+        # cudaFree per fold, which serialises on the driver when several ranks of a box train folds side by side
+        if self.enabled and getattr(trainer, "_graph_pool", None) is None:
+            trainer._graph_pool = torch.cuda.graph_pool_handle()
+        self.pool = trainer._graph_pool if self.enabled else None
 
     def run(self, key, step):
         if not self.enabled or key not in self.seen:
@@ -97,12 +101,36 @@ class Trainer:
     # ---- reference surface ------------------------------------------------------------------------
     def reset(self):
         """Reset between two folds of the cross-validation"""
-        self.model = self._init_model()
-        if torch.cuda.is_available():
-            torch.cuda.empty_cache()
+        new = self._init_model()
+        # (the reference empties the CUDA caching allocator here, models/__init__.py:21: a synchronising round of
+        # cudaFree that changes no result; the cached blocks are simply reused by the next fold)
         if self.hps.use_cuda:
-            self.model.cuda()
+            new.cuda()
+        old = getattr(self, "model", None)
+        if old is not None and self._same_layout(old, new):
+            # Same architecture as the previous fold: the freshly initialised weights are copied INTO the existing
+            # tensors, so every address the previous folds' CUDA graphs captured stays valid and the per-video step
+            # graphs (and the optimizer object, whose state _train_supervised zeroes) are reused instead of being
+            # re-captured fold after fold (capture was ~60 % of a 20-epoch SumMe / TVSum fold).
+            best = getattr(self, "best_weights", None)
+            if best is not None:       # it aliases the live parameters (as the reference): detach it before they change
+                self.best_weights = {k: v.detach().clone() for k, v in best.items()}
+            with torch.no_grad():
+                for dst, src in zip(old.state_dict().values(), new.state_dict().values()):
+                    dst.copy_(src)
+            self._invalidate_shadows()
+        else:
+            self.model = new
+            self._step_graphs, self._opt_key = None, None
         return self
+
+    @staticmethod
+    def _same_layout(a, b):
+        if type(a) is not type(b):
+            return False
+        sa, sb = a.state_dict(), b.state_dict()
+        return list(sa.keys()) == list(sb.keys()) and all(
+            x.shape == y.shape and x.dtype == y.dtype and x.device == y.device for x, y in zip(sa.values(), sb.values()))
 
     def _get_train_test_keys(self, fold):
         """Train/Test keys from current split file and fold"""
@@ -274,12 +302,23 @@ class Trainer:
         ep = self.hps.extra_params or {}
         use_graphs = (fused and dist is None and getattr(self.model, "max_length", None) is None
                       and str(ep.get("cuda_graphs", "yes")).lower() not in ("no", "0", "false"))
-        self.optimizer = torch.optim.Adam(params, lr=self.hps.lr, weight_decay=self.hps.weight_decay, fused=fused,
-                                          capturable=use_graphs) if params else None
+        opt_key = (tuple(id(p) for p in params), float(self.hps.lr), float(self.hps.weight_decay), fused, use_graphs)
+        if use_graphs and getattr(self, "_opt_key", None) == opt_key and getattr(self, "_step_graphs", None) is not None:
+            # a later fold on the same parameter tensors (see reset()): a fresh optimizer = the old one with its state
+            # zeroed in place, and the step graphs captured by the earlier folds replay as they are
+            for st in self.optimizer.state.values():
+                for t in st.values():
+                    if torch.is_tensor(t):
+                        t.zero_()
+            graphs = self._step_graphs
+        else:
+            self.optimizer = torch.optim.Adam(params, lr=self.hps.lr, weight_decay=self.hps.weight_decay, fused=fused,
+                                              capturable=use_graphs) if params else None
+            graphs = StepGraphs(self, use_graphs)
+            self._step_graphs, self._opt_key = (graphs, opt_key) if use_graphs else (None, None)
         best_corr, best_avg_f_score, best_max_f_score = -1.0, 0.0, 0.0
         if dist is not None:
             self._dp_sync_model(dist)
-        graphs = StepGraphs(self, use_graphs)
 
         def forward_backward(key):
             seq, target = self._video_tensors(key)

@@ -155,3 +155,36 @@ def test_positional_embedding_does_not_accumulate_in_cached_features(tmp_path):
     res = t.train(0)
     assert np.isfinite(res).all()
     assert torch.equal(before, t._video_tensors(keys[0])[0])
+
+
+def test_reset_reuses_tensors_and_step_graphs_across_folds(tmp_path):
+    """reset() between folds re-initialises the weights INTO the existing tensors (same RNG stream as a fresh model), so
+    the CUDA graphs captured for the per-video training steps and the optimizer survive from fold to fold; the best
+    weights of the previous fold are detached first (the reference's best_weights aliases the live parameters)."""
+    hps = make_hps(tmp_path, splits_files="summe", epochs=4, test_every_epochs=2, lr=1e-4)
+    t = hps.model_class(hps, hps.splits_files[0])
+    torch.manual_seed(7)
+    t.reset()
+    ptrs = [p.data_ptr() for p in t.model.parameters()]
+    r0 = t.train(0)
+    graphs0 = t._step_graphs
+    assert graphs0 is not None and len(graphs0.graphs) > 0
+    best0 = {k: v.clone() for k, v in t.best_weights.items()}
+    torch.manual_seed(11)
+    t.reset()
+    assert [p.data_ptr() for p in t.model.parameters()] == ptrs                  # same tensors ...
+    torch.manual_seed(11)
+    fresh = hps.model_class(hps, hps.splits_files[0]).reset()
+    for a, b in zip(t.model.state_dict().values(), fresh.model.state_dict().values()):
+        assert torch.equal(a, b)                                                 # ... holding a fresh initialisation
+    for k, v in t.best_weights.items():
+        assert torch.equal(v, best0[k])                                          # fold 0's best weights survived the reset
+    n_before = len(graphs0.graphs)
+    r1 = t.train(1)
+    assert t._step_graphs is graphs0 and len(graphs0.graphs) >= n_before         # graphs reused (new videos add theirs)
+    assert all(torch.count_nonzero(st["exp_avg"]) > 0 for st in t.optimizer.state.values())
+    assert np.isfinite(list(r0) + list(r1)).all()
+    # a fold trained on reused graphs behaves like one trained by a fresh trainer: same initial weights, same data ->
+    # the first epoch's loss agrees up to the dropout draw
+    avg_corr, (avg_f, max_f) = t.test(1)
+    assert 0 <= avg_f <= max_f <= 1 and -1 <= avg_corr <= 1
