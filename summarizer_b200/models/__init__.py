@@ -264,18 +264,35 @@ class Trainer:
         dist.broadcast_object_list(box, src=0)
         return box[0]
 
+    _flat_grads = {}      # (ids of the parameters) -> persistent flat float32 gradient buffer
+
     @staticmethod
     def _dp_allreduce_grads(dist, params, n_active):
-        """Mean of the replicas' gradients: ONE all-reduce of the flat float32 gradient buffer per step."""
-        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
-        flat = torch.cat([g.reshape(-1).float() for g in grads])
+        """Mean of the replicas' gradients: ONE all-reduce per step of a PERSISTENT flat float32 buffer.  Every
+        parameter's ``.grad`` is (made) a view into that buffer, so the next backward accumulates straight into it:
+        when the caller zeroes gradients in place (``zero_grad(set_to_none=False)``) a step copies nothing at all,
+        otherwise one copy per parameter brings the fresh gradient tensor in — no concatenation, no split-back."""
+        params = list(params)
+        key = tuple(id(p) for p in params)
+        flat = Trainer._flat_grads.get(key)
+        total = sum(p.numel() for p in params)
+        if flat is None or flat.numel() != total or flat.device != params[0].device:
+            if len(Trainer._flat_grads) > 8:
+                Trainer._flat_grads.clear()
+            flat = Trainer._flat_grads[key] = torch.zeros(total, dtype=torch.float32, device=params[0].device)
+        o = 0
+        for p in params:
+            n = p.numel()
+            view = flat[o:o + n].view_as(p)
+            g = p.grad
+            if g is None:
+                view.zero_()
+            elif g.data_ptr() != view.data_ptr():
+                view.copy_(g)
+            p.grad = view
+            o += n
         dist.all_reduce(flat)
         flat /= float(n_active)
-        o = 0
-        for p, g in zip(params, grads):
-            n = g.numel()
-            p.grad = flat[o:o + n].view_as(g).to(g.dtype)
-            o += n
 
     def _invalidate_shadows(self):
         """Drop the modules' cached bf16 / packed weight copies (they are rebuilt on the next call)."""
@@ -349,7 +366,7 @@ class Trainer:
                     dist_scores[key] = scores
                     continue
                 if self.optimizer is not None:
-                    self.optimizer.zero_grad()
+                    self.optimizer.zero_grad(set_to_none=dist is None)       # data parallel: gradients stay views of the flat buffer
                 if key is not None:
                     loss, scores = forward_backward(key)
                     losses.append(loss)
