@@ -124,7 +124,7 @@ def test_summe_shaped_batch_knapsack():
 
 
 def test_tvsum_shaped_batch_knapsack_and_rank():
-    vids, scores = _dataset_videos("tvsum", 12)
+    vids, scores = _dataset_videos("tvsum", 50)          # the whole TVSum-shaped dataset
     _check_batch_against_oracle(vids, scores, "knapsack")
     _check_batch_against_oracle(vids, scores, "rank")
 
