@@ -1,3 +1,8 @@
-timeout 600 python -m pytest tests/test_trainer_gpu.py tests/test_train_golden_gpu.py tests/test_dsn_gpu.py tests/test_sumgan_gpu.py -x -q -m gpu 2>&1 | tail -5
-python scripts/dev/cv_time.py 2>&1 | grep "^rank"
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29872 scripts/dev/cv_time.py 2>&1 | grep "^rank"
+timeout 600 python -m pytest tests/test_eval_gpu.py tests/test_trainer_gpu.py tests/test_abi.py -x -q -m gpu 2>&1 | tail -3
+for cfg in "" "SMZ_NO_FUSED_POOL=1"; do echo "== $cfg"; env $cfg timeout 300 python scripts/eval_perf.py 10000 2>&1 | tail -1; done
+for cfg in "A=1" "SMZ_NO_FUSED_POOL=1"; do
+echo "== $cfg"
+env $cfg python bench.py --steps 5 --warmup 3 --cpu-seconds 1 > gpurun_out/tmp_bench.json 2>gpurun_out/tmp_bench.err
+python -c "
+import json; d=json.load(open('gpurun_out/tmp_bench.json')); print(d['value'], d['stages_ms'], d['roofline_eval']['eval_path_frac'], d['clocks']['sm_mhz'])"
+done

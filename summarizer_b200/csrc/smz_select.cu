@@ -137,15 +137,15 @@ struct RegularFrames {   // upsample of a regular pick grid: scores staged in sh
     __device__ __forceinline__ float at(int f) const { return sc[min((int)__umulhi((uint32_t)f, magic), last)]; }
 };
 
-__global__ void __launch_bounds__(POOL_REG_THREADS)
-pool_regular_kernel(const smz_video_desc *__restrict__ desc, int v0, const float *__restrict__ scores,
-                    const int32_t *__restrict__ picks, const int32_t *__restrict__ cps, int max_intervals,
-                    float *__restrict__ out_mean, int32_t *__restrict__ out_values, int32_t *__restrict__ status) {
-    extern __shared__ float s_sc[];          // max_intervals scores, then 4 * max_n_segs ints (segment lists)
+// One video, all POOL_REG_THREADS threads of the CTA; s_sc: max_intervals + 4 * d.n_segs words of shared memory (scores,
+// then the segment lists).  Also called by the 16-bit knapsack kernel for the video it is about to solve (fused pooling).
+__device__ void pool_regular_video(const smz_video_desc &d, int v, const float *__restrict__ scores,
+                                   const int32_t *__restrict__ picks, const int32_t *__restrict__ cps, int max_intervals,
+                                   float *s_sc, float *__restrict__ out_mean, int32_t *__restrict__ out_values,
+                                   int32_t *__restrict__ status) {
     __shared__ int s_class[4];
     constexpr int NT = POOL_REG_THREADS;
-    const int v = v0 + blockIdx.x, tid = threadIdx.x;
-    const smz_video_desc d = desc[v];
+    const int tid = threadIdx.x;
     const int n = d.n_segs, n_frames = d.n_frames, n_picks = d.n_picks;
     const int32_t *pk = picks + d.picks_off;
     const float *sc = scores + d.score_off;
@@ -200,6 +200,16 @@ pool_regular_kernel(const smz_video_desc *__restrict__ desc, int v0, const float
     }
 }
 
+__global__ void __launch_bounds__(POOL_REG_THREADS)
+pool_regular_kernel(const smz_video_desc *__restrict__ desc, int v0, const float *__restrict__ scores,
+                    const int32_t *__restrict__ picks, const int32_t *__restrict__ cps, int max_intervals,
+                    float *__restrict__ out_mean, int32_t *__restrict__ out_values, int32_t *__restrict__ status) {
+    extern __shared__ float s_pool[];        // max_intervals scores, then 4 * max_n_segs ints (segment lists)
+    const int v = v0 + blockIdx.x;
+    const smz_video_desc d = desc[v];
+    pool_regular_video(d, v, scores, picks, cps, max_intervals, s_pool, out_mean, out_values, status);
+}
+
 // ------------------------------------------------------------------------------------------
 // evaluation tail fused into the knapsack kernels: summary vector + mask (utils/eval.py:111-122) and
 // the per-annotator F-score (utils/eval.py:125-165) of the video the CTA has just solved
@@ -221,6 +231,14 @@ struct EvalTail {
     int32_t *overlap, *gsum;
     float *f;
     double *avg_f, *max_f;
+    // fused segment pooling (16-bit knapsack kernel only): when pool_scores is given the CTA pools the video it is about
+    // to solve itself (pool_regular_video) — no pooling kernel runs in front, its latency-bound work hides behind the
+    // other CTAs' DP / streaming
+    const float *pool_scores;
+    const int32_t *pool_picks, *pool_cps;
+    int pool_max_intervals;
+    float *pool_seg_mean;
+    int32_t *pool_values, *pool_status;
 };
 
 __host__ __device__ inline int tail_words(int max_n_segs, int max_n_frames) {
@@ -230,6 +248,7 @@ __host__ __device__ inline int tail_words(int max_n_segs, int max_n_frames) {
 // Called by all DP_THREADS (= FSCORE_THREADS) threads.  spk: picked flags, swp: (weight, value) per segment, both in
 // shared memory; mem: tail_words() words of shared memory that the DP no longer needs.  v: index of the video in the
 // arrays that are indexed per video (msum, avg_f, max_f).
+static_assert(DP_THREADS == POOL_REG_THREADS, "the 16-bit knapsack kernel runs pool_regular_video on its own CTA");
 static_assert(DP_THREADS == FSCORE_THREADS, "the fused tail runs the F-score chunk code on the DP kernel's CTA");
 __device__ void eval_tail_video(const EvalTail &t, const smz_video_desc &d, int v, const int *spk, const int2 *swp,
                                 uint32_t *mem) {
@@ -613,12 +632,17 @@ dp16_kernel(const smz_video_desc *__restrict__ desc, int n_videos, const int32_t
         const int v = order[s_next];
         const smz_video_desc d = desc[v];
         const int n = d.n_segs, cap = d.capacity;
+        if (tail.pool_scores != nullptr) {          // fused pooling: segment means -> integer values of THIS video
+            pool_regular_video(d, v, tail.pool_scores, tail.pool_picks, tail.pool_cps, tail.pool_max_intervals,
+                               reinterpret_cast<float *>(smem), tail.pool_seg_mean, tail.pool_values, tail.pool_status);
+            __syncthreads();                        // the values this CTA just wrote are read (through L2) below
+        }
         // ---- weights / values and what decides the path: sum of weights, value / weight ranges of the usable items
         int wsum = 0, bad = 0, maxw = 0, maxp = 0, minp = 0, psum = 0;
         const int vlim = value_limit(n);
         for (int i = tid; i < n; i += NT) {
             const int w = __ldg(nfps + d.seg_off + i);
-            const int p = __ldg(values + d.seg_off + i);
+            const int p = __ldcg(values + d.seg_off + i);
             if (p > vlim || p < -vlim || w < 0) bad = 1;        // dp_kernel flags and clips these
             swp[i] = make_int2(w, p);
             sdp[i] = w <= cap ? make_int2(w, p) : make_int2(0, 0);
@@ -1313,6 +1337,8 @@ static int select_launch(const smz_video_desc *desc, int n_videos, const float *
         return SMZ_OK;
     }
     const int32_t *vals = values_in;
+    bool fused_pool = false;
+    int fused_pool_intervals = 0;
     if (values_in == nullptr) {
         SMZ_REQUIRE(values != nullptr, "values output is required (it feeds the DP kernel)");
         SMZ_REQUIRE(method == SMZ_METHOD_KNAPSACK || seg_mean != nullptr, "seg_mean output is required by method 'rank'");
@@ -1321,7 +1347,17 @@ static int select_launch(const smz_video_desc *desc, int n_videos, const float *
         constexpr int kPoolWords = 12288 - 16;       // 48 KB less the kernel's static shared memory (s_class)
         int max_intervals = max_n_frames + 1 < kPoolWords ? max_n_frames + 1 : kPoolWords;  // staged scores per CTA, with the
         if (max_intervals + 4 * max_n_segs > kPoolWords) max_intervals = kPoolWords - 4 * max_n_segs > 0 ? kPoolWords - 4 * max_n_segs : 0;   // segment lists <= 48 KB
-        if (tiles > 0 && max_n_segs <= 2048 && !getenv("SMZ_NO_POOL_REGULAR")) {
+        // 16-bit knapsack plan: the DP kernel pools each video itself (pool_regular_video on the rows region of its shared
+        // memory, before the rows are needed) — no pooling kernel in front
+        if (tiles > 0 && max_n_segs <= 2048 && !getenv("SMZ_NO_POOL_REGULAR") && method == SMZ_METHOD_KNAPSACK && plan.kw16 > 0 &&
+            !getenv("SMZ_NO_FUSED_POOL")) {
+            const Dp16Smem L = dp16_layout(plan.kw16, plan.mk16, max_n_segs, plan.front_words);
+            int mi = max_intervals;
+            if (mi + 4 * max_n_segs > L.wp) mi = L.wp - 4 * max_n_segs;
+            if (mi >= 64) { fused_pool = true; fused_pool_intervals = mi; }
+        }
+        if (fused_pool) {
+        } else if (tiles > 0 && max_n_segs <= 2048 && !getenv("SMZ_NO_POOL_REGULAR")) {
             for (int v0 = 0; v0 < n_videos; v0 += 65535) {
                 const int nv = n_videos - v0 < 65535 ? n_videos - v0 : 65535;
                 pool_regular_kernel<<<nv, POOL_REG_THREADS, ((size_t)max_intervals + 4 * (size_t)max_n_segs) * sizeof(float), st>>>(
@@ -1354,6 +1390,10 @@ static int select_launch(const smz_video_desc *desc, int n_videos, const float *
     if (method == SMZ_METHOD_KNAPSACK && plan.kw16 > 0) {
         // 16-bit pass over every video, then the 32-bit kernel over whatever it handed back (usually nothing)
         dp16_fn fn16 = dp16_fn_for(plan.kw16, plan.mk16);
+        if (fused_pool) {
+            tail.pool_scores = scores; tail.pool_picks = picks; tail.pool_cps = cps; tail.pool_max_intervals = fused_pool_intervals;
+            tail.pool_seg_mean = seg_mean; tail.pool_values = values; tail.pool_status = status;
+        }
         fn16<<<plan.grid16, DP_THREADS, plan.smem16_bytes, st>>>(desc, n_videos, nfps, vals, max_n_segs, picked,
                                                                  (uint32_t *)ws, plan.ws16_words_per_cta, queue, order, fallback,
                                                                  plan.front_words, tail);
