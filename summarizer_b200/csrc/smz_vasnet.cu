@@ -1,27 +1,28 @@
 // VASNet scorer (models/vasnet.py:92-148) on the tcgen05 GEMM building block.
 //
-// forward, per row chunk of the packed batch (rows of all videos, [sum T, 1024]):
+// Two forward paths over the packed batch (rows of all videos, [sum T, 1024]), chunked by rows:
+//
+// (1) the literal chain — training (the whole batch is one chunk, every intermediate stays in the work buffer for
+//     smz_vasnet_backward) and the wide-range inference path (no status word; all bf16 / fp32):
 //   xb  = bf16(x)                                              (skipped when the features are bf16)
 //   QK  = xb . [Wq;Wk]^T                      [R, 2048] bf16    vasnet.py:114-115, one packed GEMM
 //   Vt  = Wv . xb^T                           [1024, R] bf16    vasnet.py:116, produced transposed so that
 //                                                               alpha.V is a K-major GEMM too (training; inference
 //                                                               packs Q|K|V into ONE [R, 3072] GEMM and alpha.V reads
 //                                                               V in place as an MN-major B operand)
-//   per attention sub-chunk (logits stay L2-resident):
+//   per attention sub-chunk:
 //     S   = scale * Q_v . K_v^T               [T, T]   fp32     vasnet.py:118-119, one GEMM problem per video
 //     P   = dropout(softmax(mask(S)))         [T, ld]  bf16     vasnet.py:121-130 (zero padded columns)
 //     O   = P . V_v                           [R, 1024] bf16    vasnet.py:131
 //   Y   = O . Wo^T + x                        [R, 1024] fp32    vasnet.py:132-135
 //   Yn  = LayerNorm(dropout(Y))               bf16              vasnet.py:136-137
-//   H   = relu(Yn . W1^T + b1)                fp32              vasnet.py:140-141
+//   H   = relu(Yn . W1^T + b1)                fp32              vasnet.py:140-141  (inference: never stored, head epilogue)
 //   s   = sigmoid(LayerNorm(dropout(H)) . w2 + b2)              vasnet.py:142-145
-// In training mode the whole batch is one chunk and every intermediate stays in the work buffer for
-// smz_vasnet_backward.  Inference fuses the row-wise steps into the GEMM epilogues: the softmax is exp + row sums in
-// the logits epilogue and a 1 / row-sum scale in the alpha.V epilogue; the first LayerNorm is folded into k1
-// (W1.LN(y) = rstd (W1 diag(g) y - mean W1 g) + W1 b: the output projection emits bf16 y plus per-row sum / sum of
-// squares slots, k1 runs on y with W1 diag(g) and un-does the mean / applies rstd in its epilogue); the regressor head
-// is three more row sums of the k1 epilogue.  Per chunk: QKV, (logits, alpha.V) per sub-chunk, out, k1, head — no
-// row kernel reads a [R, 1024] activation.
+//
+// (2) the fast inference path (fast_chunk below): the same function with its linear maps folded and every row-wise
+//     step in a GEMM epilogue — [V'|G] projection, exp-logits, alpha.V' (+ scale, residual, LayerNorm sums), k1 (+ folded
+//     LayerNorm, head sums), one per-row kernel; float16 where the range can be checked, a status word instead of a
+//     device-side fallback.
 #include <stdlib.h>
 
 #include <vector>
