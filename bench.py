@@ -418,7 +418,8 @@ def train_stage(dev, seconds=4.0):
     torch.manual_seed(0)
     vas = VASNet().to(dev).train()
     dsn = DSN().to(dev).train()
-    opt = torch.optim.Adam(vas.parameters(), lr=5e-5, weight_decay=1e-5, fused=True, capturable=True)
+    from summarizer_b200.optim import Adam, clip_grad_norm_
+    opt = Adam(vas.parameters(), lr=5e-5, weight_decay=1e-5)          # the library's Adam kernel (what the trainers use)
 
     def vas_step(x, tgt):
         opt.zero_grad(set_to_none=True)
@@ -428,7 +429,7 @@ def train_stage(dev, seconds=4.0):
     f_train = sum(24 * T * FEAT * FEAT + 12 * T * T * FEAT + 6 * T * FEAT for T in lens)
     out["vasnet_train_tflops"] = out["vasnet_train_frames_per_s"] / sum(lens) * f_train / 1e12
 
-    opt2 = torch.optim.Adam(dsn.parameters(), lr=5e-5, weight_decay=1e-5, fused=True, capturable=True)
+    opt2 = Adam(dsn.parameters(), lr=5e-5, weight_decay=1e-5)
     base = torch.zeros((), device=dev)
 
     def dsn_step(x, tgt):
@@ -438,9 +439,9 @@ def train_stage(dev, seconds=4.0):
         actions = dist.sample((5,))
         rewards = compute_rewards(x, actions.reshape(5, -1))
         loss = -(dist.log_prob(actions).reshape(5, -1).mean(1) * (rewards - base)).sum() / 5.
-        loss.backward(); torch.nn.utils.clip_grad_norm_(dsn.parameters(), 5.0); opt2.step()
+        loss.backward(); clip_grad_norm_(list(dsn.parameters()), 5.0); opt2.step()
     out["dsn_reinforce_frames_per_s"], out["dsn_reinforce_frames_per_s_eager"] = timed(dsn_step)
-    out["step_replay"] = "one CUDA graph per video (forward, loss, backward, clip, Adam)"
+    out["step_replay"] = "one CUDA graph per video (forward, loss, backward, clip, Adam: all library kernels)"
     del vas, dsn, opt, opt2
 
     # BASELINE config 4 (SUM-GAN-style LSTM generator/discriminator): the reference's three updates per video
@@ -528,7 +529,8 @@ def train_dp_stage(dev, rank, world, dist, seconds=3.0):
     o = 0
     for p in params:
         p.grad = flat[o:o + p.numel()].view_as(p); o += p.numel()
-    opt = torch.optim.Adam(params, lr=5e-5, weight_decay=1e-5, fused=True)
+    from summarizer_b200.optim import Adam
+    opt = Adam(params, lr=5e-5, weight_decay=1e-5)
     ar0, ar1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ar_ms = []
 
@@ -564,7 +566,7 @@ def train_dp_stage(dev, rank, world, dist, seconds=3.0):
     out = {"model": "VASNet", "videos_per_step": world, "steps": n_steps, "frames_per_s": frames * world / (t.item() / 1e3),
            "ms_per_step": t.item() / n_steps, "allreduce_ms": float(np.median(ar_ms)), "allreduce_mb": flat.numel() * 4 / 1e6,
            "gradients_equal_across_ranks": replicas_equal, "what": "eager step: forward + MSE + backward (smz kernels), one "
-           "NCCL all-reduce of the flat gradient buffer, fused Adam; every rank a different video"}
+           "NCCL all-reduce of the flat gradient buffer, the library's Adam kernel; every rank a different video"}
     del vas, opt, flat
     return out
 

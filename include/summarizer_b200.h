@@ -164,6 +164,28 @@ int smz_rank_correlation(const smz_corr_desc *desc, int n_videos, int max_n_fram
                          const float *machine, const float *user, int metric, float *rank_ws, double *corr,
                          double *corr_avg, void *stream);
 
+/* ---- optimizer step of the training loops ----------------------------------------------------------
+ * torch.optim.Adam (L2 term in the gradient; models/vasnet.py:160-161,211-212, models/dsn.py:100,147-149,
+ * models/sumgan.py:268-275) and torch.nn.utils.clip_grad_norm_ (dsn.py:147, sumgan.py:433-436) over a whole parameter
+ * list in a few launches.  tensors: HOST array (pointers inside are device pointers, float32, n elements each; grad may
+ * be NULL = parameter skipped); it is copied into the kernel parameters, nothing captured in a CUDA graph points at it.
+ *   smz_grad_sqnorm: *sqnorm (device float) = sum of squares of all gradients, summed in a fixed order (bit-stable);
+ *                    ws: device scratch of smz_grad_sqnorm_workspace_floats() floats.
+ *   smz_clip_grads:  g *= min(1, max_norm / (sqrt(*sqnorm) + 1e-6)) in place (clip_grad_norm_'s coefficient).
+ *   smz_adam_step:   one Adam update; every tensor's *step (device float, completed updates of that tensor, as torch
+ *                    counts per parameter) is read by the update and incremented behind it on the stream, so graph
+ *                    replays advance it. */
+#define SMZ_OPTIM_MAX_TENSORS 64     /* tensors per kernel launch (longer lists take several launches) */
+typedef struct smz_optim_tensor {
+    float *param, *grad, *exp_avg, *exp_avg_sq, *step;
+    int64_t n;
+} smz_optim_tensor;
+int smz_grad_sqnorm_workspace_floats(const smz_optim_tensor *tensors, int n_tensors, int64_t *floats);
+int smz_grad_sqnorm(const smz_optim_tensor *tensors, int n_tensors, float *sqnorm, float *ws, int64_t ws_floats, void *stream);
+int smz_clip_grads(const smz_optim_tensor *tensors, int n_tensors, const float *sqnorm, float max_norm, void *stream);
+int smz_adam_step(const smz_optim_tensor *tensors, int n_tensors, double lr, double beta1, double beta2, double eps,
+                  double weight_decay, void *stream);
+
 /* ---- dense building block ------------------------------------------------------------------------
  * C[M,N] = epilogue(alpha * A[M,K] * B[N,K]^T) on the tcgen05 tensor cores: A and B bfloat16, K
  * contiguous (lda/ldb in elements, multiples of 8, 16-byte aligned bases), fp32 accumulation.

@@ -41,6 +41,27 @@ def open_dataset(path, log=None):
     raise FileNotFoundError(f"dataset {path} not found and no synthetic stand-in is defined for it")
 
 
+def make_adam(params, lr, weight_decay, capturable=False):
+    """torch.optim.Adam's update rule (the reference's optimizer everywhere) on the library's kernel
+    (summarizer_b200.optim.Adam: one launch per 64 tensors, device-side step counters, graph-replayable) when every
+    parameter is a float32 CUDA tensor; host-only models (tests of the host logic, Rand / Logistic on the CPU) keep
+    torch's implementation."""
+    params = list(params)
+    if params and all(p.is_cuda and p.dtype == torch.float32 for p in params):
+        from ..optim import Adam
+        return Adam(params, lr=lr, weight_decay=weight_decay)
+    return torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, capturable=capturable and bool(params) and all(p.is_cuda for p in params))
+
+
+def clip_grad_norm_(parameters, max_norm):
+    """torch.nn.utils.clip_grad_norm_ on the library's kernels for float32 CUDA gradients (else torch's)."""
+    params = [p for p in parameters if p.grad is not None]
+    if params and all(p.grad.is_cuda and p.grad.dtype == torch.float32 and p.grad.is_contiguous() for p in params):
+        from ..optim import clip_grad_norm_ as clip
+        return clip(params, max_norm)
+    return torch.nn.utils.clip_grad_norm_(params, max_norm)
+
+
 class StepGraphs:
     """Per-video optimizer steps replayed as CUDA graphs.
 
@@ -310,8 +331,8 @@ class Trainer:
         self.draw_gtscores(fold, train_keys)
         criterion = torch.nn.MSELoss()
         params = [p for p in self.model.parameters() if p.requires_grad] if optimizer_params is None else optimizer_params
-        # same update rule as the reference's torch.optim.Adam (L2 term in the gradient); fused=True runs it as one
-        # multi-tensor kernel on the device
+        # same update rule as the reference's torch.optim.Adam (L2 term in the gradient), one multi-tensor kernel of the
+        # library on the device (make_adam)
         fused = bool(params) and all(p.is_cuda for p in params)
         dist, rank, world = self._dp()
         # from the second visit of a video on, its whole step (forward, loss, backward, Adam) is replayed as ONE CUDA
@@ -329,8 +350,7 @@ class Trainer:
                         t.zero_()
             graphs = self._step_graphs
         else:
-            self.optimizer = torch.optim.Adam(params, lr=self.hps.lr, weight_decay=self.hps.weight_decay, fused=fused,
-                                              capturable=use_graphs) if params else None
+            self.optimizer = make_adam(params, self.hps.lr, self.hps.weight_decay, capturable=use_graphs) if params else None
             graphs = StepGraphs(self, use_graphs)
             self._step_graphs, self._opt_key = (graphs, opt_key) if use_graphs else (None, None)
         best_corr, best_avg_f_score, best_max_f_score = -1.0, 0.0, 0.0

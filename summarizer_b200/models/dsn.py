@@ -101,7 +101,7 @@ class DSN(nn.Module):
 
 from torch.distributions import Bernoulli  # noqa: E402
 
-from . import StepGraphs, Trainer  # noqa: E402
+from . import StepGraphs, Trainer, clip_grad_norm_, make_adam  # noqa: E402
 
 
 def compute_rewards(seq, actions, far_sim=False, temp_dist_thre=20, workspace=None):
@@ -157,8 +157,7 @@ class DSNTrainer(Trainer):
         train_keys, _ = self._get_train_test_keys(fold)
         self.draw_gtscores(fold, train_keys)
         self.log.debug("Parameters: {}".format(sum(p.numel() for p in self.model.parameters())))
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.hps.lr, weight_decay=self.hps.weight_decay,
-                                          fused=all(p.is_cuda for p in self.model.parameters()))
+        self.optimizer = make_adam(self.model.parameters(), self.hps.lr, self.hps.weight_decay)
         loss_BCE = torch.nn.BCELoss()
         dev = self._device()
         key_index = {key: i for i, key in enumerate(sorted(train_keys))}
@@ -172,10 +171,7 @@ class DSNTrainer(Trainer):
         ep = self.hps.extra_params or {}
         use_graphs = (dist_ is None and all(p.is_cuda for p in params)
                       and str(ep.get("cuda_graphs", "yes")).lower() not in ("no", "0", "false"))
-        if use_graphs:                                            # capturable Adam keeps its step counter on the device
-            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.hps.lr, weight_decay=self.hps.weight_decay,
-                                              fused=True, capturable=True)
-        graphs = StepGraphs(self, use_graphs)
+        graphs = StepGraphs(self, use_graphs)            # the library's Adam keeps its step counters on the device: replayable
 
         def forward_backward(key):
             """REINFORCE loss of one video and its backward pass -> (loss, probs, mean reward, baseline delta)."""
@@ -204,7 +200,7 @@ class DSNTrainer(Trainer):
             self.optimizer.zero_grad(set_to_none=True)
             loss, probs, mean_reward, delta = forward_backward(key)
             baselines.add_(delta)
-            torch.nn.utils.clip_grad_norm_(self.model.parameters(), 5.0)
+            clip_grad_norm_(self.model.parameters(), 5.0)
             self.optimizer.step()
             return loss, probs, mean_reward
 
@@ -235,7 +231,7 @@ class DSNTrainer(Trainer):
                     self._dp_allreduce_grads(dist_, params, len(group))
                     dist_.all_reduce(delta)                                       # every replica keeps every video's baseline
                 baselines.add_(delta)
-                torch.nn.utils.clip_grad_norm_(self.model.parameters(), 5.0)
+                clip_grad_norm_(self.model.parameters(), 5.0)
                 self.optimizer.step()
             seen = [k for k in train_keys if len(reward_writers[k]) > epoch]
             epoch_avg_reward = float(torch.stack([reward_writers[key][epoch] for key in seen]).mean())

@@ -193,7 +193,7 @@ class SumGAN(nn.Module):
         return self.summarizer.s_lstm(x)
 
 
-from . import Trainer  # noqa: E402
+from . import Trainer, clip_grad_norm_, make_adam  # noqa: E402
 
 
 class SumGANTrainer(Trainer):
@@ -257,9 +257,7 @@ class SumGANTrainer(Trainer):
 
     # ---- optimisation ----------------------------------------------------------------------------------
     def _adam(self, params):
-        params = list(params)
-        return torch.optim.Adam(params, lr=self.hps.lr, weight_decay=self.hps.weight_decay,
-                                fused=all(p.is_cuda for p in params))
+        return make_adam(params, self.hps.lr, self.hps.weight_decay)
 
     def _update(self, optimizer, loss, dp, n_active):
         """zero_grad of THIS optimizer, backward, clip over ALL parameters (stale gradients of the other
@@ -273,7 +271,7 @@ class SumGANTrainer(Trainer):
         if loss is not None:
             loss.backward()
         if dp is None:
-            nn.utils.clip_grad_norm_(self.model.parameters(), 5.0)
+            clip_grad_norm_(self.model.parameters(), 5.0)
         else:
             self._dp_allreduce_grads(dp, [p for g in optimizer.param_groups for p in g["params"]], n_active)
             grads = [p.grad for p in self.model.parameters() if p.grad is not None]
