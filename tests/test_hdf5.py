@@ -167,3 +167,17 @@ def test_reader_only_features(tmp_path):
         assert np.array_equal(f["b_cont"][...], b_vals)
         assert np.array_equal(f["c_chunked"][...], c_vals)
         assert f["d_name"][()] == "Vidéo_42"
+
+
+def test_summary_tool_reads_predictions(tmp_path):
+    """summary.py:40-43: the mp4 tool picks ``machine_summary`` of one video out of the predictions file and maps kept
+    frame i to ``%06d.jpg % (i + 1)`` (summary.py:14-16)."""
+    from summarizer_b200 import summary as tool
+    path = str(tmp_path / "summe_splits.json_preds.h5")
+    ms = np.array([0, 1, 1, 0, 0, 1], np.float32)
+    with hdf5.File(path, "w") as f:
+        g = f.create_group("summe.h5").create_group("video_3")
+        g.create_dataset("machine_summary", data=ms)
+    got = tool.read_machine_summary(path, "summe.h5", "video_3")
+    assert got.dtype == np.float32 and np.array_equal(got, ms)
+    assert tool.kept_frame_names(got) == ["000002.jpg", "000003.jpg", "000006.jpg"]
