@@ -369,8 +369,7 @@ def train_stage(dev, seconds=4.0):
     steps (vasnet.py:193-212: forward + MSE + backward + Adam; dsn.py:96-149: forward + 5 REINFORCE episodes with
     rewards + backward + clip + Adam) on TVSum-shaped synthetic videos, one video per optimizer step."""
     import torch
-    from torch.distributions import Bernoulli
-    from summarizer_b200.models.dsn import DSN, compute_rewards
+    from summarizer_b200.models.dsn import DSN, compute_rewards, episode_state, sample_episodes
     from summarizer_b200.models.vasnet import VASNet
     rng = np.random.default_rng(2)
     lens = [int(t) for t in rng.integers(167, 1295, size=16)]
@@ -431,14 +430,14 @@ def train_stage(dev, seconds=4.0):
 
     opt2 = Adam(dsn.parameters(), lr=5e-5, weight_decay=1e-5)
     base = torch.zeros((), device=dev)
+    episode_rng = episode_state(dev)
 
     def dsn_step(x, tgt):
         opt2.zero_grad(set_to_none=True)
         probs = dsn(x)
-        dist = Bernoulli(probs, validate_args=False)
-        actions = dist.sample((5,))
-        rewards = compute_rewards(x, actions.reshape(5, -1))
-        loss = -(dist.log_prob(actions).reshape(5, -1).mean(1) * (rewards - base)).sum() / 5.
+        log_probs, actions = sample_episodes(probs, 5, episode_rng)
+        rewards = compute_rewards(x, actions)
+        loss = -(log_probs * (rewards - base)).sum() / 5.
         loss.backward(); clip_grad_norm_(list(dsn.parameters()), 5.0); opt2.step()
     out["dsn_reinforce_frames_per_s"], out["dsn_reinforce_frames_per_s_eager"] = timed(dsn_step)
     out["step_replay"] = "one CUDA graph per video (forward, loss, backward, clip, Adam: all library kernels)"

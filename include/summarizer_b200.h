@@ -325,6 +325,19 @@ int smz_dsn_reward_workspace_bytes(int T, int n_episodes, int64_t *bytes);
 int smz_dsn_reward(const float *x, int T, const uint8_t *actions, int n_episodes, int temp_dist_thre, int far_sim,
                    float *rewards, void *ws, int64_t ws_bytes, void *stream);
 
+/* ---- DSN episode sampling: replaces models/dsn.py:112,125-126 (Bernoulli(probs); dist.sample(); dist.log_prob)
+ * for ALL episodes of a step in one launch.  probs: float32 [T] in (0,1); state: three device uint64 words
+ * {Philox seed, call number, 0 (ticket, kept at 0 by the kernel)} — the call number is advanced on the device, so a
+ * captured step draws fresh episodes at every graph replay; given: NULL, or uint8 [n_episodes,T] actions to evaluate
+ * instead of drawing (tests replay the reference's draws; the call number is then left alone).  Out: actions uint8
+ * [n_episodes,T] (1 = frame picked, action = u < p as torch's bernoulli), logp_mean float32 [n_episodes] = mean over
+ * the frames of log_prob(action) with the logs clamped at -100 as torch's binary_cross_entropy.
+ * smz_bernoulli_logprob_backward: dprobs[t] = sum_e dlogp[e] * (a - p) / max(p (1 - p), 1e-12) / T. */
+int smz_bernoulli_logprob(const float *probs, int T, int n_episodes, uint64_t *state, const uint8_t *given,
+                          uint8_t *actions, float *logp_mean, void *stream);
+int smz_bernoulli_logprob_backward(const float *probs, const uint8_t *actions, const float *dlogp, int T,
+                                   int n_episodes, float *dprobs, void *stream);
+
 /* ---- annotator summaries as 1 bit per frame (staging form for host -> device copies) --------------
  * evaluate_summary binarises user_summary first (utils/eval.py:148-149), so (x > 0) is all it reads.
  * smz_host_pack_user_summary runs on HOST threads over HOST pointers (it is the copy's staging step): row u of

@@ -64,6 +64,8 @@ SIGNATURES = {
     "smz_dsn_backward": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _L, _P]),
     "smz_dsn_reward_workspace_bytes": (_I, [_I, _I, C.POINTER(C.c_int64)]),
     "smz_dsn_reward": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _L, _P]),
+    "smz_bernoulli_logprob": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
+    "smz_bernoulli_logprob_backward": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "smz_host_pack_user_summary": (_I, [_P, _I, _P, _P, _P, _I]),
     "smz_fscore_packed": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "smz_pack_user_bits": (_I, [_P, _I, _P, _P, _P, _P]),

@@ -173,3 +173,104 @@ extern "C" int smz_dsn_reward(const float *x, int T, const uint8_t *actions, int
     SMZ_CUDA_CHECK(cudaGetLastError());
     return SMZ_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Episode sampling: dsn.py:112,125-126 — dist = Bernoulli(probs); actions = dist.sample(); dist.log_prob(actions)
+// for every episode of a step in ONE launch: Philox4x32-10 draws (key = seed, counter = (frame quad, episode,
+// call number)), action = u < p as torch's bernoulli, log-probability as torch's binary_cross_entropy (logs clamped
+// at -100), mean over the frames per episode.  The call number lives on the device next to the seed and is bumped by
+// the last CTA to finish, so a captured step draws fresh episodes at every replay.
+namespace {
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c.x), l0 = 0xD2511F53u * c.x;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c.z), l1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(h1 ^ c.y ^ k.x, l1, h0 ^ c.w ^ k.y, l0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__device__ __forceinline__ float bern_logp(float p, bool a) {
+    return fmaxf(a ? logf(p) : logf(1.f - p), -100.f);
+}
+
+__global__ void __launch_bounds__(256) bernoulli_logprob_kernel(const float *__restrict__ probs, int T, int E,
+                                                                  unsigned long long *__restrict__ state,
+                                                                  const uint8_t *__restrict__ given,
+                                                                  uint8_t *__restrict__ actions, float *__restrict__ logp,
+                                                                  unsigned int *__restrict__ ticket) {
+    const int e = blockIdx.x;
+    const unsigned long long seed = state[0], call = state[1];
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    float acc = 0.f;
+    for (int q = threadIdx.x; q * 4 < T; q += blockDim.x) {
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (given == nullptr) r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)e, (uint32_t)call, (uint32_t)(call >> 32)), key);
+        const uint32_t rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int t = q * 4 + i;
+            if (t >= T) break;
+            const float p = probs[t];
+            const bool a = given != nullptr ? given[(int64_t)e * T + t] != 0 : (float)(rv[i] >> 8) * 0x1p-24f < p;
+            actions[(int64_t)e * T + t] = a ? 1 : 0;
+            acc += bern_logp(p, a);
+        }
+    }
+    __shared__ float s_part[8];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 8; i++) s += s_part[i];                  // fixed order: the same draws give the same bits
+        logp[e] = s / (float)T;
+        __threadfence();
+        if (atomicAdd(ticket, 1u) == (unsigned)E - 1u) {             // every CTA has read the call number by now
+            *ticket = 0u;
+            if (given == nullptr) state[1] = call + 1ull;
+        }
+    }
+}
+
+// d mean_t log_prob(a_e) / d p_t, chained with the episodes' upstream gradients g[e] (torch's BCE backward:
+// (a - p) / max(p (1 - p), 1e-12))
+__global__ void bernoulli_logprob_bwd_kernel(const float *__restrict__ probs, const uint8_t *__restrict__ actions,
+                                             const float *__restrict__ g, int T, int E, float *__restrict__ dprobs) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const float p = probs[t], den = fmaxf(p * (1.f - p), 1e-12f);
+    float acc = 0.f;
+    for (int e = 0; e < E; e++) acc += g[e] * ((actions[(int64_t)e * T + t] ? 1.f : 0.f) - p);
+    dprobs[t] = acc / (den * (float)T);
+}
+
+}  // namespace
+
+extern "C" int smz_bernoulli_logprob(const float *probs, int T, int n_episodes, uint64_t *state, const uint8_t *given,
+                                     uint8_t *actions, float *logp_mean, void *stream) {
+    SMZ_REQUIRE(probs && state && actions && logp_mean, "bernoulli_logprob: NULL pointer");
+    SMZ_REQUIRE(T > 0 && n_episodes >= 1 && n_episodes <= 1024, "bernoulli_logprob: T > 0 and 1..1024 episodes");
+    int rc = smz_device_check();
+    if (rc != SMZ_OK) return rc;
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "state words");
+    unsigned long long *s = reinterpret_cast<unsigned long long *>(state);
+    bernoulli_logprob_kernel<<<n_episodes, 256, 0, (cudaStream_t)stream>>>(probs, T, n_episodes, s, given, actions, logp_mean,
+                                                                            reinterpret_cast<unsigned int *>(s + 2));
+    SMZ_CUDA_CHECK(cudaGetLastError());
+    return SMZ_OK;
+}
+
+extern "C" int smz_bernoulli_logprob_backward(const float *probs, const uint8_t *actions, const float *dlogp, int T,
+                                              int n_episodes, float *dprobs, void *stream) {
+    SMZ_REQUIRE(probs && actions && dlogp && dprobs, "bernoulli_logprob_backward: NULL pointer");
+    SMZ_REQUIRE(T > 0 && n_episodes >= 1, "bernoulli_logprob_backward: T > 0 and >= 1 episode");
+    int rc = smz_device_check();
+    if (rc != SMZ_OK) return rc;
+    bernoulli_logprob_bwd_kernel<<<(T + 255) / 256, 256, 0, (cudaStream_t)stream>>>(probs, actions, dlogp, T, n_episodes, dprobs);
+    SMZ_CUDA_CHECK(cudaGetLastError());
+    return SMZ_OK;
+}

@@ -99,7 +99,6 @@ class DSN(nn.Module):
         return p.view(batch_size, seq_len, 1).permute(1, 0, 2)
 
 
-from torch.distributions import Bernoulli  # noqa: E402
 
 from . import StepGraphs, Trainer, clip_grad_norm_, make_adam  # noqa: E402
 
@@ -120,6 +119,52 @@ def compute_rewards(seq, actions, far_sim=False, temp_dist_thre=20, workspace=No
     return rewards
 
 
+class _EpisodeLogProb(torch.autograd.Function):
+    """mean_t log_prob(actions_e) for every episode (dsn.py:126,135) with the draw itself (dsn.py:125) in the same
+    kernel; the gradient w.r.t. ``probs`` is torch's ``Bernoulli.log_prob`` backward."""
+
+    @staticmethod
+    def forward(ctx, probs, n_episodes, state, given):
+        p = probs.detach().reshape(-1).float().contiguous()
+        T = p.numel()
+        actions = torch.empty(n_episodes, T, dtype=torch.uint8, device=p.device)
+        logp = torch.empty(n_episodes, dtype=torch.float32, device=p.device)
+        N.check(N.lib().smz_bernoulli_logprob(N.ptr(p), T, n_episodes, N.ptr(state), N.ptr(given) if given is not None else None,
+                                              N.ptr(actions), N.ptr(logp), N.current_stream()))
+        ctx.save_for_backward(p, actions)
+        ctx.shape = probs.shape
+        ctx.mark_non_differentiable(actions)
+        return logp, actions
+
+    @staticmethod
+    def backward(ctx, dlogp, _dactions):
+        p, actions = ctx.saved_tensors
+        E, T = actions.shape
+        dprobs = torch.empty_like(p)
+        N.check(N.lib().smz_bernoulli_logprob_backward(N.ptr(p), N.ptr(actions), N.ptr(dlogp.float().contiguous()), T, E,
+                                                       N.ptr(dprobs), N.current_stream()))
+        return dprobs.reshape(ctx.shape), None, None, None
+
+
+def sample_episodes(probs, n_episodes, state, given=None):
+    """All episodes of a REINFORCE step in one launch (dsn.py:112,125-126): draws ``actions ~ Bernoulli(probs)`` for
+    every episode and returns ``(mean_t log_prob(actions_e) float32 (E,), actions uint8 (E, T))``.  ``state`` is the
+    device-resident draw state of ``episode_state`` (advanced on the device: graph replays draw fresh episodes);
+    ``given`` = (E, T) 0/1 actions to evaluate instead of drawing."""
+    N.require_device()
+    if given is not None:
+        given = given.detach().reshape(n_episodes, -1).to(torch.uint8).contiguous()
+    return _EpisodeLogProb.apply(probs, int(n_episodes), state, given)
+
+
+def episode_state(device, seed=None):
+    """{Philox seed, call number, 0} as three device int64 words; the seed comes from torch's generator unless given,
+    so ``torch.manual_seed`` makes the episode draws reproducible."""
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return torch.tensor([seed, 0, 0], dtype=torch.int64, device=device)
+
+
 class DSNTrainer(Trainer):
     """models/dsn.py:50-236 — REINFORCE with the diversity-representativeness reward; extra parameters parsed as
     the reference does (dsn.py:52-57; note ``beta = int(0.01) = 0`` unless ``--beta`` >= 1)."""
@@ -135,10 +180,10 @@ class DSNTrainer(Trainer):
         self._reward_ws = _Workspace()
         return DSN()
 
-    def _draw_actions(self, dist):
-        """The frame selections of all episodes of a step (dsn.py:124-126 draws them one ``dist.sample()`` at a time):
-        (num_episodes, T, 1, 1) float 0/1.  A method so that tests can replay the reference's draws."""
-        return dist.sample((self.num_episodes,))
+    def _draw_actions(self, probs):
+        """Hook for tests that replay the reference's draws (dsn.py:124-126): return (num_episodes, T) 0/1 actions to
+        use for this step, or None (default) to let the sampling kernel draw them."""
+        return None
 
     def compute_reward(self, seq, actions, far_sim=False, temp_dist_thre=20):
         """One episode (reference signature, dsn.py:185): seq (T,1,1024), actions (T,1,1) -> scalar tensor."""
@@ -162,6 +207,7 @@ class DSNTrainer(Trainer):
         dev = self._device()
         key_index = {key: i for i, key in enumerate(sorted(train_keys))}
         baselines = torch.zeros(len(train_keys), device=dev)                      # device-resident: no sync per step
+        episode_rng = episode_state(dev)                                          # Philox seed + call number, on the device
         reward_writers = {key: [] for key in train_keys}
         best_corr, best_avg_f_score, best_max_f_score = -1.0, 0.0, 0.0
         dist_, rank, world = self._dp()
@@ -177,17 +223,15 @@ class DSNTrainer(Trainer):
             """REINFORCE loss of one video and its backward pass -> (loss, probs, mean reward, baseline delta)."""
             seq, target = self._video_tensors(key)
             probs = self.model(seq)                                           # (T,1,1), autograd through the device BPTT
-            dist = Bernoulli(probs, validate_args=False)
             loss = self.beta * (probs.mean() - self.eps) ** 2                 # summary-length penalty [Eq.11]
             if self.sup:
                 loss = loss + loss_BCE(probs, target)
-            actions = self._draw_actions(dist)                                # (E,T,1,1): the E episodes in one draw
-            rewards = compute_rewards(seq, actions.reshape(self.num_episodes, -1), self.far_sim, self.temp_dist_thre,
-                                      self._reward_ws)
+            # the E episodes of dsn.py:122-126 in one launch: draws + mean log-probabilities (smz_bernoulli_logprob)
+            log_probs, actions = sample_episodes(probs, self.num_episodes, episode_rng, self._draw_actions(probs))
+            rewards = compute_rewards(seq, actions, self.far_sim, self.temp_dist_thre, self._reward_ws)
             base = baselines[key_index[key]].detach().clone()
             # policy gradient [Eq.10], dsn.py:134-138 for all episodes at once:
             #   loss -= sum_e mean_t(log_prob(actions_e)) * (reward_e - baseline)
-            log_probs = dist.log_prob(actions).reshape(self.num_episodes, -1).mean(1)
             loss = loss - (log_probs * (rewards - base)).sum()
             loss = loss / float(self.num_episodes)
             loss.backward()

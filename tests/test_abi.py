@@ -95,3 +95,12 @@ def test_struct_sizes_match_header():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", os.path.join(d, "s")])
         sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "s")]).split()]
     assert sizes == [ctypes.sizeof(LstmSeq), ctypes.sizeof(LstmDecode), ctypes.sizeof(DsnParams), N.VIDEO_DESC.itemsize]
+
+
+def test_episode_sampling_argument_validation():
+    L = N.lib()
+    one = ctypes.c_void_p(16)
+    assert L.smz_bernoulli_logprob(None, 10, 5, one, None, one, one, None) < 0 and b"NULL pointer" in L.smz_last_error()
+    assert L.smz_bernoulli_logprob(one, 0, 5, one, None, one, one, None) < 0
+    assert L.smz_bernoulli_logprob(one, 10, 0, one, None, one, one, None) < 0 and b"episodes" in L.smz_last_error()
+    assert L.smz_bernoulli_logprob_backward(one, one, None, 10, 5, one, None) < 0

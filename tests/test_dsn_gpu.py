@@ -124,3 +124,61 @@ def test_dsn_trainer_reinforce_runs(tmp_path):
                             epochs=2, test_every_epochs=1, extra_params={}))
     (res,) = train(hps)
     assert np.isfinite(res[1:]).all() and 0 <= res[2] <= res[3] <= 1
+
+
+@pytest.mark.gpu
+def test_sample_episodes_logprob_and_gradient_match_torch():
+    """smz_bernoulli_logprob on GIVEN actions = torch's Bernoulli(probs).log_prob(actions).mean over the frames
+    (dsn.py:112,126,135), and its backward = torch's autograd through it, including probabilities at the clamp."""
+    from torch.distributions import Bernoulli
+    from summarizer_b200.models.dsn import episode_state, sample_episodes
+    T, E = 1003, 5
+    g = torch.Generator().manual_seed(4)
+    probs = torch.rand(T, 1, 1, generator=g)
+    probs[:4, 0, 0] = torch.tensor([1e-9, 1 - 1e-7, 0.5, 0.999])
+    actions = (torch.rand(E, T, generator=g) < 0.4).float()
+    actions[:, 0] = 1; actions[:, 1] = 0                       # improbable actions: steep log-probabilities
+    w = torch.randn(E, generator=g)
+
+    p_ref = probs.clone().cuda().requires_grad_(True)
+    lp_ref = Bernoulli(p_ref, validate_args=False).log_prob(actions.cuda().reshape(E, T, 1, 1)).reshape(E, -1).mean(1)
+    (lp_ref * w.cuda()).sum().backward()
+
+    p = probs.clone().cuda().requires_grad_(True)
+    state = episode_state(p.device, seed=7)
+    lp, act = sample_episodes(p, E, state, given=actions.cuda())
+    (lp * w.cuda()).sum().backward()
+    assert act.dtype == torch.uint8 and torch.equal(act.float().cpu(), actions)
+    assert state.tolist() == [7, 0, 0]                          # given actions: no draw consumed
+    assert torch.allclose(lp, lp_ref, rtol=1e-5, atol=1e-6), (lp, lp_ref)
+    assert torch.allclose(p.grad, p_ref.grad, rtol=1e-4, atol=1e-7), (p.grad - p_ref.grad).abs().max()
+
+
+@pytest.mark.gpu
+def test_sample_episodes_draws_are_bernoulli_and_advance_on_the_device():
+    """Drawn episodes: P(action = 1) = p per frame, independent between episodes and calls; the call number is bumped
+    on the device (a captured step draws new episodes at every replay); the same seed reproduces the draws."""
+    from summarizer_b200.models.dsn import episode_state, sample_episodes
+    T, E = 4099, 8
+    probs = torch.linspace(0.02, 0.98, T).cuda()
+    state = episode_state(probs.device, seed=123)
+    draws = []
+    for call in range(16):
+        lp, act = sample_episodes(probs, E, state)
+        assert state.tolist() == [123, call + 1, 0]
+        ref = torch.where(act.bool(), probs.log(), (1 - probs).log()).mean(1)
+        assert torch.allclose(lp, ref, rtol=1e-5, atol=1e-6)
+        draws.append(act)
+    allv = torch.stack(draws).reshape(-1, T).float()            # 128 independent draws per frame
+    # mean over frames of (action - p) ~ N(0, sum p(1-p)) / n
+    z = (allv - probs).sum() / torch.sqrt((probs * (1 - probs)).sum() * allv.shape[0])
+    assert abs(float(z)) < 4.0, float(z)
+    by_bucket = (allv.mean(0).reshape(-1)[:4096].reshape(16, 256).mean(1) - probs[:4096].reshape(16, 256).mean(1)).abs()
+    assert float(by_bucket.max()) < 0.01, by_bucket
+    rows = allv.reshape(-1, T)
+    assert len({bytes(r.to(torch.uint8).cpu().numpy().tobytes()) for r in rows}) == rows.shape[0]   # no repeated episode
+    again = episode_state(probs.device, seed=123)
+    _, act0 = sample_episodes(probs, E, again)
+    assert torch.equal(act0, draws[0])
+    other = episode_state(probs.device, seed=124)
+    assert not torch.equal(sample_episodes(probs, E, other)[1], draws[0])

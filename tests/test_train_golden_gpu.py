@@ -98,15 +98,15 @@ def test_dsn_trainer_follows_the_reference_trajectory(tmp_path, monkeypatch):
     offs = np.concatenate([[0], np.cumsum(lens)])
     state = {"n": 0}
 
-    def replay_actions(self, dist):
-        E, T = self.num_episodes, dist.probs.shape[0]
+    def replay_actions(self, probs):
+        E, T = self.num_episodes, probs.shape[0]
         rows = []
         for e in range(E):
             k = state["n"]
             assert lens[k] == T
-            rows.append(torch.from_numpy(acts[offs[k]:offs[k + 1]].astype(np.float32)))
+            rows.append(torch.from_numpy(acts[offs[k]:offs[k + 1]].astype(np.uint8)))
             state["n"] += 1
-        return torch.stack(rows).reshape(E, T, 1, 1).to(dist.probs.device)
+        return torch.stack(rows).reshape(E, T).to(probs.device)
 
     monkeypatch.setattr(DSNTrainer, "_draw_actions", replay_actions)
     before = G.sampled_params(t.model)
