@@ -212,6 +212,16 @@ int smz_cvt_bf16_multi(const float *const *src, void *const *dst, const int64_t 
 int smz_gemm_bf16(int a_mn, int b_mn, const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc,
                   int M, int N, int K, float alpha, const float *bias, const void *residual, int64_t ldr, int flags,
                   void *stream);
+/* Float32-accurate form (the reference's torch.matmul / nn.Linear compute in float32, vasnet.py:114-140): every
+ * operand is a hi + lo pair of bfloat16 arrays of the same layout, hi = bf16(x), lo = bf16(x - hi)
+ * (smz_split_bf16_multi makes them from float32; *_lo == NULL: that operand is exact in bf16), and the kernel
+ * accumulates A_hi.B_hi + A_lo.B_hi + A_hi.B_lo in float32: ~2^-17 relative per product instead of 2^-9.  C_lo != NULL
+ * (bf16 output only): the result is written as hi + lo planes as well, ready to be the next operand. */
+int smz_gemm_bf16_split(int a_mn, int b_mn, const void *A, const void *A_lo, int64_t lda, const void *B,
+                        const void *B_lo, int64_t ldb, void *C, void *C_lo, int64_t ldc, int M, int N, int K, float alpha,
+                        const float *bias, const void *residual, int64_t ldr, int flags, void *stream);
+int smz_split_bf16_multi(const float *const *src, void *const *hi, void *const *lo, const int64_t *n, int count,
+                         void *stream);
 
 /* ---- VASNet scorer: replaces models/vasnet.py:92-148 VASNet.forward (and, with
  *      smz_vasnet_backward, the autograd graph behind vasnet.py:209-211) -------------------------
@@ -252,7 +262,16 @@ typedef struct smz_vasnet_params {
     const float *ln_c, *b1f;
     const void *wgv, *wgv16;
     int32_t *status;
+    /* optional, all four together: the FLOAT32-ACCURATE mode (training layout only, i.e. training != 0 in
+     * smz_vasnet_forward, and smz_vasnet_backward).  The reference computes in float32 (vasnet.py:114-145); bf16 operands
+     * cost 2^-9 per product.  Here every 16-bit operand becomes a hi + lo pair of bf16 arrays (hi = bf16(x),
+     * lo = bf16(x - hi)) and every contraction runs the three products hi.hi + lo.hi + hi.lo into the float32 accumulator
+     * (~2^-17 per product; 3 x the tensor-core work of the bf16 mode, immaterial for batch-1 training steps that are
+     * launch-bound).  w*_lo = the lo planes of wqk / wv / wo / w1 (smz_split_bf16_multi makes them); the activations'
+     * lo planes live in the second half of the work buffer: size it with training | SMZ_VASNET_SPLIT. */
+    const void *wqk_lo, *wv_lo, *wo_lo, *w1_lo;
 } smz_vasnet_params;
+#define SMZ_VASNET_SPLIT 4   /* OR into `training` of smz_vasnet_workspace_bytes: room for the activations' lo planes */
 
 /* x: packed features [sum T, 1024] (float32, or bfloat16 when x_is_bf16), video v owns rows
  * h_cu_seqlens[v] .. h_cu_seqlens[v+1]-1 (HOST array of n_videos+1 prefix offsets, [0] == 0; the
@@ -331,8 +350,9 @@ int smz_dsn_reward(const float *x, int T, const uint8_t *actions, int n_episodes
  * captured step draws fresh episodes at every graph replay; given: NULL, or uint8 [n_episodes,T] actions to evaluate
  * instead of drawing (tests replay the reference's draws; the call number is then left alone).  Out: actions uint8
  * [n_episodes,T] (1 = frame picked, action = u < p as torch's bernoulli), logp_mean float32 [n_episodes] = mean over
- * the frames of log_prob(action) with the logs clamped at -100 as torch's binary_cross_entropy.
- * smz_bernoulli_logprob_backward: dprobs[t] = sum_e dlogp[e] * (a - p) / max(p (1 - p), 1e-12) / T. */
+ * the frames of log_prob(action) as torch.distributions.Bernoulli computes it (probabilities clamped to
+ * [2^-23, 1 - 2^-23]).
+ * smz_bernoulli_logprob_backward: dprobs[t] = sum_e dlogp[e] * (a - p) / (p (1 - p)) / T, 0 where p was clamped. */
 int smz_bernoulli_logprob(const float *probs, int T, int n_episodes, uint64_t *state, const uint8_t *given,
                           uint8_t *actions, float *logp_mean, void *stream);
 int smz_bernoulli_logprob_backward(const float *probs, const uint8_t *actions, const float *dlogp, int T,

@@ -77,11 +77,13 @@ SIGNATURES = {
     "smz_lstm_decode_forward": (_I, [_P, _P, _P]),
     "smz_lstm_decode_backward": (_I, [_P, _P, _P]),
     "smz_cvt_bf16_multi": (_I, [_P, _P, _P, _I, _P]),
+    "smz_split_bf16_multi": (_I, [_P, _P, _P, _P, _I, _P]),
     "smz_grad_sqnorm_workspace_floats": (_I, [_P, _I, C.POINTER(C.c_int64)]),
     "smz_grad_sqnorm": (_I, [_P, _I, _P, _P, _L, _P]),
     "smz_clip_grads": (_I, [_P, _I, _P, C.c_float, _P]),
     "smz_adam_step": (_I, [_P, _I, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P]),
     "smz_gemm_bf16": (_I, [_I, _I, _P, _L, _P, _L, _P, _L, _I, _I, _I, C.c_float, _P, _P, _L, _I, _P]),
+    "smz_gemm_bf16_split": (_I, [_I, _I, _P, _P, _L, _P, _P, _L, _P, _P, _L, _I, _I, _I, C.c_float, _P, _P, _L, _I, _P]),
     "smz_gemm_bf16_tn": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, C.c_float, _P, _P, _L, _I, _P]),
 }
 

@@ -81,11 +81,20 @@ __device__ __forceinline__ float4 ld_f4(const float *p) { return *reinterpret_ca
 // special modes cannot be paid for by the plain one): EPI_PLAIN = alpha / bias or row scale / residual / ReLU /
 // store; EPI_HEAD = bias + ReLU + three row sums, no store (GEMM_ROWSTATS | GEMM_NO_STORE); EPI_EXP = masked exp +
 // row sum + bf16 store (GEMM_EXP | GEMM_ROWSTATS).
-enum { EPI_PLAIN = 0, EPI_HEAD = 1, EPI_EXP = 2 };
+// EPI_SPLIT = the plain epilogue whose 16-bit output is written as hi + lo planes (GemmEpilogue::c_lo): its own
+// instantiation so that the tuned plain epilogue carries none of its registers.
+enum { EPI_PLAIN = 0, EPI_HEAD = 1, EPI_EXP = 2, EPI_SPLIT = 3 };
 
-template <bool A_MN, bool B_MN, bool PAIR, int EPI>
+template <bool A_MN, bool B_MN, bool PAIR, int EPI_T>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params P) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_lo, const Params P) {
+    constexpr bool SPLIT_OUT = EPI_T == EPI_SPLIT;
+    constexpr int EPI = SPLIT_OUT ? (int)EPI_PLAIN : EPI_T;
+    // passes of the k loop: hi.hi, then A_lo.B_hi (when A has a lo plane), then A_hi.B_lo (when B has one)
+    const int pass_a = P.epi.a_lo != 0 ? 1 : -1;
+    const int pass_b = P.epi.b_lo != 0 ? (P.epi.a_lo != 0 ? 2 : 1) : -1;
+    const int npass = 1 + (P.epi.a_lo != 0 ? 1 : 0) + (P.epi.b_lo != 0 ? 1 : 0);
     constexpr int STAGES = Cfg<PAIR>::STAGES, B_STAGE = Cfg<PAIR>::B_STAGE, B_ROWS = Cfg<PAIR>::B_ROWS;
     constexpr int TILE_M = Cfg<PAIR>::TILE_M;
     extern __shared__ uint8_t smem_raw[];
@@ -108,6 +117,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (npass > 1) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
         for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], PAIR ? 2 : 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], (PAIR ? 2 : 1) * 32 * EPI_WARPS); }
         fence_mbar_init();
@@ -133,7 +143,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int a_mn = (A_MN ? c.cur.a_col0 : c.cur.a_row0) + mt * TILE_M + rank * BM;
                 const int b_mn = (B_MN ? c.cur.b_col0 : c.cur.b_row0) + nt * BN + rank * B_ROWS;
                 const int a_k = A_MN ? c.cur.a_row0 : c.cur.a_col0, b_k = B_MN ? c.cur.b_row0 : c.cur.b_col0;
-                for (int kb = 0; kb < nkb; kb++) {
+                for (int kbp = 0; kbp < nkb * npass; kbp++) {
+                    const int pass = kbp / nkb, kb = kbp - pass * nkb;
+                    const CUtensorMap *mapA = pass == pass_a ? &tmA_lo : &tmA, *mapB = pass == pass_b ? &tmB_lo : &tmB;
                     mbar_wait(&empty[stage], phase ^ 1u);
                     if (elect_one()) {
                         // the bytes of BOTH CTAs are accounted on the leader's barrier, which the MMA thread waits on
@@ -143,16 +155,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         if (A_MN) {
 #pragma unroll
                             for (int j = 0; j < BM / 64; j++)
-                                tma_load<PAIR>(sA + stage * A_STAGE + j * 8192, &tmA, &full[stage], a_mn + 64 * j, a_k + kb * BK);
+                                tma_load<PAIR>(sA + stage * A_STAGE + j * 8192, mapA, &full[stage], a_mn + 64 * j, a_k + kb * BK);
                         } else {
-                            tma_load<PAIR>(sA + stage * A_STAGE, &tmA, &full[stage], a_k + kb * BK, a_mn);
+                            tma_load<PAIR>(sA + stage * A_STAGE, mapA, &full[stage], a_k + kb * BK, a_mn);
                         }
                         if (B_MN) {
 #pragma unroll
                             for (int j = 0; j < B_ROWS / 64; j++)
-                                tma_load<PAIR>(sB + stage * B_STAGE + j * 8192, &tmB, &full[stage], b_mn + 64 * j, b_k + kb * BK);
+                                tma_load<PAIR>(sB + stage * B_STAGE + j * 8192, mapB, &full[stage], b_mn + 64 * j, b_k + kb * BK);
                         } else {
-                            tma_load<PAIR>(sB + stage * B_STAGE, &tmB, &full[stage], b_k + kb * BK, b_mn);
+                            tma_load<PAIR>(sB + stage * B_STAGE, mapB, &full[stage], b_k + kb * BK, b_mn);
                         }
                     }
                     __syncwarp();
@@ -176,7 +188,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             int it = 0;
             for (int tile = first_tile; tile < P.total_tiles; tile += tile_step, ++it) {
                 c.seek(P, tile);
-                const int nkb = (c.cur.K + BK - 1) / BK;
+                const int nkb = ((c.cur.K + BK - 1) / BK) * npass;     // split operands: the k extent once per kept product
                 const int as = it & 1;
                 mbar_wait(&tempty[as], (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue(s) drained this accumulator
                 tc_fence_after();
@@ -275,6 +287,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int n0 = nt * BN + c0;
                 if (n0 >= n_store) break;   // warp-uniform
                 uint32_t v[32];
+                uint32_t lo_pk[SPLIT_OUT ? 16 : 1];     // EPI_SPLIT: the lo plane of this thread's 32 outputs, packed
                 __syncwarp();           // tcgen05.ld is .sync.aligned: reconverge after the row mask
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
                 if (c0 + 32 < (half + 1) * (BN / 2)) res_fetch(n0 + 32, rnext);
@@ -423,12 +436,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                            pack_f16x2(x[j + 4], x[j + 5]), pack_f16x2(x[j + 6], x[j + 7])) :
                                 make_uint4(pack_bf16x2(x[j], x[j + 1]), pack_bf16x2(x[j + 2], x[j + 3]),
                                            pack_bf16x2(x[j + 4], x[j + 5]), pack_bf16x2(x[j + 6], x[j + 7]));
+                        if constexpr (SPLIT_OUT) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                const uint32_t hi = pack_bf16x2(x[j], x[j + 1]);
+                                lo_pk[j >> 1] = pack_bf16x2(x[j] - __uint_as_float(hi << 16), x[j + 1] - __uint_as_float(hi & 0xffff0000u));
+                            }
+                        }
                     } else if (f16) {
 #pragma unroll
                         for (int j = 0; j < 32; j++) if (n0 + j < g.N) reinterpret_cast<__half *>(dst)[j] = __float2half_rn(x[j]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; j++) if (n0 + j < g.N) dst[j] = __float2bfloat16_rn(x[j]);
+                        for (int j = 0; j < 32; j++) if (n0 + j < g.N) {
+                            const __nv_bfloat16 hi = __float2bfloat16_rn(x[j]);
+                            dst[j] = hi;
+                            if (SPLIT_OUT) dst[P.epi.c_lo + j] = __float2bfloat16_rn(x[j] - __bfloat162float(hi));
+                        }
                     }
                 }
                 }   // !GEMM_NO_STORE
@@ -454,6 +478,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         if (m_base + r < g.M) *reinterpret_cast<uint4 *>(base + (int64_t)(m_base + r) * g.ldc) = w4;
                     }
                     __syncwarp();
+                    if constexpr (SPLIT_OUT) {      // the lo plane leaves the same way
+                        if (row_ok) {
+                            uint4 *pad = reinterpret_cast<uint4 *>(reinterpret_cast<uint32_t *>(stg) + lane * 20);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) pad[j] = make_uint4(lo_pk[4 * j], lo_pk[4 * j + 1], lo_pk[4 * j + 2], lo_pk[4 * j + 3]);
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const int r = 8 * i + sub;
+                            const uint4 w4 = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(stg) + r * 20 + part * 4);
+                            if (m_base + r < g.M) *reinterpret_cast<uint4 *>(base + P.epi.c_lo + (int64_t)(m_base + r) * g.ldc) = w4;
+                        }
+                        __syncwarp();
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 8; j++) rcur[j] = rnext[j];
@@ -535,13 +574,19 @@ int gemm_tile_m() { return gemm_pair_mode() ? 2 * BM : BM; }
 int gemm_tiles(int M, int N) { return ((M + gemm_tile_m() - 1) / gemm_tile_m()) * ((N + GEMM_BN - 1) / GEMM_BN); }
 
 template <bool PAIR>
-static int launch_variant(bool a_mn, bool b_mn, const CUtensorMap &ma, const CUtensorMap &mb, const Params &P, int total_tiles,
-                          cudaStream_t st) {
-    typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const Params);
+static int launch_variant(bool a_mn, bool b_mn, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &ma_lo,
+                          const CUtensorMap &mb_lo, const Params &P, int total_tiles, cudaStream_t st) {
+    typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
     const int f = P.epi.flags;
-    const int epi = (f & GEMM_EXP) ? EPI_EXP : (f & GEMM_ROWSTATS) ? EPI_HEAD : EPI_PLAIN;
+    const int epi = (f & GEMM_EXP) ? EPI_EXP : (f & GEMM_ROWSTATS) ? EPI_HEAD
+                    : (P.epi.c_lo != 0 && !(f & GEMM_OUT_F32)) ? EPI_SPLIT : EPI_PLAIN;
     kern_t kern;
-    if (epi != EPI_PLAIN) {
+    if (epi == EPI_SPLIT) {
+        if (f & (GEMM_OUT_F16 | GEMM_LN_STATS)) return fail(SMZ_ERR_UNSUPPORTED, "gemm: hi + lo output planes are bf16, without row statistics");
+        if ((P.epi.c_lo & 7) != 0) return fail(SMZ_ERR_ARG, "gemm: c_lo must be a multiple of 8 elements");
+        kern = a_mn ? (b_mn ? (kern_t)gemm_kernel<true, true, PAIR, EPI_SPLIT> : (kern_t)gemm_kernel<true, false, PAIR, EPI_SPLIT>)
+                    : (b_mn ? (kern_t)gemm_kernel<false, true, PAIR, EPI_SPLIT> : (kern_t)gemm_kernel<false, false, PAIR, EPI_SPLIT>);
+    } else if (epi != EPI_PLAIN) {
         if (a_mn || b_mn) return fail(SMZ_ERR_UNSUPPORTED, "gemm: the fused head / exp epilogues exist for K-major operands only");
         if (epi == EPI_HEAD && (!(f & GEMM_NO_STORE) || P.epi.stat_w == nullptr || P.epi.stat_out == nullptr))
             return fail(SMZ_ERR_ARG, "gemm: GEMM_ROWSTATS needs GEMM_NO_STORE, stat_w and stat_out");
@@ -552,8 +597,8 @@ static int launch_variant(bool a_mn, bool b_mn, const CUtensorMap &ma, const CUt
         kern = a_mn ? (b_mn ? (kern_t)gemm_kernel<true, true, PAIR, EPI_PLAIN> : (kern_t)gemm_kernel<true, false, PAIR, EPI_PLAIN>)
                     : (b_mn ? (kern_t)gemm_kernel<false, true, PAIR, EPI_PLAIN> : (kern_t)gemm_kernel<false, false, PAIR, EPI_PLAIN>);
     }
-    const int variant = epi != EPI_PLAIN ? 3 + epi : (a_mn ? 2 : 0) + (b_mn ? 1 : 0);
-    static bool attr_set[64][6] = {{false}};
+    const int variant = epi == EPI_SPLIT ? 6 + (a_mn ? 2 : 0) + (b_mn ? 1 : 0) : epi != EPI_PLAIN ? 3 + epi : (a_mn ? 2 : 0) + (b_mn ? 1 : 0);
+    static bool attr_set[64][10] = {{false}};
     int dev = 0;
     SMZ_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !attr_set[dev][variant]) {
@@ -575,7 +620,7 @@ static int launch_variant(bool a_mn, bool b_mn, const CUtensorMap &ma, const CUt
     } else {
         cfg.gridDim = dim3(total_tiles < sms ? total_tiles : sms);
     }
-    SMZ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ma, mb, P));
+    SMZ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ma, mb, ma_lo, mb_lo, P));
     return SMZ_OK;
 }
 
@@ -591,14 +636,23 @@ int gemm_bf16(bool a_mn, bool b_mn, const void *A, int64_t a_rows, int64_t a_col
     if (rc != SMZ_OK) return rc;
     rc = make_map(&mb, B, b_rows, b_cols, ldb, b_mn ? 64 : (pair ? BN / 2 : BN));
     if (rc != SMZ_OK) return rc;
+    alignas(64) CUtensorMap ma_lo = ma, mb_lo = mb;       // the lo planes of split-bf16 operands: same shape, other base
+    if (epi.a_lo != 0) {
+        rc = make_map(&ma_lo, reinterpret_cast<const uint16_t *>(A) + epi.a_lo, a_rows, a_cols, lda, a_mn ? 64 : BM);
+        if (rc != SMZ_OK) return rc;
+    }
+    if (epi.b_lo != 0) {
+        rc = make_map(&mb_lo, reinterpret_cast<const uint16_t *>(B) + epi.b_lo, b_rows, b_cols, ldb, b_mn ? 64 : (pair ? BN / 2 : BN));
+        if (rc != SMZ_OK) return rc;
+    }
     Params P;
     P.probs = d_probs;
     P.single = single;
     P.n_probs = n_probs;
     P.total_tiles = total_tiles;
     P.epi = epi;
-    return pair ? launch_variant<true>(a_mn, b_mn, ma, mb, P, total_tiles, st)
-                : launch_variant<false>(a_mn, b_mn, ma, mb, P, total_tiles, st);
+    return pair ? launch_variant<true>(a_mn, b_mn, ma, mb, ma_lo, mb_lo, P, total_tiles, st)
+                : launch_variant<false>(a_mn, b_mn, ma, mb, ma_lo, mb_lo, P, total_tiles, st);
 }
 
 }  // namespace smz
@@ -635,6 +689,34 @@ extern "C" int smz_gemm_bf16(int a_mn, int b_mn, const void *A, int64_t lda, con
     g.ldc = (int32_t)ldc; g.ldr = (int32_t)ldr;
     g.tiles_n = (N + smz::GEMM_BN - 1) / smz::GEMM_BN;
     smz::GemmEpilogue e = {C, bias, residual, alpha, flags};
+    return smz::gemm_bf16(a_mn != 0, b_mn != 0, A, a_mn ? K : M, a_mn ? M : K, lda, B, b_mn ? K : N, b_mn ? N : K, ldb,
+                          nullptr, 1, smz::gemm_tiles(M, N), g, e, (cudaStream_t)stream);
+}
+
+// Split-bf16 form of smz_gemm_bf16 (float32-accurate products): every operand is a pair of bf16 arrays of the same
+// layout, hi = bf16(x) and lo = bf16(x - hi) (smz_split_bf16_multi makes them); A_lo / B_lo may be NULL (that operand
+// is exact in bf16).  C_lo != NULL with a bf16 output: the result is written as hi + lo planes too.
+extern "C" int smz_gemm_bf16_split(int a_mn, int b_mn, const void *A, const void *A_lo, int64_t lda, const void *B,
+                                   const void *B_lo, int64_t ldb, void *C, void *C_lo, int64_t ldc, int M, int N, int K,
+                                   float alpha, const float *bias, const void *residual, int64_t ldr, int flags,
+                                   void *stream) {
+    if (M == 0 || N == 0) return SMZ_OK;
+    SMZ_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape %d x %d x %d", M, N, K);
+    SMZ_REQUIRE(ldc >= N && lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K), "gemm: leading dimension smaller than the row length");
+    SMZ_REQUIRE(C_lo == nullptr || !(flags & smz::GEMM_OUT_F32), "gemm: a float32 output has no lo plane");
+    int rc = smz_device_check();
+    if (rc != SMZ_OK) return rc;
+    smz::GemmProblem g = {};
+    g.M = M; g.N = N; g.K = K;
+    g.ldc = (int32_t)ldc; g.ldr = (int32_t)ldr;
+    g.tiles_n = (N + smz::GEMM_BN - 1) / smz::GEMM_BN;
+    smz::GemmEpilogue e = {C, bias, residual, alpha, flags};
+    auto delta = [](const void *lo, const void *hi) -> int64_t {
+        return lo == nullptr ? 0 : (reinterpret_cast<const char *>(lo) - reinterpret_cast<const char *>(hi)) / 2;
+    };
+    e.a_lo = delta(A_lo, A); e.b_lo = delta(B_lo, B); e.c_lo = delta(C_lo, C);
+    SMZ_REQUIRE((A_lo == nullptr || e.a_lo != 0) && (B_lo == nullptr || e.b_lo != 0) && (C_lo == nullptr || e.c_lo != 0),
+                "gemm: a lo plane must be a different array than its hi plane");
     return smz::gemm_bf16(a_mn != 0, b_mn != 0, A, a_mn ? K : M, a_mn ? M : K, lda, B, b_mn ? K : N, b_mn ? N : K, ldb,
                           nullptr, 1, smz::gemm_tiles(M, N), g, e, (cudaStream_t)stream);
 }

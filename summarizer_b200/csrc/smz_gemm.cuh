@@ -66,6 +66,12 @@ struct GemmEpilogue {
     const float *ln_c = nullptr;     // GEMM_LN_FOLD: [N] row sums of the B operand (W * diag(gamma)) as the tensor core sees it
     int ln_slots = 0, ln_width = 0;
     float ln_eps = 0.f;
+    // Split-bf16 ("hi + lo planes") operands, the float32-accurate mode: element offsets (from A / B / C) of a second
+    // bf16 array of the same layout holding x - float(bf16(x)); 0 = the operand has no lo plane.  The k loop then runs
+    // once per product kept — A_hi.B_hi, A_lo.B_hi, A_hi.B_lo (A_lo.B_lo ~ 2^-18 is dropped) — into the same float32
+    // accumulator: ~2^-17 relative per product instead of 2^-9.  c_lo (16-bit outputs of the plain epilogue only): the
+    // epilogue also writes the lo plane of C.
+    int64_t a_lo = 0, b_lo = 0, c_lo = 0;
 };
 
 constexpr int GEMM_BN = 256;

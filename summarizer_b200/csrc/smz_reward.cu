@@ -177,8 +177,8 @@ extern "C" int smz_dsn_reward(const float *x, int T, const uint8_t *actions, int
 // ---------------------------------------------------------------------------------------------------
 // Episode sampling: dsn.py:112,125-126 — dist = Bernoulli(probs); actions = dist.sample(); dist.log_prob(actions)
 // for every episode of a step in ONE launch: Philox4x32-10 draws (key = seed, counter = (frame quad, episode,
-// call number)), action = u < p as torch's bernoulli, log-probability as torch's binary_cross_entropy (logs clamped
-// at -100), mean over the frames per episode.  The call number lives on the device next to the seed and is bumped by
+// call number)), action = u < p as torch's bernoulli, log-probability as torch's Bernoulli.log_prob (probabilities
+// clamped to [eps, 1 - eps]), mean over the frames per episode.  The call number lives on the device next to the seed and is bumped by
 // the last CTA to finish, so a captured step draws fresh episodes at every replay.
 namespace {
 
@@ -193,8 +193,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 
+// torch.distributions.Bernoulli(probs).log_prob: probs are clamped to [eps, 1 - eps] (float32 eps = 2^-23) on their
+// way to logits, and log_prob = -binary_cross_entropy_with_logits(logits, action) = log(p_c) resp. log(1 - p_c)
+constexpr float kProbEps = 1.1920928955078125e-07f;
 __device__ __forceinline__ float bern_logp(float p, bool a) {
-    return fmaxf(a ? logf(p) : logf(1.f - p), -100.f);
+    const float pc = fminf(fmaxf(p, kProbEps), 1.f - kProbEps);
+    return a ? logf(pc) : log1pf(-pc);
 }
 
 __global__ void __launch_bounds__(256) bernoulli_logprob_kernel(const float *__restrict__ probs, int T, int E,
@@ -236,16 +240,17 @@ __global__ void __launch_bounds__(256) bernoulli_logprob_kernel(const float *__r
     }
 }
 
-// d mean_t log_prob(a_e) / d p_t, chained with the episodes' upstream gradients g[e] (torch's BCE backward:
-// (a - p) / max(p (1 - p), 1e-12))
+// d mean_t log_prob(a_e) / d p_t, chained with the episodes' upstream gradients g[e]: (a - p) / (p (1 - p)) inside
+// the clamp range, 0 outside
 __global__ void bernoulli_logprob_bwd_kernel(const float *__restrict__ probs, const uint8_t *__restrict__ actions,
                                              const float *__restrict__ g, int T, int E, float *__restrict__ dprobs) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
-    const float p = probs[t], den = fmaxf(p * (1.f - p), 1e-12f);
+    const float p = probs[t];
+    if (!(p >= kProbEps && p <= 1.f - kProbEps)) { dprobs[t] = 0.f; return; }     // clamped: no gradient, as torch
     float acc = 0.f;
     for (int e = 0; e < E; e++) acc += g[e] * ((actions[(int64_t)e * T + t] ? 1.f : 0.f) - p);
-    dprobs[t] = acc / (den * (float)T);
+    dprobs[t] = acc / (p * (1.f - p) * (float)T);
 }
 
 }  // namespace

@@ -29,15 +29,27 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+// four consecutive bf16 outputs; lo != 0: also the lo plane (x - float(bf16(x))) at p + lo (float32-accurate mode)
+__device__ __forceinline__ void st_bf16x4(__nv_bfloat16 *p, int64_t lo, float a, float b, float c, float d) {
+    const uint32_t w0 = pack2(a, b), w1 = pack2(c, d);
+    *reinterpret_cast<uint2 *>(p) = make_uint2(w0, w1);
+    if (lo != 0)
+        *reinterpret_cast<uint2 *>(p + lo) = make_uint2(pack2(a - bf_lo(w0), b - bf_hi(w0)), pack2(c - bf_lo(w1), d - bf_hi(w1)));
+}
 
-__global__ void cvt_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, int64_t n) {
+__global__ void cvt_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, int64_t n, int64_t lo) {
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
     if (i + 8 <= n) {
         const float4 a = *reinterpret_cast<const float4 *>(x + i);
         const float4 b = *reinterpret_cast<const float4 *>(x + i + 4);
-        *reinterpret_cast<uint4 *>(y + i) = make_uint4(pack2(a.x, a.y), pack2(a.z, a.w), pack2(b.x, b.y), pack2(b.z, b.w));
+        st_bf16x4(y + i, lo, a.x, a.y, a.z, a.w);
+        st_bf16x4(y + i + 4, lo, b.x, b.y, b.z, b.w);
     } else {
-        for (int64_t j = i; j < n; j++) y[j] = __float2bfloat16_rn(x[j]);
+        for (int64_t j = i; j < n; j++) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(x[j]);
+            y[j] = h;
+            if (lo != 0) y[lo + j] = __float2bfloat16_rn(x[j] - __bfloat162float(h));
+        }
     }
 }
 
@@ -62,18 +74,29 @@ __global__ void cvt_f16_kernel(const float *__restrict__ x, __half *__restrict__
 }
 
 // up to 8 float32 -> bfloat16 conversions in one launch (the parameter copies of a training step): blockIdx.y = segment
-struct CvtSegments { const float *src[8]; __nv_bfloat16 *dst[8]; long long n[8]; };
+// lo[i] (optional): the segment is split into hi + lo planes (hi = bf16(x), lo = bf16(x - hi)), the operand form of
+// the float32-accurate GEMM mode
+struct CvtSegments { const float *src[8]; __nv_bfloat16 *dst[8]; __nv_bfloat16 *lo[8]; long long n[8]; };
 __global__ void cvt_bf16_segments_kernel(const CvtSegments seg) {
     const float *x = seg.src[blockIdx.y];
     __nv_bfloat16 *y = seg.dst[blockIdx.y];
+    __nv_bfloat16 *yl = seg.lo[blockIdx.y];
     const long long n = seg.n[blockIdx.y];
     for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += (long long)gridDim.x * blockDim.x * 8) {
         if (i + 8 <= n) {
             const float4 a = *reinterpret_cast<const float4 *>(x + i);
             const float4 b = *reinterpret_cast<const float4 *>(x + i + 4);
-            *reinterpret_cast<uint4 *>(y + i) = make_uint4(pack2(a.x, a.y), pack2(a.z, a.w), pack2(b.x, b.y), pack2(b.z, b.w));
+            const uint4 h = make_uint4(pack2(a.x, a.y), pack2(a.z, a.w), pack2(b.x, b.y), pack2(b.z, b.w));
+            *reinterpret_cast<uint4 *>(y + i) = h;
+            if (yl != nullptr)
+                *reinterpret_cast<uint4 *>(yl + i) = make_uint4(pack2(a.x - bf_lo(h.x), a.y - bf_hi(h.x)), pack2(a.z - bf_lo(h.y), a.w - bf_hi(h.y)),
+                                                                pack2(b.x - bf_lo(h.z), b.y - bf_hi(h.z)), pack2(b.z - bf_lo(h.w), b.w - bf_hi(h.w)));
         } else {
-            for (long long j = i; j < n; j++) y[j] = __float2bfloat16_rn(x[j]);
+            for (long long j = i; j < n; j++) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(x[j]);
+                y[j] = h;
+                if (yl != nullptr) yl[j] = __float2bfloat16_rn(x[j] - __bfloat162float(h));
+            }
         }
     }
 }
@@ -97,7 +120,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 softmax_kernel(const GemmProblem *__restrict__ probs, int n_probs, int total_rows, const float *__restrict__ S,
                __nv_bfloat16 *__restrict__ alpha, __nv_bfloat16 *__restrict__ P, const uint8_t *__restrict__ drop,
                const int64_t *__restrict__ drop_off, int aperture, int ignore_self, const int *__restrict__ gate,
-               float *__restrict__ sum_slots, int n_slots) {
+               float *__restrict__ sum_slots, int n_slots, int64_t lop) {
     if (gate != nullptr && __ldg(gate) == 0) return;
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
@@ -162,9 +185,8 @@ softmax_kernel(const GemmProblem *__restrict__ probs, int n_probs, int total_row
         for (int k = 0; k < NV; k++) {
             const int j = lane * 4 + 128 * k;
             if (j < W64) {
-                uint2 o = make_uint2(0u, 0u);
-                if (j < T) o = make_uint2(pack2(v[k][0] * inv, v[k][1] * inv), pack2(v[k][2] * inv, v[k][3] * inv));
-                *reinterpret_cast<uint2 *>(P + off + j) = o;
+                if (j < T) st_bf16x4(P + off + j, lop, v[k][0] * inv, v[k][1] * inv, v[k][2] * inv, v[k][3] * inv);
+                else st_bf16x4(P + off + j, lop, 0.f, 0.f, 0.f, 0.f);
             }
         }
         return;
@@ -201,9 +223,8 @@ softmax_kernel(const GemmProblem *__restrict__ probs, int n_probs, int total_row
             p[t] = a[t];
             if (keep != nullptr && j >= 0 && j < T) p[t] = keep[j] ? 2.f * a[t] : 0.f;   // nn.Dropout(0.5), vasnet.py:130
         }
-        if (alpha != nullptr && alpha != P)
-            *reinterpret_cast<uint2 *>(alpha + off + jo) = make_uint2(pack2(a[0], a[1]), pack2(a[2], a[3]));
-        *reinterpret_cast<uint2 *>(P + off + jo) = make_uint2(pack2(p[0], p[1]), pack2(p[2], p[3]));
+        if (alpha != nullptr && alpha != P) st_bf16x4(alpha + off + jo, lop, a[0], a[1], a[2], a[3]);
+        st_bf16x4(P + off + jo, lop, p[0], p[1], p[2], p[3]);
     }
 }
 
@@ -211,7 +232,7 @@ softmax_kernel(const GemmProblem *__restrict__ probs, int n_probs, int total_row
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 layernorm_kernel(const float *__restrict__ y, const uint8_t *__restrict__ keep, const float *__restrict__ g,
                  const float *__restrict__ b, float eps, int rows, __nv_bfloat16 *__restrict__ yn,
-                 float *__restrict__ mean, float *__restrict__ rstd) {
+                 float *__restrict__ mean, float *__restrict__ rstd, int64_t lo) {
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     if (r >= rows) return;
@@ -246,7 +267,7 @@ layernorm_kernel(const float *__restrict__ y, const uint8_t *__restrict__ keep, 
         const float4 bb = *reinterpret_cast<const float4 *>(b + c);
         const float o0 = (x[4 * k] - mu) * rs * gg.x + bb.x, o1 = (x[4 * k + 1] - mu) * rs * gg.y + bb.y;
         const float o2 = (x[4 * k + 2] - mu) * rs * gg.z + bb.z, o3 = (x[4 * k + 3] - mu) * rs * gg.w + bb.w;
-        *reinterpret_cast<uint2 *>(yn + (int64_t)r * kFeat + c) = make_uint2(pack2(o0, o1), pack2(o2, o3));
+        st_bf16x4(yn + (int64_t)r * kFeat + c, lo, o0, o1, o2, o3);
     }
 }
 
@@ -335,7 +356,7 @@ head_bwd_kernel(const float *__restrict__ h, const uint8_t *__restrict__ keep, c
                 const float *__restrict__ b, const float *__restrict__ w2, const float *__restrict__ mean,
                 const float *__restrict__ rstd, const float *__restrict__ scores, const float *__restrict__ dscores,
                 int rows, __nv_bfloat16 *__restrict__ dh, float *__restrict__ d_w2, float *__restrict__ d_b2,
-                float *__restrict__ d_g, float *__restrict__ d_b, float *__restrict__ d_b1) {
+                float *__restrict__ d_g, float *__restrict__ d_b, float *__restrict__ d_b1, int64_t lo) {
     extern __shared__ float s_acc[];
     ColAcc<4> A{s_acc};
     A.zero();
@@ -391,7 +412,7 @@ head_bwd_kernel(const float *__restrict__ h, const uint8_t *__restrict__ keep, c
                 o[t] = ((live >> (4 * k + t)) & 1u) ? d : 0.f;
                 A.add(3, c + t, o[t]);           // d k1.bias
             }
-            *reinterpret_cast<uint2 *>(dh + (int64_t)r * kFeat + c) = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
+            st_bf16x4(dh + (int64_t)r * kFeat + c, lo, o[0], o[1], o[2], o[3]);
         }
         if (lane == 0) db2 += dz;
     }
@@ -404,7 +425,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 layernorm_bwd_kernel(const float *__restrict__ dyn, const float *__restrict__ y, const uint8_t *__restrict__ keep,
                      const float *__restrict__ g, const float *__restrict__ mean, const float *__restrict__ rstd,
                      int rows, __nv_bfloat16 *__restrict__ dy, float *__restrict__ dy_f32, float *__restrict__ d_g,
-                     float *__restrict__ d_b) {
+                     float *__restrict__ d_b, int64_t lo) {
     extern __shared__ float s_acc[];
     ColAcc<2> A{s_acc};
     A.zero();
@@ -450,7 +471,7 @@ layernorm_bwd_kernel(const float *__restrict__ dyn, const float *__restrict__ y,
                 const float d = rs * (dx[4 * k + t] - c1 - xh[4 * k + t] * c2) * dscale;
                 o[t] = ((kept_bits >> (4 * k + t)) & 1u) ? d : 0.f;
             }
-            *reinterpret_cast<uint2 *>(dy + (int64_t)r * kFeat + c) = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
+            st_bf16x4(dy + (int64_t)r * kFeat + c, lo, o[0], o[1], o[2], o[3]);
             if (dy_f32 != nullptr)
                 *reinterpret_cast<float4 *>(dy_f32 + (int64_t)r * kFeat + c) = make_float4(o[0], o[1], o[2], o[3]);
         }
@@ -461,7 +482,7 @@ layernorm_bwd_kernel(const float *__restrict__ dyn, const float *__restrict__ y,
 
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 softmax_bwd_kernel(const float *__restrict__ dP, const __nv_bfloat16 *__restrict__ alpha,
-                   const uint8_t *__restrict__ keep, int T, int ld, __nv_bfloat16 *__restrict__ dS) {
+                   const uint8_t *__restrict__ keep, int T, int ld, __nv_bfloat16 *__restrict__ dS, int64_t lo) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     if (i >= T) return;
@@ -472,7 +493,7 @@ softmax_bwd_kernel(const float *__restrict__ dP, const __nv_bfloat16 *__restrict
     for (int j = lane; j < T; j += 32) {
         float da = dp[j];
         if (kp != nullptr) da = kp[j] ? 2.f * da : 0.f;
-        dot += da * __bfloat162float(al[j]);
+        dot += da * (__bfloat162float(al[j]) + (lo != 0 ? __bfloat162float(al[lo + j]) : 0.f));
     }
     dot = warp_sum(dot);
     const int W64 = (T + 63) & ~63;
@@ -481,9 +502,11 @@ softmax_bwd_kernel(const float *__restrict__ dP, const __nv_bfloat16 *__restrict
         if (j < T) {
             float da = dp[j];
             if (kp != nullptr) da = kp[j] ? 2.f * da : 0.f;
-            o = __bfloat162float(al[j]) * (da - dot);
+            o = (__bfloat162float(al[j]) + (lo != 0 ? __bfloat162float(al[lo + j]) : 0.f)) * (da - dot);
         }
-        dS[(int64_t)i * ld + j] = __float2bfloat16_rn(o);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(o);
+        dS[(int64_t)i * ld + j] = hi;
+        if (lo != 0) dS[lo + (int64_t)i * ld + j] = __float2bfloat16_rn(o - __bfloat162float(hi));
     }
 }
 
@@ -501,32 +524,33 @@ int launch_head_from_stats(const float *stats, int slots, const float *c, float 
 
 int launch_head_bwd(const float *h, const uint8_t *keep, const float *g, const float *b, const float *w2,
                     const float *mean, const float *rstd, const float *scores, const float *dscores, int rows,
-                    __nv_bfloat16 *dh, float *d_w2, float *d_b2, float *d_g, float *d_b, float *d_b1, cudaStream_t st) {
+                    __nv_bfloat16 *dh, float *d_w2, float *d_b2, float *d_g, float *d_b, float *d_b1, cudaStream_t st,
+                    int64_t lo) {
     if (rows <= 0) return SMZ_OK;
     int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
     if (grid > 2 * sm_count()) grid = 2 * sm_count();
     head_bwd_kernel<<<grid, ROW_WARPS * 32, 4 * kFeat * sizeof(float), st>>>(h, keep, g, b, w2, mean, rstd, scores, dscores,
-                                                                           rows, dh, d_w2, d_b2, d_g, d_b, d_b1);
+                                                                           rows, dh, d_w2, d_b2, d_g, d_b, d_b1, lo);
     SMZ_CUDA_CHECK(cudaGetLastError());
     return SMZ_OK;
 }
 
 int launch_layernorm_bwd(const float *dyn, const float *y, const uint8_t *keep, const float *g, const float *mean,
                          const float *rstd, int rows, __nv_bfloat16 *dy, float *dy_f32, float *d_g, float *d_b,
-                         cudaStream_t st) {
+                         cudaStream_t st, int64_t lo) {
     if (rows <= 0) return SMZ_OK;
     int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
     if (grid > 2 * sm_count()) grid = 2 * sm_count();
     layernorm_bwd_kernel<<<grid, ROW_WARPS * 32, 2 * kFeat * sizeof(float), st>>>(dyn, y, keep, g, mean, rstd, rows, dy,
-                                                                                dy_f32, d_g, d_b);
+                                                                                dy_f32, d_g, d_b, lo);
     SMZ_CUDA_CHECK(cudaGetLastError());
     return SMZ_OK;
 }
 
 int launch_softmax_bwd(const float *dP, const __nv_bfloat16 *alpha, const uint8_t *keep, int T, int ld,
-                       __nv_bfloat16 *dS, cudaStream_t st) {
+                       __nv_bfloat16 *dS, cudaStream_t st, int64_t lo) {
     if (T <= 0) return SMZ_OK;
-    softmax_bwd_kernel<<<(T + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, st>>>(dP, alpha, keep, T, ld, dS);
+    softmax_bwd_kernel<<<(T + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, st>>>(dP, alpha, keep, T, ld, dS, lo);
     SMZ_CUDA_CHECK(cudaGetLastError());
     return SMZ_OK;
 }
@@ -535,14 +559,16 @@ int launch_softmax_bwd(const float *dP, const __nv_bfloat16 *alpha, const uint8_
 
 // float32 -> bfloat16 copies of up to 8 tensors in ONE launch: src[i] (n[i] floats, 16-byte aligned) -> dst[i].  What a
 // training step uses to refresh the bf16 weight copies (replaces one torch cast kernel per parameter).
-extern "C" int smz_cvt_bf16_multi(const float *const *src, void *const *dst, const int64_t *n, int count, void *stream) {
+static int cvt_segments(const float *const *src, void *const *dst, void *const *lo, const int64_t *n, int count, void *stream) {
     SMZ_REQUIRE(src && dst && n && count >= 1 && count <= 8, "cvt_bf16_multi: 1..8 segments");
     CvtSegments seg = {};
     long long most = 0;
     for (int i = 0; i < count; i++) {
-        SMZ_REQUIRE(src[i] && dst[i] && n[i] >= 0, "cvt_bf16_multi: bad segment %d", i);
-        SMZ_REQUIRE(((uintptr_t)src[i] & 15) == 0 && ((uintptr_t)dst[i] & 15) == 0, "cvt_bf16_multi: segment %d is not 16-byte aligned", i);
+        SMZ_REQUIRE(src[i] && dst[i] && n[i] >= 0 && (lo == nullptr || lo[i]), "cvt_bf16_multi: bad segment %d", i);
+        SMZ_REQUIRE(((uintptr_t)src[i] & 15) == 0 && ((uintptr_t)dst[i] & 15) == 0 && (lo == nullptr || ((uintptr_t)lo[i] & 15) == 0),
+                    "cvt_bf16_multi: segment %d is not 16-byte aligned", i);
         seg.src[i] = src[i]; seg.dst[i] = reinterpret_cast<__nv_bfloat16 *>(dst[i]); seg.n[i] = n[i];
+        seg.lo[i] = lo != nullptr ? reinterpret_cast<__nv_bfloat16 *>(lo[i]) : nullptr;
         most = n[i] > most ? n[i] : most;
     }
     if (most == 0) return SMZ_OK;
@@ -553,12 +579,24 @@ extern "C" int smz_cvt_bf16_multi(const float *const *src, void *const *dst, con
     return SMZ_OK;
 }
 
+extern "C" int smz_cvt_bf16_multi(const float *const *src, void *const *dst, const int64_t *n, int count, void *stream) {
+    return cvt_segments(src, dst, nullptr, n, count, stream);
+}
+
+// The same with hi + lo planes: hi[i] = bf16(src[i]), lo[i] = bf16(src[i] - hi[i]) — the operand form of the
+// float32-accurate (split-bf16) GEMM mode.
+extern "C" int smz_split_bf16_multi(const float *const *src, void *const *hi, void *const *lo, const int64_t *n, int count,
+                                    void *stream) {
+    SMZ_REQUIRE(lo != nullptr, "split_bf16_multi: lo is NULL");
+    return cvt_segments(src, hi, lo, n, count, stream);
+}
+
 namespace smz {
 
-int launch_cvt_bf16(const float *x, __nv_bfloat16 *y, int64_t n, cudaStream_t st) {
+int launch_cvt_bf16(const float *x, __nv_bfloat16 *y, int64_t n, cudaStream_t st, int64_t lo) {
     if (n <= 0) return SMZ_OK;
     const int64_t blocks = (n + 8 * 256 - 1) / (8 * 256);
-    cvt_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, n);
+    cvt_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, n, lo);
     SMZ_CUDA_CHECK(cudaGetLastError());
     return SMZ_OK;
 }
@@ -573,18 +611,18 @@ int launch_cvt_f16(const float *x, void *y, int64_t n, int *guard, int bit, cuda
 
 int launch_softmax(const GemmProblem *d_probs, int n_probs, int total_rows, const float *S, __nv_bfloat16 *alpha,
                    __nv_bfloat16 *P, const uint8_t *drop, const int64_t *d_drop_off, int aperture, int ignore_self,
-                   cudaStream_t st, const int *gate, float *sum_slots, int n_slots) {
+                   cudaStream_t st, const int *gate, float *sum_slots, int n_slots, int64_t lo) {
     if (total_rows <= 0) return SMZ_OK;
     softmax_kernel<<<(total_rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, st>>>(
-        d_probs, n_probs, total_rows, S, alpha, P, drop, d_drop_off, aperture, ignore_self, gate, sum_slots, n_slots);
+        d_probs, n_probs, total_rows, S, alpha, P, drop, d_drop_off, aperture, ignore_self, gate, sum_slots, n_slots, lo);
     SMZ_CUDA_CHECK(cudaGetLastError());
     return SMZ_OK;
 }
 
 int launch_layernorm(const float *y, const uint8_t *keep, const float *g, const float *b, float eps, int rows,
-                     __nv_bfloat16 *yn, float *mean, float *rstd, cudaStream_t st) {
+                     __nv_bfloat16 *yn, float *mean, float *rstd, cudaStream_t st, int64_t lo) {
     if (rows <= 0) return SMZ_OK;
-    layernorm_kernel<<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, st>>>(y, keep, g, b, eps, rows, yn, mean, rstd);
+    layernorm_kernel<<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, st>>>(y, keep, g, b, eps, rows, yn, mean, rstd, lo);
     SMZ_CUDA_CHECK(cudaGetLastError());
     return SMZ_OK;
 }

@@ -9,7 +9,9 @@ namespace smz {
 
 constexpr int kFeat = 1024;   // feature / hidden width of VASNet (vasnet.py:18)
 
-int launch_cvt_bf16(const float *x, __nv_bfloat16 *y, int64_t n, cudaStream_t st);
+// lo != 0 (everywhere below): the bf16 output is written as hi + lo planes, the lo plane `lo` elements behind the hi
+// plane (x - float(bf16(x)) as bf16) — the operand form of the float32-accurate GEMM mode (GemmEpilogue::a_lo)
+int launch_cvt_bf16(const float *x, __nv_bfloat16 *y, int64_t n, cudaStream_t st, int64_t lo = 0);
 // float32 -> float16 with a range check: |x| > 60000 or NaN ORs `bit` into *guard (the VASNet fast path's feature copy)
 int launch_cvt_f16(const float *x, void *y, int64_t n, int *guard, int bit, cudaStream_t st);
 
@@ -23,11 +25,11 @@ int launch_cvt_f16(const float *x, void *y, int64_t n, int *guard, int bit, cuda
 // GEMM's GEMM_SCALE_STATS row scale becomes 1 (see smz_vasnet.cu).
 int launch_softmax(const GemmProblem *d_probs, int n_probs, int total_rows, const float *S, __nv_bfloat16 *alpha,
                    __nv_bfloat16 *P, const uint8_t *drop, const int64_t *d_drop_off, int aperture, int ignore_self,
-                   cudaStream_t st, const int *gate = nullptr, float *sum_slots = nullptr, int n_slots = 0);
+                   cudaStream_t st, const int *gate = nullptr, float *sum_slots = nullptr, int n_slots = 0, int64_t lo = 0);
 
 // yn = LayerNorm(2*keep*y or y) * g + b  (vasnet.py:136-137), rows of 1024; optional mean / rstd.
 int launch_layernorm(const float *y, const uint8_t *keep, const float *g, const float *b, float eps, int rows,
-                     __nv_bfloat16 *yn, float *mean, float *rstd, cudaStream_t st);
+                     __nv_bfloat16 *yn, float *mean, float *rstd, cudaStream_t st, int64_t lo = 0);
 
 // score = sigmoid(LayerNorm(2*keep*h or h) . w2 + b2)  (vasnet.py:142-145); h is post-ReLU float32.
 int launch_head(const float *h, const uint8_t *keep, const float *g, const float *b, float eps,
@@ -45,13 +47,14 @@ int launch_head_from_stats(const float *stats, int slots, const float *c, float 
 // (+=, float32 atomics) d_w2, d_b2, d_g, d_b (LayerNorm affine) and d_b1 (column sums of dh).
 int launch_head_bwd(const float *h, const uint8_t *keep, const float *g, const float *b, const float *w2,
                     const float *mean, const float *rstd, const float *scores, const float *dscores, int rows,
-                    __nv_bfloat16 *dh, float *d_w2, float *d_b2, float *d_g, float *d_b, float *d_b1, cudaStream_t st);
+                    __nv_bfloat16 *dh, float *d_w2, float *d_b2, float *d_g, float *d_b, float *d_b1, cudaStream_t st,
+                    int64_t lo = 0);
 // First LayerNorm (+ dropout): dy = d(loss)/d(y before dropout) as bf16 (and float32 when dy_f32 != NULL).
 int launch_layernorm_bwd(const float *dyn, const float *y, const uint8_t *keep, const float *g, const float *mean,
                          const float *rstd, int rows, __nv_bfloat16 *dy, float *dy_f32, float *d_g, float *d_b,
-                         cudaStream_t st);
+                         cudaStream_t st, int64_t lo = 0);
 // Softmax (+ attention dropout) of ONE video: dS = alpha * (dalpha - rowsum(dalpha * alpha)), dalpha = 2*keep*dP.
 int launch_softmax_bwd(const float *dP, const __nv_bfloat16 *alpha, const uint8_t *keep, int T, int ld,
-                       __nv_bfloat16 *dS, cudaStream_t st);
+                       __nv_bfloat16 *dS, cudaStream_t st, int64_t lo = 0);
 
 }  // namespace smz

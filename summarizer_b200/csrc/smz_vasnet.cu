@@ -321,9 +321,10 @@ extern "C" int smz_vasnet_workspace_bytes(const int32_t *h_cu_seqlens, int n_vid
                                           int64_t *bytes) {
     SMZ_REQUIRE(bytes != nullptr, "bytes is NULL");
     Plan pl;
-    int rc = make_plan(h_cu_seqlens, n_videos, training != 0, x_is_bf16 != 0, &pl);
+    SMZ_REQUIRE(!(training & SMZ_VASNET_SPLIT) || (training & 1), "vasnet: the split-bf16 mode uses the training layout (training = 1 | SMZ_VASNET_SPLIT)");
+    int rc = make_plan(h_cu_seqlens, n_videos, (training & ~SMZ_VASNET_SPLIT) != 0, x_is_bf16 != 0, &pl);
     if (rc != SMZ_OK) return rc;
-    *bytes = pl.total;
+    *bytes = (training & SMZ_VASNET_SPLIT) ? 2 * pl.total : pl.total;     // second half: the lo planes, same offsets
     return SMZ_OK;
 }
 
@@ -358,9 +359,19 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
     Plan pl;
     rc = make_plan(h_cu_seqlens, n_videos, training != 0, x_is_bf16 != 0, &pl);
     if (rc != SMZ_OK) return rc;
-    SMZ_REQUIRE(ws_bytes >= pl.total, "vasnet_forward: work buffer too small (%lld < %lld bytes)", (long long)ws_bytes,
-                (long long)pl.total);
+    // float32-accurate mode (split-bf16 operands): the lo plane of every 16-bit activation sits LO elements behind it
+    const bool precise = p->wqk_lo != nullptr;
+    SMZ_REQUIRE(!precise || (training && p->wv_lo && p->wo_lo && p->w1_lo),
+                "vasnet_forward: the split-bf16 mode needs the training layout and all four lo weight planes");
+    const int64_t LO = precise ? pl.total / 2 : 0;
+    SMZ_REQUIRE(ws_bytes >= (precise ? 2 : 1) * pl.total, "vasnet_forward: work buffer too small (%lld < %lld bytes)", (long long)ws_bytes,
+                (long long)((precise ? 2 : 1) * pl.total));
     SMZ_REQUIRE(training || (!drop_att && !drop_y && !drop_h), "dropout masks are only meaningful in training mode");
+    const int64_t XLO = (precise && !x_is_bf16) ? LO : 0;        // bfloat16 features are exact: no lo plane
+    auto wlo = [&](const void *lo, const void *hi) -> int64_t {
+        return precise ? (reinterpret_cast<const char *>(lo) - reinterpret_cast<const char *>(hi)) / 2 : 0;
+    };
+    auto split = [](GemmEpilogue e, int64_t a_lo, int64_t b_lo, int64_t c_lo) { e.a_lo = a_lo; e.b_lo = b_lo; e.c_lo = c_lo; return e; };
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t *w = reinterpret_cast<uint8_t *>(ws);
     const int n = n_videos;
@@ -425,7 +436,7 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
             bf16 *dst = reinterpret_cast<bf16 *>(w + pl.off_xb + lb) + rb * kFeat;
             const float *src = reinterpret_cast<const float *>(x) + (int64_t)c.row0 * kFeat;
             rc = fast ? smz::launch_cvt_f16(src, dst, (int64_t)R * kFeat, p->status, SMZ_VASNET_STATUS_F16_RANGE, st)   // float16 features
-                      : smz::launch_cvt_bf16(src, dst, (int64_t)R * kFeat, st);
+                      : smz::launch_cvt_bf16(src, dst, (int64_t)R * kFeat, st, XLO);
             if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "cvt");
             xb = dst;
@@ -458,13 +469,15 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
             SMZ_DEBUG_STEP(st, "gemm_qkv");
         } else {
             rc = smz::gemm_bf16_tn(xb, R, kFeat, kFeat, p->wqk, 2 * kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, 2 * kFeat),
-                                   dense_problem(R, 2 * kFeat, kFeat, qld, 0), GemmEpilogue{qk, nullptr, nullptr, 1.f, 0}, st);
+                                   dense_problem(R, 2 * kFeat, kFeat, qld, 0),
+                                   split(GemmEpilogue{qk, nullptr, nullptr, 1.f, 0}, XLO, wlo(p->wqk_lo, p->wqk), LO), st);
             if (rc != SMZ_OK) return rc;
             SMZ_DEBUG_STEP(st, "gemm_qk");
             smz::profile_mark(st, "gemm_vt");
             if (training)       // V^T [1024, R]
                 rc = smz::gemm_bf16_tn(p->wv, kFeat, kFeat, kFeat, xb, R, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(kFeat, R),
-                                       dense_problem(kFeat, R, kFeat, (int)Rpad, 0), GemmEpilogue{vt, nullptr, nullptr, 1.f, 0}, st_v);
+                                       dense_problem(kFeat, R, kFeat, (int)Rpad, 0),
+                                       split(GemmEpilogue{vt, nullptr, nullptr, 1.f, 0}, wlo(p->wv_lo, p->wv), XLO, LO), st_v);
             else                // V into columns [2048, 3072) of the packed rows
                 rc = smz::gemm_bf16_tn(xb, R, kFeat, kFeat, p->wv, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
                                        dense_problem(R, kFeat, kFeat, qld, 0), GemmEpilogue{qk + 2 * kFeat, nullptr, nullptr, 1.f, 0}, st_v);
@@ -484,13 +497,13 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
             const bool inference = !training;
             {   // fp32 logits + max-subtracted softmax (dropout in training mode)
                 smz::profile_mark(st, "gemm_logits");
-                GemmEpilogue e{S, nullptr, nullptr, p->scale, smz::GEMM_OUT_F32};
+                const GemmEpilogue e = split(GemmEpilogue{S, nullptr, nullptr, p->scale, smz::GEMM_OUT_F32}, LO, LO, 0);
                 rc = smz::gemm_bf16_tn(qk, R, qld, qld, qk, R, qld, qld, d_probs + s.v0, nv, tiles_s, GemmProblem{}, e, st);
                 if (rc != SMZ_OK) return rc;
                 SMZ_DEBUG_STEP(st, "gemm_logits");
                 smz::profile_mark(st, "softmax");
                 rc = smz::launch_softmax(d_probs + s.v0, nv, s.rows, S, alpha, P, drop_att, d_dropoff ? d_dropoff + s.v0 : nullptr,
-                                         p->aperture, p->ignore_self, st);
+                                         p->aperture, p->ignore_self, st, nullptr, nullptr, 0, LO);
                 if (rc != SMZ_OK) return rc;
                 SMZ_DEBUG_STEP(st, "softmax");
             }
@@ -501,7 +514,7 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
                 rc = smz::gemm_bf16(false, true, P, s.rows, s.ld, s.ld, qk, R, qld, qld, d_probs + n + s.v0, nv, tiles_pv, GemmProblem{}, e, st);
                 if (rc != SMZ_OK) return rc;
             } else {
-                GemmEpilogue e{o, nullptr, nullptr, 1.f, 0};
+                const GemmEpilogue e = split(GemmEpilogue{o, nullptr, nullptr, 1.f, 0}, LO, LO, LO);
                 rc = smz::gemm_bf16_tn(P, s.rows, s.ld, s.ld, vt, kFeat, R, Rpad, d_probs + n + s.v0, nv, tiles_pv, GemmProblem{}, e, st);
                 if (rc != SMZ_OK) return rc;
             }
@@ -514,12 +527,13 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
         smz::profile_mark(st, "gemm_out");
         rc = smz::gemm_bf16_tn(o, R, kFeat, kFeat, p->wo, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
                                dense_problem(R, kFeat, kFeat, kFeat, kFeat),
-                               GemmEpilogue{y, nullptr, res, 1.f, smz::GEMM_OUT_F32 | (x_is_bf16 ? 0 : smz::GEMM_RES_F32)}, st);
+                               split(GemmEpilogue{y, nullptr, res, 1.f, smz::GEMM_OUT_F32 | (x_is_bf16 ? 0 : smz::GEMM_RES_F32)},
+                                     LO, wlo(p->wo_lo, p->wo), 0), st);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "gemm_out");
         smz::profile_mark(st, "layernorm");
         rc = smz::launch_layernorm(y, drop_y ? drop_y + (int64_t)c.row0 * kFeat : nullptr, p->ln_g, p->ln_b, p->eps, R, yn,
-                                   stats, stats ? stats + Rs : nullptr, st);
+                                   stats, stats ? stats + Rs : nullptr, st, LO);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "layernorm");
         smz::profile_mark(st, "gemm_k1");
@@ -538,7 +552,8 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
             if (rc != SMZ_OK) return rc;
         } else {
         rc = smz::gemm_bf16_tn(yn, R, kFeat, kFeat, p->w1, kFeat, kFeat, kFeat, nullptr, 1, smz::gemm_tiles(R, kFeat),
-                               dense_problem(R, kFeat, kFeat, kFeat, 0), GemmEpilogue{h, p->b1, nullptr, 1.f, smz::GEMM_RELU | smz::GEMM_OUT_F32}, st);
+                               dense_problem(R, kFeat, kFeat, kFeat, 0),
+                               split(GemmEpilogue{h, p->b1, nullptr, 1.f, smz::GEMM_RELU | smz::GEMM_OUT_F32}, LO, wlo(p->w1_lo, p->w1), 0), st);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "gemm_k1");
         smz::profile_mark(st, "head");
@@ -596,8 +611,16 @@ extern "C" int smz_vasnet_backward(const void *x, int x_is_bf16, const int32_t *
     Plan pl;
     rc = make_plan(h_cu_seqlens, n_videos, true, x_is_bf16 != 0, &pl);
     if (rc != SMZ_OK) return rc;
-    SMZ_REQUIRE(ws_bytes >= pl.total, "vasnet_backward: work buffer too small (%lld < %lld bytes)", (long long)ws_bytes,
-                (long long)pl.total);
+    const bool precise = p->wqk_lo != nullptr;                   // float32-accurate mode, see smz_vasnet_forward
+    SMZ_REQUIRE(!precise || (p->wv_lo && p->wo_lo && p->w1_lo), "vasnet_backward: the split-bf16 mode needs all four lo weight planes");
+    const int64_t LO = precise ? pl.total / 2 : 0;
+    const int64_t XLO = (precise && !x_is_bf16) ? LO : 0;
+    SMZ_REQUIRE(ws_bytes >= (precise ? 2 : 1) * pl.total, "vasnet_backward: work buffer too small (%lld < %lld bytes)", (long long)ws_bytes,
+                (long long)((precise ? 2 : 1) * pl.total));
+    auto wlo = [&](const void *lo, const void *hi) -> int64_t {
+        return precise ? (reinterpret_cast<const char *>(lo) - reinterpret_cast<const char *>(hi)) / 2 : 0;
+    };
+    auto split = [](GemmEpilogue e, int64_t a_lo, int64_t b_lo, int64_t c_lo) { e.a_lo = a_lo; e.b_lo = b_lo; e.c_lo = c_lo; return e; };
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t *w = reinterpret_cast<uint8_t *>(ws);
     const int64_t Rs = pl.rows_cap;
@@ -645,48 +668,48 @@ extern "C" int smz_vasnet_backward(const void *x, int x_is_bf16, const int32_t *
         // regressor head, second LayerNorm, dropout, ReLU  ->  dh (k1 pre-activation gradient)
         rc = smz::launch_head_bwd(h, drop_h ? drop_h + rb * kFeat : nullptr, p->ln_g, p->ln_b, p->w2, stats + 2 * Rs,
                                   stats + 3 * Rs, scores + rb, dscores + rb, T, dh, gr->w2, gr->b2, gr->ln_g, gr->ln_b,
-                                  gr->b1, st);
+                                  gr->b1, st, LO);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "head_bwd");
         rc = fork_to_side(1);                                    // dh is ready
         if (rc != SMZ_OK) return rc;
         // k1: dYn = dh . W1 ; dW1 += dh^T . Yn
         rc = gemm1(false, true, dh, T, kFeat, kFeat, p->w1, kFeat, kFeat, kFeat, prob(T, kFeat, kFeat, kFeat),
-                   GemmEpilogue{dyn, nullptr, nullptr, 1.f, smz::GEMM_OUT_F32}, st);
+                   split(GemmEpilogue{dyn, nullptr, nullptr, 1.f, smz::GEMM_OUT_F32}, LO, wlo(p->w1_lo, p->w1), 0), st);
         if (rc != SMZ_OK) return rc;
         rc = gemm1(true, true, dh, T, kFeat, kFeat, yn, T, kFeat, kFeat, prob(kFeat, kFeat, T, kFeat, 0, kFeat),
-                   GemmEpilogue{gr->w1, nullptr, gr->w1, 1.f, F32ACC}, sd);
+                   split(GemmEpilogue{gr->w1, nullptr, gr->w1, 1.f, F32ACC}, LO, LO, 0), sd);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "k1_bwd");
         // first LayerNorm + dropout -> dY (also the gradient of the residual branch)
         rc = smz::launch_layernorm_bwd(dyn, y, drop_y ? drop_y + rb * kFeat : nullptr, p->ln_g, stats, stats + Rs, T, dy, dyf,
-                                       gr->ln_g, gr->ln_b, st);
+                                       gr->ln_g, gr->ln_b, st, LO);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "ln_bwd");
         rc = fork_to_side(2);                                    // dY is ready
         if (rc != SMZ_OK) return rc;
         // output projection: dO = dY . Wo ; dWo += dY^T . O
         rc = gemm1(false, true, dy, T, kFeat, kFeat, p->wo, kFeat, kFeat, kFeat, prob(T, kFeat, kFeat, kFeat),
-                   GemmEpilogue{dO, nullptr, nullptr, 1.f, 0}, st);
+                   split(GemmEpilogue{dO, nullptr, nullptr, 1.f, 0}, LO, wlo(p->wo_lo, p->wo), LO), st);
         if (rc != SMZ_OK) return rc;
         rc = gemm1(true, true, dy, T, kFeat, kFeat, o, T, kFeat, kFeat, prob(kFeat, kFeat, T, kFeat, 0, kFeat),
-                   GemmEpilogue{gr->wo, nullptr, gr->wo, 1.f, F32ACC}, sd);
+                   split(GemmEpilogue{gr->wo, nullptr, gr->wo, 1.f, F32ACC}, LO, LO, 0), sd);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "out_bwd");
         rc = fork_to_side(3);                                    // dO is ready
         if (rc != SMZ_OK) return rc;
         // attention: dP = dO . V^T (B = V^T stored [d][j]: MN-major) ; dV^T = dO^T . P ; dWv += dV^T . xb
         rc = gemm1(false, true, dO, T, kFeat, kFeat, vt, kFeat, T, Tpad, prob(T, T, kFeat, ld),
-                   GemmEpilogue{dP, nullptr, nullptr, 1.f, smz::GEMM_OUT_F32}, st);
+                   split(GemmEpilogue{dP, nullptr, nullptr, 1.f, smz::GEMM_OUT_F32}, LO, LO, 0), st);
         if (rc != SMZ_OK) return rc;
         rc = gemm1(true, true, dO, T, kFeat, kFeat, P, T, T, ld, prob(kFeat, T, T, (int)Tpad),
-                   GemmEpilogue{dvt, nullptr, nullptr, 1.f, 0}, sd);
+                   split(GemmEpilogue{dvt, nullptr, nullptr, 1.f, 0}, LO, LO, LO), sd);
         if (rc != SMZ_OK) return rc;
         rc = gemm1(false, true, dvt, kFeat, T, Tpad, xb, T, kFeat, kFeat, prob(kFeat, kFeat, T, kFeat, 0, kFeat),
-                   GemmEpilogue{gr->wv, nullptr, gr->wv, 1.f, F32ACC}, sd);
+                   split(GemmEpilogue{gr->wv, nullptr, gr->wv, 1.f, F32ACC}, LO, XLO, 0), sd);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "att_bwd1");
-        rc = smz::launch_softmax_bwd(dP, alpha, drop_att ? drop_att + att_off : nullptr, T, ld, dS, st);
+        rc = smz::launch_softmax_bwd(dP, alpha, drop_att ? drop_att + att_off : nullptr, T, ld, dS, st, LO);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "softmax_bwd");
         rc = fork_to_side(4);                                    // dS is ready
@@ -695,10 +718,10 @@ extern "C" int smz_vasnet_backward(const void *x, int x_is_bf16, const int32_t *
         {
             GemmProblem g = prob(T, kFeat, T, 2 * kFeat, 0);
             g.b_col0 = kFeat;
-            rc = gemm1(false, true, dS, T, T, ld, qk, T, 2 * kFeat, 2 * kFeat, g, GemmEpilogue{dqk, nullptr, nullptr, p->scale, 0}, st);
+            rc = gemm1(false, true, dS, T, T, ld, qk, T, 2 * kFeat, 2 * kFeat, g, split(GemmEpilogue{dqk, nullptr, nullptr, p->scale, 0}, LO, LO, LO), st);
             if (rc != SMZ_OK) return rc;
             g = prob(T, kFeat, T, 2 * kFeat, kFeat);
-            rc = gemm1(true, true, dS, T, T, ld, qk, T, 2 * kFeat, 2 * kFeat, g, GemmEpilogue{dqk, nullptr, nullptr, p->scale, 0}, sd);
+            rc = gemm1(true, true, dS, T, T, ld, qk, T, 2 * kFeat, 2 * kFeat, g, split(GemmEpilogue{dqk, nullptr, nullptr, p->scale, 0}, LO, LO, LO), sd);
             if (rc != SMZ_OK) return rc;
         }
         SMZ_DEBUG_STEP(st, "att_bwd2");
@@ -708,17 +731,17 @@ extern "C" int smz_vasnet_backward(const void *x, int x_is_bf16, const int32_t *
         }
         // projections: dWqk += [dQ|dK]^T . xb
         rc = gemm1(true, true, dqk, T, 2 * kFeat, 2 * kFeat, xb, T, kFeat, kFeat, prob(2 * kFeat, kFeat, T, kFeat, 0, kFeat),
-                   GemmEpilogue{gr->wqk, nullptr, gr->wqk, 1.f, F32ACC}, st);
+                   split(GemmEpilogue{gr->wqk, nullptr, gr->wqk, 1.f, F32ACC}, LO, XLO, 0), st);
         if (rc != SMZ_OK) return rc;
         SMZ_DEBUG_STEP(st, "proj_bwd");
         if (gr->dx != nullptr) {
             float *dx = gr->dx + rb * kFeat;
             // dx = dY + [dQ|dK] . Wqk   (B = Wqk stored [c][i]: MN-major), then += dV . Wv (A = dV^T: MN-major)
             rc = gemm1(false, true, dqk, T, 2 * kFeat, 2 * kFeat, p->wqk, 2 * kFeat, kFeat, kFeat,
-                       prob(T, kFeat, 2 * kFeat, kFeat, 0, kFeat), GemmEpilogue{dx, nullptr, dyf, 1.f, F32ACC}, st);
+                       prob(T, kFeat, 2 * kFeat, kFeat, 0, kFeat), split(GemmEpilogue{dx, nullptr, dyf, 1.f, F32ACC}, LO, wlo(p->wqk_lo, p->wqk), 0), st);
             if (rc != SMZ_OK) return rc;
             rc = gemm1(true, true, dvt, kFeat, T, Tpad, p->wv, kFeat, kFeat, kFeat, prob(T, kFeat, kFeat, kFeat, 0, kFeat),
-                       GemmEpilogue{dx, nullptr, dx, 1.f, F32ACC}, st);
+                       split(GemmEpilogue{dx, nullptr, dx, 1.f, F32ACC}, LO, wlo(p->wv_lo, p->wv), 0), st);
             if (rc != SMZ_OK) return rc;
             SMZ_DEBUG_STEP(st, "dx");
         }

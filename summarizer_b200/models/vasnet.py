@@ -25,7 +25,11 @@ class VasnetParams(C.Structure):
                 ("ln_b", C.c_void_p), ("scale", C.c_float), ("eps", C.c_float), ("aperture", C.c_int32),
                 ("ignore_self", C.c_int32), ("head_gw", C.c_void_p), ("head_c", C.c_void_p),
                 ("w1g", C.c_void_p), ("ln_c", C.c_void_p), ("b1f", C.c_void_p), ("wgv", C.c_void_p), ("wgv16", C.c_void_p),
-                ("status", C.c_void_p)]
+                ("status", C.c_void_p),
+                ("wqk_lo", C.c_void_p), ("wv_lo", C.c_void_p), ("wo_lo", C.c_void_p), ("w1_lo", C.c_void_p)]
+
+SPLIT = 4      # SMZ_VASNET_SPLIT: OR into `training` of smz_vasnet_workspace_bytes (room for the lo planes)
+LO_KEYS = ("wqk_lo", "wv_lo", "wo_lo", "w1_lo")
 
 
 def _cu_seqlens(lengths):
@@ -48,8 +52,14 @@ class _Workspace:
 
 class VASNet(nn.Module):
     def __init__(self, input_size=1024, max_length=None, pos_embed="simple", ignore_self=False,
-                 attention_aperture=None, scale=None, epsilon=1e-6, weight_init="xavier"):
+                 attention_aperture=None, scale=None, epsilon=1e-6, weight_init="xavier", precision="bf16"):
+        """Reference constructor (vasnet.py:18-21) + ``precision``: "bf16" (default: bf16 / float16 tensor-core operands,
+        scores within 1e-2 of the float32 reference) or "fp32" (split-bf16 operands, every contraction as three
+        tensor-core products: scores within 1e-4 of the float32 reference, forward AND backward; ~3 x the GEMM time)."""
         super().__init__()
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision = precision
         if input_size != 1024:
             raise ValueError("the sm_100a VASNet kernels are built for 1024-d features (GoogLeNet pool5)")
         self.input_size = input_size
@@ -112,11 +122,26 @@ class VASNet(nn.Module):
         ps = (self.Q.weight, self.K.weight, self.V.weight, self.attention_head_projection.weight,
               self.k1.weight, self.k1.bias, self.k2.weight, self.k2.bias, self.layer_norm.weight,
               self.layer_norm.bias)
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        key = tuple((p.data_ptr(), p._version) for p in ps) + (self.precision,)
+        if self.precision == "fp32":
+            fast = False                     # the folded 16-bit fast path is the bf16 mode's
         if not inference or self._shadow_key is None or key != self._shadow_key:
             with torch.no_grad():
                 big = (self.Q.weight, self.K.weight, self.V.weight, self.attention_head_projection.weight, self.k1.weight)
-                if all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for t in big):
+                lo = None
+                if self.precision == "fp32":
+                    # float32-accurate mode: hi + lo bf16 planes of the five matrices in one launch
+                    src_t = [t.detach().float().contiguous() for t in big]
+                    flat = torch.empty(2, 5 * 1024 * 1024, dtype=torch.bfloat16, device=big[0].device)
+                    src = (C.c_void_p * 5)(*(t.data_ptr() for t in src_t))
+                    dst = (C.c_void_p * 5)(*(flat[0].data_ptr() + 2 * 1024 * 1024 * i for i in range(5)))
+                    dlo = (C.c_void_p * 5)(*(flat[1].data_ptr() + 2 * 1024 * 1024 * i for i in range(5)))
+                    cnt = (C.c_int64 * 5)(*([1024 * 1024] * 5))
+                    N.check(N.lib().smz_split_bf16_multi(src, dst, dlo, cnt, 5, N.current_stream()))
+                    w, wl = flat[0].view(5 * 1024, 1024), flat[1].view(5 * 1024, 1024)
+                    wqk, wv, wo, w1 = w[:2048], w[2048:3072], w[3072:4096], w[4096:]
+                    lo = dict(wqk_lo=wl[:2048], wv_lo=wl[2048:3072], wo_lo=wl[3072:4096], w1_lo=wl[4096:])
+                elif all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for t in big):
                     # one launch: [Q;K] | V | O | k1 -> one bf16 buffer (no fp32 concatenation, no cast kernel per tensor)
                     flat = torch.empty(5 * 1024 * 1024, dtype=torch.bfloat16, device=big[0].device)
                     src = (C.c_void_p * 5)(*(t.data_ptr() for t in big))
@@ -133,6 +158,8 @@ class VASNet(nn.Module):
                     b1=self.k1.bias.float().contiguous(), w2=self.k2.weight.float().reshape(-1).contiguous(),
                     b2=self.k2.bias.float().contiguous(), ln_g=self.layer_norm.weight.float().contiguous(),
                     ln_b=self.layer_norm.bias.float().contiguous())
+                if lo is not None:
+                    sh.update(lo)
             self._shadow, self._shadow_key = sh, (key if inference else None)
         sh = self._shadow
         if inference and "head_gw" not in sh:
@@ -159,7 +186,8 @@ class VASNet(nn.Module):
                           -1 if self.aperture is None else int(self.aperture), int(bool(self.ignore_self)),
                           *((sh[k].data_ptr() if inference else None) for k in ("head_gw", "head_c", "w1g", "ln_c", "b1f")),
                           *((sh[k].data_ptr() if (inference and fast and sh["fast_ok"]) else None) for k in ("wgv", "wgv16")),
-                          self._status_word(sh["ln_g"].device).data_ptr() if (inference and fast and sh["fast_ok"]) else None)
+                          self._status_word(sh["ln_g"].device).data_ptr() if (inference and fast and sh["fast_ok"]) else None,
+                          *((sh[k].data_ptr() if k in sh else None) for k in LO_KEYS))
         return sh, st
 
     def _status_word(self, device):
@@ -193,6 +221,8 @@ class VASNet(nn.Module):
         x = x.contiguous()
         cu = _cu_seqlens(lengths)
         assert x.shape == (int(cu[-1]), self.input_size)
+        if self.precision == "fp32":
+            return self._score_packed_split(x, lengths)
         _, st = self._weights(fast=not exact)
         nbytes = C.c_int64(0)
         cu_p = cu.ctypes.data_as(C.c_void_p)
@@ -204,6 +234,27 @@ class VASNet(nn.Module):
                                            N.ptr(scores), N.ptr(ws), ws.numel(), N.current_stream()))
         if check and not exact and not self.check_status():
             return self.score_packed(x, lengths, exact=True)
+        return scores
+
+    def _score_packed_split(self, x, lengths, max_rows=8192):
+        """float32-accurate inference: the training-layout forward (every intermediate kept per video, no dropout) on
+        split-bf16 operands, a few videos per call so that the doubled work buffer stays small."""
+        _, st = self._weights()
+        scores = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        is_bf16 = int(x.dtype == torch.bfloat16)
+        v0, row0 = 0, 0
+        while v0 < len(lengths):
+            v1, rows = v0, 0
+            while v1 < len(lengths) and (v1 == v0 or rows + lengths[v1] <= max_rows):
+                rows += int(lengths[v1]); v1 += 1
+            cu = _cu_seqlens(lengths[v0:v1])
+            cu_p = cu.ctypes.data_as(C.c_void_p)
+            nbytes = C.c_int64(0)
+            N.check(N.lib().smz_vasnet_workspace_bytes(cu_p, v1 - v0, 1 | SPLIT, is_bf16, C.byref(nbytes)))
+            ws = self._ws.get(nbytes.value, x.device)
+            N.check(N.lib().smz_vasnet_forward(N.ptr(x[row0:row0 + rows]), is_bf16, cu_p, v1 - v0, C.byref(st), 1, None, None,
+                                               None, N.ptr(scores[row0:row0 + rows]), N.ptr(ws), ws.numel(), N.current_stream()))
+            v0, row0 = v1, row0 + rows
         return scores
 
     def forward(self, x):
@@ -250,7 +301,8 @@ class VASNetTrainer(Trainer):
             attention_aperture=int(ep["local"]) if "local" in ep else None,
             scale=float(ep["scale"]) if "scale" in ep else None,
             epsilon=float(ep.get("epsilon", 1e-6)),
-            weight_init=ep.get("weight_init", "xavier"))
+            weight_init=ep.get("weight_init", "xavier"),
+            precision=str(ep.get("precision", "bf16")))
         if self.hps.use_cuda:
             self.log.info(f"Setting CUDA device: {self.hps.cuda_device}")
             torch.cuda.set_device(self.hps.cuda_device)

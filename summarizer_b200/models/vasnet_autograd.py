@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from .. import _native as N
-from .vasnet import VasnetParams, _cu_seqlens
+from .vasnet import LO_KEYS, SPLIT, VasnetParams, _cu_seqlens
 
 
 class VasnetGrads(C.Structure):
@@ -40,7 +40,8 @@ class _VasnetFunction(torch.autograd.Function):
         is_bf16 = int(x.dtype == torch.bfloat16)
         sh, st = module._weights(inference=False)
         nbytes = C.c_int64(0)
-        N.check(N.lib().smz_vasnet_workspace_bytes(cu_p, len(lengths), 1, is_bf16, C.byref(nbytes)))
+        split = SPLIT if module.precision == "fp32" else 0            # room for the activations' lo planes
+        N.check(N.lib().smz_vasnet_workspace_bytes(cu_p, len(lengths), 1 | split, is_bf16, C.byref(nbytes)))
         ws = torch.empty(max(nbytes.value, 1024), dtype=torch.uint8, device=x.device)   # lives until backward
         scores = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
         m_att, m_y, m_h = masks if masks is not None else (None, None, None)
@@ -70,7 +71,7 @@ class _VasnetFunction(torch.autograd.Function):
         sh = ctx.shadow   # the bf16 weights the forward used
         st = VasnetParams(*(sh[k].data_ptr() for k in ("wqk", "wv", "wo", "w1", "b1", "w2", "b2", "ln_g", "ln_b")),
                           float(m.scale), float(m.epsilon), -1 if m.aperture is None else int(m.aperture),
-                          int(bool(m.ignore_self)), *([None] * 8))
+                          int(bool(m.ignore_self)), *([None] * 8), *((sh[k].data_ptr() if k in sh else None) for k in LO_KEYS))
         m_att, m_y, m_h = ctx.masks if ctx.masks is not None else (None, None, None)
         cu = ctx.cu
         N.check(N.lib().smz_vasnet_backward(N.ptr(x), int(x.dtype == torch.bfloat16), cu.ctypes.data_as(C.c_void_p),

@@ -88,13 +88,16 @@ def test_struct_sizes_match_header():
     import subprocess, tempfile
     from summarizer_b200.models.lstm_stack import LstmDecode, LstmSeq
     from summarizer_b200.models.dsn import DsnParams
-    src = '#include <stdio.h>\n#include "summarizer_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(smz_lstm_seq), sizeof(smz_lstm_decode), sizeof(smz_dsn_params), sizeof(smz_video_desc));return 0;}\n'
+    from summarizer_b200.models.vasnet import VasnetParams
+    from summarizer_b200.models.vasnet_autograd import VasnetGrads
+    src = '#include <stdio.h>\n#include "summarizer_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(smz_lstm_seq), sizeof(smz_lstm_decode), sizeof(smz_dsn_params), sizeof(smz_video_desc), sizeof(smz_vasnet_params), sizeof(smz_vasnet_grads));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
         open(c, "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", os.path.join(d, "s")])
         sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "s")]).split()]
-    assert sizes == [ctypes.sizeof(LstmSeq), ctypes.sizeof(LstmDecode), ctypes.sizeof(DsnParams), N.VIDEO_DESC.itemsize]
+    assert sizes == [ctypes.sizeof(LstmSeq), ctypes.sizeof(LstmDecode), ctypes.sizeof(DsnParams), N.VIDEO_DESC.itemsize,
+                     ctypes.sizeof(VasnetParams), ctypes.sizeof(VasnetGrads)]
 
 
 def test_episode_sampling_argument_validation():

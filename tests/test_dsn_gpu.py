@@ -166,7 +166,7 @@ def test_sample_episodes_draws_are_bernoulli_and_advance_on_the_device():
     for call in range(16):
         lp, act = sample_episodes(probs, E, state)
         assert state.tolist() == [123, call + 1, 0]
-        ref = torch.where(act.bool(), probs.log(), (1 - probs).log()).mean(1)
+        ref = torch.where(act.bool(), probs.log(), torch.log1p(-probs)).mean(1)
         assert torch.allclose(lp, ref, rtol=1e-5, atol=1e-6)
         draws.append(act)
     allv = torch.stack(draws).reshape(-1, T).float()            # 128 independent draws per frame

@@ -151,3 +151,57 @@ def test_gemm_float16_operands(a16, b16, out16):
     rel = 2.0 ** (-11 if out16 else -8)
     assert ((got.float() - want).abs() <= rel * want.abs() + 1e-3 * K ** 0.5).all()
     assert ((got.float() - want).abs() / want.abs().clamp_min(1.0)).max().item() < 1.01 * rel + 2e-3
+
+
+def split_planes(x32):
+    """hi + lo bf16 planes of a float32 matrix through smz_split_bf16_multi, checked against the definition."""
+    hi = torch.empty_like(x32, dtype=torch.bfloat16)
+    lo = torch.empty_like(x32, dtype=torch.bfloat16)
+    src = (C.c_void_p * 1)(x32.data_ptr()); dh = (C.c_void_p * 1)(hi.data_ptr()); dl = (C.c_void_p * 1)(lo.data_ptr())
+    cnt = (C.c_int64 * 1)(x32.numel())
+    N.check(N.lib().smz_split_bf16_multi(src, dh, dl, cnt, 1, N.current_stream()))
+    assert torch.equal(hi, x32.bfloat16()) and torch.equal(lo, (x32 - x32.bfloat16().float()).bfloat16())
+    return hi, lo
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,Nn,K", [(128, 256, 64), (304, 1024, 1024), (712, 704, 712), (2000, 1024, 2000)])
+def test_gemm_split_bf16_is_float32_accurate(a_mn, b_mn, M, Nn, K):
+    """smz_gemm_bf16_split (hi.hi + lo.hi + hi.lo in one float32 accumulator) vs a float64 product of the float32
+    operands: ~1e-5 of the result's scale where plain bf16 operands give ~3e-3; float32 output, then hi + lo output
+    planes whose sum carries the same accuracy."""
+    N.require_device()
+    g = torch.Generator(device="cuda"); g.manual_seed(M + 3 * Nn + 7 * K + a_mn + 2 * b_mn)
+    a32 = torch.randn((K, M) if a_mn else (M, K), generator=g, device="cuda")
+    b32 = torch.randn((K, Nn) if b_mn else (Nn, K), generator=g, device="cuda")
+    a32 = a32 * torch.rand(a32.shape[1], generator=g, device="cuda") * 3        # uneven column scales
+    (ah, al), (bh, bl) = split_planes(a32), split_planes(b32)
+    want = ((a32.double().t() if a_mn else a32.double()) @ (b32.double() if b_mn else b32.double().t()))
+    # error measure: |C - want| against sum_k |a_ik| |b_kj| (what a per-product relative error is a fraction of)
+    scale = ((a32.double().abs().t() if a_mn else a32.double().abs()) @ (b32.double().abs() if b_mn else b32.double().abs().t()))
+
+    def run(flags, c, c_lo, a_lo=al, b_lo=bl):
+        N.check(N.lib().smz_gemm_bf16_split(a_mn, b_mn, N.ptr(ah), N.ptr(a_lo), ah.stride(0), N.ptr(bh), N.ptr(b_lo), bh.stride(0),
+                                            N.ptr(c), N.ptr(c_lo), c.stride(0), M, Nn, K, C.c_float(1.0), None, None, 0, flags,
+                                            N.current_stream()))
+    out = torch.full((M, Nn), float("nan"), device="cuda")
+    run(OUT_F32, out, None)
+    err = ((out.double() - want).abs() / scale).max().item()
+    plain = torch.empty_like(out)
+    run(OUT_F32, plain, None, a_lo=None, b_lo=None)
+    err_plain = ((plain.double() - want).abs() / scale).max().item()
+    print(f"split-bf16 max err / (|A|.|B|) = {err:.2e} (bf16 operands: {err_plain:.2e})")
+    assert err < 1e-5 and err_plain > 20 * err, (err, err_plain)      # worst case per product: 3 * 2^-18 = 1.1e-5
+    # one-sided: B exact in bf16 -> two passes
+    out2 = torch.empty_like(out)
+    run(OUT_F32, out2, None, b_lo=None)
+    want2 = ((a32.double().t() if a_mn else a32.double()) @ (bh.double() if b_mn else bh.double().t()))
+    assert ((out2.double() - want2).abs() / scale).max().item() < 1e-5
+    # hi + lo output planes
+    if Nn % 8 == 0:
+        ch = torch.full((M, Nn), float("nan"), device="cuda", dtype=torch.bfloat16)
+        cl = torch.full((M, Nn), float("nan"), device="cuda", dtype=torch.bfloat16)
+        run(0, ch, cl)
+        assert torch.equal(ch, out.bfloat16()), describe_mismatch(ch, out.bfloat16().float(), 0)
+        rec = ch.double() + cl.double()
+        assert (rec - out.double()).abs().max().item() <= 2.0 ** -16 * out.abs().max().item()

@@ -27,7 +27,7 @@ REL = 1e-2
 CORR_ABS = 5e-2
 
 
-def make_trainer(tmp_path, model, name):
+def make_trainer(tmp_path, model, name, **more_extra):
     run = G.RUNS[name]
     ds = synthetic.ArrayDataset(G.tiny_videos(run["frames"]), name="summe")
     h5 = synthetic.write_dataset_h5(ds, str(tmp_path / "summarizer_dataset_summe_tiny.h5"))
@@ -38,6 +38,7 @@ def make_trainer(tmp_path, model, name):
     hps.log_root, hps.tensorboard, hps.datasets = str(tmp_path), False, [h5]
     extra = dict(run["extra"])
     extra["cuda_graphs"] = "no"                  # the replayed draws come from the host, step by step
+    extra.update(more_extra)
     hps.load_from_args(dict(model=model, use_cuda="yes", splits_files=sf, log_level="error", epochs=run["epochs"],
                             lr=run["lr"], weight_decay=G.WEIGHT_DECAY, test_every_epochs=1, extra_params=extra))
     hps.writer = G.Recorder()
@@ -67,9 +68,14 @@ def check_updates(name, model, before, min_cos, max_rel):
     return cos, rel
 
 
-def test_vasnet_trainer_follows_the_reference_trajectory(tmp_path, monkeypatch):
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_vasnet_trainer_follows_the_reference_trajectory(tmp_path, monkeypatch, precision):
+    """precision="fp32" (split-bf16 operands, --extra_params precision=fp32): the same trajectory at the float32 bar —
+    losses to 1e-4, Adam updates to 2 % (Adam's first steps are sign-like: lr * g / (|g| + eps), so entries whose
+    gradient is ~0 amplify any difference)."""
     from summarizer_b200.models import vasnet_autograd
-    t, hps, run = make_trainer(tmp_path, "vasnet", "vasnet")
+    t, hps, run = make_trainer(tmp_path, "vasnet", "vasnet", precision=precision)
+    assert t.model.precision == precision
     step = {"n": 0}
 
     def replay_masks(lengths, device, generator=None):
@@ -83,12 +89,12 @@ def test_vasnet_trainer_follows_the_reference_trajectory(tmp_path, monkeypatch):
     random.seed(run["seed"])
     ret = t.train(0)
     assert step["n"] == run["epochs"] * 2
-    check_scalars("vasnet", hps, ["Train/Loss"])
-    check_scalars("vasnet", hps, ["Test/Correlation"], rel=0, abs_tol=CORR_ABS)
+    check_scalars("vasnet", hps, ["Train/Loss"], rel=REL if precision == "bf16" else 1e-4)
+    check_scalars("vasnet", hps, ["Test/Correlation"], rel=0, abs_tol=CORR_ABS if precision == "bf16" else 1e-3)
     check_scalars("vasnet", hps, ["Test/F-score_avg", "Test/F-score_max"], rel=1e-6)
     np.testing.assert_allclose(np.asarray(ret, dtype=np.float64)[1:], GOLDEN["vasnet/return"][1:], rtol=1e-6)
-    cos, rel = check_updates("vasnet", t.model, before, min_cos=0.99, max_rel=0.15)
-    print(f"vasnet: loss {hps.writer.scalars['Train/Loss']} vs {GOLDEN['vasnet/Train/Loss']}; updates cos {cos:.4f} rel {rel:.3f}")
+    cos, rel = check_updates("vasnet", t.model, before, *((0.99, 0.15) if precision == "bf16" else (0.9995, 0.03)))
+    print(f"vasnet ({precision}): loss {hps.writer.scalars['Train/Loss']} vs {GOLDEN['vasnet/Train/Loss']}; updates cos {cos:.4f} rel {rel:.3f}")
 
 
 def test_dsn_trainer_follows_the_reference_trajectory(tmp_path, monkeypatch):
