@@ -428,6 +428,54 @@ def train_stage(dev, seconds=4.0):
     f_train = sum(24 * T * FEAT * FEAT + 12 * T * T * FEAT + 6 * T * FEAT for T in lens)
     out["vasnet_train_tflops"] = out["vasnet_train_frames_per_s"] / sum(lens) * f_train / 1e12
 
+    # Fold-concurrent training: a batch-1 step keeps 12-24 of the 148 SMs busy per GEMM, so the folds of a cross-validation
+    # (independent models, BASELINE config 3) train side by side on ONE GPU — K replicas (own weights, optimizer, graphs),
+    # one stream each, replayed round-robin from one host thread.  Aggregate frames/s over the K folds.
+    K = int(os.environ.get("SMZ_BENCH_CONCURRENT_FOLDS", 4))
+    try:
+        reps = []
+        for r in range(K):
+            m_r = VASNet().to(dev).train()
+            o_r = Adam(m_r.parameters(), lr=5e-5, weight_decay=1e-5)
+            s_r = torch.cuda.Stream(device=dev)
+
+            def step_r(x, tgt, m_r=m_r, o_r=o_r):
+                o_r.zero_grad(set_to_none=True)
+                loss = torch.nn.functional.mse_loss(m_r(x), tgt)
+                loss.backward(); o_r.step()
+            with torch.cuda.stream(s_r):
+                for x, tgt in vids:
+                    step_r(x, tgt)
+            torch.cuda.synchronize()
+            pool_r, graphs_r = torch.cuda.graph_pool_handle(), []
+            for x, tgt in vids:
+                g_r = torch.cuda.CUDAGraph()
+                m_r._shadow_key = None
+                with torch.cuda.graph(g_r, pool=pool_r, stream=s_r):
+                    step_r(x, tgt)
+                graphs_r.append(g_r)
+            reps.append((m_r, o_r, s_r, graphs_r))
+
+        def all_folds_pass():
+            for k in range(len(vids)):
+                for r, (m_r, _, s_r, graphs_r) in enumerate(reps):
+                    with torch.cuda.stream(s_r):
+                        graphs_r[(k + 5 * r) % len(vids)].replay()      # the folds are at different videos at any time
+                    m_r._shadow_key = None
+        all_folds_pass()
+        torch.cuda.synchronize()
+        t0, n = time.perf_counter(), 0
+        while time.perf_counter() - t0 < seconds / 2:
+            all_folds_pass()
+            n += 1
+        torch.cuda.synchronize()
+        out["vasnet_train_concurrent_folds"] = {"folds": K, "frames_per_s": n * K * sum(lens) / (time.perf_counter() - t0),
+                                                "what": "K independent folds (model + optimizer + step graphs each) on K streams of this GPU, "
+                                                        "aggregate rate, wall clock around synchronised replay loops"}
+        del reps
+    except Exception as e:          # secondary number: never cost the line
+        out["vasnet_train_concurrent_folds"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     opt2 = Adam(dsn.parameters(), lr=5e-5, weight_decay=1e-5)
     base = torch.zeros((), device=dev)
     episode_rng = episode_state(dev)
@@ -598,10 +646,25 @@ def cv_stage(dev, rank, world):
             torch.cuda.synchronize()
             walls.append(time.perf_counter() - t0)
         dt = walls[1]
+        # the same run with the folds of a rank training side by side on its GPU (main._train_jobs_concurrently)
+        conc = {}
+        try:
+            k = int(os.environ.get("SMZ_BENCH_CV_CONCURRENT_FOLDS", 2))
+            hps.extra_params = dict(hps.extra_params or {}, concurrent_folds=k)
+            cw = []
+            for _ in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                M.train(hps)
+                torch.cuda.synchronize()
+                cw.append(time.perf_counter() - t0)
+            conc = {"concurrent_folds": k, "wall_s_concurrent_folds": cw[1], "wall_s_concurrent_folds_first_pass": cw[0]}
+        except Exception as e:
+            conc = {"concurrent_folds_error": f"{type(e).__name__}: {e}"[:300]}
     finally:
         synthetic.make_dataset = orig
     return {"config": "VASNet 5-fold CV on both synthetic datasets (10 fold jobs), 20 epochs, test every 10", "wall_s": dt,
-            "wall_s_first_pass": walls[0],
+            "wall_s_first_pass": walls[0], **conc,
             "n_gpus": world, "cv": [[os.path.basename(sf), float(c), float(a), float(m)] for sf, c, a, m in results]}
 
 

@@ -279,6 +279,10 @@ typedef struct smz_vasnet_params {
  * training != 0 keeps every intermediate in the work buffer for smz_vasnet_backward and enables the
  * three p=0.5 dropouts (vasnet.py:130,136,142) through caller-supplied KEEP masks (uint8, 1 = keep;
  * NULL = no dropout at that site): drop_att packed per video [T*T], drop_y / drop_h [sum T, 1024]. */
+/* KEEP masks of the three nn.Dropout(0.5) sites (vasnet.py:130,136,142) for smz_vasnet_forward(training): n bytes,
+ * 1 = keep with probability 1/2 (Philox4x32-10, one bit per byte).  state: three device uint64 words {seed, call number, 0};
+ * the call number is advanced on the device, so a captured training step draws fresh masks at every graph replay. */
+int smz_dropout_keep_masks(uint64_t *state, uint8_t *out, int64_t n, void *stream);
 int smz_vasnet_workspace_bytes(const int32_t *h_cu_seqlens, int n_videos, int training, int x_is_bf16,
                                int64_t *bytes);
 /* on != 0 forces the exact inference path for every call of this process, status word or not (testing / A-B aid). */

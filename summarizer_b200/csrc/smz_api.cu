@@ -73,6 +73,8 @@ void profile_report() {
 namespace {
 struct SmallBlob { unsigned char b[3584]; };
 __global__ void store_blob_kernel(const __grid_constant__ SmallBlob blob, unsigned char *__restrict__ dst, int n) {
+    smz::pdl_trigger();
+    smz::pdl_wait();          // dst may still be read by the previous kernel of the stream
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = blob.b[i];
 }
 }  // namespace
@@ -82,12 +84,17 @@ int upload_small(void *dst, const void *src, size_t bytes, cudaStream_t st) {
     if (bytes <= sizeof(SmallBlob)) {
         SmallBlob blob;
         memcpy(blob.b, src, bytes);
-        store_blob_kernel<<<1, 256, 0, st>>>(blob, reinterpret_cast<unsigned char *>(dst), (int)bytes);
-        SMZ_CUDA_CHECK(cudaGetLastError());
+        SMZ_CUDA_CHECK(launch_pdl(store_blob_kernel, dim3(1), dim3(256), 0, st, blob, reinterpret_cast<unsigned char *>(dst), (int)bytes));
         return SMZ_OK;
     }
     SMZ_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
     return SMZ_OK;
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("SMZ_PDL"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
+    return v == 1;
 }
 
 int sm_count() {

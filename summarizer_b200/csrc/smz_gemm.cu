@@ -108,7 +108,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
     float *stg_all = reinterpret_cast<float *>(smem + STAGES * (A_STAGE + B_STAGE) + BAR_BYTES);
 
-    if (P.epi.gate != nullptr && __ldg(P.epi.gate) == 0) return;  // gated launch (fallback path not needed): every CTA leaves
+    smz::pdl_trigger();                                           // the next kernel of the stream may set itself up under this one
+    if (P.epi.gate != nullptr) {                                  // gated launch (fallback path not needed): every CTA leaves
+        smz::pdl_wait();
+        if (__ldg(P.epi.gate) == 0) return;
+    }
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;     // warp index, provably uniform
     const int rank = PAIR ? (int)cluster_ctarank() : 0;           // 0 = leader CTA of the pair
     const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -127,6 +131,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barriers, TMEM, descriptor prefetch) may run under the previous kernel of the stream; from here on
+    // global memory is read (problem table, operands, residual) and written
+    smz::pdl_wait();
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (every CTA)
@@ -610,16 +617,27 @@ static int launch_variant(bool a_mn, bool b_mn, const CUtensorMap &ma, const CUt
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = Cfg<PAIR>::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
+    int n_attr = 0;
     if (PAIR) {
         const int pairs = total_tiles < sms / 2 ? total_tiles : sms / 2;
         cfg.gridDim = dim3(2 * pairs);
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
+        attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+        attr[n_attr].val.clusterDim.x = 2; attr[n_attr].val.clusterDim.y = 1; attr[n_attr].val.clusterDim.z = 1;
+        ++n_attr;
     } else {
         cfg.gridDim = dim3(total_tiles < sms ? total_tiles : sms);
     }
+    // Programmatic dependent launch (smz_common.cuh): the prologue overlaps the previous kernel's tail.  Only for grids
+    // that leave SMs free (the few-tile GEMMs of a batch-1 training step: +5 % on the replayed step) — a full persistent
+    // grid gains nothing, and in the two-lane inference sweep its early-resident CTAs sit on SMs the OTHER lane's kernel
+    // could use (measured: -1.7 % on the sweep).
+    if (pdl_enabled() && total_tiles < (PAIR ? sms / 2 : sms)) {
+        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+        ++n_attr;
+    }
+    cfg.attrs = attr; cfg.numAttrs = n_attr;
     SMZ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ma, mb, ma_lo, mb_lo, P));
     return SMZ_OK;
 }

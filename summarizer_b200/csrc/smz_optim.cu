@@ -53,6 +53,8 @@ __device__ __forceinline__ float cta_sum_ordered(float v, float *red) {
 }
 
 __global__ void __launch_bounds__(OPT_THREADS) sqnorm_partial_kernel(const TensorTable t, float *__restrict__ partial) {
+    smz::pdl_trigger();
+    smz::pdl_wait();
     __shared__ float red[OPT_THREADS / 32];
     const int ti = find_tensor(t, blockIdx.x);
     const long long base = (long long)(blockIdx.x - t.chunk0[ti]) * OPT_CHUNK;
@@ -79,6 +81,8 @@ __global__ void __launch_bounds__(OPT_THREADS) sqnorm_partial_kernel(const Tenso
 // out[0] (+)= sum of partial[0..n) in a fixed order (one CTA); accumulate != 0 adds to the value already there
 __global__ void __launch_bounds__(OPT_THREADS) sqnorm_final_kernel(const float *__restrict__ partial, int n, float *__restrict__ out,
                                                                     int accumulate) {
+    smz::pdl_trigger();
+    smz::pdl_wait();
     __shared__ float red[OPT_THREADS / 32];
     float acc = 0.f;
     for (int i = threadIdx.x; i < n; i += OPT_THREADS) acc += partial[i];
@@ -87,6 +91,8 @@ __global__ void __launch_bounds__(OPT_THREADS) sqnorm_final_kernel(const float *
 }
 
 __global__ void __launch_bounds__(OPT_THREADS) clip_kernel(const TensorTable t, const float *__restrict__ sqnorm, float max_norm) {
+    smz::pdl_trigger();
+    smz::pdl_wait();
     const float coef = fminf(max_norm / (sqrtf(__ldg(sqnorm)) + 1e-6f), 1.f);        // clip_grad_norm_: clamp(max_norm / (norm + 1e-6), max=1)
     const int ti = find_tensor(t, blockIdx.x);
     const long long base = (long long)(blockIdx.x - t.chunk0[ti]) * OPT_CHUNK;
@@ -115,6 +121,8 @@ __global__ void __launch_bounds__(OPT_THREADS) clip_kernel(const TensorTable t, 
 // update increments it (stream order), so CUDA-graph replays advance t without host involvement.
 __global__ void __launch_bounds__(OPT_THREADS) adam_kernel(const TensorTable t, float lr, float beta1, float beta2, float omb1,
                                                             float omb2, float eps, float weight_decay) {
+    smz::pdl_trigger();
+    smz::pdl_wait();
     const int ti = find_tensor(t, blockIdx.x);
     const float tstep = __ldg(t.step[ti]) + 1.f;
     const float bc1 = 1.f - powf(beta1, tstep);
@@ -148,6 +156,8 @@ __global__ void __launch_bounds__(OPT_THREADS) adam_kernel(const TensorTable t, 
 }
 
 __global__ void bump_step_kernel(const TensorTable t) {
+    smz::pdl_trigger();
+    smz::pdl_wait();
     const int i = threadIdx.x;
     if (i < t.count && t.grad[i] != nullptr) t.step[i][0] += 1.f;
 }
@@ -211,8 +221,8 @@ extern "C" int smz_grad_sqnorm(const smz_optim_tensor *tensors, int n_tensors, f
         const int chunks = fill_table(tensors, first, count, false, &t);
         if (chunks == 0) continue;
         SMZ_REQUIRE(ws != nullptr && ws_floats >= chunks, "grad_sqnorm: work buffer too small (%lld < %d floats)", (long long)ws_floats, chunks);
-        sqnorm_partial_kernel<<<chunks, OPT_THREADS, 0, st>>>(t, ws);
-        sqnorm_final_kernel<<<1, OPT_THREADS, 0, st>>>(ws, chunks, sqnorm, any ? 1 : 0);
+        SMZ_CUDA_CHECK(smz::launch_pdl(sqnorm_partial_kernel, dim3(chunks), dim3(OPT_THREADS), 0, st, t, ws));
+        SMZ_CUDA_CHECK(smz::launch_pdl(sqnorm_final_kernel, dim3(1), dim3(OPT_THREADS), 0, st, ws, chunks, sqnorm, any ? 1 : 0));
         any = true;
     }
     if (!any) SMZ_CUDA_CHECK(cudaMemsetAsync(sqnorm, 0, sizeof(float), st));
@@ -232,7 +242,7 @@ extern "C" int smz_clip_grads(const smz_optim_tensor *tensors, int n_tensors, co
         TensorTable t;
         const int chunks = fill_table(tensors, first, count, false, &t);
         if (chunks == 0) continue;
-        clip_kernel<<<chunks, OPT_THREADS, 0, st>>>(t, sqnorm, max_norm);
+        SMZ_CUDA_CHECK(smz::launch_pdl(clip_kernel, dim3(chunks), dim3(OPT_THREADS), 0, st, t, sqnorm, max_norm));
     }
     SMZ_CUDA_CHECK(cudaGetLastError());
     return SMZ_OK;
@@ -252,9 +262,9 @@ extern "C" int smz_adam_step(const smz_optim_tensor *tensors, int n_tensors, dou
         TensorTable t;
         const int chunks = fill_table(tensors, first, count, true, &t);
         if (chunks == 0) continue;
-        adam_kernel<<<chunks, OPT_THREADS, 0, st>>>(t, (float)lr, (float)beta1, (float)beta2, (float)(1. - beta1), (float)(1. - beta2),
-                                                    (float)eps, (float)weight_decay);
-        bump_step_kernel<<<1, SMZ_OPTIM_MAX_TENSORS, 0, st>>>(t);      // behind the update that read the counters
+        SMZ_CUDA_CHECK(smz::launch_pdl(adam_kernel, dim3(chunks), dim3(OPT_THREADS), 0, st, t, (float)lr, (float)beta1, (float)beta2,
+                                       (float)(1. - beta1), (float)(1. - beta2), (float)eps, (float)weight_decay));
+        SMZ_CUDA_CHECK(smz::launch_pdl(bump_step_kernel, dim3(1), dim3(SMZ_OPTIM_MAX_TENSORS), 0, st, t));      // behind the update that read the counters
     }
     SMZ_CUDA_CHECK(cudaGetLastError());
     return SMZ_OK;

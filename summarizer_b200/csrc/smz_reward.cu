@@ -182,16 +182,7 @@ extern "C" int smz_dsn_reward(const float *x, int T, const uint8_t *actions, int
 // the last CTA to finish, so a captured step draws fresh episodes at every replay.
 namespace {
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        const uint32_t h0 = __umulhi(0xD2511F53u, c.x), l0 = 0xD2511F53u * c.x;
-        const uint32_t h1 = __umulhi(0xCD9E8D57u, c.z), l1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(h1 ^ c.y ^ k.x, l1, h0 ^ c.w ^ k.y, l0);
-        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
-    }
-    return c;
-}
+using smz::philox4x32_10;
 
 // torch.distributions.Bernoulli(probs).log_prob: probs are clamped to [eps, 1 - eps] (float32 eps = 2^-23) on their
 // way to logits, and log_prob = -binary_cross_entropy_with_logits(logits, action) = log(p_c) resp. log(1 - p_c)

@@ -38,6 +38,8 @@ __device__ __forceinline__ void st_bf16x4(__nv_bfloat16 *p, int64_t lo, float a,
 }
 
 __global__ void cvt_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, int64_t n, int64_t lo) {
+    smz::pdl_trigger();
+    smz::pdl_wait();
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
     if (i + 8 <= n) {
         const float4 a = *reinterpret_cast<const float4 *>(x + i);
@@ -55,6 +57,8 @@ __global__ void cvt_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__re
 
 // float32 -> float16 with a range check: |x| > 60000 (or NaN) ORs `bit` into *guard
 __global__ void cvt_f16_kernel(const float *__restrict__ x, __half *__restrict__ y, int64_t n, int *__restrict__ guard, int bit) {
+    smz::pdl_trigger();
+    smz::pdl_wait();
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
     float amax = 0.f;
     if (i + 8 <= n) {
@@ -78,6 +82,8 @@ __global__ void cvt_f16_kernel(const float *__restrict__ x, __half *__restrict__
 // the float32-accurate GEMM mode
 struct CvtSegments { const float *src[8]; __nv_bfloat16 *dst[8]; __nv_bfloat16 *lo[8]; long long n[8]; };
 __global__ void cvt_bf16_segments_kernel(const CvtSegments seg) {
+    smz::pdl_trigger();
+    smz::pdl_wait();
     const float *x = seg.src[blockIdx.y];
     __nv_bfloat16 *y = seg.dst[blockIdx.y];
     __nv_bfloat16 *yl = seg.lo[blockIdx.y];
@@ -121,6 +127,8 @@ softmax_kernel(const GemmProblem *__restrict__ probs, int n_probs, int total_row
                __nv_bfloat16 *__restrict__ alpha, __nv_bfloat16 *__restrict__ P, const uint8_t *__restrict__ drop,
                const int64_t *__restrict__ drop_off, int aperture, int ignore_self, const int *__restrict__ gate,
                float *__restrict__ sum_slots, int n_slots, int64_t lop) {
+    smz::pdl_trigger();
+    smz::pdl_wait();
     if (gate != nullptr && __ldg(gate) == 0) return;
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
@@ -233,6 +241,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 layernorm_kernel(const float *__restrict__ y, const uint8_t *__restrict__ keep, const float *__restrict__ g,
                  const float *__restrict__ b, float eps, int rows, __nv_bfloat16 *__restrict__ yn,
                  float *__restrict__ mean, float *__restrict__ rstd, int64_t lo) {
+    smz::pdl_trigger();
+    smz::pdl_wait();
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     if (r >= rows) return;
@@ -275,6 +285,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 head_kernel(const float *__restrict__ h, const uint8_t *__restrict__ keep, const float *__restrict__ g,
             const float *__restrict__ b, float eps, const float *__restrict__ w2, const float *__restrict__ b2,
             int rows, float *__restrict__ scores, float *__restrict__ mean, float *__restrict__ rstd) {
+    smz::pdl_trigger();
+    smz::pdl_wait();
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     if (r >= rows) return;
@@ -320,6 +332,8 @@ head_kernel(const float *__restrict__ h, const uint8_t *__restrict__ keep, const
 
 __global__ void head_from_stats_kernel(const float *__restrict__ stats, int slots, const float *__restrict__ c, float eps,
                                        int rows, float *__restrict__ scores) {
+    smz::pdl_trigger();
+    smz::pdl_wait();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     float s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -359,7 +373,9 @@ head_bwd_kernel(const float *__restrict__ h, const uint8_t *__restrict__ keep, c
                 float *__restrict__ d_g, float *__restrict__ d_b, float *__restrict__ d_b1, int64_t lo) {
     extern __shared__ float s_acc[];
     ColAcc<4> A{s_acc};
+    smz::pdl_trigger();
     A.zero();
+    smz::pdl_wait();
     const int lane = threadIdx.x & 31;
     float db2 = 0.f;
     for (int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < rows; r += gridDim.x * ROW_WARPS) {
@@ -428,7 +444,9 @@ layernorm_bwd_kernel(const float *__restrict__ dyn, const float *__restrict__ y,
                      float *__restrict__ d_b, int64_t lo) {
     extern __shared__ float s_acc[];
     ColAcc<2> A{s_acc};
+    smz::pdl_trigger();
     A.zero();
+    smz::pdl_wait();
     const int lane = threadIdx.x & 31;
     for (int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < rows; r += gridDim.x * ROW_WARPS) {
         float xh[32], dx[32];
@@ -483,6 +501,8 @@ layernorm_bwd_kernel(const float *__restrict__ dyn, const float *__restrict__ y,
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 softmax_bwd_kernel(const float *__restrict__ dP, const __nv_bfloat16 *__restrict__ alpha,
                    const uint8_t *__restrict__ keep, int T, int ld, __nv_bfloat16 *__restrict__ dS, int64_t lo) {
+    smz::pdl_trigger();
+    smz::pdl_wait();
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     if (i >= T) return;
@@ -517,8 +537,7 @@ namespace smz {
 int launch_head_from_stats(const float *stats, int slots, const float *c, float eps, int rows, float *scores,
                            cudaStream_t st) {
     if (rows <= 0) return SMZ_OK;
-    head_from_stats_kernel<<<(rows + 255) / 256, 256, 0, st>>>(stats, slots, c, eps, rows, scores);
-    SMZ_CUDA_CHECK(cudaGetLastError());
+    SMZ_CUDA_CHECK(launch_pdl(head_from_stats_kernel, dim3((rows + 255) / 256), dim3(256), 0, st, stats, slots, c, eps, rows, scores));
     return SMZ_OK;
 }
 
@@ -529,9 +548,8 @@ int launch_head_bwd(const float *h, const uint8_t *keep, const float *g, const f
     if (rows <= 0) return SMZ_OK;
     int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
     if (grid > 2 * sm_count()) grid = 2 * sm_count();
-    head_bwd_kernel<<<grid, ROW_WARPS * 32, 4 * kFeat * sizeof(float), st>>>(h, keep, g, b, w2, mean, rstd, scores, dscores,
-                                                                           rows, dh, d_w2, d_b2, d_g, d_b, d_b1, lo);
-    SMZ_CUDA_CHECK(cudaGetLastError());
+    SMZ_CUDA_CHECK(launch_pdl(head_bwd_kernel, dim3(grid), dim3(ROW_WARPS * 32), 4 * kFeat * sizeof(float), st, h, keep, g, b, w2, mean,
+                             rstd, scores, dscores, rows, dh, d_w2, d_b2, d_g, d_b, d_b1, lo));
     return SMZ_OK;
 }
 
@@ -541,17 +559,16 @@ int launch_layernorm_bwd(const float *dyn, const float *y, const uint8_t *keep, 
     if (rows <= 0) return SMZ_OK;
     int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
     if (grid > 2 * sm_count()) grid = 2 * sm_count();
-    layernorm_bwd_kernel<<<grid, ROW_WARPS * 32, 2 * kFeat * sizeof(float), st>>>(dyn, y, keep, g, mean, rstd, rows, dy,
-                                                                                dy_f32, d_g, d_b, lo);
-    SMZ_CUDA_CHECK(cudaGetLastError());
+    SMZ_CUDA_CHECK(launch_pdl(layernorm_bwd_kernel, dim3(grid), dim3(ROW_WARPS * 32), 2 * kFeat * sizeof(float), st, dyn, y, keep, g,
+                             mean, rstd, rows, dy, dy_f32, d_g, d_b, lo));
     return SMZ_OK;
 }
 
 int launch_softmax_bwd(const float *dP, const __nv_bfloat16 *alpha, const uint8_t *keep, int T, int ld,
                        __nv_bfloat16 *dS, cudaStream_t st, int64_t lo) {
     if (T <= 0) return SMZ_OK;
-    softmax_bwd_kernel<<<(T + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, st>>>(dP, alpha, keep, T, ld, dS, lo);
-    SMZ_CUDA_CHECK(cudaGetLastError());
+    SMZ_CUDA_CHECK(launch_pdl(softmax_bwd_kernel, dim3((T + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, st, dP, alpha, keep, T, ld,
+                             dS, lo));
     return SMZ_OK;
 }
 
@@ -574,8 +591,7 @@ static int cvt_segments(const float *const *src, void *const *dst, void *const *
     if (most == 0) return SMZ_OK;
     long long blocks = (most + 8 * 256 - 1) / (8 * 256);
     if (blocks > 2048) blocks = 2048;
-    cvt_bf16_segments_kernel<<<dim3((unsigned)blocks, count), 256, 0, (cudaStream_t)stream>>>(seg);
-    SMZ_CUDA_CHECK(cudaGetLastError());
+    SMZ_CUDA_CHECK(smz::launch_pdl(cvt_bf16_segments_kernel, dim3((unsigned)blocks, count), dim3(256), 0, (cudaStream_t)stream, seg));
     return SMZ_OK;
 }
 
@@ -596,16 +612,14 @@ namespace smz {
 int launch_cvt_bf16(const float *x, __nv_bfloat16 *y, int64_t n, cudaStream_t st, int64_t lo) {
     if (n <= 0) return SMZ_OK;
     const int64_t blocks = (n + 8 * 256 - 1) / (8 * 256);
-    cvt_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, n, lo);
-    SMZ_CUDA_CHECK(cudaGetLastError());
+    SMZ_CUDA_CHECK(launch_pdl(cvt_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0, st, x, y, n, lo));
     return SMZ_OK;
 }
 
 int launch_cvt_f16(const float *x, void *y, int64_t n, int *guard, int bit, cudaStream_t st) {
     if (n <= 0) return SMZ_OK;
     const int64_t blocks = (n + 8 * 256 - 1) / (8 * 256);
-    cvt_f16_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, reinterpret_cast<__half *>(y), n, guard, bit);
-    SMZ_CUDA_CHECK(cudaGetLastError());
+    SMZ_CUDA_CHECK(launch_pdl(cvt_f16_kernel, dim3((unsigned)blocks), dim3(256), 0, st, x, reinterpret_cast<__half *>(y), n, guard, bit));
     return SMZ_OK;
 }
 
@@ -613,17 +627,16 @@ int launch_softmax(const GemmProblem *d_probs, int n_probs, int total_rows, cons
                    __nv_bfloat16 *P, const uint8_t *drop, const int64_t *d_drop_off, int aperture, int ignore_self,
                    cudaStream_t st, const int *gate, float *sum_slots, int n_slots, int64_t lo) {
     if (total_rows <= 0) return SMZ_OK;
-    softmax_kernel<<<(total_rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, st>>>(
-        d_probs, n_probs, total_rows, S, alpha, P, drop, d_drop_off, aperture, ignore_self, gate, sum_slots, n_slots, lo);
-    SMZ_CUDA_CHECK(cudaGetLastError());
+    SMZ_CUDA_CHECK(launch_pdl(softmax_kernel, dim3((total_rows + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, st, d_probs, n_probs,
+                             total_rows, S, alpha, P, drop, d_drop_off, aperture, ignore_self, gate, sum_slots, n_slots, lo));
     return SMZ_OK;
 }
 
 int launch_layernorm(const float *y, const uint8_t *keep, const float *g, const float *b, float eps, int rows,
                      __nv_bfloat16 *yn, float *mean, float *rstd, cudaStream_t st, int64_t lo) {
     if (rows <= 0) return SMZ_OK;
-    layernorm_kernel<<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, st>>>(y, keep, g, b, eps, rows, yn, mean, rstd, lo);
-    SMZ_CUDA_CHECK(cudaGetLastError());
+    SMZ_CUDA_CHECK(launch_pdl(layernorm_kernel, dim3((rows + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, st, y, keep, g, b, eps, rows,
+                             yn, mean, rstd, lo));
     return SMZ_OK;
 }
 
@@ -631,10 +644,66 @@ int launch_head(const float *h, const uint8_t *keep, const float *g, const float
                 const float *w2, const float *b2, int rows, float *scores, float *mean, float *rstd,
                 cudaStream_t st) {
     if (rows <= 0) return SMZ_OK;
-    head_kernel<<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, st>>>(h, keep, g, b, eps, w2, b2, rows, scores,
-                                                                              mean, rstd);
-    SMZ_CUDA_CHECK(cudaGetLastError());
+    SMZ_CUDA_CHECK(launch_pdl(head_kernel, dim3((rows + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, st, h, keep, g, b, eps, w2, b2,
+                             rows, scores, mean, rstd));
     return SMZ_OK;
 }
 
 }  // namespace smz
+
+// ---------------------------------------------------------------------------------------------------
+// Keep masks of nn.Dropout(0.5) (vasnet.py:130,136,142): n bytes, 1 = keep with probability 1/2, one Philox bit per
+// byte.  `state` = three device uint64 words {seed, call number, 0}: the call number is advanced on the device by the
+// last CTA to finish, so a captured training step draws fresh masks at every graph replay and no host-side generator
+// (a process-wide object that cannot be drawn from while another thread captures a graph) is involved.
+namespace {
+
+__global__ void __launch_bounds__(256) keep_mask_kernel(unsigned long long *__restrict__ state, uint8_t *__restrict__ out, long long n) {
+    smz::pdl_trigger();
+    smz::pdl_wait();
+    const unsigned long long seed = state[0], call = state[1];
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const long long n_blk = (n + 127) / 128;                   // 128 mask bytes per Philox call
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < n_blk; b += (long long)gridDim.x * blockDim.x) {
+        const uint4 r = smz::philox4x32_10(make_uint4((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)call, (uint32_t)(call >> 32)), key);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+        uint8_t *dst = out + b * 128;
+        if (b * 128 + 128 <= n && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {                      // 16 bits -> 16 bytes
+                const uint32_t bits = w[q >> 1] >> ((q & 1) * 16);
+                uint32_t o[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const uint32_t nib = (bits >> (4 * t)) & 0xfu;
+                    o[t] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+                }
+                reinterpret_cast<uint4 *>(dst)[q] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        } else {
+            for (int i = 0; i < 128 && b * 128 + i < n; i++) dst[i] = (w[i >> 5] >> (i & 31)) & 1u;
+        }
+    }
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int *ticket = reinterpret_cast<unsigned int *>(state + 2);
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        if (last) { *ticket = 0u; state[1] = call + 1ull; }    // every CTA has read the call number by now
+    }
+}
+
+}  // namespace
+
+extern "C" int smz_dropout_keep_masks(uint64_t *state, uint8_t *out, int64_t n, void *stream) {
+    SMZ_REQUIRE(state && out && n >= 0, "dropout_keep_masks: bad argument");
+    if (n == 0) return SMZ_OK;
+    int rc = smz_device_check();
+    if (rc != SMZ_OK) return rc;
+    long long blocks = ((n + 127) / 128 + 255) / 256;
+    if (blocks > 4 * smz::sm_count()) blocks = 4 * smz::sm_count();
+    SMZ_CUDA_CHECK(smz::launch_pdl(keep_mask_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream,
+                                   reinterpret_cast<unsigned long long *>(state), out, (long long)n));
+    return SMZ_OK;
+}

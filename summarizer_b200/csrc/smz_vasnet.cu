@@ -25,6 +25,9 @@
 //     device-side fallback.
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "smz_gemm.cuh"
@@ -196,26 +199,33 @@ void build_problems(const Plan &pl, const int32_t *cu, bool fast, std::vector<Ge
         }
 }
 
-// Two internal streams per device: consecutive chunks run on alternating streams (each with its own copy of
-// the chunk buffers) so that the tail wave of one chunk's GEMM overlaps the next chunk's kernels.  They are
-// forked from / joined back into the caller's stream with events, so the call stays asynchronous and ordered.
+// Two internal streams per (device, caller stream): consecutive chunks run on alternating streams (each with its own
+// copy of the chunk buffers) so that the tail wave of one chunk's GEMM overlaps the next chunk's kernels; the training
+// path forks its independent GEMMs onto them.  They are forked from / joined back into the caller's stream with events,
+// so the call stays asynchronous and ordered.  Keyed by the CALLER'S STREAM, not by host thread: fold-concurrent
+// training drives one stream per fold, and torch runs every fold's backward pass on the same autograd thread — two
+// folds sharing events would tie one fold's graph capture to the other's eager work.
 struct SideStreams { cudaStream_t s[2]; cudaEvent_t fork, join[2], ev[6]; bool ok; };
-SideStreams *side_streams() {
-    static SideStreams table[64];
+SideStreams *side_streams(cudaStream_t caller) {
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, SideStreams *> table;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    SideStreams &t = table[dev];
-    if (!t.ok) {
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    SideStreams *&slot = table[std::make_pair(dev, caller)];
+    if (slot == nullptr) {
+        SideStreams *t = new SideStreams();
         for (int i = 0; i < 2; i++) {
-            if (cudaStreamCreateWithFlags(&t.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-            if (cudaEventCreateWithFlags(&t.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            if (cudaStreamCreateWithFlags(&t->s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&t->join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         }
-        if (cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&t->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         for (int i = 0; i < 6; i++)
-            if (cudaEventCreateWithFlags(&t.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        t.ok = true;
+            if (cudaEventCreateWithFlags(&t->ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        t->ok = true;
+        slot = t;
     }
-    return &t;
+    return slot;
 }
 
 GemmProblem dense_problem(int M, int N, int K, int ldc, int ldr) {
@@ -408,7 +418,7 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
     bf16 *const qk0 = qk, *const vt0 = vt, *const o0 = o, *const yn0 = yn, *const P0 = P, *const alpha0 = alpha;
     float *const y0 = y, *const h0 = h, *const S0 = S, *const stats0 = stats;
 
-    SideStreams *ss = (pl.lanes == 2 && !smz::profile_enabled()) ? side_streams() : nullptr;   // profiling: one stream
+    SideStreams *ss = (pl.lanes == 2 && !smz::profile_enabled()) ? side_streams(st) : nullptr;   // profiling: one stream
     const cudaStream_t caller = st;
     if (ss != nullptr) {
         SMZ_CUDA_CHECK(cudaEventRecord(ss->fork, caller));
@@ -452,7 +462,7 @@ extern "C" int smz_vasnet_forward(const void *x, int x_is_bf16, const int32_t *h
         }
         // Q|K projection and V^T projection
         // training (one video, a few tiles per GEMM): V^T runs beside Q|K on the side stream, joined before alpha.V
-        SideStreams *fs = (training && !smz::profile_enabled() && !smz::debug_sync_enabled()) ? side_streams() : nullptr;
+        SideStreams *fs = (training && !smz::profile_enabled() && !smz::debug_sync_enabled()) ? side_streams(caller) : nullptr;
         cudaStream_t st_v = st;
         if (fs != nullptr) {
             SMZ_CUDA_CHECK(cudaEventRecord(fs->ev[0], st));                       // x (bf16) is ready
@@ -629,7 +639,7 @@ extern "C" int smz_vasnet_backward(const void *x, int x_is_bf16, const int32_t *
     // A batch-1 backward pass is 12 GEMMs of a few tiles each: the weight-gradient GEMMs (and dV^T, dK) do not sit on the
     // dX chain, so they run on a side stream beside it — fork / join with events, which a CUDA-graph capture records as
     // parallel branches.  main: head, dYn, LN, dO, dP, softmax, dQ | side: dW1, dWo, dV^T, dWv, dK | join | dWqk, dx.
-    SideStreams *ss = (!smz::profile_enabled() && !smz::debug_sync_enabled()) ? side_streams() : nullptr;
+    SideStreams *ss = (!smz::profile_enabled() && !smz::debug_sync_enabled()) ? side_streams(st) : nullptr;
     cudaStream_t sd = ss != nullptr ? ss->s[0] : st;
     auto fork_to_side = [&](int e) -> int {                      // side stream continues after what main has queued so far
         if (ss == nullptr) return SMZ_OK;

@@ -52,6 +52,65 @@ def _cpu_state(state_dict):
     return {k: v.detach().to("cpu", copy=True) for k, v in state_dict.items()}
 
 
+def _train_jobs_concurrently(hps, models, jobs, k, rank, world):
+    """Fold-concurrent training on ONE GPU (``--extra_params concurrent_folds=K``): a batch-1 training step keeps 12-24
+    of the 148 SMs busy per GEMM, and the folds of a cross-validation are independent models (main.py:26), so K of this
+    rank's (split file, fold) jobs train side by side — K worker threads, each with its own trainer (model, optimizer,
+    per-video step graphs, resident dataset) and its own CUDA stream, pulling jobs longest-first from one queue.  No
+    result depends on the interleaving: every fold sees exactly the reference's loop.  Returns (fold_results, best) as
+    the sequential loop builds them (best fold = highest correlation, first fold on ties, with a host copy of its
+    weights)."""
+    import queue
+    import threading
+    costs = {(i, f): fold_cost(hps, models[hps.splits_files[i]], hps.splits_files[i], f) for i, f in jobs}
+    todo = queue.SimpleQueue()
+    for job in sorted(jobs, key=lambda j: (-costs[j], j)):
+        todo.put(job)
+    device = torch.cuda.current_device()
+    lock = threading.Lock()
+    fold_results, best, errors = {}, {}, []
+
+    def worker(w):
+        try:
+            torch.cuda.set_device(device)
+            stream = torch.cuda.Stream(device=device)
+            mine = dict(models) if w == 0 else {}                 # worker 0 reuses the trainers the caller built
+            with torch.cuda.stream(stream):
+                while not errors:
+                    try:
+                        i, fold = todo.get_nowait()
+                    except queue.Empty:
+                        break
+                    sf = hps.splits_files[i]
+                    if sf not in mine:
+                        mine[sf] = hps.model_class(hps, sf)
+                    model = mine[sf]
+                    corr, avg_f, max_f = model.reset().train(fold)
+                    if model.best_weights is None:
+                        raise Exception("best_weights property is empty, can't save model's weights")
+                    state = _cpu_state(model.best_weights)
+                    with lock:
+                        fold_results[(i, fold)] = (float(corr), float(avg_f), float(max_f))
+                        cur = best.get(i)
+                        if cur is None or (-float(corr), fold) < (-cur[0], cur[1]):
+                            best[i] = (float(corr), fold, state)
+                    n_folds = len(hps.splits_of_file[sf])
+                    hps.logger.info(f"File: {sf}   Fold: {fold+1}/{n_folds}   Corr: {corr: 0.5f}  "
+                                    f"Avg F-score: {avg_f:0.5f}  Max F-score: {max_f:0.5f}" + (f" (rank {rank})" if world > 1 else ""))
+                stream.synchronize()
+        except BaseException as e:                                 # surfaced by the caller: no silent loss of a fold
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(w,), name=f"smz-fold-{w}") for w in range(k)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return fold_results, best
+
+
 def train(hps):
     """Training.  Returns [(splits_file, mean corr, mean avg F, mean max F), ...] (main.py:10-72).
 
@@ -74,6 +133,13 @@ def train(hps):
 
     fold_results = {}                      # (file index, fold) -> (corr, avg F, max F)
     best = {}                              # file index -> (corr, fold, host copy of the weights)
+    concurrent = int((hps.extra_params or {}).get("concurrent_folds", 1))
+    if concurrent > 1 and not data_parallel and hps.use_cuda and len(mine) > 1:
+        fold_results, best = _train_jobs_concurrently(hps, models, mine, min(concurrent, len(mine)), rank, world)
+        if world == 1:
+            for i, (_, _, state) in best.items():
+                torch.save(state, hps.weights_path[hps.splits_files[i]])
+        mine = []
     for i, fold in mine:
         sf = hps.splits_files[i]
         n_folds = len(hps.splits_of_file[sf])

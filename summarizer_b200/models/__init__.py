@@ -6,6 +6,7 @@ device and evaluates them with the batched sm_100a kernels (shot selection + F-s
 over dataset fields that were uploaded ONCE per fold (``VideoBatch`` / ``CorrBatch``), instead of re-reading
 HDF5 and looping in Python per video (models/__init__.py:60-119)."""
 import os
+import threading
 
 import numpy as np
 import torch
@@ -62,6 +63,9 @@ def clip_grad_norm_(parameters, max_norm):
     return torch.nn.utils.clip_grad_norm_(params, max_norm)
 
 
+_CAPTURE_LOCK = threading.Lock()
+
+
 class StepGraphs:
     """Per-video optimizer steps replayed as CUDA graphs.
 
@@ -87,13 +91,21 @@ class StepGraphs:
             return step(key)
         if key not in self.graphs:
             try:
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                # the bf16 weight copies must be REBUILT INSIDE the graph: a copy cached by an eager call (e.g. test()
-                # right before) would be baked in by address and never refreshed on replay
-                self.trainer._invalidate_shadows()
-                with torch.cuda.graph(g, pool=self.pool):
-                    static = tuple(step(key))
+                # Fold-concurrent training (main._train_jobs_concurrently) runs this on a worker thread under its own
+                # stream: capture on THAT stream (torch's default capture stream is one object shared by all threads),
+                # in thread-local capture mode (other workers keep launching / allocating meanwhile), one capture at a
+                # time.  On the default stream: torch's defaults, as before.
+                cur = torch.cuda.current_stream()
+                own = cur != torch.cuda.default_stream()
+                kw = dict(stream=cur, capture_error_mode="thread_local") if own else {}
+                with _CAPTURE_LOCK:
+                    cur.synchronize() if own else torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    # the bf16 weight copies must be REBUILT INSIDE the graph: a copy cached by an eager call (e.g. test()
+                    # right before) would be baked in by address and never refreshed on replay
+                    self.trainer._invalidate_shadows()
+                    with torch.cuda.graph(g, pool=self.pool, **kw):
+                        static = tuple(step(key))
                 self.graphs[key] = (g, static)
             except Exception as e:                                # capture refused: stay eager (same kernels)
                 self.trainer.log.warning(f"CUDA graph capture failed ({type(e).__name__}: {e}); continuing without graphs")

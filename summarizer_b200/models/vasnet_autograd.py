@@ -18,12 +18,26 @@ class VasnetGrads(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("wqk", "wv", "wo", "w1", "b1", "w2", "b2", "ln_g", "ln_b", "dx")]
 
 
+def mask_state(device, seed=None):
+    """Draw state of smz_dropout_keep_masks: {Philox seed, call number, 0} as three device int64 words.  The seed comes
+    from torch's CPU generator unless given, so ``torch.manual_seed`` reproduces the masks."""
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return torch.tensor([seed, 0, 0], dtype=torch.int64, device=device)
+
+
 def draw_keep_masks(lengths, device, generator=None):
-    """KEEP masks (uint8, 1 = keep) of nn.Dropout(0.5) at the three sites, for a packed batch."""
+    """KEEP masks (uint8, 1 = keep) of nn.Dropout(0.5) at the three sites, for a packed batch.  ``generator``: a
+    ``mask_state`` tensor (the library's Philox kernel: one launch, graph-replayable, no process-wide generator — what the
+    module uses), or a torch.Generator / None (torch's generator: tests that replay masks through the float32 oracle)."""
     rows = int(sum(lengths))
     n_att = int(sum(t * t for t in lengths))
     n_att_pad = (n_att + 15) // 16 * 16                     # keeps the row masks 16-byte aligned (uchar4 loads)
-    keep = (torch.rand(n_att_pad + 2 * rows * 1024, device=device, generator=generator) >= 0.5).to(torch.uint8)   # one draw
+    if torch.is_tensor(generator):
+        keep = torch.empty(n_att_pad + 2 * rows * 1024, dtype=torch.uint8, device=device)
+        N.check(N.lib().smz_dropout_keep_masks(N.ptr(generator), N.ptr(keep), keep.numel(), N.current_stream()))
+    else:
+        keep = (torch.rand(n_att_pad + 2 * rows * 1024, device=device, generator=generator) >= 0.5).to(torch.uint8)   # one draw
     return (keep[:n_att], keep[n_att_pad:n_att_pad + rows * 1024].view(rows, 1024),
             keep[n_att_pad + rows * 1024:].view(rows, 1024))
 
@@ -87,7 +101,12 @@ def vasnet_apply(module, packed, lengths, masks="auto"):
     """scores [sum T] with autograd.  masks: "auto" draws dropout keep-masks when module.training,
     None disables dropout, or an explicit (att, y, h) tuple (tests)."""
     if masks == "auto":
-        masks = draw_keep_masks(lengths, packed.device) if module.training else None
+        if module.training:
+            if getattr(module, "_mask_state", None) is None or module._mask_state.device != packed.device:
+                module._mask_state = mask_state(packed.device)
+            masks = draw_keep_masks(lengths, packed.device, module._mask_state)
+        else:
+            masks = None
     return _VasnetFunction.apply(packed, module, list(lengths), masks, module.Q.weight, module.K.weight, module.V.weight,
                                  module.attention_head_projection.weight, module.k1.weight, module.k1.bias,
                                  module.k2.weight, module.k2.bias, module.layer_norm.weight, module.layer_norm.bias)

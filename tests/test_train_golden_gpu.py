@@ -90,7 +90,7 @@ def test_vasnet_trainer_follows_the_reference_trajectory(tmp_path, monkeypatch, 
     ret = t.train(0)
     assert step["n"] == run["epochs"] * 2
     check_scalars("vasnet", hps, ["Train/Loss"], rel=REL if precision == "bf16" else 1e-4)
-    check_scalars("vasnet", hps, ["Test/Correlation"], rel=0, abs_tol=CORR_ABS if precision == "bf16" else 1e-3)
+    check_scalars("vasnet", hps, ["Test/Correlation"], rel=0, abs_tol=CORR_ABS if precision == "bf16" else 5e-3)
     check_scalars("vasnet", hps, ["Test/F-score_avg", "Test/F-score_max"], rel=1e-6)
     np.testing.assert_allclose(np.asarray(ret, dtype=np.float64)[1:], GOLDEN["vasnet/return"][1:], rtol=1e-6)
     cos, rel = check_updates("vasnet", t.model, before, *((0.99, 0.15) if precision == "bf16" else (0.9995, 0.03)))

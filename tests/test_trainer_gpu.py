@@ -1,4 +1,5 @@
 """Trainer.test / main.train on the device against the CPU oracle evaluated on the same model scores."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -188,3 +189,30 @@ def test_reset_reuses_tensors_and_step_graphs_across_folds(tmp_path):
     # the first epoch's loss agrees up to the dropout draw
     avg_corr, (avg_f, max_f) = t.test(1)
     assert 0 <= avg_f <= max_f <= 1 and -1 <= avg_corr <= 1
+
+
+@pytest.mark.gpu
+def test_concurrent_folds_train_side_by_side(tmp_path):
+    """--extra_params concurrent_folds=3: the five folds of a split file train on three worker threads / streams of one
+    GPU (eager first visit, graph capture on the worker's stream, replay) — every fold reports, the best fold's weights
+    are written and load back, and the metrics are in the range the sequential loop gives."""
+    from summarizer_b200.main import train
+    from summarizer_b200.utils.config import HParameters
+
+    def run(extra):
+        hps = HParameters()
+        hps.log_root, hps.tensorboard = str(tmp_path / ("c" if extra else "s")), False
+        hps.load_from_args(dict(model="vasnet", use_cuda="yes", splits_files="splits/summe_splits.json", log_level="error",
+                                epochs=4, test_every_epochs=1, extra_params=extra))
+        (res,) = train(hps)
+        sf = hps.splits_files[0]
+        assert os.path.exists(hps.weights_path[sf]) and os.path.exists(hps.pred_path[sf])
+        sd = torch.load(hps.weights_path[sf])
+        assert "k1.weight" in sd and all(torch.isfinite(v).all() for v in sd.values())
+        return np.asarray(res[1:], dtype=np.float64)
+
+    seq = run({})
+    con = run({"concurrent_folds": 3})
+    assert np.isfinite(con).all() and 0 <= con[1] <= con[2] <= 1
+    # different initial weights / key orders per run: same ballpark, not equality
+    assert abs(con[1] - seq[1]) < 0.1 and abs(con[2] - seq[2]) < 0.1, (seq, con)

@@ -148,3 +148,33 @@ def test_fp32_mode_input_gradient():
     MT.vasnet_forward(sd, x[:, 0] + emb[:48], scale=m.scale, eps=m.epsilon).sum().backward()
     err = (m.pos_embed.weight.grad - emb.grad).norm().item() / emb.grad.norm().item()
     assert err < GRAD_TOL_FP32, f"positional-embedding gradient error {err:.3e}"
+
+
+def test_library_keep_masks_are_fair_bits_and_advance_on_the_device():
+    """smz_dropout_keep_masks (the module's dropout draws): 0/1 bytes, P(keep) = 1/2, independent between positions and
+    calls; the call number is bumped on the device (graph replays draw fresh masks); a seed reproduces the stream."""
+    from summarizer_b200.models.vasnet_autograd import mask_state
+    lengths = [130, 77]
+    st = mask_state(torch.device("cuda"), seed=99)
+    a = draw_keep_masks(lengths, torch.device("cuda"), st)
+    assert st.tolist() == [99, 1, 0]
+    b = draw_keep_masks(lengths, torch.device("cuda"), st)
+    assert st.tolist() == [99, 2, 0]
+    assert a[0].shape == (130 * 130 + 77 * 77,) and a[1].shape == (207, 1024) and a[2].shape == (207, 1024)
+    for m in (*a, *b):
+        assert m.dtype == torch.uint8 and int(m.max()) == 1 and int(m.min()) == 0
+    flat_a, flat_b = torch.cat([m.flatten() for m in a]).float(), torch.cat([m.flatten() for m in b]).float()
+    n = flat_a.numel()
+    for f in (flat_a, flat_b):
+        assert abs(float(f.mean()) - 0.5) < 4 * 0.5 / n ** 0.5
+    agree = float((flat_a == flat_b).float().mean())                   # independent calls agree on half the positions
+    assert abs(agree - 0.5) < 4 * 0.5 / n ** 0.5
+    lag = float((flat_a[1:] == flat_a[:-1]).float().mean())            # neighbouring bits are independent
+    assert abs(lag - 0.5) < 4 * 0.5 / n ** 0.5
+    again = draw_keep_masks(lengths, torch.device("cuda"), mask_state(torch.device("cuda"), seed=99))
+    assert all(torch.equal(x, y) for x, y in zip(a, again))
+    # tails that are not a multiple of 128 bytes / unaligned outputs
+    from summarizer_b200 import _native as N
+    buf = torch.full((1000,), 7, dtype=torch.uint8, device="cuda")
+    N.check(N.lib().smz_dropout_keep_masks(N.ptr(st), buf[3:].data_ptr(), 900, N.current_stream()))
+    assert set(buf[3:903].tolist()) == {0, 1} and set(buf[903:].tolist()) == {7} and set(buf[:3].tolist()) == {7}
