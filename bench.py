@@ -649,6 +649,8 @@ def cv_stage(dev, rank, world):
         # the same run with the folds of a rank training side by side on its GPU (main._train_jobs_concurrently)
         conc = {}
         try:
+            if world > 1:          # with several ranks per box the host cores are already shared by the ranks' interpreters
+                raise StopIteration
             k = int(os.environ.get("SMZ_BENCH_CV_CONCURRENT_FOLDS", 2))
             hps.extra_params = dict(hps.extra_params or {}, concurrent_folds=k)
             cw = []
@@ -659,6 +661,8 @@ def cv_stage(dev, rank, world):
                 torch.cuda.synchronize()
                 cw.append(time.perf_counter() - t0)
             conc = {"concurrent_folds": k, "wall_s_concurrent_folds": cw[1], "wall_s_concurrent_folds_first_pass": cw[0]}
+        except StopIteration:
+            conc = {}
         except Exception as e:
             conc = {"concurrent_folds_error": f"{type(e).__name__}: {e}"[:300]}
     finally:
