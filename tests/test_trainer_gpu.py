@@ -216,3 +216,16 @@ def test_concurrent_folds_train_side_by_side(tmp_path):
     assert np.isfinite(con).all() and 0 <= con[1] <= con[2] <= 1
     # different initial weights / key orders per run: same ballpark, not equality
     assert abs(con[1] - seq[1]) < 0.1 and abs(con[2] - seq[2]) < 0.1, (seq, con)
+
+
+@pytest.mark.gpu
+def test_concurrent_folds_dsn(tmp_path):
+    """concurrent_folds with the REINFORCE trainer: the episode draws come from per-trainer device-side Philox state, so
+    one fold capturing its step graphs does not block another fold's eager draws."""
+    hps = HParameters()
+    hps.log_root, hps.tensorboard = str(tmp_path), False
+    hps.load_from_args(dict(model="dsn", use_cuda="yes", splits_files="splits/summe_splits.json", log_level="error",
+                            epochs=3, test_every_epochs=1, extra_params={"concurrent_folds": 2}))
+    (res,) = train(hps)
+    assert np.isfinite(res[1:]).all() and 0 <= res[2] <= res[3] <= 1
+    assert os.path.exists(hps.weights_path[hps.splits_files[0]])
