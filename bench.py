@@ -369,6 +369,7 @@ def train_stage(dev, seconds=4.0):
     steps (vasnet.py:193-212: forward + MSE + backward + Adam; dsn.py:96-149: forward + 5 REINFORCE episodes with
     rewards + backward + clip + Adam) on TVSum-shaped synthetic videos, one video per optimizer step."""
     import torch
+    from summarizer_b200.models import no_gc_during_capture
     from summarizer_b200.models.dsn import DSN, compute_rewards, episode_state, sample_episodes
     from summarizer_b200.models.vasnet import VASNet
     rng = np.random.default_rng(2)
@@ -404,7 +405,7 @@ def train_stage(dev, seconds=4.0):
         for x, tgt in vids:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
+            with no_gc_during_capture(), torch.cuda.graph(g, pool=pool):
                 step(x, tgt)
             graphs.append(g)
 
@@ -417,12 +418,12 @@ def train_stage(dev, seconds=4.0):
     torch.manual_seed(0)
     vas = VASNet().to(dev).train()
     dsn = DSN().to(dev).train()
-    from summarizer_b200.optim import Adam, clip_grad_norm_
+    from summarizer_b200.optim import Adam, clip_grad_norm_, mse_loss
     opt = Adam(vas.parameters(), lr=5e-5, weight_decay=1e-5)          # the library's Adam kernel (what the trainers use)
 
     def vas_step(x, tgt):
         opt.zero_grad(set_to_none=True)
-        loss = torch.nn.functional.mse_loss(vas(x), tgt)
+        loss = mse_loss(vas(x), tgt)
         loss.backward(); opt.step()
     out["vasnet_train_frames_per_s"], out["vasnet_train_frames_per_s_eager"] = timed(vas_step)
     f_train = sum(24 * T * FEAT * FEAT + 12 * T * T * FEAT + 6 * T * FEAT for T in lens)
@@ -441,7 +442,7 @@ def train_stage(dev, seconds=4.0):
 
             def step_r(x, tgt, m_r=m_r, o_r=o_r):
                 o_r.zero_grad(set_to_none=True)
-                loss = torch.nn.functional.mse_loss(m_r(x), tgt)
+                loss = mse_loss(m_r(x), tgt)
                 loss.backward(); o_r.step()
             with torch.cuda.stream(s_r):
                 for x, tgt in vids:
@@ -451,7 +452,7 @@ def train_stage(dev, seconds=4.0):
             for x, tgt in vids:
                 g_r = torch.cuda.CUDAGraph()
                 m_r._shadow_key = None
-                with torch.cuda.graph(g_r, pool=pool_r, stream=s_r):
+                with no_gc_during_capture(), torch.cuda.graph(g_r, pool=pool_r, stream=s_r):
                     step_r(x, tgt)
                 graphs_r.append(g_r)
             reps.append((m_r, o_r, s_r, graphs_r))

@@ -185,6 +185,9 @@ int smz_grad_sqnorm(const smz_optim_tensor *tensors, int n_tensors, float *sqnor
 int smz_clip_grads(const smz_optim_tensor *tensors, int n_tensors, const float *sqnorm, float max_norm, void *stream);
 int smz_adam_step(const smz_optim_tensor *tensors, int n_tensors, double lr, double beta1, double beta2, double eps,
                   double weight_decay, void *stream);
+/* torch.nn.MSELoss() (mean reduction; vasnet.py:199,208 and the supervised baselines): loss[0] = mean((scores - target)^2)
+ * and, when dscores != NULL, dscores[i] = 2 (scores[i] - target[i]) / n in the same launch (float32, device). */
+int smz_mse_loss(const float *scores, const float *target, int64_t n, float *loss, float *dscores, void *stream);
 
 /* ---- dense building block ------------------------------------------------------------------------
  * C[M,N] = epilogue(alpha * A[M,K] * B[N,K]^T) on the tcgen05 tensor cores: A and B bfloat16, K

@@ -200,6 +200,8 @@ done:
  * numpy 2 computes in when no padding happens).  avg/max: float32 pairwise mean widened to double,
  * unless some user has overlap 0 — then the reference's list holds a Python float 0. and
  * np.mean/np.max run in float64 over the float32-valued entries (utils/eval.py:156-164).
+ * A summary shorter than n_frames is padded with float64 zeros (utils/eval.py:143-145): everything but
+ * gt_summary.sum() + 1e-8 is float64 then (f[u] holds the float32 rounding of the float64 F).
  * Returns 0. */
 int smzo_evaluate_summary(const float *machine, int64_t m_len, const float *user, int n_users,
                           int64_t n_frames, int64_t user_ld, int32_t *overlap, int32_t *gsum,
@@ -210,7 +212,9 @@ int smzo_evaluate_summary(const float *machine, int64_t m_len, const float *user
     if (msum) *msum = (int32_t)ms;
     float fs[4096];
     int any_zero = 0;
-    fs[0] = 0.f;
+    const int padded = m_len < n_frames;   /* utils/eval.py:143-145: np.zeros (float64) padding promotes the summary */
+    double fd[4096];
+    fs[0] = 0.f; fd[0] = 0.0;
     if (n_users > 4096) return -1;
     for (int u = 0; u < n_users; u++) {
         const float *g = user + (int64_t)u * user_ld;
@@ -222,6 +226,15 @@ int smzo_evaluate_summary(const float *machine, int64_t m_len, const float *user
         }
         if (overlap) overlap[u] = (int32_t)ov;
         if (gsum) gsum[u] = (int32_t)gs;
+        if (padded) {   /* float64 overlap / precision / recall / F; gt_summary.sum() + 1e-8 still float32 */
+            double dov = (double)ov;
+            double dp = dov / ((double)ms + 1e-8);
+            double dr = dov / (double)((float)gs + 1e-8f);
+            fd[u] = (dp == 0.0 && dr == 0.0) ? 0.0 : ((2.0 * dp) * dr) / (dp + dr);
+            fs[u] = (float)fd[u];
+            if (f) f[u] = fs[u];
+            continue;
+        }
         float fov = (float)ov;
         float precision = fov / ((float)ms + 1e-8f);
         float recall = fov / ((float)gs + 1e-8f);
@@ -230,6 +243,11 @@ int smzo_evaluate_summary(const float *machine, int64_t m_len, const float *user
         else any_zero = 1;
         fs[u] = fsc;
         if (f) f[u] = fsc;
+    }
+    if (padded) {
+        if (avg_f) *avg_f = n_users <= 0 ? 0.0 : pairwise_sum_f64(fd, n_users) / (double)n_users;
+        if (max_f) { double m = fd[0]; for (int u = 1; u < n_users; u++) if (fd[u] > m) m = fd[u]; *max_f = m; }
+        return 0;
     }
     if (avg_f) {
         if (n_users <= 0) *avg_f = 0.0;

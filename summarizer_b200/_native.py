@@ -79,6 +79,7 @@ SIGNATURES = {
     "smz_cvt_bf16_multi": (_I, [_P, _P, _P, _I, _P]),
     "smz_split_bf16_multi": (_I, [_P, _P, _P, _P, _I, _P]),
     "smz_dropout_keep_masks": (_I, [_P, _P, _L, _P]),
+    "smz_mse_loss": (_I, [_P, _P, _L, _P, _P, _P]),
     "smz_grad_sqnorm_workspace_floats": (_I, [_P, _I, C.POINTER(C.c_int64)]),
     "smz_grad_sqnorm": (_I, [_P, _I, _P, _P, _L, _P]),
     "smz_clip_grads": (_I, [_P, _I, _P, C.c_float, _P]),

@@ -58,7 +58,7 @@ __global__ void fscore_final_kernel(const smz_video_desc *__restrict__ desc, int
     if (v >= n_videos) return;
     const smz_video_desc d = desc[v];
     fscore_final_video(d.n_users, msum[v], overlap + d.ucount_off, gsum + d.ucount_off, f + d.ucount_off,
-                       avg_f ? avg_f + v : nullptr, max_f ? max_f + v : nullptr);
+                       avg_f ? avg_f + v : nullptr, max_f ? max_f + v : nullptr, d.summ_len < d.n_frames);
 }
 
 // utils/eval.py:136-145: binarise, truncate / zero-pad to n_frames, pack 32 frames per word

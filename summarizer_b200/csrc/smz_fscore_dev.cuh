@@ -136,10 +136,38 @@ __device__ __forceinline__ void fscore_rows_acc(const smz_video_desc &d, int f0,
     else fscore_rows_acc_impl<1, false>(d, f0, f1, user, vm, s_ov, s_gs);
 }
 
-// utils/eval.py:151-164 for ONE video in float32 (numpy 2 / NEP 50 semantics when no zero padding happened); one thread.
+// utils/eval.py:151-164 for ONE video: float32 (numpy 2 / NEP 50 semantics) when no zero padding happened, float64 when
+// the summary was shorter than n_frames (`padded`); one thread.
 // overlap / gsum: the video's per-annotator counts (any address space); f: the video's slice of the F output.
+// The float64 case of utils/eval.py:143-145: a machine summary SHORTER than n_frames is zero-padded with np.zeros (float64),
+// which promotes it — overlap, machine_summary.sum(), precision, recall and F are float64 then, while gt_summary.sum() + 1e-8
+// is still formed in float32.  F of annotator u, recomputed on demand (one thread, rare path).
+struct PaddedF64Cursor {
+    const int32_t *overlap, *gsum;
+    double ms;
+    __device__ __forceinline__ double at(int u) const {
+        const double ov = (double)overlap[u];
+        const double precision = __ddiv_rn(ov, ms);
+        const double recall = __ddiv_rn(ov, (double)__fadd_rn((float)gsum[u], 1e-8f));
+        if (precision == 0. && recall == 0.) return 0.;
+        return __ddiv_rn(__dmul_rn(__dmul_rn(2., precision), recall), __dadd_rn(precision, recall));
+    }
+};
+
 __device__ inline void fscore_final_video(int n_users, int msum, const int32_t *overlap, const int32_t *gsum, float *fv,
-                                          double *avg_f, double *max_f) {
+                                          double *avg_f, double *max_f, bool padded = false) {
+    if (padded) {
+        PaddedF64Cursor c{overlap, gsum, __dadd_rn((double)msum, 1e-8)};
+        double mx = 0.;
+        for (int u = 0; u < n_users; u++) {
+            const double fs = c.at(u);
+            fv[u] = (float)fs;
+            mx = (u == 0) ? fs : fmax(mx, fs);
+        }
+        if (avg_f) *avg_f = n_users <= 0 ? 0. : __ddiv_rn(pw_sum<double>(c, 0, n_users), (double)n_users);
+        if (max_f) *max_f = mx;
+        return;
+    }
     const float ms = __fadd_rn((float)msum, 1e-8f);
     float mx = 0.f;
     bool any_zero = false;  // a Python-float 0. entry promotes the reference's list to float64

@@ -269,3 +269,40 @@ extern "C" int smz_adam_step(const smz_optim_tensor *tensors, int n_tensors, dou
     SMZ_CUDA_CHECK(cudaGetLastError());
     return SMZ_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// torch.nn.MSELoss() of the supervised trainers (vasnet.py:199,208): loss = mean((s - t)^2) AND its gradient
+// d loss / d s = 2 (s - t) / n in one launch — torch spends six tiny kernels on the pair per step (square, mean, two fills,
+// mse_backward, a fill) in a step that is launch-bound.  One CTA, fixed summation order (bit-stable).
+namespace {
+__global__ void __launch_bounds__(1024) mse_loss_kernel(const float *__restrict__ s, const float *__restrict__ t, long long n,
+                                                         float *__restrict__ loss, float *__restrict__ ds) {
+    smz::pdl_trigger();
+    smz::pdl_wait();
+    __shared__ float red[32];
+    const float inv = 1.f / (float)n;
+    float acc = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const float d = s[i] - t[i];
+        acc = fmaf(d, d, acc);
+        if (ds != nullptr) ds[i] = 2.f * d * inv;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) loss[0] = v * inv;
+    }
+}
+}  // namespace
+
+extern "C" int smz_mse_loss(const float *scores, const float *target, int64_t n, float *loss, float *dscores, void *stream) {
+    SMZ_REQUIRE(scores && target && loss && n > 0, "mse_loss: bad argument");
+    int rc = smz_device_check();
+    if (rc != SMZ_OK) return rc;
+    SMZ_CUDA_CHECK(smz::launch_pdl(mse_loss_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, scores, target, (long long)n, loss,
+                                   dscores));
+    return SMZ_OK;
+}

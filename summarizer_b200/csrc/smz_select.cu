@@ -352,7 +352,8 @@ __device__ void eval_tail_video(const EvalTail &t, const smz_video_desc &d, int 
     }
     if (tid == 0)
         fscore_final_video(n_users, s_msum, reinterpret_cast<const int32_t *>(s_ov), reinterpret_cast<const int32_t *>(s_gs),
-                           t.f + d.ucount_off, t.avg_f ? t.avg_f + v : nullptr, t.max_f ? t.max_f + v : nullptr);
+                           t.f + d.ucount_off, t.avg_f ? t.avg_f + v : nullptr, t.max_f ? t.max_f + v : nullptr,
+                           d.summ_len < d.n_frames);
     __syncthreads();
 }
 

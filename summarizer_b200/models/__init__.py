@@ -5,8 +5,11 @@ What differs from the reference is where the work runs: ``test()`` scores the fo
 device and evaluates them with the batched sm_100a kernels (shot selection + F-score + rank correlation)
 over dataset fields that were uploaded ONCE per fold (``VideoBatch`` / ``CorrBatch``), instead of re-reading
 HDF5 and looping in Python per video (models/__init__.py:60-119)."""
+import contextlib
+import gc
 import os
 import threading
+import weakref
 
 import numpy as np
 import torch
@@ -66,6 +69,22 @@ def clip_grad_norm_(parameters, max_norm):
 _CAPTURE_LOCK = threading.Lock()
 
 
+@contextlib.contextmanager
+def no_gc_during_capture():
+    """Python's cyclic garbage collector must not run while a stream capture is open: it can run in ANY thread that
+    executes Python (the autograd thread runs the custom Functions' backward) and finalise a ``torch.cuda.CUDAGraph`` left
+    in a reference cycle by an earlier fold / trainer — ``cudaGraphExecDestroy`` inside a global-mode capture invalidates
+    it ("operation failed due to a previous error during capture"; ``torch.cuda.graph`` no longer collects up front).
+    The collector is switched off for the duration of the capture (process-wide, a few milliseconds)."""
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
+
+
 class StepGraphs:
     """Per-video optimizer steps replayed as CUDA graphs.
 
@@ -77,7 +96,9 @@ class StepGraphs:
     return a tuple of tensors; replays hand back clones of them.  Same kernels and arithmetic as the eager step."""
 
     def __init__(self, trainer, enabled):
-        self.trainer, self.enabled = trainer, bool(enabled)
+        # a weak reference: trainer -> StepGraphs -> trainer would keep the CUDA graphs alive until a cyclic collection,
+        # i.e. destroy them at an arbitrary later time (see no_gc_during_capture)
+        self.trainer, self.enabled = (weakref.proxy(trainer) if trainer is not None else None), bool(enabled)
         self.graphs, self.seen = {}, set()
         # ONE graph memory pool per trainer, reused fold after fold: a fresh pool per fold meant a round of cudaMalloc /
         # cudaFree per fold, which serialises on the driver when several ranks of a box train folds side by side
@@ -98,7 +119,7 @@ class StepGraphs:
                 cur = torch.cuda.current_stream()
                 own = cur != torch.cuda.default_stream()
                 kw = dict(stream=cur, capture_error_mode="thread_local") if own else {}
-                with _CAPTURE_LOCK:
+                with _CAPTURE_LOCK, no_gc_during_capture():
                     cur.synchronize() if own else torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
                     # the bf16 weight copies must be REBUILT INSIDE the graph: a copy cached by an eager call (e.g. test()
@@ -341,7 +362,7 @@ class Trainer:
         self.model.train()
         train_keys, _ = self._get_train_test_keys(fold)
         self.draw_gtscores(fold, train_keys)
-        criterion = torch.nn.MSELoss()
+        from ..optim import mse_loss as criterion                 # torch.nn.MSELoss() in one launch with its gradient
         params = [p for p in self.model.parameters() if p.requires_grad] if optimizer_params is None else optimizer_params
         # same update rule as the reference's torch.optim.Adam (L2 term in the gradient), one multi-tensor kernel of the
         # library on the device (make_adam)

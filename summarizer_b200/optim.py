@@ -101,3 +101,32 @@ class Adam(torch.optim.Optimizer):
             for k in ("step", "exp_avg", "exp_avg_sq"):
                 if k in s:
                     s[k].zero_()
+
+
+class _MseLoss(torch.autograd.Function):
+    """mean((scores - target)^2) and its gradient w.r.t. the scores in one launch (smz_mse_loss)."""
+
+    @staticmethod
+    def forward(ctx, scores, target):
+        s = scores.detach().reshape(-1).contiguous()
+        t = target.detach().reshape(-1).contiguous()
+        loss = torch.empty((), dtype=torch.float32, device=s.device)
+        ds = torch.empty_like(s)
+        N.check(N.lib().smz_mse_loss(N.ptr(s), N.ptr(t), s.numel(), N.ptr(loss), N.ptr(ds), N.current_stream()))
+        ctx.save_for_backward(ds)
+        ctx.shape = scores.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad):
+        (ds,) = ctx.saved_tensors
+        return (ds * grad).reshape(ctx.shape), None
+
+
+def mse_loss(scores, target):
+    """``torch.nn.MSELoss()(scores, target)`` (the supervised trainers' criterion, vasnet.py:199,208) on the library's kernel
+    for float32 CUDA tensors of equal shape whose target needs no gradient; torch's implementation otherwise."""
+    if (scores.is_cuda and scores.dtype == torch.float32 and target.dtype == torch.float32 and target.is_cuda
+            and scores.shape == target.shape and not target.requires_grad and scores.numel() > 0):
+        return _MseLoss.apply(scores, target)
+    return torch.nn.functional.mse_loss(scores, target)

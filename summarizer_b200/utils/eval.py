@@ -87,19 +87,6 @@ def generate_summary(scores, cps, n_frames, nfps, positions, proportion=0.15, me
     return b.summary_of(0).cpu().numpy()
 
 
-def _fscores_padded(overlap, msum, gsum):
-    """utils/eval.py:151-159 for the one case numpy runs in float64: the machine summary was shorter
-    than n_frames, so np.concatenate with np.zeros (float64) promoted it (utils/eval.py:143-145);
-    ``gt_summary.sum() + 1e-8`` is still evaluated in float32 first."""
-    out = []
-    for ov, gs in zip(overlap.tolist(), gsum.tolist()):
-        precision = np.float64(ov) / (np.float64(msum) + 1e-8)
-        recall = np.float64(ov) / np.float64(np.float32(gs) + np.float32(1e-8))
-        out.append(np.float64(0.0) if (precision == 0 and recall == 0)
-                   else (2 * precision * recall) / (precision + recall))
-    return out
-
-
 def evaluate_summary(machine_summary, user_summary):
     """Compare machine summary with user summary (keyshot-based) (utils/eval.py:125-165).
     Input
@@ -121,10 +108,9 @@ def evaluate_summary(machine_summary, user_summary):
     b.pack_summary(torch.from_numpy(machine) if machine.size else torch.zeros(1))
     b.fscore()
     overlap = b.overlap[:n_users].cpu().numpy()
-    if machine.size < n_frames:
-        f = _fscores_padded(overlap, int(b.msum[0]), b.gsum[:n_users].cpu().numpy())
-        return np.mean(f), np.max(f)
     avg_f, max_f = b.avg_f[0].item(), b.max_f[0].item()
+    if machine.size < n_frames:       # zero-padded with float64 zeros (utils/eval.py:143-145): the kernel's float64 branch
+        return np.float64(avg_f), np.float64(max_f)
     if (overlap == 0).any():          # the reference's list then holds a Python 0. -> float64 results
         return np.float64(avg_f), np.float64(max_f)
     return np.float32(avg_f), np.float32(max_f)

@@ -99,12 +99,10 @@ def _check_batch_against_oracle(videos, scores_list, method="knapsack", pad_user
             assert np.array_equal(gsum[uo:uo + nu], r["gsum"]), i
             assert f[uo:uo + nu].tobytes() == r["f"].tobytes(), i
             assert avg_f[i] == r["avg_f"] and max_f[i] == r["max_f"], i
-            # and the numpy restatement (which follows numpy's dtype promotion) agrees
-            # (not for summaries shorter than n_frames: there numpy promotes to float64, which
-            #  only the per-video wrapper reproduces — the batched kernel stays in float32)
-            if sl >= nf:
-                a2, m2 = E.evaluate_summary(ref_sum, v["user_summary"])
-                assert _same(avg_f[i], a2) and _same(max_f[i], m2), i
+            # and the numpy restatement (which follows numpy's dtype promotion, including the float64 case of a
+            # summary shorter than n_frames, utils/eval.py:143-145) agrees
+            a2, m2 = E.evaluate_summary(ref_sum, v["user_summary"])
+            assert _same(avg_f[i], a2) and _same(max_f[i], m2), i
     return b
 
 

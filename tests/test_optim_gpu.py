@@ -84,3 +84,23 @@ def test_rejects_non_float32_or_cpu():
         O.Adam([p]).step()
     with pytest.raises(Exception):
         O.clip_grad_norm_([p], 1.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 45, 1000, 4097])
+def test_mse_loss_matches_torch(n):
+    """optim.mse_loss (smz_mse_loss: loss and gradient in one launch) vs torch.nn.MSELoss() and its autograd."""
+    from summarizer_b200.optim import mse_loss
+    g = torch.Generator(device="cuda"); g.manual_seed(n)
+    s = torch.rand(n, 1, 1, generator=g, device="cuda", requires_grad=True)
+    t = torch.rand(n, 1, 1, generator=g, device="cuda")
+    s_ref = s.detach().clone().requires_grad_(True)
+    loss = mse_loss(s, t)
+    ref = torch.nn.MSELoss()(s_ref, t)
+    (3.0 * loss).backward(); (3.0 * ref).backward()
+    assert loss.shape == ref.shape == ()
+    assert torch.allclose(loss, ref, rtol=1e-6, atol=0)
+    assert torch.allclose(s.grad, s_ref.grad, rtol=1e-6, atol=1e-12)
+    # shapes torch would broadcast, or a target that needs a gradient: torch's implementation
+    t2 = t.clone().requires_grad_(True)
+    assert torch.allclose(mse_loss(s.detach(), t2), torch.nn.functional.mse_loss(s.detach(), t2))
