@@ -1270,6 +1270,13 @@ static int select_plan(int n_videos, int max_n_segs, int max_capacity, int max_n
                 plan->kw16 = kw; plan->mk16 = mk; plan->smem16_bytes = smem16;
                 const int g16 = smz::sm_count() * per_sm16;
                 plan->grid16 = n_videos < g16 ? n_videos : g16;
+                // More videos than resident CTAs: every CTA works through ceil(n / grid) videos of near-equal cost, so a
+                // grid that does not divide n leaves a last round in which part of the CTAs idle (10 000 videos on 740
+                // CTAs: 13.5 rounds).  Shrink the grid to the smallest one with the same number of rounds.
+                if (n_videos > g16 && !getenv("SMZ_EVAL_FULL_GRID")) {
+                    const int rounds = (n_videos + g16 - 1) / g16;
+                    plan->grid16 = (n_videos + rounds - 1) / rounds;
+                }
                 plan->ws16_words_per_cta = (int64_t)((max_n_segs + 15) / 16) * kw * DP_THREADS;
             }
         }
