@@ -429,53 +429,77 @@ def train_stage(dev, seconds=4.0):
     f_train = sum(24 * T * FEAT * FEAT + 12 * T * T * FEAT + 6 * T * FEAT for T in lens)
     out["vasnet_train_tflops"] = out["vasnet_train_frames_per_s"] / sum(lens) * f_train / 1e12
 
-    # Fold-concurrent training: a batch-1 step keeps 12-24 of the 148 SMs busy per GEMM, so the folds of a cross-validation
-    # (independent models, BASELINE config 3) train side by side on ONE GPU — K replicas (own weights, optimizer, graphs),
-    # one stream each, replayed round-robin from one host thread.  Aggregate frames/s over the K folds.
+    # Fold-concurrent training: a batch-1 step keeps 12-24 of the 148 SMs busy per GEMM (DSN: 16 CTAs per recurrence), so the
+    # folds of a cross-validation (independent models, BASELINE config 3) train side by side on ONE GPU — K replicas (own
+    # weights, optimizer, graphs), one stream each, replayed round-robin from one host thread.  Aggregate frames/s over the K folds.
     K = int(os.environ.get("SMZ_BENCH_CONCURRENT_FOLDS", 4))
-    try:
-        reps = []
-        for r in range(K):
-            m_r = VASNet().to(dev).train()
-            o_r = Adam(m_r.parameters(), lr=5e-5, weight_decay=1e-5)
-            s_r = torch.cuda.Stream(device=dev)
 
-            def step_r(x, tgt, m_r=m_r, o_r=o_r):
-                o_r.zero_grad(set_to_none=True)
-                loss = mse_loss(m_r(x), tgt)
-                loss.backward(); o_r.step()
-            with torch.cuda.stream(s_r):
+    def concurrent_folds(make_replica, k_folds):
+        """make_replica() -> (step(x, tgt), module): aggregate frames/s of k_folds replicas replayed on k_folds streams."""
+        try:
+            reps = []
+            for r in range(k_folds):
+                step_r, m_r = make_replica()
+                s_r = torch.cuda.Stream(device=dev)
+                with torch.cuda.stream(s_r):
+                    for x, tgt in vids:
+                        step_r(x, tgt)
+                torch.cuda.synchronize()
+                pool_r, graphs_r = torch.cuda.graph_pool_handle(), []
                 for x, tgt in vids:
-                    step_r(x, tgt)
-            torch.cuda.synchronize()
-            pool_r, graphs_r = torch.cuda.graph_pool_handle(), []
-            for x, tgt in vids:
-                g_r = torch.cuda.CUDAGraph()
-                m_r._shadow_key = None
-                with no_gc_during_capture(), torch.cuda.graph(g_r, pool=pool_r, stream=s_r):
-                    step_r(x, tgt)
-                graphs_r.append(g_r)
-            reps.append((m_r, o_r, s_r, graphs_r))
-
-        def all_folds_pass():
-            for k in range(len(vids)):
-                for r, (m_r, _, s_r, graphs_r) in enumerate(reps):
-                    with torch.cuda.stream(s_r):
-                        graphs_r[(k + 5 * r) % len(vids)].replay()      # the folds are at different videos at any time
+                    g_r = torch.cuda.CUDAGraph()
                     m_r._shadow_key = None
-        all_folds_pass()
-        torch.cuda.synchronize()
-        t0, n = time.perf_counter(), 0
-        while time.perf_counter() - t0 < seconds / 2:
+                    with no_gc_during_capture(), torch.cuda.graph(g_r, pool=pool_r, stream=s_r):
+                        step_r(x, tgt)
+                    graphs_r.append(g_r)
+                reps.append((m_r, step_r, s_r, graphs_r))
+
+            def all_folds_pass():
+                for k in range(len(vids)):
+                    for r, (m_r, _, s_r, graphs_r) in enumerate(reps):
+                        with torch.cuda.stream(s_r):
+                            graphs_r[(k + 5 * r) % len(vids)].replay()      # the folds are at different videos at any time
+                        m_r._shadow_key = None
             all_folds_pass()
-            n += 1
-        torch.cuda.synchronize()
-        out["vasnet_train_concurrent_folds"] = {"folds": K, "frames_per_s": n * K * sum(lens) / (time.perf_counter() - t0),
-                                                "what": "K independent folds (model + optimizer + step graphs each) on K streams of this GPU, "
-                                                        "aggregate rate, wall clock around synchronised replay loops"}
-        del reps
-    except Exception as e:          # secondary number: never cost the line
-        out["vasnet_train_concurrent_folds"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.synchronize()
+            t0, n = time.perf_counter(), 0
+            while time.perf_counter() - t0 < seconds / 2:
+                all_folds_pass()
+                n += 1
+            torch.cuda.synchronize()
+            res = {"folds": k_folds, "frames_per_s": n * k_folds * sum(lens) / (time.perf_counter() - t0),
+                   "what": "K independent folds (model + optimizer + step graphs each) on K streams of this GPU, "
+                           "aggregate rate, wall clock around synchronised replay loops"}
+            del reps
+            return res
+        except Exception as e:          # secondary number: never cost the line
+            return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    def vasnet_replica():
+        m_r = VASNet().to(dev).train()
+        o_r = Adam(m_r.parameters(), lr=5e-5, weight_decay=1e-5)
+
+        def step_r(x, tgt):
+            o_r.zero_grad(set_to_none=True)
+            loss = mse_loss(m_r(x), tgt)
+            loss.backward(); o_r.step()
+        return step_r, m_r
+    out["vasnet_train_concurrent_folds"] = concurrent_folds(vasnet_replica, K)
+
+    def dsn_replica():
+        m_r = DSN().to(dev).train()
+        o_r = Adam(m_r.parameters(), lr=5e-5, weight_decay=1e-5)
+        rng_r, base_r = episode_state(dev), torch.zeros((), device=dev)
+
+        def step_r(x, tgt):
+            o_r.zero_grad(set_to_none=True)
+            probs = m_r(x)
+            log_probs, actions = sample_episodes(probs, 5, rng_r)
+            rewards = compute_rewards(x, actions)
+            loss = -(log_probs * (rewards - base_r)).sum() / 5.
+            loss.backward(); clip_grad_norm_(list(m_r.parameters()), 5.0); o_r.step()
+        return step_r, m_r
+    out["dsn_reinforce_concurrent_folds"] = concurrent_folds(dsn_replica, 2 * K)
 
     opt2 = Adam(dsn.parameters(), lr=5e-5, weight_decay=1e-5)
     base = torch.zeros((), device=dev)

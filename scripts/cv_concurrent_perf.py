@@ -5,12 +5,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from summarizer_b200 import main as M, synthetic
 from summarizer_b200.utils.config import HParameters
 epochs = int(os.environ.get("EPOCHS", 60))
+model = os.environ.get("MODEL", "vasnet")
 cache = {n: synthetic.make_dataset(n) for n in ("tvsum", "summe")}
 synthetic.make_dataset = lambda name, *a, **k: cache[name]
-out = {"epochs": epochs}
+out = {"epochs": epochs, "model": model}
 for k in [1] + [int(x) for x in os.environ.get("KS", "2,4").split(",")]:
     hps = HParameters()
-    hps.load_from_args({"use_cuda": "yes", "cuda_device": 0, "model": "vasnet", "epochs": epochs, "test_every_epochs": max(epochs // 3, 1),
+    hps.load_from_args({"use_cuda": "yes", "cuda_device": 0, "model": model, "epochs": epochs, "test_every_epochs": max(epochs // 3, 1),
                         "splits_files": "splits/tvsum_splits.json,splits/summe_splits.json", "log_level": "error",
                         "log_root": tempfile.mkdtemp(prefix="smz_cv_"), "tensorboard": False,
                         "extra_params": {"concurrent_folds": k} if k > 1 else {}})
