@@ -931,7 +931,7 @@ def run_native(args):
         hbm, tf_sus, tf_burst, which = peaks()
         traffic = None       # DRAM bytes of the scoring stage per step, from the committed ncu capture (per video x videos)
         try:
-            with open(os.path.join(ROOT, "profiles", "r02e_scoring_stage_dram_traffic.json")) as fh:
+            with open(os.path.join(ROOT, "profiles", "r02i_scoring_stage_dram_traffic.json")) as fh:
                 traffic = float(json.load(fh)["dram_bytes_per_video"]) * V
         except Exception:
             pass
@@ -960,7 +960,7 @@ def run_native(args):
                          "flops_note": "achieved / frac count the ALGORITHMIC flops of the reference's forward (SURVEY 8d: 10TD^2 + "
                                        "4T^2D); the fast path executes 6TD^2 + 4T^2D (K and output projections folded into the "
                                        "weights) - frac_executed is the tensor-pipe utilisation", "traffic": traffic,
-                         "traffic_source": "profiles/r02e_scoring_stage_dram_traffic.json: ncu dram__bytes_read+write of every kernel of the "
+                         "traffic_source": "profiles/r02i_scoring_stage_dram_traffic.json: ncu dram__bytes_read+write of every kernel of the "
                                            "stage on 64 videos, per video x videos (47.9 MB per video; 4.1 MB of it is the input); a committed "
                                            "capture of this code, not a counter of this run",
                          "peak_source": which + " (sustained)",
