@@ -66,16 +66,20 @@ def _train_jobs_concurrently(hps, models, jobs, k, rank, world):
     todo = queue.SimpleQueue()
     for job in sorted(jobs, key=lambda j: (-costs[j], j)):
         todo.put(job)
-    device = torch.cuda.current_device()
+    import contextlib
+    on_gpu = bool(hps.use_cuda) and torch.cuda.is_available()     # host-only models (Rand / Logistic on the CPU): plain threads
+    device = torch.cuda.current_device() if on_gpu else None
     lock = threading.Lock()
     fold_results, best, errors = {}, {}, []
 
     def worker(w):
         try:
-            torch.cuda.set_device(device)
-            stream = torch.cuda.Stream(device=device)
+            stream = None
+            if on_gpu:
+                torch.cuda.set_device(device)
+                stream = torch.cuda.Stream(device=device)
             mine = dict(models) if w == 0 else {}                 # worker 0 reuses the trainers the caller built
-            with torch.cuda.stream(stream):
+            with (torch.cuda.stream(stream) if on_gpu else contextlib.nullcontext()):
                 while not errors:
                     try:
                         i, fold = todo.get_nowait()
@@ -97,7 +101,8 @@ def _train_jobs_concurrently(hps, models, jobs, k, rank, world):
                     n_folds = len(hps.splits_of_file[sf])
                     hps.logger.info(f"File: {sf}   Fold: {fold+1}/{n_folds}   Corr: {corr: 0.5f}  "
                                     f"Avg F-score: {avg_f:0.5f}  Max F-score: {max_f:0.5f}" + (f" (rank {rank})" if world > 1 else ""))
-                stream.synchronize()
+                if stream is not None:
+                    stream.synchronize()
         except BaseException as e:                                 # surfaced by the caller: no silent loss of a fold
             errors.append(e)
 
@@ -134,7 +139,7 @@ def train(hps):
     fold_results = {}                      # (file index, fold) -> (corr, avg F, max F)
     best = {}                              # file index -> (corr, fold, host copy of the weights)
     concurrent = int((hps.extra_params or {}).get("concurrent_folds", 1))
-    if concurrent > 1 and not data_parallel and hps.use_cuda and len(mine) > 1:
+    if concurrent > 1 and not data_parallel and len(mine) > 1:
         fold_results, best = _train_jobs_concurrently(hps, models, mine, min(concurrent, len(mine)), rank, world)
         if world == 1:
             for i, (_, _, state) in best.items():

@@ -148,3 +148,52 @@ def test_step_graphs_disabled_is_plain_eager():
     for key in ("a", "b", "a", "a"):
         assert g.run(key, lambda k: (calls.append(k) or (k,))) == (key,)
     assert calls == ["a", "b", "a", "a"] and g.graphs == {} and g.pool is None
+
+
+def test_concurrent_fold_runner_schedules_reports_and_propagates_errors():
+    """main._train_jobs_concurrently (--extra_params concurrent_folds=K) with stand-in trainers on the CPU: every
+    (split file, fold) job runs exactly once, heaviest first; the best fold per file is the highest correlation with the
+    FIRST fold on ties (main.py:33-35) and carries a host copy of its weights; a failing fold surfaces as the caller's
+    exception."""
+    import logging
+    import threading
+    import time
+    import types
+    import torch
+    from summarizer_b200 import main as M
+    started, lock = [], threading.Lock()
+    corr = {(0, 0): 0.2, (0, 1): 0.7, (0, 2): 0.7, (1, 0): 0.1, (1, 1): -0.3}
+
+    class FakeTrainer:
+        def __init__(self, hps, sf):
+            self.sf, self.i = sf, hps.splits_files.index(sf)
+            self.dataset = {f"v{k}": {"features": np.zeros((10 * (k + 1) * (self.i + 1), 4))} for k in range(3)}
+            self.best_weights = None
+
+        def reset(self):
+            return self
+
+        def train(self, fold):
+            with lock:
+                started.append((self.i, fold))
+            if hps.fail_on == (self.i, fold):
+                raise RuntimeError("fold blew up")
+            time.sleep(0.01)
+            self.best_weights = {"w": torch.full((2,), float(10 * self.i + fold))}
+            return corr[(self.i, fold)], 0.5, 0.6
+
+    hps = types.SimpleNamespace(splits_files=["a.json", "b.json"], epochs=2, use_cuda=False, fail_on=None,
+                                logger=logging.getLogger("test"), model_class=FakeTrainer,
+                                splits_of_file={"a.json": [{"train_keys": ["v0", "v1", "v2"]}, {"train_keys": ["v0"]}, {"train_keys": ["v1"]}],
+                                                "b.json": [{"train_keys": ["v2"]}, {"train_keys": ["v0", "v2"]}]})
+    models = {sf: FakeTrainer(hps, sf) for sf in hps.splits_files}
+    jobs = [(0, 0), (0, 1), (0, 2), (1, 0), (1, 1)]
+    res, best = M._train_jobs_concurrently(hps, models, jobs, 3, 0, 1)
+    assert sorted(started) == jobs and set(res) == set(jobs)
+    assert started[0] == (1, 1)                                   # heaviest job first: 2 epochs x (20 + 60) frames
+    assert res[(0, 1)] == (0.7, 0.5, 0.6)
+    assert best[0][:2] == (0.7, 1) and best[1][:2] == (0.1, 0)    # tie between folds 1 and 2 of file 0 -> the first
+    assert torch.equal(best[0][2]["w"], torch.full((2,), 1.0)) and torch.equal(best[1][2]["w"], torch.full((2,), 10.0))
+    hps.fail_on = (0, 2)
+    with pytest.raises(RuntimeError, match="fold blew up"):
+        M._train_jobs_concurrently(hps, models, jobs, 2, 0, 1)
