@@ -639,6 +639,45 @@ def train_dp_stage(dev, rank, world, dist, seconds=3.0):
            "ms_per_step": t.item() / n_steps, "allreduce_ms": float(np.median(ar_ms)), "allreduce_mb": flat.numel() * 4 / 1e6,
            "gradients_equal_across_ranks": replicas_equal, "what": "eager step: forward + MSE + backward (smz kernels), one "
            "NCCL all-reduce of the flat gradient buffer, the library's Adam kernel; every rank a different video"}
+    # The same step as ONE CUDA graph per video, the NCCL all-reduce captured inside it (thread-local capture mode: NCCL's
+    # watchdog thread polls events): what the data-parallel trainers replay from the second visit of a video on.
+    try:
+        if os.environ.get("SMZ_BENCH_DP_GRAPH", "0") != "1":     # measured on 2 GPUs (profiles/r02i_train_dp_graph_n2.json); opt-in:
+            raise StopIteration                                   # a collective inside a capture cannot be bounded by a timeout
+        from summarizer_b200.models import no_gc_during_capture
+        s_cap = torch.cuda.Stream(device=dev)
+        graphs = []
+        torch.cuda.synchronize(); dist.barrier()
+        for k in range(len(vids)):
+            gk = torch.cuda.CUDAGraph()
+            vas._shadow_key = None
+            with no_gc_during_capture(), torch.cuda.graph(gk, stream=s_cap, capture_error_mode="thread_local"):
+                step(k)
+            graphs.append(gk)
+        for k in range(4):
+            graphs[k].replay(); vas._shadow_key = None
+        torch.cuda.synchronize(); dist.barrier()
+        e0.record()
+        frames = 0
+        for k in range(n_steps):
+            graphs[k % len(vids)].replay(); vas._shadow_key = None
+            frames += vids[k % len(vids)][0].shape[0]
+        e1.record(); torch.cuda.synchronize()
+        tg = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        same = flat.clone(); dist.all_reduce(same, op=dist.ReduceOp.MAX)
+        chk = torch.stack([p.detach().float().abs().sum() for p in params]).sum().reshape(1).double()
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        out["graph"] = {"frames_per_s": frames * world / (tg.item() / 1e3), "ms_per_step": tg.item() / n_steps,
+                        "gradients_equal_across_ranks": bool(torch.equal(same, flat)),
+                        "weights_equal_across_ranks": bool(lo.item() == hi.item()),
+                        "what": "the whole step incl. the NCCL all-reduce replayed as one CUDA graph per video"}
+        del graphs
+    except StopIteration:
+        pass
+    except Exception as e:
+        out["graph"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     del vas, opt, flat
     return out
 

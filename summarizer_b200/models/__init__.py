@@ -95,7 +95,10 @@ class StepGraphs:
     ``set_to_none=True`` first, forward, loss, backward, optimizer step, in-place updates of persistent tensors) and
     return a tuple of tensors; replays hand back clones of them.  Same kernels and arithmetic as the eager step."""
 
-    def __init__(self, trainer, enabled):
+    def __init__(self, trainer, enabled, isolated=False):
+        # isolated: always capture in thread-local mode (data-parallel steps hold an NCCL collective, and NCCL's watchdog
+        # thread polls events — a "potentially unsafe" call for a global-mode capture)
+        self.isolated = bool(isolated)
         # a weak reference: trainer -> StepGraphs -> trainer would keep the CUDA graphs alive until a cyclic collection,
         # i.e. destroy them at an arbitrary later time (see no_gc_during_capture)
         self.trainer, self.enabled = (weakref.proxy(trainer) if trainer is not None else None), bool(enabled)
@@ -118,7 +121,8 @@ class StepGraphs:
                 # time.  On the default stream: torch's defaults, as before.
                 cur = torch.cuda.current_stream()
                 own = cur != torch.cuda.default_stream()
-                kw = dict(stream=cur, capture_error_mode="thread_local") if own else {}
+                kw = dict(stream=cur, capture_error_mode="thread_local") if own else (
+                    dict(capture_error_mode="thread_local") if self.isolated else {})
                 with _CAPTURE_LOCK, no_gc_during_capture():
                     cur.synchronize() if own else torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
@@ -371,7 +375,14 @@ class Trainer:
         # from the second visit of a video on, its whole step (forward, loss, backward, Adam) is replayed as ONE CUDA
         # graph (StepGraphs); `--cuda_graphs no` keeps it eager
         ep = self.hps.extra_params or {}
-        use_graphs = (fused and dist is None and getattr(self.model, "max_length", None) is None
+        # Data-parallel mode: the step can be replayed as a graph with the NCCL all-reduce captured INSIDE it
+        # (`--extra_params dp_cuda_graphs=yes`; 2 B200s: 5.3 s -> 1.5 s for a 12-epoch TVSum cross-validation, replicas
+        # identical).  OPT-IN: replicas capture at different steps (their own second visit of a video), and whether NCCL's
+        # graph-time buffer registration tolerates that on every topology (NVLS on 8 GPUs) has not been established —
+        # the default keeps data-parallel steps eager.
+        dp_graphable = dist is None or (str(dist.get_backend()).lower() == "nccl"
+                                        and str(ep.get("dp_cuda_graphs", "no")).lower() in ("yes", "1", "true"))
+        use_graphs = (fused and dp_graphable and getattr(self.model, "max_length", None) is None
                       and str(ep.get("cuda_graphs", "yes")).lower() not in ("no", "0", "false"))
         opt_key = (tuple(id(p) for p in params), float(self.hps.lr), float(self.hps.weight_decay), fused, use_graphs)
         if use_graphs and getattr(self, "_opt_key", None) == opt_key and getattr(self, "_step_graphs", None) is not None:
@@ -384,7 +395,7 @@ class Trainer:
             graphs = self._step_graphs
         else:
             self.optimizer = make_adam(params, self.hps.lr, self.hps.weight_decay, capturable=use_graphs) if params else None
-            graphs = StepGraphs(self, use_graphs)
+            graphs = StepGraphs(self, use_graphs, isolated=dist is not None)
             self._step_graphs, self._opt_key = (graphs, opt_key) if use_graphs else (None, None)
         best_corr, best_avg_f_score, best_max_f_score = -1.0, 0.0, 0.0
         if dist is not None:
@@ -404,6 +415,14 @@ class Trainer:
             self.optimizer.step()
             return out
 
+        def full_step_dp(job):                                   # data parallel: (video of this replica, replicas with a video)
+            key, n_active = job
+            self.optimizer.zero_grad(set_to_none=False)          # gradients stay views of the flat all-reduce buffer
+            out = forward_backward(key)
+            self._dp_allreduce_grads(dist, params, n_active)
+            self.optimizer.step()
+            return out
+
         for epoch in range(self.hps.epochs):
             losses, dist_scores = [], {}
             if dist is not None:
@@ -413,8 +432,18 @@ class Trainer:
             for i in range(0, len(train_keys), world):
                 group = train_keys[i:i + world]                  # one video per replica and optimizer step
                 key = group[rank] if rank < len(group) else None
-                if use_graphs:
+                if use_graphs and dist is None:
                     loss, scores = graphs.run(key, full_step)
+                    losses.append(loss)
+                    dist_scores[key] = scores
+                    continue
+                if use_graphs and key is not None:
+                    # one graph per (video, group size) on this replica: forward, loss, backward, the NCCL all-reduce of the
+                    # flat gradient buffer and Adam.  Replicas capture at different steps (their own second visit of a
+                    # video); a capture only records, the replay right behind it executes — every replica still issues
+                    # exactly one all-reduce per step, eager or replayed.  A replica without a video (last, partial group)
+                    # takes the eager path below.
+                    loss, scores = graphs.run((key, len(group)), full_step_dp)
                     losses.append(loss)
                     dist_scores[key] = scores
                     continue
