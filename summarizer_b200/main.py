@@ -53,7 +53,7 @@ def _cpu_state(state_dict):
 
 
 def _train_jobs_concurrently(hps, models, jobs, k, rank, world):
-    """Fold-concurrent training on ONE GPU (``--extra_params concurrent_folds=K``): a batch-1 training step keeps 12-24
+    """Fold-concurrent training on ONE GPU (``--concurrent_folds K``): a batch-1 training step keeps 12-24
     of the 148 SMs busy per GEMM, and the folds of a cross-validation are independent models (main.py:26), so K of this
     rank's (split file, fold) jobs train side by side — K worker threads, each with its own trainer (model, optimizer,
     per-video step graphs, resident dataset) and its own CUDA stream, pulling jobs longest-first from one queue.  No

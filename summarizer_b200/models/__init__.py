@@ -376,7 +376,7 @@ class Trainer:
         # graph (StepGraphs); `--cuda_graphs no` keeps it eager
         ep = self.hps.extra_params or {}
         # Data-parallel mode: the step can be replayed as a graph with the NCCL all-reduce captured INSIDE it
-        # (`--extra_params dp_cuda_graphs=yes`; 2 B200s: 5.3 s -> 1.5 s for a 12-epoch TVSum cross-validation, replicas
+        # (`--dp_cuda_graphs yes`; 2 B200s: 5.3 s -> 1.5 s for a 12-epoch TVSum cross-validation, replicas
         # identical).  OPT-IN: replicas capture at different steps (their own second visit of a video), and whether NCCL's
         # graph-time buffer registration tolerates that on every topology (NVLS on 8 GPUs) has not been established —
         # the default keeps data-parallel steps eager.

@@ -151,7 +151,7 @@ def test_step_graphs_disabled_is_plain_eager():
 
 
 def test_concurrent_fold_runner_schedules_reports_and_propagates_errors():
-    """main._train_jobs_concurrently (--extra_params concurrent_folds=K) with stand-in trainers on the CPU: every
+    """main._train_jobs_concurrently (--concurrent_folds K) with stand-in trainers on the CPU: every
     (split file, fold) job runs exactly once, heaviest first; the best fold per file is the highest correlation with the
     FIRST fold on ties (main.py:33-35) and carries a host copy of its weights; a failing fold surfaces as the caller's
     exception."""

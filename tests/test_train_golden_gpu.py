@@ -70,7 +70,7 @@ def check_updates(name, model, before, min_cos, max_rel):
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
 def test_vasnet_trainer_follows_the_reference_trajectory(tmp_path, monkeypatch, precision):
-    """precision="fp32" (split-bf16 operands, --extra_params precision=fp32): the same trajectory at the float32 bar —
+    """precision="fp32" (split-bf16 operands, --precision fp32): the same trajectory at the float32 bar —
     losses to 1e-4, Adam updates to 2 % (Adam's first steps are sign-like: lr * g / (|g| + eps), so entries whose
     gradient is ~0 amplify any difference)."""
     from summarizer_b200.models import vasnet_autograd

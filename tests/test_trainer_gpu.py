@@ -194,7 +194,7 @@ def test_reset_reuses_tensors_and_step_graphs_across_folds(tmp_path):
 
 @pytest.mark.gpu
 def test_concurrent_folds_train_side_by_side(tmp_path):
-    """--extra_params concurrent_folds=3: the five folds of a split file train on three worker threads / streams of one
+    """--concurrent_folds 3: the five folds of a split file train on three worker threads / streams of one
     GPU (eager first visit, graph capture on the worker's stream, replay) — every fold reports, the best fold's weights
     are written and load back, and the metrics are in the range the sequential loop gives."""
     from summarizer_b200.main import train
