@@ -252,6 +252,11 @@ def main(argv=None):
             torch.cuda.set_device(local)
             hps_init["cuda_device"] = local
         if torch.cuda.is_available() and hps_init["extra_params"].get("data_parallel", False):
+            if str(hps_init["extra_params"].get("dp_cuda_graphs", "no")).lower() in ("yes", "1", "true"):
+                # replicas capture their step graphs at DIFFERENT steps: NCCL must not turn a capture into a collective
+                # host-side operation (graph-time buffer registration exchanges handles between the ranks; for NVLS it is
+                # collective).  A precaution — the 8-GPU run of this mode is still to be confirmed.
+                os.environ.setdefault("NCCL_GRAPH_REGISTER", "0")
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         else:
             dist.init_process_group("gloo")
